@@ -1,0 +1,276 @@
+"""Low-level object wrapper of the fsgpu C ABI: one `Context` per (mesh, device)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import BeamParams, ShellParams, check, f64, i64, lib, ptr
+
+
+@dataclass
+class SparseMatrixCSC:
+    """What Julia's `SparseMatrixCSC{Float64,Int64}` holds: 1-based colptr/rowval."""
+
+    m: int
+    n: int
+    colptr: np.ndarray
+    rowval: np.ndarray
+    nzval: np.ndarray
+    csr: bool = False  # CSR_SYMM target: colptr is rowptr, rowval is colval
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        cls = sp.csr_matrix if self.csr else sp.csc_matrix
+        return cls((self.nzval, self.rowval - 1, self.colptr - 1), shape=(self.m, self.n))
+
+
+class Context:
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        check(lib.fsgpu_create(C.byref(h), device))
+        self._h = h
+        self.target = None
+
+    def close(self):
+        if self._h:
+            lib.fsgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data ------------------------------------------------------------------------
+    def set_mesh(self, conn, xyz):
+        """conn: (nelem, nnpe) 1-based ints (row e = fes.conn[e]); xyz: (nnodes, 3)."""
+        conn = np.ascontiguousarray(conn, dtype=np.int64)  # C order == nnpe x nelem column-major
+        xyz = f64(xyz, "F")
+        self.nelem, self.nnpe = conn.shape
+        self.nnodes = xyz.shape[0]
+        check(lib.fsgpu_set_mesh(self._h, self.nnpe, self.nelem, ptr(conn), self.nnodes, ptr(xyz)))
+
+    def set_dofnums(self, dofnums, nfree, nall=None):
+        d = i64(dofnums, "F")
+        self.nfree = int(nfree)
+        self.nall = int(d.size if nall is None else nall)
+        check(lib.fsgpu_set_dofnums(self._h, ptr(d), self.nfree, self.nall))
+
+    def set_normals(self, normals, valid):
+        n = f64(normals, "F")
+        v = np.ascontiguousarray(valid, dtype=np.uint8)
+        check(lib.fsgpu_set_normals(self._h, ptr(n), ptr(v)))
+
+    def associategeometry(self, threshold_angle=30.0, fixed_dir=None, accumulate=False):
+        fd = None if fixed_dir is None else f64(fixed_dir)
+        check(lib.fsgpu_associategeometry(self._h, float(threshold_angle), ptr(fd), 1 if accumulate else 0))
+
+    def get_normals(self):
+        n = np.zeros((self.nnodes, 3), order="F")
+        v = np.zeros(self.nnodes, dtype=np.uint8)
+        check(lib.fsgpu_get_normals(self._h, ptr(n), ptr(v)))
+        return n, v.astype(bool)
+
+    def set_thickness(self, t):
+        t = f64(np.atleast_1d(t), "C").ravel()
+        check(lib.fsgpu_set_thickness(self._h, ptr(t), t.size))
+
+    def set_stab_factor(self, f):
+        if f is None:
+            check(lib.fsgpu_set_stab_factor(self._h, None, 0))
+        else:
+            f = f64(f, "C").ravel()
+            check(lib.fsgpu_set_stab_factor(self._h, ptr(f), f.size))
+
+    def element_sizes(self):
+        h = np.zeros(self.nelem)
+        check(lib.fsgpu_element_sizes(self._h, ptr(h)))
+        return h
+
+    def set_rule(self, pc, w):
+        pc = np.asarray(pc, dtype=np.float64)
+        xi = np.ascontiguousarray(pc[:, 0])
+        eta = np.ascontiguousarray(pc[:, 1])
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        self.npts = len(w)
+        check(lib.fsgpu_set_rule(self._h, len(w), ptr(xi), ptr(eta), ptr(w)))
+
+    def set_layup(self, group_data, group_of_elem, csmat):
+        """group_data (ngroups, 34); group_of_elem (nelem,) 1-based or None; csmat (..., 3, 3)."""
+        g = f64(group_data, "C").reshape(-1, 34)
+        go = None if group_of_elem is None else i64(group_of_elem, "C")
+        cs = np.asarray(csmat, dtype=np.float64).reshape(-1, 3, 3)
+        cs_cm = np.ascontiguousarray(np.transpose(cs, (0, 2, 1)))  # each 3x3 column-major
+        check(lib.fsgpu_set_layup(self._h, g.shape[0], ptr(g), ptr(go), ptr(cs_cm), cs.shape[0]))
+
+    def set_beam_sections(self, A, I1, I2, I3, J, A2s, A3s, x1x2):
+        arrs = [f64(a, "C").ravel() for a in (A, I1, I2, I3, J, A2s, A3s)]
+        xx = np.ascontiguousarray(np.asarray(x1x2, dtype=np.float64).reshape(-1, 3))  # 3 x nelem column-major
+        check(lib.fsgpu_set_beam_sections(self._h, *[ptr(a) for a in arrs], ptr(xx)))
+
+    def set_state(self, u1, Rfield1):
+        u = f64(u1, "F")
+        R = f64(Rfield1, "F")
+        check(lib.fsgpu_set_state(self._h, ptr(u), ptr(R)))
+
+    def set_stream(self, cuda_stream):
+        check(lib.fsgpu_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        check(lib.fsgpu_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(lib.fsgpu_launch_count(self._h))
+
+    # ---- symbolic / numeric -------------------------------------------------------------
+    def symbolic(self, target):
+        nr, nc, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.fsgpu_symbolic(self._h, int(target), C.byref(nr), C.byref(nc), C.byref(nnz)))
+        self.target = int(target)
+        return nr.value, nc.value, nnz.value
+
+    def shell_op(self, name, params: ShellParams):
+        check(getattr(lib, f"fsgpu_{name}")(self._h, C.byref(params)))
+
+    def beam_op(self, name, params: BeamParams, *extra):
+        check(getattr(lib, f"fsgpu_corotbeam_{name}")(self._h, C.byref(params), *extra))
+
+    def shell_mass_diag(self, params, kind, nfree_only=False):
+        check(lib.fsgpu_shell_mass_diag(self._h, C.byref(params), kind, 1 if nfree_only else 0))
+
+    def result_size(self):
+        nr, nc, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.fsgpu_result_size(self._h, C.byref(nr), C.byref(nc), C.byref(nnz)))
+        return nr.value, nc.value, nnz.value
+
+    def fetch_matrix(self, out=None):
+        """makematrix!: returns SparseMatrixCSC (Julia-layout arrays).  `out`: optional
+        preallocated (colptr, rowval, nzval) numpy arrays (e.g. views of pinned memory)."""
+        m, n, nnz = self.result_size()
+        if out is None:
+            colptr = np.empty(n + 1, dtype=np.int64)
+            rowval = np.empty(nnz, dtype=np.int64)
+            nzval = np.empty(nnz, dtype=np.float64)
+        else:
+            colptr, rowval, nzval = out
+        check(lib.fsgpu_fetch_matrix(self._h, ptr(colptr), ptr(rowval), ptr(nzval)))
+        return SparseMatrixCSC(m, n, colptr, rowval, nzval, csr=(self.target == L.CSR_SYMM))
+
+    def fetch_values(self, nzval):
+        check(lib.fsgpu_fetch_matrix(self._h, None, None, ptr(nzval)))
+        return nzval
+
+    def fetch_vector(self, n):
+        out = np.empty(n)
+        check(lib.fsgpu_fetch_vector(self._h, ptr(out), n))
+        return out
+
+    def element_matrices(self, kind, op, params):
+        n = 6 * self.nnpe
+        out = np.zeros((self.nelem, n, n))  # [e][col][row]
+        check(lib.fsgpu_element_matrices(self._h, kind, op, C.byref(params), ptr(out)))
+        return np.transpose(out, (0, 2, 1))  # -> [e][row][col]
+
+    def element_vectors(self, params):
+        out = np.zeros((self.nelem, 12))
+        check(lib.fsgpu_element_vectors(self._h, C.byref(params), ptr(out)))
+        return out
+
+    def update_rotation_field(self, dchi_values):
+        d = f64(dchi_values, "F")
+        out = np.zeros((self.nnodes, 9), order="F")
+        check(lib.fsgpu_update_rotation_field(self._h, ptr(d), ptr(out)))
+        return out
+
+    def coo_to_csc(self, I, J, V, m, n):
+        I, J, V = i64(I, "C"), i64(J, "C"), f64(V, "C")
+        nnz = C.c_int64()
+        check(lib.fsgpu_coo_to_csc(self._h, m, n, I.size, ptr(I), ptr(J), ptr(V), C.byref(nnz), None, None, None))
+        colptr = np.empty(n + 1, dtype=np.int64)
+        rowval = np.empty(nnz.value, dtype=np.int64)
+        nzval = np.empty(nnz.value)
+        check(lib.fsgpu_coo_to_csc(self._h, m, n, I.size, ptr(I), ptr(J), ptr(V), C.byref(nnz), ptr(colptr), ptr(rowval), ptr(nzval)))
+        return SparseMatrixCSC(m, n, colptr, rowval, nzval)
+
+
+class Explicit:
+    """Device-resident central-difference integrator (fsgpu_explicit_*)."""
+
+    def __init__(self, ctx: Context, K=None, mdiag=None, c_scale=0.0, dt=0.0):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if K is None:
+            check(lib.fsgpu_explicit_create_from_ctx(C.byref(h), ctx._h, float(c_scale), float(dt)))
+            self.n = ctx.result_size()[0]
+        else:
+            rowptr, colval, nzval = K  # Int64 1-based CSR
+            rowptr, colval, nzval = i64(rowptr, "C"), i64(colval, "C"), f64(nzval, "C")
+            md = f64(mdiag, "C")
+            self.n = md.size
+            check(lib.fsgpu_explicit_create(C.byref(h), ctx._h, self.n, ptr(rowptr), ptr(colval), ptr(nzval), ptr(md), float(c_scale), float(dt)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib.fsgpu_explicit_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, U0=None, V0=None):
+        U0 = None if U0 is None else f64(U0, "C")
+        V0 = None if V0 is None else f64(V0, "C")
+        check(lib.fsgpu_explicit_set_state(self._h, ptr(U0), ptr(V0)))
+
+    def set_load(self, F0):
+        F0 = None if F0 is None else f64(F0, "C")
+        check(lib.fsgpu_explicit_set_load(self._h, ptr(F0)))
+
+    def start(self, fscale0=1.0):
+        check(lib.fsgpu_explicit_start(self._h, float(fscale0)))
+
+    def step(self, nsteps, fscale=None):
+        fs = None if fscale is None else f64(fscale, "C")
+        check(lib.fsgpu_explicit_step(self._h, int(nsteps), ptr(fs)))
+
+    def step_begin(self):
+        check(lib.fsgpu_explicit_step_begin(self._h))
+
+    def step_end(self, fscale=1.0):
+        check(lib.fsgpu_explicit_step_end(self._h, float(fscale)))
+
+    def get_state(self):
+        U, V, A = np.empty(self.n), np.empty(self.n), np.empty(self.n)
+        check(lib.fsgpu_explicit_get_state(self._h, ptr(U), ptr(V), ptr(A)))
+        return U, V, A
+
+    def spmv(self, x):
+        x = f64(x, "C")
+        y = np.empty(self.n)
+        check(lib.fsgpu_explicit_spmv(self._h, ptr(x), ptr(y)))
+        return y
+
+    def omega_max_sq(self, maxit=30):
+        lam = C.c_double()
+        check(lib.fsgpu_explicit_omega_max(self._h, int(maxit), C.byref(lam)))
+        return lam.value
+
+    def kinetic_energy(self):
+        ke = C.c_double()
+        check(lib.fsgpu_explicit_kinetic_energy(self._h, C.byref(ke)))
+        return ke.value
+
+    def device_state(self):
+        p = [C.c_void_p() for _ in range(4)]
+        check(lib.fsgpu_explicit_device_state(self._h, *[C.byref(x) for x in p]))
+        return tuple(x.value for x in p)  # U, V, A, E device addresses

@@ -1,0 +1,1038 @@
+// libfsgpu core: context, data hand-over, nodal normals, symbolic phase (CSC pattern
+// bit-exact to Julia `sparse` + element-entry slot map), result hand-back, COO->CSC.
+#include <stdarg.h>
+
+#include <cub/cub.cuh>
+
+#include "fsgpu_internal.cuh"
+#include "fsgpu_math.cuh"
+
+namespace fs {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int check_ctx(fsgpu_ctx* c) {
+  FS_REQUIRE(c != nullptr, FSGPU_ERR_ARG, "null context");
+  FS_CUDA(cudaSetDevice(c->device));
+  return FSGPU_OK;
+}
+
+int upload(fsgpu_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return FSGPU_OK;
+  FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return FSGPU_OK;
+}
+int download(fsgpu_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return FSGPU_OK;
+  FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return FSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// conversion kernels (Julia layout -> device layout)
+// ------------------------------------------------------------------------------------
+__global__ void k_conn_convert(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n, int64_t nnodes,
+                               int32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t v = in[i];
+  if (v < 1 || v > nnodes) {
+    atomicExch(flag, 1);
+    v = 1;
+  }
+  out[i] = (int32_t)(v - 1);
+}
+__global__ void k_pack3(const double* __restrict__ in, double4* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = make_double4(in[i], in[n + i], in[2 * n + i], 0.0);
+}
+__global__ void k_pack_normals(const double* __restrict__ in, const unsigned char* __restrict__ valid,
+                               double4* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = make_double4(in[i], in[n + i], in[2 * n + i], valid[i] ? 1.0 : 0.0);
+}
+__global__ void k_unpack_normals(const double4* __restrict__ in, double* __restrict__ out, unsigned char* __restrict__ valid,
+                                 int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 v = in[i];
+  out[i] = v.x;
+  out[n + i] = v.y;
+  out[2 * n + i] = v.z;
+  valid[i] = v.w != 0.0 ? 1 : 0;
+}
+__global__ void k_dof_convert(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t nnodes, int64_t nall,
+                              int32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // i = node*6 + d
+  if (i >= nnodes * 6) return;
+  int64_t node = i / 6, d = i % 6;
+  int64_t v = in[d * nnodes + node];
+  if (v < 1 || v > nall) {
+    atomicExch(flag, 1);
+    v = 1;
+  }
+  out[i] = (int32_t)(v - 1);
+}
+__global__ void k_transpose_rows(const double* __restrict__ in, double* __restrict__ out, int64_t nrows, int ncols) {
+  // column-major nrows x ncols  ->  row-major [nrows][ncols]
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nrows * ncols) return;
+  int64_t r = i / ncols;
+  int c = (int)(i % ncols);
+  out[i] = in[(int64_t)c * nrows + r];
+}
+__global__ void k_csmat_convert(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
+  // each 3x3 column-major -> row-major
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * 9) return;
+  int64_t m = i / 9;
+  int k = (int)(i % 9), r = k / 3, cc = k % 3;
+  out[i] = in[m * 9 + cc * 3 + r];
+}
+__global__ void k_i64_minus1_to_i32(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n, int64_t lo,
+                                    int64_t hi, int32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t v = in[i];
+  if (v < lo || v > hi) {
+    atomicExch(flag, 1);
+    v = lo;
+  }
+  out[i] = (int32_t)(v - 1);
+}
+__global__ void k_i32_plus1_to_i64(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (int64_t)in[i] + 1;
+}
+
+static int ensure_flag(fsgpu_ctx* c) {
+  FS_TRY(c->flag.ensure(8));
+  FS_CUDA(cudaMemsetAsync(c->flag.p, 0, 8 * sizeof(int32_t), c->stream));
+  return FSGPU_OK;
+}
+static int read_flag(fsgpu_ctx* c, int idx, int32_t* v) {
+  FS_CUDA(cudaMemcpyAsync(v, c->flag.p + idx, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  return FSGPU_OK;
+}
+
+// stage a host array on the device scratch buffer `tmp`
+static int stage(fsgpu_ctx* c, const void* host, size_t bytes, void** dev) {
+  FS_TRY(c->tmp.ensure(bytes));
+  FS_TRY(upload(c, c->tmp.p, host, bytes));
+  *dev = c->tmp.p;
+  return FSGPU_OK;
+}
+
+#define LAUNCH(ctx, kern, n, ...)                                              \
+  do {                                                                         \
+    if ((n) > 0) {                                                             \
+      kern<<<fs::grid_for((n), 256), 256, 0, (ctx)->stream>>>(__VA_ARGS__);    \
+      (ctx)->launches++;                                                       \
+    }                                                                          \
+  } while (0)
+
+}  // namespace fs
+
+using namespace fs;
+
+// ------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------
+extern "C" const char* fsgpu_last_error(void) { return fs::g_err.c_str(); }
+extern "C" int fsgpu_version(void) { return 100; }
+
+extern "C" int fsgpu_create(fsgpu_ctx** out, int device) {
+  FS_REQUIRE(out != nullptr, FSGPU_ERR_ARG, "null output pointer");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); libfsgpu has no CPU fallback", cudaGetErrorString(e));
+    return FSGPU_ERR_CUDA;
+  }
+  FS_REQUIRE(device >= 0 && device < n, FSGPU_ERR_ARG, "device %d out of range (have %d)", device, n);
+  FS_CUDA(cudaSetDevice(device));
+  fsgpu_ctx* c = new fsgpu_ctx();
+  c->device = device;
+  *out = c;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_destroy(fsgpu_ctx* c) {
+  if (!c) return FSGPU_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  delete c;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_host_alloc(void** p, int64_t bytes) {
+  FS_REQUIRE(p && bytes >= 0, FSGPU_ERR_ARG, "bad arguments");
+  FS_CUDA(cudaMallocHost(p, (size_t)bytes));
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_host_free(void* p) {
+  if (p) FS_CUDA(cudaFreeHost(p));
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_set_stream(fsgpu_ctx* c, void* s) {
+  FS_TRY(check_ctx(c));
+  c->stream = (cudaStream_t)s;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_sync(fsgpu_ctx* c) {
+  FS_TRY(check_ctx(c));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  return FSGPU_OK;
+}
+extern "C" int64_t fsgpu_launch_count(fsgpu_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------
+// data hand-over
+// ------------------------------------------------------------------------------------
+extern "C" int fsgpu_set_mesh(fsgpu_ctx* c, int32_t nnpe, int64_t nelem, const int64_t* conn, int64_t nnodes,
+                              const double* xyz) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(nnpe >= 2 && nnpe <= 4, FSGPU_ERR_ARG, "nnpe must be 2, 3 or 4 (got %d)", nnpe);
+  FS_REQUIRE(nelem >= 0 && nnodes >= 0 && nnodes < (int64_t)INT32_MAX / 8, FSGPU_ERR_ARG, "bad mesh sizes");
+  FS_REQUIRE((conn || nelem == 0) && (xyz || nnodes == 0), FSGPU_ERR_ARG, "null mesh arrays");
+  c->nnpe = nnpe;
+  c->nelem = nelem;
+  c->nnodes = nnodes;
+  c->target = -1;
+  c->have_matrix = c->have_vector = false;
+  c->associated = false;
+  c->have_sections = c->have_state = false;
+  c->ngroups = 0;
+  c->nthick = c->nstab = 0;
+  FS_TRY(ensure_flag(c));
+  void* d;
+  FS_TRY(c->conn.ensure((size_t)nelem * nnpe));
+  FS_TRY(stage(c, conn, (size_t)nelem * nnpe * sizeof(int64_t), &d));
+  LAUNCH(c, k_conn_convert, nelem * nnpe, (const int64_t*)d, c->conn.p, nelem * nnpe, nnodes, c->flag.p);
+  FS_TRY(c->xyz.ensure((size_t)nnodes));
+  FS_TRY(c->tmp2.ensure((size_t)nnodes * 3 * sizeof(double)));
+  FS_TRY(upload(c, c->tmp2.p, xyz, (size_t)nnodes * 3 * sizeof(double)));
+  LAUNCH(c, k_pack3, nnodes, (const double*)c->tmp2.p, c->xyz.p, nnodes);
+  int32_t f;
+  FS_TRY(read_flag(c, 0, &f));
+  FS_REQUIRE(f == 0, FSGPU_ERR_ARG, "connectivity refers to a node outside 1..%lld", (long long)nnodes);
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_set_dofnums(fsgpu_ctx* c, const int64_t* dofnums, int64_t nfree, int64_t nall) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->nnpe > 0, FSGPU_ERR_STATE, "set the mesh first");
+  FS_REQUIRE(dofnums != nullptr, FSGPU_ERR_ARG, "null dofnums");
+  FS_REQUIRE(nfree >= 0 && nfree <= nall && nall < (int64_t)INT32_MAX, FSGPU_ERR_ARG, "bad nfree/nall");
+  FS_TRY(ensure_flag(c));
+  void* d;
+  FS_TRY(c->dof.ensure((size_t)c->nnodes * 6));
+  FS_TRY(stage(c, dofnums, (size_t)c->nnodes * 6 * sizeof(int64_t), &d));
+  LAUNCH(c, k_dof_convert, c->nnodes * 6, (const int64_t*)d, c->dof.p, c->nnodes, nall, c->flag.p);
+  int32_t f;
+  FS_TRY(read_flag(c, 0, &f));
+  // FinEtools assemble!: "Row degree of freedom < 1" / "> size"
+  FS_REQUIRE(f == 0, FSGPU_ERR_DOF_RANGE, "degree of freedom < 1 or > nalldofs (%lld)", (long long)nall);
+  c->nfree = nfree;
+  c->nall = nall;
+  c->have_dofs = true;
+  c->target = -1;
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_set_normals(fsgpu_ctx* c, const double* normals, const uint8_t* valid) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->nnpe > 0, FSGPU_ERR_STATE, "set the mesh first");
+  FS_REQUIRE(normals && valid, FSGPU_ERR_ARG, "null normals");
+  const int64_t n = c->nnodes;
+  FS_TRY(c->nrm.ensure((size_t)n));
+  FS_TRY(c->tmp.ensure((size_t)n * 3 * sizeof(double)));
+  FS_TRY(c->tmp2.ensure((size_t)n));
+  FS_TRY(upload(c, c->tmp.p, normals, (size_t)n * 3 * sizeof(double)));
+  FS_TRY(upload(c, c->tmp2.p, valid, (size_t)n));
+  LAUNCH(c, k_pack_normals, n, (const double*)c->tmp.p, (const unsigned char*)c->tmp2.p, c->nrm.p, n);
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->associated = true;
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_get_normals(fsgpu_ctx* c, double* normals, uint8_t* valid) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->associated, FSGPU_ERR_STATE, "geometry not associated");
+  const int64_t n = c->nnodes;
+  FS_TRY(c->tmp.ensure((size_t)n * 3 * sizeof(double)));
+  FS_TRY(c->tmp2.ensure((size_t)n));
+  LAUNCH(c, k_unpack_normals, n, c->nrm.p, (double*)c->tmp.p, (unsigned char*)c->tmp2.p, n);
+  FS_TRY(download(c, normals, c->tmp.p, (size_t)n * 3 * sizeof(double)));
+  FS_TRY(download(c, valid, c->tmp2.p, (size_t)n));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  return FSGPU_OK;
+}
+
+// ---- associategeometry! on the device ------------------------------------------------
+// pass 1: accumulate (weighted) element normals at the nodes; pass 2: normalise;
+// pass 3: mark nodes whose nodal normal deviates from an adjacent element normal.
+__device__ inline fsm::V3 ldxyz(const double4* p, int i) {
+  double4 v = p[i];
+  return fsm::v3(v.x, v.y, v.z);
+}
+__device__ inline fsm::V3 elem_normal_at(const double4* xyz, const int32_t* cn, int nnpe, int k, double& wgt) {
+  using namespace fsm;
+  if (nnpe == 3) {
+    V3 a = ldxyz(xyz, cn[0]), b = ldxyz(xyz, cn[1]), cc = ldxyz(xyz, cn[2]);
+    wgt = 1.0;  // T3: unweighted (src/FEMMShellT3FFModule.jl:583-586)
+    return element_triad(b - a, cc - a).e3;
+  }
+  V3 X[4] = {ldxyz(xyz, cn[0]), ldxyz(xyz, cn[1]), ldxyz(xyz, cn[2]), ldxyz(xyz, cn[3])};
+  const double px[4] = {-1, 1, 1, -1}, py[4] = {-1, -1, 1, 1};  // NodalTensorProductRule(2)
+  Q4Geom g = q4_geometry(X, px[k], py[k]);
+  wgt = g.Jac;  // Q4: Jacobian weighted (src/FEMMShellQ4RSModule.jl:489-494)
+  return g.E.e3;
+}
+__global__ void k_normals_accumulate(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe,
+                                     int64_t nelem, double* __restrict__ acc /*[nnodes][3]*/, int use_fixed, double fx,
+                                     double fy, double fz) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nelem * nnpe) return;
+  int64_t e = i / nnpe;
+  int k = (int)(i % nnpe);
+  const int32_t* cn = conn + e * nnpe;
+  double w;
+  fsm::V3 n = elem_normal_at(xyz, cn, nnpe, k, w);
+  if (use_fixed) n = fsm::v3(fx, fy, fz);
+  double* a = acc + (int64_t)cn[k] * 3;
+  atomicAdd(a + 0, w * n.x);
+  atomicAdd(a + 1, w * n.y);
+  atomicAdd(a + 2, w * n.z);
+}
+__global__ void k_normals_normalize(const double* __restrict__ acc, double4* __restrict__ nrm, int64_t n, int keep_valid) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = acc[3 * i], y = acc[3 * i + 1], z = acc[3 * i + 2];
+  double nn = sqrt(x * x + y * y + z * z);
+  if (nn > 0.0) {
+    x /= nn;
+    y /= nn;
+    z /= nn;
+  }
+  double v = keep_valid ? nrm[i].w : 1.0;
+  nrm[i] = make_double4(x, y, z, v);
+}
+__global__ void k_normals_validate(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe,
+                                   int64_t nelem, double4* __restrict__ nrm, double limit, int use_fixed, double fx,
+                                   double fy, double fz, int fixed_in_check) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nelem * nnpe) return;
+  int64_t e = i / nnpe;
+  int k = (int)(i % nnpe);
+  const int32_t* cn = conn + e * nnpe;
+  double w;
+  fsm::V3 n = elem_normal_at(xyz, cn, nnpe, k, w);
+  if (use_fixed && fixed_in_check) n = fsm::v3(fx, fy, fz);
+  double4 nn = nrm[cn[k]];
+  double nd = nn.x * n.x + nn.y * n.y + nn.z * n.z;
+  if (nd < limit) nrm[cn[k]].w = 0.0;  // benign race: every writer stores 0
+}
+__global__ void k_unpack_acc(const double4* __restrict__ nrm, double* __restrict__ acc, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 v = nrm[i];
+  acc[3 * i] = v.x;
+  acc[3 * i + 1] = v.y;
+  acc[3 * i + 2] = v.z;
+}
+
+extern "C" int fsgpu_associategeometry(fsgpu_ctx* c, double threshold_angle_deg, const double* fixed_dir,
+                                       int32_t accumulate) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->nnpe == 3 || c->nnpe == 4, FSGPU_ERR_STATE, "associategeometry needs a T3 or Q4 mesh");
+  const int64_t n = c->nnodes;
+  const bool had = c->associated && c->nrm.p != nullptr;
+  FS_TRY(c->nrm.ensure((size_t)n));
+  FS_TRY(c->tmp.ensure((size_t)n * 3 * sizeof(double)));
+  double* acc = (double*)c->tmp.p;
+  const int keep = (accumulate && had) ? 1 : 0;
+  if (keep) {
+    LAUNCH(c, k_unpack_acc, n, c->nrm.p, acc, n);
+  } else {
+    FS_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * 3 * sizeof(double), c->stream));
+  }
+  const int uf = fixed_dir ? 1 : 0;
+  const double fx = uf ? fixed_dir[0] : 0, fy = uf ? fixed_dir[1] : 0, fz = uf ? fixed_dir[2] : 0;
+  LAUNCH(c, k_normals_accumulate, c->nelem * c->nnpe, c->conn.p, c->xyz.p, c->nnpe, c->nelem, acc, uf, fx, fy, fz);
+  LAUNCH(c, k_normals_normalize, n, acc, c->nrm.p, n, keep);
+  const double s = sin(threshold_angle_deg / 180 * M_PI);
+  const double ntol = 1 - sqrt(1 - s * s);
+  // T3 (homogeneous and composite) checks against the ELEMENT normal (src/FEMMShellT3FFModule.jl:601-611,
+  // ...CompModule.jl:528-538); Q4 checks against the csys normal (src/FEMMShellQ4RSModule.jl:508-519).
+  const int fixed_in_check = (c->nnpe == 4) ? 1 : 0;
+  LAUNCH(c, k_normals_validate, c->nelem * c->nnpe, c->conn.p, c->xyz.p, c->nnpe, c->nelem, c->nrm.p, 1 - ntol, uf, fx,
+         fy, fz, fixed_in_check);
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->associated = true;
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_set_thickness(fsgpu_ctx* c, const double* t, int64_t n) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(t && n >= 1, FSGPU_ERR_ARG, "bad thickness array");
+  FS_TRY(c->thick.ensure((size_t)n));
+  FS_TRY(upload(c, c->thick.p, t, (size_t)n * sizeof(double)));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->nthick = n;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_set_stab_factor(fsgpu_ctx* c, const double* f, int64_t n) {
+  FS_TRY(check_ctx(c));
+  if (!f || n == 0) {
+    c->nstab = 0;
+    return FSGPU_OK;
+  }
+  FS_REQUIRE(n == c->nelem, FSGPU_ERR_ARG, "stab factor array must have nelem entries");
+  FS_TRY(c->stabf.ensure((size_t)n));
+  FS_TRY(upload(c, c->stabf.p, f, (size_t)n * sizeof(double)));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->nstab = n;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_set_rule(fsgpu_ctx* c, int32_t npts, const double* xi, const double* eta, const double* w) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(npts >= 1 && npts <= kMaxGP && xi && eta && w, FSGPU_ERR_ARG, "rule must have 1..%d points", kMaxGP);
+  c->rule.npts = npts;
+  for (int i = 0; i < npts; ++i) {
+    c->rule.xi[i] = xi[i];
+    c->rule.eta[i] = eta[i];
+    c->rule.w[i] = w[i];
+  }
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_set_layup(fsgpu_ctx* c, int32_t ngroups, const double* group_data, const int64_t* group_of_elem,
+                               const double* csmat, int64_t ncs) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->nnpe > 0, FSGPU_ERR_STATE, "set the mesh first");
+  FS_REQUIRE(ngroups >= 1 && group_data && csmat && ncs >= 1, FSGPU_ERR_ARG, "bad layup arguments");
+  FS_REQUIRE(ngroups == 1 || group_of_elem, FSGPU_ERR_ARG, "group_of_elem required for more than one group");
+  FS_TRY(ensure_flag(c));
+  FS_TRY(c->group_data.ensure((size_t)ngroups * 34));
+  FS_TRY(upload(c, c->group_data.p, group_data, (size_t)ngroups * 34 * sizeof(double)));
+  FS_TRY(c->group_of.ensure((size_t)c->nelem));
+  if (group_of_elem) {
+    void* d;
+    FS_TRY(stage(c, group_of_elem, (size_t)c->nelem * sizeof(int64_t), &d));
+    LAUNCH(c, k_i64_minus1_to_i32, c->nelem, (const int64_t*)d, c->group_of.p, c->nelem, (int64_t)1, (int64_t)ngroups,
+           c->flag.p);
+  } else {
+    FS_CUDA(cudaMemsetAsync(c->group_of.p, 0, (size_t)c->nelem * sizeof(int32_t), c->stream));
+  }
+  FS_TRY(c->csmat.ensure((size_t)ncs * 9));
+  FS_TRY(c->tmp2.ensure((size_t)ncs * 9 * sizeof(double)));
+  FS_TRY(upload(c, c->tmp2.p, csmat, (size_t)ncs * 9 * sizeof(double)));
+  LAUNCH(c, k_csmat_convert, ncs * 9, (const double*)c->tmp2.p, c->csmat.p, ncs);
+  int32_t f;
+  FS_TRY(read_flag(c, 0, &f));
+  FS_REQUIRE(f == 0, FSGPU_ERR_ARG, "layup group index outside 1..%d", ngroups);
+  c->ngroups = ngroups;
+  c->ncs = ncs;
+  return FSGPU_OK;
+}
+__global__ void k_pack_sections(const double* A, const double* I1, const double* I2, const double* I3, const double* J,
+                                const double* A2s, const double* A3s, const double* x1x2, double* out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* o = out + i * 10;
+  o[0] = A[i];
+  o[1] = I1[i];
+  o[2] = I2[i];
+  o[3] = I3[i];
+  o[4] = J[i];
+  o[5] = A2s[i];
+  o[6] = A3s[i];
+  o[7] = x1x2[3 * i];
+  o[8] = x1x2[3 * i + 1];
+  o[9] = x1x2[3 * i + 2];
+}
+extern "C" int fsgpu_set_beam_sections(fsgpu_ctx* c, const double* A, const double* I1, const double* I2, const double* I3,
+                                       const double* J, const double* A2s, const double* A3s, const double* x1x2) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->nnpe == 2, FSGPU_ERR_STATE, "beam sections need an L2 mesh");
+  FS_REQUIRE(A && I1 && I2 && I3 && J && A2s && A3s && x1x2, FSGPU_ERR_ARG, "null section array");
+  const int64_t n = c->nelem;
+  FS_TRY(c->sec.ensure((size_t)n * 10));
+  FS_TRY(c->tmp.ensure((size_t)n * 10 * sizeof(double)));
+  double* t = (double*)c->tmp.p;
+  const double* src[7] = {A, I1, I2, I3, J, A2s, A3s};
+  for (int k = 0; k < 7; ++k) FS_TRY(upload(c, t + k * n, src[k], (size_t)n * sizeof(double)));
+  FS_TRY(upload(c, t + 7 * n, x1x2, (size_t)n * 3 * sizeof(double)));
+  LAUNCH(c, k_pack_sections, n, t, t + n, t + 2 * n, t + 3 * n, t + 4 * n, t + 5 * n, t + 6 * n, t + 7 * n, c->sec.p, n);
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_sections = true;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_set_state(fsgpu_ctx* c, const double* u1, const double* Rfield1) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->nnpe > 0, FSGPU_ERR_STATE, "set the mesh first");
+  FS_REQUIRE(u1 && Rfield1, FSGPU_ERR_ARG, "null state arrays");
+  const int64_t n = c->nnodes;
+  FS_TRY(c->u1.ensure((size_t)n));
+  FS_TRY(c->R1.ensure((size_t)n * 9));
+  FS_TRY(c->tmp.ensure((size_t)n * 9 * sizeof(double)));
+  FS_TRY(upload(c, c->tmp.p, u1, (size_t)n * 3 * sizeof(double)));
+  LAUNCH(c, k_pack3, n, (const double*)c->tmp.p, c->u1.p, n);
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  FS_TRY(upload(c, c->tmp.p, Rfield1, (size_t)n * 9 * sizeof(double)));
+  LAUNCH(c, k_transpose_rows, n * 9, (const double*)c->tmp.p, c->R1.p, n, 9);
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_state = true;
+  return FSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// symbolic phase
+// ------------------------------------------------------------------------------------
+namespace fs {
+
+struct TargetInfo {
+  bool diag_only;
+  int64_t nr, nc;  // matrix size; rows/cols with dof index >= nr/nc are dropped
+};
+static TargetInfo target_info(const fsgpu_ctx* c, int target) {
+  switch (target) {
+    case FSGPU_FFBLOCK:
+      return {false, c->nfree, c->nfree};
+    case FSGPU_FFBLOCK_DIAG:
+      return {true, c->nfree, c->nfree};
+    case FSGPU_SPARSE_DIAG:
+      return {true, c->nall, c->nall};
+    default:
+      return {false, c->nall, c->nall};
+  }
+}
+
+__global__ void k_pair_keys(const int32_t* __restrict__ conn, int nnpe, int64_t nelem, uint64_t* __restrict__ keys) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t n = nelem * nnpe * nnpe;
+  if (i >= n) return;
+  int64_t e = i / (nnpe * nnpe);
+  int r = (int)(i % (nnpe * nnpe));
+  uint64_t a = (uint64_t)conn[e * nnpe + r / nnpe], b = (uint64_t)conn[e * nnpe + r % nnpe];
+  keys[i] = (a << 32) | b;
+}
+__global__ void k_adj_count(const uint64_t* __restrict__ ukeys, int64_t n, int32_t* __restrict__ deg) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomicAdd(deg + (int32_t)(ukeys[i] >> 32), 1);
+}
+__global__ void k_adj_fill(const uint64_t* __restrict__ ukeys, int64_t n, int32_t* __restrict__ adj) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  adj[i] = (int32_t)(ukeys[i] & 0xffffffffu);
+}
+// number of row-included dofs per node
+__global__ void k_node_rowcount(const int32_t* __restrict__ dof, int64_t nnodes, int64_t nr, int32_t* __restrict__ cnt) {
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= nnodes) return;
+  int n = 0;
+  for (int d = 0; d < 6; ++d) n += (dof[a * 6 + d] < nr) ? 1 : 0;
+  cnt[a] = n;
+}
+__global__ void k_col_count(const int32_t* __restrict__ dof, const int32_t* __restrict__ adjptr,
+                            const int32_t* __restrict__ adj, const int32_t* __restrict__ nodecnt, int64_t nnodes,
+                            int64_t nc, int diag_only, int64_t* __restrict__ colcnt) {
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= nnodes) return;
+  const int b0 = adjptr[a], b1 = adjptr[a + 1];
+  int64_t total = 0;
+  if (diag_only) {
+    total = (b1 > b0) ? 1 : 0;
+  } else {
+    for (int p = b0; p < b1; ++p) total += nodecnt[adj[p]];
+  }
+  for (int d = 0; d < 6; ++d) {
+    int32_t cdof = dof[a * 6 + d];
+    if (cdof < nc) colcnt[cdof] = total;
+  }
+}
+__global__ void k_colptr_narrow(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (int32_t)in[i];
+}
+__global__ void k_fill_rowval(const int32_t* __restrict__ dof, const int32_t* __restrict__ adjptr,
+                              const int32_t* __restrict__ adj, const int32_t* __restrict__ colptr, int64_t nnodes,
+                              int64_t nr, int64_t nc, int diag_only, int32_t* __restrict__ rowval) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // node*6 + d
+  if (i >= nnodes * 6) return;
+  const int64_t a = i / 6;
+  const int32_t cdof = dof[i];
+  if (cdof >= nc) return;
+  const int b0 = adjptr[a], b1 = adjptr[a + 1];
+  if (b1 == b0) return;
+  int p0 = colptr[cdof];
+  if (diag_only) {
+    rowval[p0] = cdof;
+    return;
+  }
+  int p = p0;
+  for (int q = b0; q < b1; ++q) {
+    const int32_t* db = dof + (int64_t)adj[q] * 6;
+    for (int d = 0; d < 6; ++d) {
+      int32_t r = db[d];
+      if (r < nr) {
+        // insertion into the sorted prefix [p0, p)
+        int k = p;
+        while (k > p0 && rowval[k - 1] > r) {
+          rowval[k] = rowval[k - 1];
+          --k;
+        }
+        rowval[k] = r;
+        ++p;
+      }
+    }
+  }
+}
+__device__ inline int find_row(const int32_t* __restrict__ rowval, int lo, int hi, int32_t r) {
+  // first position in [lo,hi) with rowval >= r; caller guarantees presence
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (rowval[mid] < r)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+// slot[k][i][e][j], k = c*6 + r : nzval index of entry (row dof r of node i, col dof c of node j)
+__global__ void k_slot_map(const int32_t* __restrict__ conn, const int32_t* __restrict__ dof,
+                           const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowval, int nnpe,
+                           int64_t nelem, int64_t nr, int64_t nc, int diag_only, int32_t* __restrict__ slot) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // e*nnpe + j
+  if (t >= nelem * nnpe) return;
+  const int64_t e = t / nnpe;
+  const int j = (int)(t % nnpe);
+  const int32_t* cj = dof + (int64_t)conn[e * nnpe + j] * 6;
+  const int64_t plane = nelem * nnpe;  // elements of one (k,i) plane
+  for (int i = 0; i < nnpe; ++i) {
+    const int32_t* ri = dof + (int64_t)conn[e * nnpe + i] * 6;
+    for (int cc = 0; cc < 6; ++cc) {
+      const int32_t cd = cj[cc];
+      const bool cin = cd < nc;
+      int lo = 0, hi = 0;
+      if (cin) {
+        lo = colptr[cd];
+        hi = colptr[cd + 1];
+      }
+      for (int rr = 0; rr < 6; ++rr) {
+        const int32_t rd = ri[rr];
+        int s = -1;
+        if (cin && rd < nr) {
+          if (diag_only) {
+            if (rd == cd) s = lo;
+          } else {
+            s = find_row(rowval, lo, hi, rd);
+          }
+        }
+        slot[((int64_t)((cc * 6 + rr) * nnpe + i)) * plane + t] = s;
+      }
+    }
+  }
+}
+__global__ void k_diag_slot(const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowval, int64_t nall,
+                            int64_t nc, int32_t* __restrict__ diagslot) {
+  int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (d >= nall) return;
+  int s = -1;
+  if (d < nc) {
+    int lo = colptr[d], hi = colptr[d + 1];
+    int p = find_row(rowval, lo, hi, (int32_t)d);
+    if (p < hi && rowval[p] == (int32_t)d) s = p;
+  }
+  diagslot[d] = s;
+}
+
+}  // namespace fs
+
+extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int64_t* ncols, int64_t* nnz) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->nnpe > 0 && c->have_dofs, FSGPU_ERR_STATE, "set mesh and dofnums before the symbolic phase");
+  FS_REQUIRE(target >= 0 && target <= 5, FSGPU_ERR_ARG, "unknown assembler target %d", target);
+  const TargetInfo ti = target_info(c, target);
+  const int nnpe = c->nnpe;
+  const int64_t ne = c->nelem, nn = c->nnodes;
+  cudaStream_t st = c->stream;
+
+  // (1) node adjacency from unique (a,b) pairs
+  const int64_t npairs = ne * nnpe * nnpe;
+  DBuf<uint64_t> keys, keys2;
+  DBuf<int32_t> deg, adjptr, adj, nodecnt;
+  DBuf<int64_t> colcnt, nsel;
+  FS_TRY(keys.ensure((size_t)npairs + 1));
+  FS_TRY(keys2.ensure((size_t)npairs + 1));
+  FS_TRY(nsel.ensure(1));
+  LAUNCH(c, k_pair_keys, npairs, c->conn.p, nnpe, ne, keys.p);
+  int nbits = 1;
+  while (((int64_t)1 << nbits) < nn + 1) ++nbits;
+  size_t tb = 0, tb2 = 0;
+  if (npairs > 0) {
+    FS_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, keys.p, keys2.p, npairs, 0, 32 + nbits, st));
+    FS_CUDA(cub::DeviceSelect::Unique(nullptr, tb2, keys2.p, keys.p, nsel.p, npairs, st));
+    FS_TRY(c->tmp.ensure(tb > tb2 ? tb : tb2));
+    FS_CUDA(cub::DeviceRadixSort::SortKeys(c->tmp.p, tb, keys.p, keys2.p, npairs, 0, 32 + nbits, st));
+    FS_CUDA(cub::DeviceSelect::Unique(c->tmp.p, tb2, keys2.p, keys.p, nsel.p, npairs, st));
+    c->launches += 8;
+  }
+  int64_t nuniq = 0;
+  if (npairs > 0) {
+    FS_CUDA(cudaMemcpyAsync(&nuniq, nsel.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaStreamSynchronize(st));
+  }
+  FS_TRY(deg.ensure((size_t)nn + 1));
+  FS_TRY(adjptr.ensure((size_t)nn + 1));
+  FS_TRY(adj.ensure((size_t)nuniq + 1));
+  FS_CUDA(cudaMemsetAsync(deg.p, 0, ((size_t)nn + 1) * sizeof(int32_t), st));
+  LAUNCH(c, k_adj_count, nuniq, keys.p, nuniq, deg.p);
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, deg.p, adjptr.p, nn + 1, st));
+  FS_TRY(c->tmp.ensure(tb));
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, deg.p, adjptr.p, nn + 1, st));
+  c->launches += 2;
+  LAUNCH(c, k_adj_fill, nuniq, keys.p, nuniq, adj.p);
+
+  // (2) column counts -> colptr
+  FS_TRY(nodecnt.ensure((size_t)nn + 1));
+  LAUNCH(c, k_node_rowcount, nn, c->dof.p, nn, ti.nr, nodecnt.p);
+  FS_TRY(colcnt.ensure((size_t)ti.nc + 1));
+  FS_CUDA(cudaMemsetAsync(colcnt.p, 0, ((size_t)ti.nc + 1) * sizeof(int64_t), st));
+  LAUNCH(c, k_col_count, nn, c->dof.p, adjptr.p, adj.p, nodecnt.p, nn, ti.nc, ti.diag_only ? 1 : 0, colcnt.p);
+  DBuf<int64_t> colptr64;
+  FS_TRY(colptr64.ensure((size_t)ti.nc + 1));
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, colcnt.p, colptr64.p, ti.nc + 1, st));
+  FS_TRY(c->tmp.ensure(tb));
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, colcnt.p, colptr64.p, ti.nc + 1, st));
+  c->launches += 2;
+  int64_t total = 0;
+  FS_CUDA(cudaMemcpyAsync(&total, colptr64.p + ti.nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  FS_CUDA(cudaStreamSynchronize(st));
+  FS_REQUIRE(total < (int64_t)INT32_MAX, FSGPU_ERR_ARG, "pattern has %lld entries; the int32 slot map limit is 2^31-1",
+             (long long)total);
+  FS_TRY(c->colptr.ensure((size_t)ti.nc + 1));
+  LAUNCH(c, k_colptr_narrow, ti.nc + 1, colptr64.p, c->colptr.p, ti.nc + 1);
+
+  // (3) rowval, sorted ascending within each column
+  FS_TRY(c->rowval.ensure((size_t)total + 1));
+  LAUNCH(c, k_fill_rowval, nn * 6, c->dof.p, adjptr.p, adj.p, c->colptr.p, nn, ti.nr, ti.nc, ti.diag_only ? 1 : 0,
+         c->rowval.p);
+
+  // (4) slot maps
+  FS_TRY(c->slot.ensure((size_t)36 * nnpe * nnpe * ne + 1));
+  LAUNCH(c, k_slot_map, ne * nnpe, c->conn.p, c->dof.p, c->colptr.p, c->rowval.p, nnpe, ne, ti.nr, ti.nc,
+         ti.diag_only ? 1 : 0, c->slot.p);
+  FS_TRY(c->diagslot.ensure((size_t)c->nall + 1));
+  LAUNCH(c, k_diag_slot, c->nall, c->colptr.p, c->rowval.p, c->nall, ti.nc, c->diagslot.p);
+  FS_TRY(c->nzval.ensure((size_t)total + 1));
+  FS_CUDA(cudaStreamSynchronize(st));
+
+  c->target = target;
+  c->prows = ti.nr;
+  c->pcols = ti.nc;
+  c->pnnz = total;
+  c->have_matrix = false;
+  c->compacted = false;
+  if (nrows) *nrows = ti.nr;
+  if (ncols) *ncols = ti.nc;
+  if (nnz) *nnz = total;
+  return FSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// result finalisation and hand-back
+// ------------------------------------------------------------------------------------
+namespace fs {
+
+// SPARSE_SYMM: make the matrix exactly symmetric (the reference's S + S' is), then drop
+// exact zeros (either sign) as Julia's sparse `+` does.
+__global__ void k_symmetrize(const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowval,
+                             double* __restrict__ nz, int64_t ncols) {
+  // one thread per stored entry in the strict upper triangle copies from the mirror entry
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  for (int p = colptr[c]; p < colptr[c + 1]; ++p) {
+    int r = rowval[p];
+    if (r >= c) break;  // rows ascending: strict upper part comes first
+    // mirror entry (c, r) lives in column r
+    int q = find_row(rowval, colptr[r], colptr[r + 1], (int32_t)c);
+    nz[p] = nz[q];
+  }
+}
+__global__ void k_nonzero_flags(const double* __restrict__ nz, int64_t n, int32_t* __restrict__ f) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  f[i] = (nz[i] != 0.0) ? 1 : 0;
+}
+__global__ void k_compact(const int32_t* __restrict__ pos, const int32_t* __restrict__ rowval, const double* __restrict__ nz,
+                          int64_t n, int32_t* __restrict__ orow, double* __restrict__ onz) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (nz[i] != 0.0) {
+    orow[pos[i]] = rowval[i];
+    onz[pos[i]] = nz[i];
+  }
+}
+__global__ void k_compact_colptr(const int32_t* __restrict__ pos, const int32_t* __restrict__ colptr, int64_t ncols,
+                                 int32_t* __restrict__ ocolptr) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i > ncols) return;
+  ocolptr[i] = pos[colptr[i]];
+}
+
+int finalize_matrix(fsgpu_ctx* c) {
+  c->have_matrix = true;
+  c->rrows = c->prows;
+  c->rcols = c->pcols;
+  c->rnnz = c->pnnz;
+  c->compacted = false;
+  if (c->target != FSGPU_SPARSE_SYMM) return FSGPU_OK;
+  cudaStream_t st = c->stream;
+  const int64_t n = c->pnnz;
+  LAUNCH(c, k_symmetrize, c->pcols, c->colptr.p, c->rowval.p, c->nzval.p, c->pcols);
+  DBuf<int32_t> flags, pos;
+  FS_TRY(flags.ensure((size_t)n + 1));
+  FS_TRY(pos.ensure((size_t)n + 1));
+  FS_CUDA(cudaMemsetAsync(flags.p + n, 0, sizeof(int32_t), st));
+  LAUNCH(c, k_nonzero_flags, n, c->nzval.p, n, flags.p);
+  size_t tb = 0;
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flags.p, pos.p, n + 1, st));
+  FS_TRY(c->tmp.ensure(tb));
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, flags.p, pos.p, n + 1, st));
+  c->launches += 2;
+  int32_t kept = 0;
+  FS_CUDA(cudaMemcpyAsync(&kept, pos.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  FS_CUDA(cudaStreamSynchronize(st));
+  FS_TRY(c->c_colptr.ensure((size_t)c->pcols + 1));
+  FS_TRY(c->c_rowval.ensure((size_t)kept + 1));
+  FS_TRY(c->c_nzval.ensure((size_t)kept + 1));
+  LAUNCH(c, k_compact, n, pos.p, c->rowval.p, c->nzval.p, n, c->c_rowval.p, c->c_nzval.p);
+  LAUNCH(c, k_compact_colptr, c->pcols + 1, pos.p, c->colptr.p, c->pcols, c->c_colptr.p);
+  FS_CUDA(cudaStreamSynchronize(st));
+  c->compacted = true;
+  c->rnnz = kept;
+  return FSGPU_OK;
+}
+
+}  // namespace fs
+
+extern "C" int fsgpu_result_size(fsgpu_ctx* c, int64_t* nrows, int64_t* ncols, int64_t* nnz) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->have_matrix, FSGPU_ERR_STATE, "no matrix result available");
+  if (nrows) *nrows = c->rrows;
+  if (ncols) *ncols = c->rcols;
+  if (nnz) *nnz = c->rnnz;
+  return FSGPU_OK;
+}
+
+
+extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval, double* nzval) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->have_matrix, FSGPU_ERR_STATE, "no matrix result available");
+  const int32_t* cp = c->compacted ? c->c_colptr.p : c->colptr.p;
+  const int32_t* rv = c->compacted ? c->c_rowval.p : c->rowval.p;
+  const double* nz = c->compacted ? c->c_nzval.p : c->nzval.p;
+  const int64_t nnz = c->rnnz, nc = c->rcols;
+  DBuf<int32_t> rp2, cv2;
+  DBuf<double> v2;
+  if (c->target == FSGPU_CSR_SYMM) {
+    // src/AssemblyModule.jl:47-53: findnz -> sparsecsr
+    FS_TRY(csc_to_csr(c, cp, rv, nz, c->rrows, c->rcols, nnz, rp2, cv2, v2));
+    cp = rp2.p;
+    rv = cv2.p;
+    nz = v2.p;
+  }
+  DBuf<int64_t> wide;
+  if (colptr) {
+    FS_TRY(wide.ensure((size_t)nc + 1));
+    LAUNCH(c, k_i32_plus1_to_i64, nc + 1, cp, wide.p, nc + 1);
+    FS_TRY(download(c, colptr, wide.p, ((size_t)nc + 1) * sizeof(int64_t)));
+    FS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (rowval && nnz > 0) {
+    // widen in chunks to bound the scratch
+    const int64_t chunk = (int64_t)1 << 26;
+    FS_TRY(wide.ensure((size_t)(nnz < chunk ? nnz : chunk)));
+    for (int64_t o = 0; o < nnz; o += chunk) {
+      int64_t m = nnz - o < chunk ? nnz - o : chunk;
+      LAUNCH(c, k_i32_plus1_to_i64, m, rv + o, wide.p, m);
+      FS_TRY(download(c, rowval + o, wide.p, (size_t)m * sizeof(int64_t)));
+      FS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+  }
+  if (nzval && nnz > 0) {
+    FS_TRY(download(c, nzval, nz, (size_t)nnz * sizeof(double)));
+    FS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_fetch_vector(fsgpu_ctx* c, double* out, int64_t n) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->have_vector, FSGPU_ERR_STATE, "no vector result available");
+  FS_REQUIRE(out && n == c->vlen, FSGPU_ERR_ARG, "vector length mismatch (have %lld, asked %lld)", (long long)c->vlen,
+             (long long)n);
+  FS_TRY(download(c, out, c->vec.p, (size_t)n * sizeof(double)));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_result_device(fsgpu_ctx* c, const int32_t** colptr0, const int32_t** rowval0, const double** nzval) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->have_matrix, FSGPU_ERR_STATE, "no matrix result available");
+  if (colptr0) *colptr0 = c->compacted ? c->c_colptr.p : c->colptr.p;
+  if (rowval0) *rowval0 = c->compacted ? c->c_rowval.p : c->rowval.p;
+  if (nzval) *nzval = c->compacted ? c->c_nzval.p : c->nzval.p;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_vector_device(fsgpu_ctx* c, const double** v, int64_t* n) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->have_vector, FSGPU_ERR_STATE, "no vector result available");
+  if (v) *v = c->vec.p;
+  if (n) *n = c->vlen;
+  return FSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// COO -> CSC (Julia `sparse(I,J,V,m,n)`): stable radix sort on (col,row), segmented sum
+// in input order, explicit zeros retained.
+// ------------------------------------------------------------------------------------
+namespace fs {
+__global__ void k_coo_keys(const int64_t* __restrict__ I, const int64_t* __restrict__ J, int64_t n, int64_t m, int64_t nc,
+                           uint64_t* __restrict__ keys, int32_t* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t r = I[i], cc = J[i];
+  if (r < 1 || r > m || cc < 1 || cc > nc) {
+    atomicExch(flag, 1);
+    r = cc = 1;
+  }
+  keys[i] = ((uint64_t)(cc - 1) << 32) | (uint64_t)(r - 1);
+}
+__global__ void k_csc_from_unique(const uint64_t* __restrict__ ukeys, int64_t nu, int64_t* __restrict__ rowval,
+                                  int64_t* __restrict__ colcnt) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nu) return;
+  uint64_t k = ukeys[i];
+  rowval[i] = (int64_t)(k & 0xffffffffu) + 1;
+  atomicAdd((unsigned long long*)(colcnt + (k >> 32)), 1ull);
+}
+__global__ void k_add1_i64(int64_t* p, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] += 1;
+}
+__global__ void k_csr_keys(const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowval, int64_t ncols,
+                           uint64_t* __restrict__ keys) {
+  int64_t cidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (cidx >= ncols) return;
+  for (int p = colptr[cidx]; p < colptr[cidx + 1]; ++p) keys[p] = ((uint64_t)rowval[p] << 32) | (uint64_t)cidx;
+}
+__global__ void k_csr_unpack(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ colval,
+                             int32_t* __restrict__ rowcnt) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  colval[i] = (int32_t)(keys[i] & 0xffffffffu);
+  atomicAdd(rowcnt + (keys[i] >> 32), 1);
+}
+int csc_to_csr(fsgpu_ctx* c, const int32_t* colptr, const int32_t* rowval, const double* nz, int64_t nrows,
+               int64_t ncols, int64_t nnz, DBuf<int32_t>& rowptr, DBuf<int32_t>& colval, DBuf<double>& val) {
+  cudaStream_t st = c->stream;
+  DBuf<uint64_t> k1, k2;
+  DBuf<int32_t> cnt;
+  FS_TRY(k1.ensure((size_t)nnz + 1));
+  FS_TRY(k2.ensure((size_t)nnz + 1));
+  FS_TRY(val.ensure((size_t)nnz + 1));
+  FS_TRY(colval.ensure((size_t)nnz + 1));
+  FS_TRY(rowptr.ensure((size_t)nrows + 1));
+  FS_TRY(cnt.ensure((size_t)nrows + 1));
+  LAUNCH(c, k_csr_keys, ncols, colptr, rowval, ncols, k1.p);
+  size_t tb = 0;
+  if (nnz > 0) {
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k1.p, k2.p, nz, val.p, nnz, 0, 64, st));
+    FS_TRY(c->tmp.ensure(tb));
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k1.p, k2.p, nz, val.p, nnz, 0, 64, st));
+    c->launches += 8;
+  }
+  FS_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)nrows + 1) * sizeof(int32_t), st));
+  LAUNCH(c, k_csr_unpack, nnz, k2.p, nnz, colval.p, cnt.p);
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, rowptr.p, nrows + 1, st));
+  FS_TRY(c->tmp.ensure(tb));
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, cnt.p, rowptr.p, nrows + 1, st));
+  c->launches += 2;
+  FS_CUDA(cudaStreamSynchronize(st));
+  return FSGPU_OK;
+}
+}  // namespace fs
+
+extern "C" int fsgpu_coo_to_csc(fsgpu_ctx* c, int64_t m, int64_t n, int64_t nt, const int64_t* I, const int64_t* J,
+                                const double* V, int64_t* nnz_out, int64_t* colptr, int64_t* rowval, double* nzval) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(m >= 0 && n >= 0 && nt >= 0 && m < (int64_t)UINT32_MAX && n < (int64_t)UINT32_MAX, FSGPU_ERR_ARG, "bad sizes");
+  FS_REQUIRE(nt == 0 || (I && J && V), FSGPU_ERR_ARG, "null triples");
+  FS_REQUIRE(nnz_out, FSGPU_ERR_ARG, "null nnz");
+  cudaStream_t st = c->stream;
+  FS_TRY(ensure_flag(c));
+  DBuf<int64_t> dI, dJ;
+  DBuf<double> dV, dV2, dVr;
+  DBuf<uint64_t> k1, k2, ku;
+  DBuf<int64_t> nu_d, drow, dcnt, dptr;
+  FS_TRY(dI.ensure((size_t)nt + 1));
+  FS_TRY(dJ.ensure((size_t)nt + 1));
+  FS_TRY(dV.ensure((size_t)nt + 1));
+  FS_TRY(dV2.ensure((size_t)nt + 1));
+  FS_TRY(k1.ensure((size_t)nt + 1));
+  FS_TRY(k2.ensure((size_t)nt + 1));
+  FS_TRY(upload(c, dI.p, I, (size_t)nt * sizeof(int64_t)));
+  FS_TRY(upload(c, dJ.p, J, (size_t)nt * sizeof(int64_t)));
+  FS_TRY(upload(c, dV.p, V, (size_t)nt * sizeof(double)));
+  LAUNCH(c, k_coo_keys, nt, dI.p, dJ.p, nt, m, n, k1.p, c->flag.p);
+  int32_t f;
+  FS_TRY(read_flag(c, 0, &f));
+  FS_REQUIRE(f == 0, FSGPU_ERR_DOF_RANGE, "row or column index outside the matrix");
+  size_t tb = 0, tb2 = 0;
+  int64_t nu = 0;
+  FS_TRY(ku.ensure((size_t)nt + 1));
+  FS_TRY(dVr.ensure((size_t)nt + 1));
+  FS_TRY(nu_d.ensure(1));
+  if (nt > 0) {
+    // LSD radix sort is stable: equal (col,row) keys keep input order, so the segmented
+    // sum below adds duplicates in input order like `sparse` does.
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k1.p, k2.p, dV.p, dV2.p, nt, 0, 64, st));
+    FS_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tb2, k2.p, ku.p, dV2.p, dVr.p, nu_d.p, ::cuda::std::plus<>(), nt, st));
+    FS_TRY(c->tmp.ensure(tb > tb2 ? tb : tb2));
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k1.p, k2.p, dV.p, dV2.p, nt, 0, 64, st));
+    FS_CUDA(cub::DeviceReduce::ReduceByKey(c->tmp.p, tb2, k2.p, ku.p, dV2.p, dVr.p, nu_d.p, ::cuda::std::plus<>(), nt, st));
+    c->launches += 10;
+    FS_CUDA(cudaMemcpyAsync(&nu, nu_d.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaStreamSynchronize(st));
+  }
+  *nnz_out = nu;
+  if (!colptr && !rowval && !nzval) return FSGPU_OK;
+  FS_TRY(drow.ensure((size_t)nu + 1));
+  FS_TRY(dcnt.ensure((size_t)n + 1));
+  FS_TRY(dptr.ensure((size_t)n + 1));
+  FS_CUDA(cudaMemsetAsync(dcnt.p, 0, ((size_t)n + 1) * sizeof(int64_t), st));
+  LAUNCH(c, k_csc_from_unique, nu, ku.p, nu, drow.p, dcnt.p);
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, dcnt.p, dptr.p, n + 1, st));
+  FS_TRY(c->tmp.ensure(tb));
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, dcnt.p, dptr.p, n + 1, st));
+  c->launches += 2;
+  LAUNCH(c, k_add1_i64, n + 1, dptr.p, n + 1);
+  if (colptr) FS_TRY(download(c, colptr, dptr.p, ((size_t)n + 1) * sizeof(int64_t)));
+  if (rowval) FS_TRY(download(c, rowval, drow.p, (size_t)nu * sizeof(int64_t)));
+  if (nzval) FS_TRY(download(c, nzval, dVr.p, (size_t)nu * sizeof(double)));
+  FS_CUDA(cudaStreamSynchronize(st));
+  return FSGPU_OK;
+}

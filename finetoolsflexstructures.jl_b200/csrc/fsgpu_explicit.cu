@@ -1,0 +1,375 @@
+// libfsgpu explicit central-difference loop with lumped mass and mass-proportional
+// damping -- the reference algorithm of
+// examples/shells/dynamics/homogeneous/explicit/plate_expl_examples.jl:61-94 (`_cd_loop!`),
+// statement order preserved.  The internal force is E = K U with the assembled free-free
+// stiffness in CSR (ThreadedSparseCSR.bmul!, :87); the vector updates of :88-91 are fused
+// into the SpMV epilogue so one step is two kernels (U update; SpMV + force/velocity/
+// acceleration update).  HBM-bound: 12 B per stored entry (f64 value + i32 column).
+#include "fsgpu_internal.cuh"
+
+using namespace fs;
+
+struct fsgpu_explicit {
+  fsgpu_ctx* ctx = nullptr;
+  int64_t n = 0, nnz = 0;
+  DBuf<int32_t> rowptr, colval;
+  DBuf<double> val;
+  DBuf<double> M, C, invMC, U, V, A, F0, E, X, Y;
+  double dt = 0, c_scale = 0;
+  bool have_load = false;
+};
+
+namespace {
+
+constexpr int LPR = 8;  // lanes per row
+
+__global__ void k_setup_damping(const double* __restrict__ M, double c_scale, double dt, double* __restrict__ C,
+                                double* __restrict__ invMC, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double c = c_scale * M[i];
+  C[i] = c;
+  invMC[i] = 1.0 / (M[i] + (dt / 2) * c);
+}
+// U += dt*V + dt^2/2*A   (:85)
+__global__ void k_update_u(double* __restrict__ U, const double* __restrict__ V, const double* __restrict__ A, double dt,
+                           double dt2_2, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  U[i] += dt * V[i] + dt2_2 * A[i];
+}
+__device__ __forceinline__ double row_dot(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+                                          const double* __restrict__ val, const double* __restrict__ x, int64_t row, int sub) {
+  const int p0 = rowptr[row], p1 = rowptr[row + 1];
+  double s = 0.0;
+  for (int p = p0 + sub; p < p1; p += LPR) s = fma(val[p], __ldg(x + colval[p]), s);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+// y = K x
+__global__ void k_spmv(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colval, const double* __restrict__ val,
+                       const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = g / LPR;
+  const int sub = (int)(g % LPR);
+  const bool ok = row < n;
+  const double s = row_dot(rowptr, colval, val, x, ok ? row : n - 1, sub);
+  if (ok && sub == 0) y[row] = s;
+}
+// E = K U, then :88-91 for the row: F = fs*F0 - (E + C (V + dt/2 A)); V += dt/2 A; A = invMC F; V += dt/2 A
+__global__ void k_spmv_step(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+                            const double* __restrict__ val, const double* __restrict__ U, const double* __restrict__ F0,
+                            double fs, const double* __restrict__ C, const double* __restrict__ invMC, double* __restrict__ V,
+                            double* __restrict__ A, double* __restrict__ E, double dt_2, int64_t n) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = g / LPR;
+  const int sub = (int)(g % LPR);
+  const bool ok = row < n;
+  const double e = row_dot(rowptr, colval, val, U, ok ? row : n - 1, sub);
+  if (ok && sub == 0) {
+    const double a0 = A[row];
+    double v = V[row];
+    double f = (F0 ? fs * F0[row] : 0.0) - (e + C[row] * (v + dt_2 * a0));
+    v += dt_2 * a0;
+    const double a1 = invMC[row] * f;
+    v += dt_2 * a1;
+    V[row] = v;
+    A[row] = a1;
+    E[row] = e;
+  }
+}
+// second half alone (element-partitioned runs: E already summed across ranks)
+__global__ void k_finish_step(const double* __restrict__ E, const double* __restrict__ F0, double fs,
+                              const double* __restrict__ C, const double* __restrict__ invMC, double* __restrict__ V,
+                              double* __restrict__ A, double dt_2, int64_t n) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const double a0 = A[row];
+  double v = V[row];
+  const double f = (F0 ? fs * F0[row] : 0.0) - (E[row] + C[row] * (v + dt_2 * a0));
+  v += dt_2 * a0;
+  const double a1 = invMC[row] * f;
+  v += dt_2 * a1;
+  V[row] = v;
+  A[row] = a1;
+}
+__global__ void k_start(const double* __restrict__ F0, double fs, const double* __restrict__ invMC, double* __restrict__ A,
+                        int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  A[i] = invMC[i] * (F0 ? fs * F0[i] : 0.0);
+}
+__global__ void k_div(const double* __restrict__ y, const double* __restrict__ M, double* __restrict__ z, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) z[i] = y[i] / M[i];
+}
+__global__ void k_scale(double* __restrict__ x, const double* __restrict__ y, double s, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) x[i] = s * y[i];
+}
+__global__ void k_fill_start(double* __restrict__ x, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // deterministic pseudo-random start vector in (-1, 1)
+  uint64_t z = (uint64_t)i * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+  z ^= z >> 31;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 29;
+  x[i] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+// block-level reduction of sum_i w_i a_i b_i into out[0] (double atomics)
+__global__ void k_wdot(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ w, int64_t n,
+                       double* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += (w ? w[i] : 1.0) * a[i] * b[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+#define XL(h, kern, n, ...)                                                    \
+  do {                                                                         \
+    if ((n) > 0) {                                                             \
+      kern<<<grid_for((n), 256), 256, 0, (h)->ctx->stream>>>(__VA_ARGS__);     \
+      (h)->ctx->launches++;                                                    \
+    }                                                                          \
+  } while (0)
+
+int wdot(fsgpu_explicit* h, const double* a, const double* b, const double* w, double* result) {
+  fsgpu_ctx* c = h->ctx;
+  FS_TRY(c->flag.ensure(8));
+  double* acc = (double*)c->flag.p;  // 8 int32 = 4 doubles of scratch
+  FS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), c->stream));
+  if (h->n > 0) {
+    k_wdot<<<592, 256, 0, c->stream>>>(a, b, w, h->n, acc);
+    c->launches++;
+  }
+  FS_CUDA(cudaMemcpyAsync(result, acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  return FSGPU_OK;
+}
+
+int alloc_vectors(fsgpu_explicit* h) {
+  const size_t n = (size_t)h->n + 1;
+  FS_TRY(h->C.ensure(n));
+  FS_TRY(h->invMC.ensure(n));
+  FS_TRY(h->U.ensure(n));
+  FS_TRY(h->V.ensure(n));
+  FS_TRY(h->A.ensure(n));
+  FS_TRY(h->F0.ensure(n));
+  FS_TRY(h->E.ensure(n));
+  cudaStream_t st = h->ctx->stream;
+  FS_CUDA(cudaMemsetAsync(h->U.p, 0, n * sizeof(double), st));
+  FS_CUDA(cudaMemsetAsync(h->V.p, 0, n * sizeof(double), st));
+  FS_CUDA(cudaMemsetAsync(h->A.p, 0, n * sizeof(double), st));
+  FS_CUDA(cudaMemsetAsync(h->E.p, 0, n * sizeof(double), st));
+  XL(h, k_setup_damping, h->n, h->M.p, h->c_scale, h->dt, h->C.p, h->invMC.p, h->n);
+  FS_CUDA(cudaStreamSynchronize(st));
+  return FSGPU_OK;
+}
+
+__global__ void k_i64_to_i32_m1(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)(in[i] - 1);
+}
+
+}  // namespace
+
+extern "C" int fsgpu_explicit_create(fsgpu_explicit** out, fsgpu_ctx* c, int64_t n, const int64_t* rowptr,
+                                     const int64_t* colval, const double* nzval, const double* mdiag, double c_scale,
+                                     double dt) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(out && rowptr && colval && nzval && mdiag && n >= 0, FSGPU_ERR_ARG, "bad arguments");
+  const int64_t nnz = rowptr[n] - 1;
+  FS_REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, FSGPU_ERR_ARG, "bad rowptr");
+  fsgpu_explicit* h = new fsgpu_explicit();
+  h->ctx = c;
+  h->n = n;
+  h->nnz = nnz;
+  h->dt = dt;
+  h->c_scale = c_scale;
+  int rc = FSGPU_OK;
+  auto fail = [&](int code) {
+    delete h;
+    return code;
+  };
+  if ((rc = h->rowptr.ensure((size_t)n + 1))) return fail(rc);
+  if ((rc = h->colval.ensure((size_t)nnz + 1))) return fail(rc);
+  if ((rc = h->val.ensure((size_t)nnz + 1))) return fail(rc);
+  if ((rc = h->M.ensure((size_t)n + 1))) return fail(rc);
+  DBuf<int64_t> w;
+  if ((rc = w.ensure((size_t)(nnz > n + 1 ? nnz : n + 1) + 1))) return fail(rc);
+  if ((rc = upload(c, w.p, rowptr, ((size_t)n + 1) * sizeof(int64_t)))) return fail(rc);
+  XL(h, k_i64_to_i32_m1, n + 1, w.p, h->rowptr.p, n + 1);
+  cudaStreamSynchronize(c->stream);
+  if ((rc = upload(c, w.p, colval, (size_t)nnz * sizeof(int64_t)))) return fail(rc);
+  XL(h, k_i64_to_i32_m1, nnz, w.p, h->colval.p, nnz);
+  if ((rc = upload(c, h->val.p, nzval, (size_t)nnz * sizeof(double)))) return fail(rc);
+  if ((rc = upload(c, h->M.p, mdiag, (size_t)n * sizeof(double)))) return fail(rc);
+  cudaStreamSynchronize(c->stream);
+  if ((rc = alloc_vectors(h))) return fail(rc);
+  *out = h;
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_explicit_create_from_ctx(fsgpu_explicit** out, fsgpu_ctx* c, double c_scale, double dt) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(out, FSGPU_ERR_ARG, "null output");
+  FS_REQUIRE(c->have_matrix && c->target == FSGPU_FFBLOCK, FSGPU_ERR_STATE,
+             "the context must hold an FFBLOCK stiffness result (SysmatAssemblerFFBlock)");
+  FS_REQUIRE(c->have_vector && c->vlen == c->rrows, FSGPU_ERR_STATE,
+             "the context must hold the lumped mass vector of the free dofs (fsgpu_shell_mass_diag, nfree_only)");
+  fsgpu_explicit* h = new fsgpu_explicit();
+  h->ctx = c;
+  h->n = c->rrows;
+  h->nnz = c->rnnz;
+  h->dt = dt;
+  h->c_scale = c_scale;
+  int rc = csc_to_csr(c, c->colptr.p, c->rowval.p, c->nzval.p, c->rrows, c->rcols, c->rnnz, h->rowptr, h->colval, h->val);
+  if (rc == FSGPU_OK) rc = h->M.ensure((size_t)h->n + 1);
+  if (rc == FSGPU_OK) {
+    cudaError_t e = cudaMemcpyAsync(h->M.p, c->vec.p, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) {
+      set_error("CUDA error: %s", cudaGetErrorString(e));
+      rc = FSGPU_ERR_CUDA;
+    }
+  }
+  if (rc == FSGPU_OK) rc = alloc_vectors(h);
+  if (rc != FSGPU_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_explicit_destroy(fsgpu_explicit* h) {
+  if (!h) return FSGPU_OK;
+  cudaSetDevice(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  delete h;
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_explicit_set_state(fsgpu_explicit* h, const double* U0, const double* V0) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  FS_TRY(check_ctx(h->ctx));
+  const size_t b = (size_t)h->n * sizeof(double);
+  if (U0) FS_TRY(upload(h->ctx, h->U.p, U0, b));
+  if (V0) FS_TRY(upload(h->ctx, h->V.p, V0, b));
+  FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_set_load(fsgpu_explicit* h, const double* F0) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  FS_TRY(check_ctx(h->ctx));
+  if (F0) {
+    FS_TRY(upload(h->ctx, h->F0.p, F0, (size_t)h->n * sizeof(double)));
+    FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  }
+  h->have_load = F0 != nullptr;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_start(fsgpu_explicit* h, double fscale0) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  FS_TRY(check_ctx(h->ctx));
+  XL(h, k_start, h->n, h->have_load ? h->F0.p : nullptr, fscale0, h->invMC.p, h->A.p, h->n);
+  FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_step(fsgpu_explicit* h, int64_t nsteps, const double* fscale) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  FS_TRY(check_ctx(h->ctx));
+  const double dt = h->dt;
+  for (int64_t s = 0; s < nsteps; ++s) {
+    XL(h, k_update_u, h->n, h->U.p, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
+    XL(h, k_spmv_step, h->n * LPR, h->rowptr.p, h->colval.p, h->val.p, h->U.p, h->have_load ? h->F0.p : nullptr,
+       fscale ? fscale[s] : 1.0, h->C.p, h->invMC.p, h->V.p, h->A.p, h->E.p, dt / 2, h->n);
+  }
+  FS_CUDA(cudaGetLastError());
+  FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_step_begin(fsgpu_explicit* h) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  FS_TRY(check_ctx(h->ctx));
+  const double dt = h->dt;
+  XL(h, k_update_u, h->n, h->U.p, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
+  XL(h, k_spmv, h->n * LPR, h->rowptr.p, h->colval.p, h->val.p, h->U.p, h->E.p, h->n);
+  FS_CUDA(cudaGetLastError());
+  return FSGPU_OK;  // asynchronous: the host's exchange is enqueued on the same stream
+}
+extern "C" int fsgpu_explicit_step_end(fsgpu_explicit* h, double fscale) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  FS_TRY(check_ctx(h->ctx));
+  XL(h, k_finish_step, h->n, h->E.p, h->have_load ? h->F0.p : nullptr, fscale, h->C.p, h->invMC.p, h->V.p, h->A.p,
+     h->dt / 2, h->n);
+  FS_CUDA(cudaGetLastError());
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_get_state(fsgpu_explicit* h, double* U, double* V, double* A) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  FS_TRY(check_ctx(h->ctx));
+  const size_t b = (size_t)h->n * sizeof(double);
+  if (U) FS_TRY(download(h->ctx, U, h->U.p, b));
+  if (V) FS_TRY(download(h->ctx, V, h->V.p, b));
+  if (A) FS_TRY(download(h->ctx, A, h->A.p, b));
+  FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_device_state(fsgpu_explicit* h, double** U, double** V, double** A, double** E) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  if (U) *U = h->U.p;
+  if (V) *V = h->V.p;
+  if (A) *A = h->A.p;
+  if (E) *E = h->E.p;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_spmv(fsgpu_explicit* h, const double* x, double* y) {
+  FS_REQUIRE(h && x && y, FSGPU_ERR_ARG, "null argument");
+  FS_TRY(check_ctx(h->ctx));
+  FS_TRY(h->X.ensure((size_t)h->n + 1));
+  FS_TRY(h->Y.ensure((size_t)h->n + 1));
+  FS_TRY(upload(h->ctx, h->X.p, x, (size_t)h->n * sizeof(double)));
+  XL(h, k_spmv, h->n * LPR, h->rowptr.p, h->colval.p, h->val.p, h->X.p, h->Y.p, h->n);
+  FS_TRY(download(h->ctx, y, h->Y.p, (size_t)h->n * sizeof(double)));
+  FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_omega_max(fsgpu_explicit* h, int32_t maxit, double* lambda_max) {
+  FS_REQUIRE(h && lambda_max, FSGPU_ERR_ARG, "null argument");
+  FS_TRY(check_ctx(h->ctx));
+  FS_TRY(h->X.ensure((size_t)h->n + 1));
+  FS_TRY(h->Y.ensure((size_t)h->n + 1));
+  XL(h, k_fill_start, h->n, h->X.p, h->n);
+  double lam = 0.0;
+  for (int it = 0; it < maxit; ++it) {
+    // y = M^-1 K x ; lambda = (x' M y) / (x' M x) ; x = y / |y|
+    XL(h, k_spmv, h->n * LPR, h->rowptr.p, h->colval.p, h->val.p, h->X.p, h->Y.p, h->n);
+    XL(h, k_div, h->n, h->Y.p, h->M.p, h->Y.p, h->n);
+    double xmy, xmx, yy;
+    FS_TRY(wdot(h, h->X.p, h->Y.p, h->M.p, &xmy));
+    FS_TRY(wdot(h, h->X.p, h->X.p, h->M.p, &xmx));
+    FS_TRY(wdot(h, h->Y.p, h->Y.p, nullptr, &yy));
+    lam = xmy / xmx;
+    XL(h, k_scale, h->n, h->X.p, h->Y.p, 1.0 / sqrt(yy), h->n);
+  }
+  *lambda_max = lam;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_kinetic_energy(fsgpu_explicit* h, double* ke) {
+  FS_REQUIRE(h && ke, FSGPU_ERR_ARG, "null argument");
+  FS_TRY(check_ctx(h->ctx));
+  double s;
+  FS_TRY(wdot(h, h->V.p, h->V.p, h->M.p, &s));
+  *ke = 0.5 * s;
+  return FSGPU_OK;
+}

@@ -1,0 +1,148 @@
+// Internal definitions of libfsgpu (context, device buffers, error plumbing).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/fsgpu.h"
+
+namespace fs {
+
+// ---- error handling ---------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define FS_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      fs::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,    \
+                    cudaGetErrorString(e_));                                                   \
+      return FSGPU_ERR_CUDA;                                                                   \
+    }                                                                                          \
+  } while (0)
+
+#define FS_TRY(call)            \
+  do {                          \
+    int rc_ = (call);           \
+    if (rc_ != FSGPU_OK) return rc_; \
+  } while (0)
+
+#define FS_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) {                  \
+      fs::set_error(__VA_ARGS__);   \
+      return (code);                \
+    }                               \
+  } while (0)
+
+// ---- simple owning device buffer ---------------------------------------------------
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;  // capacity in elements
+  int ensure(size_t count) {
+    if (count <= n && p) return FSGPU_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (count == 0) return FSGPU_OK;
+    FS_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    n = count;
+    return FSGPU_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DBuf() { release(); }
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+};
+
+constexpr int kMaxGP = 9;  // Simpson13Rule(2) has 9 points
+
+struct Rule {
+  int npts = 0;
+  double xi[kMaxGP], eta[kMaxGP], w[kMaxGP];
+};
+
+}  // namespace fs
+
+// The context: device-resident mesh, fields, pattern and results.
+struct fsgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = 0;
+  int64_t launches = 0;
+
+  // mesh
+  int nnpe = 0;
+  int64_t nelem = 0, nnodes = 0;
+  fs::DBuf<int32_t> conn;     // [nelem][nnpe] 0-based
+  fs::DBuf<double4> xyz;      // (x, y, z, 0) per node: one 32 B sector per gather
+  // dofs
+  int64_t nfree = 0, nall = 0;
+  bool have_dofs = false;
+  fs::DBuf<int32_t> dof;      // [nnodes][6] 0-based
+  // normals
+  bool associated = false;
+  fs::DBuf<double4> nrm;      // (nx, ny, nz, valid ? 1 : 0)
+  // thickness / stab factor
+  int64_t nthick = 0;
+  fs::DBuf<double> thick;
+  int64_t nstab = 0;
+  fs::DBuf<double> stabf;
+  fs::Rule rule;
+  // layup
+  int ngroups = 0;
+  fs::DBuf<double> group_data;  // [ngroups][34]
+  fs::DBuf<int32_t> group_of;   // [nelem] 0-based
+  int64_t ncs = 0;
+  fs::DBuf<double> csmat;       // [ncs][9] ROW-major
+  // beam
+  bool have_sections = false;
+  fs::DBuf<double> sec;         // [nelem][10]: A I1 I2 I3 J A2s A3s x y z
+  bool have_state = false;
+  fs::DBuf<double4> u1;         // (ux,uy,uz,0)
+  fs::DBuf<double> R1;          // [nnodes][9] each column-major 3x3
+
+  // symbolic
+  int target = -1;
+  int64_t prows = 0, pcols = 0, pnnz = 0;  // pattern (before SYMM compaction)
+  fs::DBuf<int32_t> colptr;   // [pcols+1] 0-based
+  fs::DBuf<int32_t> rowval;   // [pnnz] 0-based
+  fs::DBuf<int32_t> slot;     // [36][nnpe][nelem][nnpe]  (-1 = dropped)
+  fs::DBuf<int32_t> diagslot; // [nall] slot of (d,d) or -1
+  // result matrix
+  bool have_matrix = false;
+  int64_t rrows = 0, rcols = 0, rnnz = 0;
+  fs::DBuf<double> nzval;     // [pnnz]
+  bool compacted = false;     // SPARSE_SYMM after zero dropping: use c_* below
+  fs::DBuf<int32_t> c_colptr, c_rowval;
+  fs::DBuf<double> c_nzval;
+  // result vector
+  bool have_vector = false;
+  int64_t vlen = 0;
+  fs::DBuf<double> vec;
+  // scratch
+  fs::DBuf<unsigned char> tmp, tmp2;
+  fs::DBuf<int32_t> flag;     // device error flags
+};
+
+namespace fs {
+int check_ctx(fsgpu_ctx* c);
+inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+// staging helpers
+int upload(fsgpu_ctx* c, void* dst, const void* src, size_t bytes);
+int download(fsgpu_ctx* c, void* dst, const void* src, size_t bytes);
+// after an operator has filled nzval: SPARSE_SYMM symmetrisation + zero dropping, bookkeeping
+int finalize_matrix(fsgpu_ctx* c);
+// CSC (0-based, device) -> CSR of the same matrix, by sorting entries on (row, col)
+int csc_to_csr(fsgpu_ctx* c, const int32_t* colptr, const int32_t* rowval, const double* nz, int64_t nrows,
+               int64_t ncols, int64_t nnz, DBuf<int32_t>& rowptr, DBuf<int32_t>& colval, DBuf<double>& val);
+}  // namespace fs

@@ -1,0 +1,210 @@
+/* fsgpu.h -- C ABI of libfsgpu.so: B200 (sm_100a) element-level hot path of
+ * FinEtoolsFlexStructures.jl (reference v3.6.4, citations relative to /root/reference).
+ *
+ * What a host (Julia `ccall`, Python ctypes, C) binds.  Plain pointers and sizes only.
+ * All host arrays use the JULIA layout of the reference objects, so they can be passed
+ * zero-copy under `GC.@preserve`:
+ *   conn      Int64, nnpe x nelem, 1-based  (Vector{NTuple{nnpe,Int}} of fes.conn)
+ *   xyz       Float64, nnodes x 3 column-major      (geom0.values)
+ *   dofnums   Int64,  nnodes x 6 column-major, 1-based (dchi.dofnums)
+ *   normals   Float64, nnodes x 3 column-major      (femm._normals)
+ *   valid     UInt8 (Bool), nnodes                   (femm._normal_valid)
+ *   u1        Float64, nnodes x 3 column-major      (u1.values)
+ *   Rfield1   Float64, nnodes x 9 column-major, each ROW a column-major 3x3 (Rfield1.values)
+ * Returned sparse matrices are SparseMatrixCSC{Float64,Int64} pieces: colptr (ncols+1),
+ * rowval (nnz), nzval (nnz), 1-based, rows ascending within a column, duplicates summed,
+ * explicit zeros kept (except target SPARSE_SYMM) -- the semantics of Julia `sparse`.
+ *
+ * Every function returns 0 on success or an fsgpu_status code; the message is available
+ * from fsgpu_last_error() (thread-local).  Nothing throws or aborts across the boundary.
+ * A context is single-threaded (like the reference FEMMs, src/FEMMCorotBeamModule.jl:27-53)
+ * and every call is synchronous unless stated otherwise.
+ * There is NO CPU fallback: without a CUDA device fsgpu_create fails.
+ */
+#ifndef FSGPU_H
+#define FSGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fsgpu_ctx fsgpu_ctx;
+
+enum fsgpu_status {
+  FSGPU_OK = 0,
+  FSGPU_ERR_ARG = 1,        /* bad argument / size mismatch */
+  FSGPU_ERR_CUDA = 2,       /* CUDA runtime error (message has the detail) */
+  FSGPU_ERR_STATE = 3,      /* missing prerequisite, e.g. geometry not associated
+                               (`@assert self._associatedgeometry`, src/FEMMShellT3FFModule.jl:643) */
+  FSGPU_ERR_DOF_RANGE = 4,  /* dof < 1 or > nalldofs (FinEtools assemble! error) */
+  FSGPU_ERR_SINGULAR = 5    /* "Singular metric matrix" (src/FEMMShellQ4RSModule.jl:308-311) */
+};
+
+/* Assembler semantics (FinEtools.AssemblyModule; in-tree
+ * src/AssemblyModule.jl:20-53 for CSR_SYMM). */
+enum fsgpu_target {
+  FSGPU_SPARSE = 0,       /* SysmatAssemblerSparse: nall x nall, all entries incl. zeros */
+  FSGPU_SPARSE_SYMM = 1,  /* SysmatAssemblerSparseSymm (default): S+S', exact zeros dropped */
+  FSGPU_SPARSE_DIAG = 2,  /* SysmatAssemblerSparseDiag: diagonal entries only */
+  FSGPU_FFBLOCK = 3,      /* SysmatAssemblerFFBlock(nfree): [1:nfree,1:nfree] of SPARSE */
+  FSGPU_FFBLOCK_DIAG = 4, /* SysmatAssemblerFFBlock(SysmatAssemblerSparseDiag(), nfree, nfree) */
+  FSGPU_CSR_SYMM = 5      /* SysmatAssemblerSparseCSRSymm: SPARSE returned as CSR
+                             (colptr := rowptr, rowval := colval) */
+};
+
+/* Scalar parameters of the shell operators (mutable FEMM fields,
+ * src/FEMMShellT3FFModule.jl:101-112, src/FEMMShellQ4RSModule.jl:75-85). */
+typedef struct fsgpu_shell_params {
+  double Dps[9];   /* plane-stress moduli, row-major 3x3 (_shell_material_stiffness) */
+  double Dt[4];    /* transverse-shear moduli 2x2, NOT yet multiplied by 5/6 */
+  double rho;      /* mass density (mass operator) */
+  double stab_alpha; /* stab_fun(t,h) = t^2/(t^2 + alpha h^2); ignored if stab_factor set */
+  double drilling_stiffness_scale;
+  int32_t transv_shear_formulation; /* T3FF only: 0 = AVERAGE_B (default), 1 = AVERAGE_K */
+  int32_t reserved;
+} fsgpu_shell_params;
+
+/* Scalar parameters of the corotational beam (FEMMCorotBeam.material). */
+typedef struct fsgpu_beam_params {
+  double E, nu, rho;
+  int32_t mass_type; /* MASS_TYPE_* 0..3, src/FEMMCorotBeamModule.jl:144-147 */
+  int32_t reserved;
+} fsgpu_beam_params;
+
+/* ---- context ------------------------------------------------------------------- */
+int fsgpu_create(fsgpu_ctx** ctx, int device);
+int fsgpu_destroy(fsgpu_ctx* ctx);
+const char* fsgpu_last_error(void);
+int fsgpu_version(void);
+/* pinned host buffers (optional; make the result copies run at full PCIe rate) */
+int fsgpu_host_alloc(void** p, int64_t bytes);
+int fsgpu_host_free(void* p);
+/* all work of a context goes to this stream (default: the legacy default stream) */
+int fsgpu_set_stream(fsgpu_ctx* ctx, void* cuda_stream);
+int fsgpu_sync(fsgpu_ctx* ctx);
+/* number of kernels this context has launched so far */
+int64_t fsgpu_launch_count(fsgpu_ctx* ctx);
+
+/* ---- data hand-over (host pointers; copied to the device) ---------------------- */
+/* fes.conn + geom0.values.  nnpe: 2 (L2 beam), 3 (T3), 4 (Q4).
+ * (src/FEMMShellT3FFModule.jl:671, src/FEMMCorotBeamModule.jl:1133) */
+int fsgpu_set_mesh(fsgpu_ctx* ctx, int32_t nnpe, int64_t nelem, const int64_t* conn, int64_t nnodes, const double* xyz);
+/* dchi.dofnums, nfreedofs(dchi), nalldofs(dchi) (src/FEMMShellT3FFModule.jl:667,732) */
+int fsgpu_set_dofnums(fsgpu_ctx* ctx, const int64_t* dofnums, int64_t nfree, int64_t nall);
+/* femm._normals / femm._normal_valid as left by associategeometry!
+ * (src/FEMMShellT3FFModule.jl:570-616); marks the geometry as associated. */
+int fsgpu_set_normals(fsgpu_ctx* ctx, const double* normals, const uint8_t* valid);
+/* OR compute them on the device with the default (isoparametric) csys:
+ * T3: unweighted element normals; Q4: Jacobian-weighted (src/FEMMShellQ4RSModule.jl:472-525).
+ * fixed_dir != NULL: use that direction instead (cartesian layup csys of the composite FEMMs,
+ * src/FEMMShellT3FFCompModule.jl:489-543).  accumulate != 0 reproduces the homogeneous T3FF
+ * quirk of not resetting the arrays. */
+int fsgpu_associategeometry(fsgpu_ctx* ctx, double threshold_angle_deg, const double* fixed_dir, int32_t accumulate);
+int fsgpu_get_normals(fsgpu_ctx* ctx, double* normals, uint8_t* valid);
+/* integdomain.otherdimension evaluated by the host glue: n = 1 (uniform), nelem (T3: at the
+ * centroid) or nelem*npts (Q4: per integration point, element-major).
+ * (src/FEMMShellT3FFModule.jl:677, src/FEMMShellQ4RSModule.jl:924) */
+int fsgpu_set_thickness(fsgpu_ctx* ctx, const double* t, int64_t n);
+/* optional user stab_fun values evaluated on the host, per element (overrides stab_alpha) */
+int fsgpu_set_stab_factor(fsgpu_ctx* ctx, const double* f, int64_t n);
+int fsgpu_element_sizes(fsgpu_ctx* ctx, double* h); /* h per element (T3 sqrt(2Ae), Q4 quirk diameter) */
+/* Q4 integration rule as data: npts points (xi, eta, w). */
+int fsgpu_set_rule(fsgpu_ctx* ctx, int32_t npts, const double* xi, const double* eta, const double* w);
+/* Composite layup groups (src/FEMMShellT3FFCompModule.jl:600-605): per group 34 doubles
+ * [A(9) B(9) D(9) H(4) thickness mass_density moi_density] row-major matrices, from
+ * laminate_stiffnesses!/laminate_transverse_stiffness!/laminate_inertia!;
+ * group_of_elem Int64 1-based (femm._layup_group_lookup); csmat: layup csys matrix,
+ * column-major 3x3, ncs = 1 (constant), nelem (T3 centroid) or nelem*npts (Q4, App. B.9). */
+int fsgpu_set_layup(fsgpu_ctx* ctx, int32_t ngroups, const double* group_data, const int64_t* group_of_elem,
+                    const double* csmat, int64_t ncs);
+/* FESetL2Beam per-element section arrays (src/FESetL2BeamModule.jl:20-31); x1x2 flattened 3 x nelem. */
+int fsgpu_set_beam_sections(fsgpu_ctx* ctx, const double* A, const double* I1, const double* I2, const double* I3,
+                            const double* J, const double* A2s, const double* A3s, const double* x1x2);
+/* u1.values, Rfield1.values (live for the beam, dead arguments for the shells, App. B.11) */
+int fsgpu_set_state(fsgpu_ctx* ctx, const double* u1, const double* Rfield1);
+
+/* ---- symbolic phase (once per mesh + dofnums + target) --------------------------- */
+/* startassembly! equivalent: builds the CSC pattern, bit-exact to `sparse`, and the
+ * element-entry -> nzval slot map.  For SPARSE_SYMM nnz is an upper bound until an
+ * operator has run. */
+int fsgpu_symbolic(fsgpu_ctx* ctx, int32_t target, int64_t* nrows, int64_t* ncols, int64_t* nnz);
+
+/* ---- operators: one call per reference operator --------------------------------- */
+/* Result stays on the device; fetch it with fsgpu_fetch_matrix / fsgpu_fetch_vector. */
+int fsgpu_t3ff_stiffness(fsgpu_ctx* ctx, const fsgpu_shell_params* p);     /* src/FEMMShellT3FFModule.jl:635-736 */
+int fsgpu_t3ff_mass(fsgpu_ctx* ctx, const fsgpu_shell_params* p);          /* :757-811 */
+int fsgpu_q4rs_stiffness(fsgpu_ctx* ctx, const fsgpu_shell_params* p);     /* src/FEMMShellQ4RSModule.jl:877-947 */
+int fsgpu_q4rs_mass(fsgpu_ctx* ctx, const fsgpu_shell_params* p);          /* :968-1022 */
+int fsgpu_t3ffcomp_stiffness(fsgpu_ctx* ctx, const fsgpu_shell_params* p); /* src/FEMMShellT3FFCompModule.jl:561-689 */
+int fsgpu_t3ffcomp_mass(fsgpu_ctx* ctx, const fsgpu_shell_params* p);      /* :710-770 */
+int fsgpu_q4rscomp_stiffness(fsgpu_ctx* ctx, const fsgpu_shell_params* p); /* src/FEMMShellQ4RSCompModule.jl:861-958 */
+int fsgpu_q4rscomp_mass(fsgpu_ctx* ctx, const fsgpu_shell_params* p);      /* :979-1038 */
+int fsgpu_corotbeam_stiffness(fsgpu_ctx* ctx, const fsgpu_beam_params* p);    /* src/FEMMCorotBeamModule.jl:972-1023 */
+int fsgpu_corotbeam_geostiffness(fsgpu_ctx* ctx, const fsgpu_beam_params* p); /* :1042-1094 */
+int fsgpu_corotbeam_mass(fsgpu_ctx* ctx, const fsgpu_beam_params* p);         /* :810-868 */
+/* vector operators; nfree_only != 0: SysvecAssemblerFBlock(nfree), else SysvecAssembler */
+int fsgpu_corotbeam_restoringforce(fsgpu_ctx* ctx, const fsgpu_beam_params* p, int32_t nfree_only); /* :1112-1159 */
+/* lumped shell mass as a diagonal VECTOR over all dofs (the diag(M) the explicit loop uses,
+ * examples/.../plate_expl_examples.jl:69-71); kind 3 = T3FF, 4 = Q4RS, 13 = T3FFComp, 14 = Q4RSComp */
+int fsgpu_shell_mass_diag(fsgpu_ctx* ctx, const fsgpu_shell_params* p, int32_t kind, int32_t nfree_only);
+/* R <- exp(dtheta) R per node (src/RotUtilModule.jl:29-42); dchi_values nnodes x 6 column-major */
+int fsgpu_update_rotation_field(fsgpu_ctx* ctx, const double* dchi_values, double* Rfield_out);
+
+/* parity / debug: raw element matrices, n x n x nelem column-major (Julia elmat per element).
+ * op: 0 stiffness, 1 mass, 2 geostiffness (beam).  kind as in fsgpu_shell_mass_diag, 2 = beam. */
+int fsgpu_element_matrices(fsgpu_ctx* ctx, int32_t kind, int32_t op, const void* params, double* out);
+/* element vectors of restoringforce, 12 x nelem */
+int fsgpu_element_vectors(fsgpu_ctx* ctx, const fsgpu_beam_params* p, double* out);
+
+/* ---- results -------------------------------------------------------------------- */
+int fsgpu_result_size(fsgpu_ctx* ctx, int64_t* nrows, int64_t* ncols, int64_t* nnz);
+/* makematrix! equivalent; any pointer may be NULL to skip that array */
+int fsgpu_fetch_matrix(fsgpu_ctx* ctx, int64_t* colptr, int64_t* rowval, double* nzval);
+int fsgpu_fetch_vector(fsgpu_ctx* ctx, double* out, int64_t n);
+/* device-resident handles (int32 0-based pattern, float64 values) for chaining on the GPU */
+int fsgpu_result_device(fsgpu_ctx* ctx, const int32_t** colptr0, const int32_t** rowval0, const double** nzval);
+int fsgpu_vector_device(fsgpu_ctx* ctx, const double** v, int64_t* n);
+
+/* ---- standalone COO -> CSC (Julia `sparse(I,J,V,m,n)`; makematrix! of any assembler) --- */
+/* two calls: (1) colptr/rowval/nzval NULL -> *nnz; (2) fill caller-owned arrays. */
+int fsgpu_coo_to_csc(fsgpu_ctx* ctx, int64_t m, int64_t n, int64_t ntriples, const int64_t* I, const int64_t* J,
+                     const double* V, int64_t* nnz, int64_t* colptr, int64_t* rowval, double* nzval);
+
+/* ---- explicit central-difference loop (examples/.../plate_expl_examples.jl:61-94) -- */
+typedef struct fsgpu_explicit fsgpu_explicit;
+/* K: CSR of the free-free block (Int64 1-based, as SparseMatricesCSR.sparsecsr gives it) and
+ * diag(M); both copied to the device.  c_scale = ksi*2*omegad (C = c_scale * diag(M)). */
+int fsgpu_explicit_create(fsgpu_explicit** h, fsgpu_ctx* ctx, int64_t n, const int64_t* rowptr, const int64_t* colval,
+                          const double* nzval, const double* mdiag, double c_scale, double dt);
+/* same, adopting device-resident results: K = last matrix result of `ctx` (must be FFBLOCK),
+ * M = last vector result (fsgpu_shell_mass_diag with nfree_only) */
+int fsgpu_explicit_create_from_ctx(fsgpu_explicit** h, fsgpu_ctx* ctx, double c_scale, double dt);
+int fsgpu_explicit_destroy(fsgpu_explicit* h);
+int fsgpu_explicit_set_state(fsgpu_explicit* h, const double* U0, const double* V0);
+/* constant load vector F0 scaled by a per-step factor table (force!(F,t) closures of the
+ * examples are constant or windowed sines): F(t_k) = fscale[k] * F0; fscale NULL -> 1 */
+int fsgpu_explicit_set_load(fsgpu_explicit* h, const double* F0);
+/* A0 = invMC .* F(0) (plate_expl_examples.jl:81) */
+int fsgpu_explicit_start(fsgpu_explicit* h, double fscale0);
+/* advance nsteps; fscale[nsteps] or NULL */
+int fsgpu_explicit_step(fsgpu_explicit* h, int64_t nsteps, const double* fscale);
+int fsgpu_explicit_get_state(fsgpu_explicit* h, double* U, double* V, double* A);
+/* y = K x on the device copy (ThreadedSparseCSR.bmul! equivalent) */
+int fsgpu_explicit_spmv(fsgpu_explicit* h, const double* x, double* y);
+/* largest eigenvalue of K x = lambda M x by power iteration (pwr_largest,
+ * examples/.../spherical_cap_expl_examples.jl:166) */
+int fsgpu_explicit_omega_max(fsgpu_explicit* h, int32_t maxit, double* lambda_max);
+/* kinetic energy 1/2 V' M V (peek closures) */
+int fsgpu_explicit_kinetic_energy(fsgpu_explicit* h, double* ke);
+/* multi-GPU: device pointers of U, V, A, F-scratch for halo exchange by the host's NCCL plumbing */
+int fsgpu_explicit_device_state(fsgpu_explicit* h, double** U, double** V, double** A, double** E);
+/* split step for element-partitioned runs: (1) U update + E = K_local U, (2) after the host has
+ * summed interface entries of E across ranks: finish the step */
+int fsgpu_explicit_step_begin(fsgpu_explicit* h);
+int fsgpu_explicit_step_end(fsgpu_explicit* h, double fscale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSGPU_H */
