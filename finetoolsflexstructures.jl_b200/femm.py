@@ -337,6 +337,9 @@ class _FEMMShell(_FEMMBase):
         else:
             t = idom.otherdimension
             ctx.set_thickness(t)
+        # the nodal normals belong to the FEMM (femm._normals) and survive a re-upload
+        if self._associatedgeometry and self._normals is not None:
+            ctx.set_normals(self._normals, self._normal_valid)
 
     def _params(self):
         p = ShellParams()

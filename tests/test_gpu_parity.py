@@ -1,0 +1,477 @@
+"""GPU parity tests: libfsgpu (through the C ABI / the reference-facing Python mirror)
+against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): sparsity patterns / colptr / rowval bit-exact;
+element matrices, assembled values, force vectors <= 1e-12 relative Frobenius norm (FP64).
+"""
+import numpy as np
+import pytest
+
+from oracle import beam as obeam
+from oracle import explicit as oexp
+from oracle import fe_external as fx
+from oracle import layup as oly
+from oracle import shells as osh
+from tests import meshes
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def relfro(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def fs():
+    import fsb200
+
+    return fsb200
+
+
+E_, NU_, T_, RHO_ = 200e9, 0.3, 0.01, 7850.0
+
+
+def _iso():
+    return osh.shell_material_stiffness(fx.moduli_iso(E_, NU_))
+
+
+def _layup():
+    D6 = oly.lamina_moduli(133860e6, 7706e6, 0.301, 4306e6, 4306e6, 2760e6)
+    plies = [oly.Ply(f"p{k}", D6, 0.0025, a, 1500.0) for k, a in enumerate((0, 90, 45, -30))]
+    lay = oly.CompositeLayup("test", plies)
+    th = np.deg2rad(20.0)
+    cs = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    return lay, cs
+
+
+def _fs_layup(fs, cs):
+    f = fs.femm
+    mat = f.lamina_material(1500.0, 133860e6, 7706e6, 0.301, 4306e6, 4306e6, 2760e6)
+    plies = [f.Ply(f"p{k}", mat, 0.0025, a) for k, a in enumerate((0, 90, 45, -30))]
+    return f.CompositeLayup("test", plies, cs)
+
+
+def _make_femm(fs, kind, conn, comp=False, cs=None):
+    f = fs.femm
+    if kind == "t3":
+        idom = f.IntegDomain(conn, None, T_)
+        return f.FEMMShellT3FFComp(idom, _fs_layup(fs, cs)) if comp else f.FEMMShellT3FF(idom, f.MatDeforElastIso(E_, NU_, RHO_))
+    idom = f.IntegDomain(conn, f.GaussRule2x2(), T_)
+    return f.FEMMShellQ4RSComp(idom, _fs_layup(fs, cs)) if comp else f.FEMMShellQ4RS(idom, f.MatDeforElastIso(E_, NU_, RHO_))
+
+
+def _oracle_normals(kind, xyz, conn, fixed=None):
+    if kind == "t3":
+        return osh.t3ff_associategeometry(xyz, conn, normal_dir=fixed)
+    return osh.q4rs_associategeometry(xyz, conn, normal_dir=fixed)
+
+
+def _oracle_K(kind, comp, xyz, conn, normals, valid, cs=None, drill=1.0, sheark=0):
+    Dps, Dt = _iso()
+    if comp:
+        lay, _ = _layup()
+        A, B, D = lay.laminate_stiffnesses()
+        H = lay.laminate_transverse_stiffness()
+        if kind == "t3":
+            return osh.t3ffcomp_stiffness_elmats(xyz, conn, normals, valid, A, B, D, H, lay.thickness, cs, drilling_stiffness_scale=drill, transv_shear_formulation=sheark)
+        return osh.q4rscomp_stiffness_elmats(xyz, conn, normals, valid, A, B, D, H, lay.thickness, cs, drilling_stiffness_scale=drill)
+    if kind == "t3":
+        return osh.t3ff_stiffness_elmats(xyz, conn, normals, valid, Dps, Dt, T_, drilling_stiffness_scale=drill, transv_shear_formulation=sheark)
+    return osh.q4rs_stiffness_elmats(xyz, conn, normals, valid, Dps, Dt, T_, drilling_stiffness_scale=drill)
+
+
+def _oracle_M(kind, comp, xyz, conn):
+    if comp:
+        lay, _ = _layup()
+        md, mi = lay.laminate_inertia()
+        return (osh.t3ffcomp_mass_elmats if kind == "t3" else osh.q4rscomp_mass_elmats)(xyz, conn, md, mi)
+    return (osh.t3ff_mass_elmats if kind == "t3" else osh.q4rs_mass_elmats)(xyz, conn, RHO_, T_)
+
+
+# ---------------------------------------------------------------------------------------
+# nodal normals
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["t3", "q4"])
+def test_associategeometry(fs, kind):
+    xyz, conn = meshes.shell_mesh(kind, n=9)
+    femm = _make_femm(fs, kind, conn)
+    geom0 = fs.femm.NodalField(xyz)
+    fs.femm.associategeometry(femm, geom0)
+    n_o, v_o = _oracle_normals(kind, xyz, conn)
+    assert (~v_o).sum() > 0, "test mesh must contain invalid normals"
+    assert np.array_equal(femm._normal_valid, v_o)
+    assert np.abs(femm._normals - n_o).max() < 1e-13
+
+
+# ---------------------------------------------------------------------------------------
+# raw element matrices
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,comp,sheark", [("t3", False, 0), ("t3", False, 1), ("t3", True, 0), ("t3", True, 1), ("q4", False, 0), ("q4", True, 0)])
+def test_element_stiffness(fs, kind, comp, sheark):
+    xyz, conn = meshes.shell_mesh(kind, n=7)
+    lay_cs = _layup()[1] if comp else None
+    normals, valid = _oracle_normals(kind, xyz, conn)
+    femm = _make_femm(fs, kind, conn, comp, lay_cs)
+    femm.drilling_stiffness_scale = 0.8
+    femm.transv_shear_formulation = sheark
+    geom0 = fs.femm.NodalField(xyz)
+    femm._sync_mesh(geom0)
+    femm.ctx.set_normals(normals, valid)
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    Ko = _oracle_K(kind, comp, xyz, conn, normals, valid, lay_cs, drill=0.8, sheark=sheark)
+    worst = max(relfro(Kg[e], Ko[e]) for e in range(conn.shape[0]))
+    assert worst < TOL, worst
+
+
+@pytest.mark.parametrize("kind,comp", [("t3", False), ("t3", True), ("q4", False), ("q4", True)])
+def test_element_mass(fs, kind, comp):
+    xyz, conn = meshes.shell_mesh(kind, n=5)
+    lay_cs = _layup()[1] if comp else None
+    normals, valid = _oracle_normals(kind, xyz, conn)
+    femm = _make_femm(fs, kind, conn, comp, lay_cs)
+    femm._sync_mesh(fs.femm.NodalField(xyz))
+    femm.ctx.set_normals(normals, valid)
+    Mg = femm.ctx.element_matrices(femm._kind(), 1, femm._params())
+    Mo = _oracle_M(kind, comp, xyz, conn)
+    assert relfro(Mg, Mo) < TOL
+
+
+# ---------------------------------------------------------------------------------------
+# assembled matrices, every assembler target: pattern bit-exact, values 1e-12
+# ---------------------------------------------------------------------------------------
+ASM = {"sparse": "SysmatAssemblerSparse", "symm": "SysmatAssemblerSparseSymm", "diag": "SysmatAssemblerSparseDiag", "ffblock": "ffblock", "ffblock_diag": "ffblock_diag", "csrsymm": "SysmatAssemblerSparseCSRSymm"}
+
+
+def _assembler(fs, name):
+    f = fs.femm
+    if name == "ffblock":
+        return f.SysmatAssemblerFFBlock()
+    if name == "ffblock_diag":
+        return f.SysmatAssemblerFFBlock(f.SysmatAssemblerSparseDiag())
+    return getattr(f, ASM[name])()
+
+
+def _check_matrix(S, ref, nrows):
+    cp, rv, nz = ref
+    assert S.colptr.dtype == np.int64 and S.rowval.dtype == np.int64
+    assert np.array_equal(S.colptr, cp), "colptr differs"
+    assert np.array_equal(S.rowval, rv), "rowval differs"
+    assert relfro(S.nzval, nz) < TOL, relfro(S.nzval, nz)
+    assert S.m == nrows and S.n == nrows
+
+
+@pytest.mark.parametrize("kind", ["t3", "q4"])
+@pytest.mark.parametrize("asm", ["sparse", "symm", "diag", "ffblock", "ffblock_diag", "csrsymm"])
+def test_assembled_stiffness_and_mass(fs, kind, asm):
+    xyz, conn = meshes.shell_mesh(kind, n=8)
+    od = meshes.clamp_edge_dofs(xyz)
+    femm = _make_femm(fs, kind, conn)
+    f = fs.femm
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs()
+    assert np.array_equal(dchi.dofnums, od.dofnums)
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals(kind, xyz, conn)
+    u0 = f.NodalField(np.zeros((xyz.shape[0], 3)))
+    R0 = f.initial_Rfield(xyz.shape[0])
+    K = f.stiffness(femm, _assembler(fs, asm), geom0, u0, R0, dchi)
+    M = f.mass(femm, _assembler(fs, asm), geom0, dchi)
+    dn = od.gatherdofnums(conn)
+    Ko = _oracle_K(kind, False, xyz, conn, normals, valid)
+    Mo = _oracle_M(kind, False, xyz, conn)
+    n = od.nfreedofs if asm.startswith("ffblock") else od.nalldofs
+    _check_matrix(K, fx.assemble_matrix(asm, Ko, dn, od.nalldofs, od.nfreedofs), n)
+    _check_matrix(M, fx.assemble_matrix(asm, Mo, dn, od.nalldofs, od.nfreedofs), n)
+    if asm == "symm":
+        A = K.to_scipy()
+        assert abs(A - A.T).max() == 0.0, "SparseSymm result must be exactly symmetric"
+
+
+def test_symm_drops_exact_zeros_flat_plate(fs):
+    """Flat axis-aligned plate: membrane/bending cross terms are exact zeros that
+    SysmatAssemblerSparseSymm drops (value-dependent pattern)."""
+    xy, conn = fx.t3block(2.0, 1.0, 6, 4)
+    xyz = fx.xyz3(xy)
+    f = fs.femm
+    femm = _make_femm(fs, "t3", conn)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6))).numberdofs()
+    f.associategeometry(femm, geom0)
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    K = f.stiffness(femm, geom0, u0, R0, dchi)  # default assembler = SparseSymm
+    normals, valid = _oracle_normals("t3", xyz, conn)
+    Ko = _oracle_K("t3", False, xyz, conn, normals, valid)
+    od = fx.DofField(xyz.shape[0]).numberdofs()
+    cp, rv, nz = fx.assemble_matrix("symm", Ko, od.gatherdofnums(conn), od.nalldofs)
+    full = fx.assemble_matrix("sparse", Ko, od.gatherdofnums(conn), od.nalldofs)
+    assert len(rv) < len(full[1]), "the flat plate must have droppable zeros"
+    assert len(K.rowval) < len(full[1]), "the GPU path must drop exact zeros too"
+    n = od.nalldofs
+    Kg, Kr = K.to_scipy(), fx.csc_to_scipy(cp, rv, nz, n, n)
+    assert relfro(Kg.toarray(), Kr.toarray()) < TOL
+    assert abs(Kg - Kg.T).max() == 0.0
+    # Which entries cancel to an EXACT zero depends on the floating-point operation order
+    # (the reference's own pattern depends on its BLAS); patterns may therefore differ, but
+    # only in entries at round-off level.
+    import scipy.sparse as sp
+
+    Pg = sp.csc_matrix((np.ones_like(Kg.data), Kg.indices, Kg.indptr), shape=Kg.shape)
+    Pr = sp.csc_matrix((np.ones_like(Kr.data), Kr.indices, Kr.indptr), shape=Kr.shape)
+    diff = (Pg - Pr).tocoo()
+    sel = diff.data != 0
+    vals = np.abs(np.asarray((Kg + Kr)[diff.row[sel], diff.col[sel]])).ravel()
+    assert sel.sum() < 0.01 * len(rv)
+    assert vals.size == 0 or vals.max() < 1e-12 * np.abs(nz).max()
+
+
+@pytest.mark.parametrize("kind", ["t3", "q4"])
+def test_assembled_composite(fs, kind):
+    xyz, conn = meshes.shell_mesh(kind, n=6)
+    lay, cs = _layup()
+    f = fs.femm
+    femm = _make_femm(fs, kind, conn, True, cs)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6))).numberdofs()
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals(kind, xyz, conn, fixed=cs[:, 2])
+    assert np.array_equal(femm._normal_valid, valid)
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    K = f.stiffness(femm, f.SysmatAssemblerSparse(), geom0, u0, R0, dchi)
+    M = f.mass(femm, f.SysmatAssemblerSparseDiag(), geom0, dchi)
+    od = fx.DofField(xyz.shape[0]).numberdofs()
+    dn = od.gatherdofnums(conn)
+    _check_matrix(K, fx.assemble_matrix("sparse", _oracle_K(kind, True, xyz, conn, normals, valid, cs), dn, od.nalldofs), od.nalldofs)
+    _check_matrix(M, fx.assemble_matrix("diag", _oracle_M(kind, True, xyz, conn), dn, od.nalldofs), od.nalldofs)
+
+
+def test_rcm_like_permuted_numbering(fs):
+    """numberdofs!(dchi, perm): dofs of a node are no longer monotone in the node index."""
+    xyz, conn = meshes.shell_mesh("t3", n=7)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(xyz.shape[0])
+    od = meshes.clamp_edge_dofs(xyz)
+    od.numberdofs(perm)
+    f = fs.femm
+    femm = _make_femm(fs, "t3", conn)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs(perm)
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals("t3", xyz, conn)
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, u0, R0, dchi)
+    Ko = _oracle_K("t3", False, xyz, conn, normals, valid)
+    _check_matrix(K, fx.assemble_matrix("ffblock", Ko, od.gatherdofnums(conn), od.nalldofs, od.nfreedofs), od.nfreedofs)
+
+
+# ---------------------------------------------------------------------------------------
+# corotational beam
+# ---------------------------------------------------------------------------------------
+EB, NUB, RHOB = 71240.0, 0.31, 5e-9
+
+
+def _beam(fs):
+    xyz, conn, u1, R1, sec = meshes.beam_lattice()
+    f = fs.femm
+    secs = f.FESetL2Beam(sec["A"], sec["I1"], sec["I2"], sec["I3"], sec["J"], sec["A2s"], sec["A3s"], sec["x1x2"])
+    femm = f.FEMMCorotBeam(f.IntegDomain(conn), f.MatDeforElastIso(EB, NUB, RHOB), secs)
+    od = fx.DofField(xyz.shape[0])
+    for c in range(1, 7):
+        od.setebc([0], c)
+    od.numberdofs()
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs()
+    return f, femm, xyz, conn, u1, R1, sec, od, dchi
+
+
+def test_beam_element_level(fs):
+    f, femm, xyz, conn, u1, R1, sec, od, dchi = _beam(fs)
+    femm._sync_mesh(f.NodalField(xyz))
+    femm.ctx.set_state(u1, R1)
+    for op, ref in ((0, obeam.beam_stiffness_elmats(xyz, conn, u1, R1, sec, EB, NUB)), (2, obeam.beam_geostiffness_elmats(xyz, conn, u1, R1, sec, EB, NUB))):
+        got = femm.ctx.element_matrices(2, op, femm._params())
+        assert max(relfro(got[e], ref[e]) for e in range(len(conn))) < TOL
+    for mt in range(4):
+        got = femm.ctx.element_matrices(2, 1, femm._params(mt))
+        ref = obeam.beam_mass_elmats(xyz, conn, u1, R1, sec, RHOB, mt)
+        assert max(relfro(got[e], ref[e]) for e in range(len(conn))) < TOL
+    ev = femm.ctx.element_vectors(femm._params())
+    ref = obeam.beam_restoringforce_elvecs(xyz, conn, u1, R1, sec, EB, NUB)
+    assert max(relfro(ev[e], ref[e]) for e in range(len(conn))) < TOL
+
+
+def test_beam_operators(fs):
+    f, femm, xyz, conn, u1, R1, sec, od, dchi = _beam(fs)
+    geom0, uf, Rf = f.NodalField(xyz), f.NodalField(u1), f.NodalField(R1)
+    dn = od.gatherdofnums(conn)
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, uf, Rf, dchi)
+    _check_matrix(K, fx.assemble_matrix("ffblock", obeam.beam_stiffness_elmats(xyz, conn, u1, R1, sec, EB, NUB), dn, od.nalldofs, od.nfreedofs), od.nfreedofs)
+    Kg = f.geostiffness(femm, f.SysmatAssemblerSparse(), geom0, uf, Rf, dchi)
+    _check_matrix(Kg, fx.assemble_matrix("sparse", obeam.beam_geostiffness_elmats(xyz, conn, u1, R1, sec, EB, NUB), dn, od.nalldofs), od.nalldofs)
+    M = f.mass(femm, geom0, uf, Rf, dchi, mass_type=1)
+    _check_matrix(M, fx.assemble_matrix("symm", obeam.beam_mass_elmats(xyz, conn, u1, R1, sec, RHOB, 1), dn, od.nalldofs), od.nalldofs)
+    ev = obeam.beam_restoringforce_elvecs(xyz, conn, u1, R1, sec, EB, NUB)
+    Fr = f.restoringforce(femm, f.SysvecAssemblerFBlock(), geom0, uf, Rf, dchi)
+    assert relfro(Fr, fx.assemble_vector(ev, dn, od.nalldofs, od.nfreedofs)) < TOL
+    Fa = f.restoringforce(femm, geom0, uf, Rf, dchi)
+    assert relfro(Fa, fx.assemble_vector(ev, dn, od.nalldofs)) < TOL
+
+
+def test_update_rotation_field(fs):
+    f, femm, xyz, conn, u1, R1, sec, od, dchi = _beam(fs)
+    femm._sync_mesh(f.NodalField(xyz))
+    rng = np.random.default_rng(9)
+    dchi.values[:] = rng.uniform(-1, 1, dchi.values.shape) * 0.3
+    dchi.values[3, 3:] = 0.0  # zero rotation vector branch
+    Rf = f.NodalField(R1)
+    f.update_rotation_field(femm, Rf, dchi)
+    assert np.abs(Rf.values - obeam.update_rotation_field(R1, dchi.values)).max() < 1e-14
+
+
+# ---------------------------------------------------------------------------------------
+# COO -> CSC, error paths
+# ---------------------------------------------------------------------------------------
+def test_coo_to_csc(fs):
+    rng = np.random.default_rng(11)
+    m, n, nt = 57, 43, 5000
+    I = rng.integers(1, m + 1, nt)
+    J = rng.integers(1, n + 1, nt)
+    V = rng.standard_normal(nt)
+    V[::7] = 0.0  # explicit zeros are kept
+    ctx = fs.Context()
+    S = ctx.coo_to_csc(I, J, V, m, n)
+    cp, rv, nz = fx.sparse_csc(I, J, V, m, n)
+    assert np.array_equal(S.colptr, cp) and np.array_equal(S.rowval, rv)
+    assert np.abs(S.nzval - nz).max() < 1e-13
+    E = ctx.coo_to_csc([], [], [], 5, 4)
+    assert np.array_equal(E.colptr, np.ones(5, dtype=np.int64)) and E.rowval.size == 0
+
+
+def test_reference_assembler_equivalence_vector(fs):
+    """test/test_utilities.jl:12-47 restated: two dense blocks into a 7x7 through COO->CSC."""
+    m1 = np.array([[0.24406, 0.599773, 0.833404, 0.0420141], [0.786024, 0.00206713, 0.995379, 0.780298], [0.845816, 0.198459, 0.355149, 0.224996]])
+    m2 = np.array([[0.146618, 0.53471, 0.614342, 0.737833], [0.479719, 0.41354, 0.00760941, 0.836455], [0.254868, 0.476189, 0.460794, 0.00919633], [0.159064, 0.261821, 0.317078, 0.77646], [0.643538, 0.429817, 0.59788, 0.958909]])
+    I, J, V = [], [], []
+    for mat, d in ((m1.T @ m1, [5, 2, 1, 4]), (m2.T @ m2, [2, 3, 1, 5])):
+        for j in range(4):
+            for i in range(4):
+                I.append(d[i]); J.append(d[j]); V.append(mat[i, j])
+    S = fs.Context().coo_to_csc(I, J, V, 7, 7).to_scipy().toarray()
+    ref = np.zeros((7, 7))
+    for i, j, v in zip(I, J, V):
+        ref[i - 1, j - 1] += v
+    assert relfro(S, ref) < 1e-14
+
+
+def test_error_paths(fs):
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh("t3", n=3)
+    femm = _make_femm(fs, "t3", conn)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6))).numberdofs()
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    with pytest.raises(fs.FsgpuError) as ei:  # @assert self._associatedgeometry
+        f.stiffness(femm, geom0, u0, R0, dchi)
+    assert ei.value.code == 3
+    ctx = fs.Context()
+    ctx.set_mesh(conn, xyz)
+    bad = dchi.dofnums.copy()
+    bad[0, 0] = dchi.dofnums.size + 1
+    with pytest.raises(fs.FsgpuError) as ei:  # FinEtools assemble!: dof > size
+        ctx.set_dofnums(bad, dchi.dofnums.size)
+    assert ei.value.code == 4
+    badconn = conn.copy()
+    badconn[0, 0] = xyz.shape[0] + 5
+    with pytest.raises(fs.FsgpuError):
+        ctx.set_mesh(badconn, xyz)
+    # singular metric: all four nodes coincident -> det(J'J) is an exact zero
+    xq = np.zeros((4, 3))
+    cq = np.array([[1, 2, 3, 4]])
+    fq = _make_femm(fs, "q4", cq)
+    gq = f.NodalField(xq)
+    fq._sync_mesh(gq)
+    fq._normals, fq._normal_valid = np.tile([0, 0, 1.0], (4, 1)), np.ones(4, bool)
+    fq.ctx.set_normals(fq._normals, fq._normal_valid)
+    fq._associatedgeometry = True
+    dq = f.NodalField(np.zeros((4, 6))).numberdofs()
+    with pytest.raises(fs.FsgpuError) as ei:
+        f.stiffness(fq, gq, u0, R0, dq)
+    assert ei.value.code == 5
+
+
+def test_empty_mesh(fs):
+    ctx = fs.Context()
+    ctx.set_mesh(np.zeros((0, 3), dtype=np.int64), np.zeros((4, 3)))
+    ctx.set_dofnums(np.arange(1, 25).reshape(4, 6), 24)
+    nr, nc, nnz = ctx.symbolic(0)
+    assert (nr, nc, nnz) == (24, 24, 0)
+
+
+# ---------------------------------------------------------------------------------------
+# explicit central differences
+# ---------------------------------------------------------------------------------------
+def test_explicit_loop(fs):
+    import scipy.sparse as sp
+
+    f = fs.femm
+    xy, conn = fx.t3block(1.0, 0.6, 12, 8)
+    xyz = fx.xyz3(xy)
+    xyz[:, 2] = 0.05 * np.sin(3 * xyz[:, 0])
+    od = meshes.clamp_edge_dofs(xyz, n_extra_fixed=0)
+    femm = _make_femm(fs, "t3", conn)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs()
+    f.associategeometry(femm, geom0)
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, u0, R0, dchi)
+    femm.ctx.shell_mass_diag(femm._params(), 3, nfree_only=True)
+    nf = od.nfreedofs
+    Md = femm.ctx.fetch_vector(nf)
+    # oracle K, M
+    normals, valid = _oracle_normals("t3", xyz, conn)
+    dn = od.gatherdofnums(conn)
+    cp, rv, nz = fx.assemble_matrix("ffblock", _oracle_K("t3", False, xyz, conn, normals, valid), dn, od.nalldofs, nf)
+    Ko = fx.csc_to_scipy(cp, rv, nz, nf, nf).tocsr()
+    cpm, rvm, nzm = fx.assemble_matrix("ffblock_diag", _oracle_M("t3", False, xyz, conn), dn, od.nalldofs, nf)
+    Mo = np.zeros(nf)
+    Mo[rvm - 1] = nzm
+    assert relfro(Md, Mo) < TOL
+    ex = fs.Explicit(femm.ctx, c_scale=2 * 0.02 * 2 * np.pi * 1000, dt=0.0)  # dt set below
+    lam = ex.omega_max_sq(40)
+    lam_o = oexp.pwr_largest(Ko, Mo, 200)
+    assert abs(lam - lam_o) / lam_o < 0.05
+    ex.close()
+    dt = 0.9 * 2 / np.sqrt(lam_o)
+    cs = 2 * 0.02 * 2 * np.pi * 1000
+    ex = fs.Explicit(femm.ctx, c_scale=cs, dt=dt)
+    rng = np.random.default_rng(4)
+    F0 = rng.standard_normal(nf) * 10.0
+    nsteps = 100
+    fsc = np.sin(np.arange(1, nsteps + 1) * dt * 2 * np.pi * 2000.0)
+    ex.set_load(F0)
+    ex.start(0.0)
+    ex.step(nsteps, fsc)
+    U, V, A = ex.get_state()
+    tt = lambda t: F0 * np.sin(t * 2 * np.pi * 2000.0)
+    Uo, Vo, Ao = oexp.cd_loop(Mo, Ko, cs, np.zeros(nf), np.zeros(nf), nsteps, dt, tt)
+    assert relfro(U, Uo) < 1e-9 and relfro(V, Vo) < 1e-9
+    # spmv and kinetic energy
+    x = rng.standard_normal(nf)
+    assert relfro(ex.spmv(x), Ko @ x) < TOL
+    assert abs(ex.kinetic_energy() - 0.5 * np.dot(Vo * Mo, Vo)) <= 1e-9 * abs(0.5 * np.dot(Vo * Mo, Vo))
+    # host-CSR construction path gives the same result
+    Kcsr = Ko
+    ex2 = fs.Explicit(fs.Context(), K=(Kcsr.indptr.astype(np.int64) + 1, Kcsr.indices.astype(np.int64) + 1, Kcsr.data), mdiag=Mo, c_scale=cs, dt=dt)
+    ex2.set_load(F0)
+    ex2.start(0.0)
+    ex2.step(nsteps, fsc)
+    assert relfro(ex2.get_state()[0], Uo) < 1e-9
