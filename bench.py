@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric).
+
+Workload at N=1: config[1] of BASELINE.json -- Q4RS homogeneous square plate, synthetic
+1000 x 1000 quad mesh (1M elements), stiffness assembly to CSC (SysmatAssemblerFFBlock).
+A "step" is one stiffness operator call over the whole mesh.
+
+  value   element matrices assembled per second, device-resident inputs, pattern reused
+          (numeric phase: value-array clear + element kernel + status read-back)
+  e2e     the same operator through the reference-facing API with HOST (pinned) buffers:
+          mesh/dofs/normals H2D + symbolic phase + numeric phase + CSC D2H, every step
+  roofline / fp64 / cpu_baseline: see DESIGN.md "Measurement"
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/cport,
+"port": no Julia in this image) on the box's host cores with all threads.
+
+Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+       torchrun ... bench.py --gpus N ...      (one rank per GPU, weak scaling)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic traffic / work per element of the dominant kernel
+Q4_IN_BYTES = 32 + 97  # conn (4 x Int64 on the Julia side) + 1 node x (xyz 24 + normal 24 + valid 1 + dofnums 48)
+Q4_FLOPS = 43.0e3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def dist_env():
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), ws
+
+
+def pinned(shape, dtype, order="C"):
+    import torch
+
+    n = int(np.prod(shape))
+    t = torch.empty(n, dtype={np.float64: torch.float64, np.int64: torch.int64, np.uint8: torch.uint8}[dtype], pin_memory=True)
+    a = t.numpy().reshape(shape, order=order)
+    return a, t
+
+
+def pin_copy(a):
+    order = "F" if a.flags.f_contiguous and not a.flags.c_contiguous else "C"
+    out, keep = pinned(a.shape, a.dtype.type, order)
+    out[...] = a
+    return out, keep
+
+
+# ---------------------------------------------------------------------------------------
+# CPU reference arm (the oracle's C port of the reference algorithm)
+# ---------------------------------------------------------------------------------------
+def load_refport():
+    d = os.path.join(ROOT, "oracle", "cport")
+    so = os.path.join(d, "librefport.so")
+    try:  # rebuild on this box (host CPU may differ from the build container)
+        subprocess.run(["make", "-C", d, "-s", "-B"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        pass
+    lib = C.CDLL(so)
+    lib.ref_coo_to_csc.restype = C.c_int64
+    return lib
+
+
+def cpu_q4rs_assembly(w, nelem_sample, nthreads, normals, valid):
+    """Times the reference algorithm (element loop + COO append + sparse()) on the first
+    `nelem_sample` elements of the workload.  Returns elements/s."""
+    from oracle import fe_external as fx
+    from oracle import shells as osh
+
+    lib = load_refport()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    conn = np.ascontiguousarray(w["conn"][:nelem_sample])
+    nn = conn.shape[1]
+    n = 6 * nn
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(w["E"], w["nu"]))
+    Dps, Dt = np.ascontiguousarray(Dps), np.ascontiguousarray(Dt)
+    pc, wt = fx.gauss_rule_2x2()
+    pc = np.ascontiguousarray(pc)
+    nt = nelem_sample * n * n
+    I, J, V = np.empty(nt, np.int64), np.empty(nt, np.int64), np.empty(nt)
+    v8 = np.ascontiguousarray(valid.astype(np.uint8))
+    nF = np.asfortranarray(normals)
+    nnodes = w["xyz"].shape[0]
+    nall, nfree = w["dofnums"].size, w["nfree"]
+    alpha = 0.1 if nn == 4 else 5 / 12 / 1.5
+    t0 = time.perf_counter()
+    lib.ref_shell_stiffness_coo(nn, C.c_int64(nelem_sample), P(conn), C.c_int64(nnodes), P(w["xyz"]), P(nF), P(v8),
+                                P(w["dofnums"]), P(Dps), P(Dt), C.c_double(w["thickness"]), C.c_double(alpha), C.c_double(1.0), 4,
+                                P(pc), P(wt), nthreads, P(I), P(J), P(V))
+    nnz = lib.ref_coo_to_csc(C.c_int64(nt), P(I), P(J), P(V), C.c_int64(nall), C.c_int64(nall), C.c_int64(nfree), C.c_int64(nfree), None, None, None)
+    cp, rv, nz = np.empty(nfree + 1, np.int64), np.empty(nnz, np.int64), np.empty(nnz)
+    lib.ref_coo_to_csc(C.c_int64(nt), P(I), P(J), P(V), C.c_int64(nall), C.c_int64(nall), C.c_int64(nfree), C.c_int64(nfree), P(cp), P(rv), P(nz))
+    dt = time.perf_counter() - t0
+    return nelem_sample / dt, dt
+
+
+def oracle_normals(w):
+    """Nodal normals for the CPU arm (vectorised oracle; not timed)."""
+    from oracle import shells as osh
+
+    f = osh.q4rs_associategeometry if w["kind"] == "q4" else osh.t3ff_associategeometry
+    return f(np.ascontiguousarray(w["xyz"]), w["conn"])
+
+
+# ---------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1000, help="quads per side (1000 -> 1M elements, the BASELINE config)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    metric, unit = "element matrices assembled/sec (Q4RS stiffness -> CSC)", "elements/s"
+    from fsb200 import workloads as wl  # noqa: E402  (pure numpy part of the package)
+
+    w = wl.c2_q4rs_plate(args.n)
+    nelem = w["conn"].shape[0]
+    config = {"workload": f"BASELINE configs[1]: Q4RS homogeneous square plate, synthetic {args.n}x{args.n} quad mesh "
+                          f"({nelem} elements), stiffness assembly to CSC via SysmatAssemblerFFBlock, GaussRule(2,2)",
+              "nelem": nelem, "nnodes": int(w["xyz"].shape[0]), "nfree": int(w["nfree"]),
+              "l2": "inputs+outputs (slot map 2.3 GB + values 2.6 GB at 1M elements) are larger than the 126 MB L2",
+              "pattern": "reused across steps for `value` (symbolic phase reported separately); rebuilt every step for `e2e`",
+              "parallelism": f"element-partitioned, {world} rank(s), no data-path collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ncores = os.cpu_count() or 1
+        normals, valid = oracle_normals(w)
+        sample = min(nelem, max(20000, 4000 * ncores))
+        vals = []
+        for s in range(args.warmup + args.steps):
+            v, dt = cpu_q4rs_assembly(w, sample, ncores, normals, valid)
+            if s >= args.warmup:
+                vals.append((v, dt))
+        v = float(np.mean([x[0] for x in vals]))
+        ms = float(np.mean([x[1] for x in vals])) * 1e3
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": unit, "cores": ncores, "kind": "port",
+                                 "sample": f"first {sample} elements of the workload per step: element loop + COO append + COO->CSC, OpenMP element-parallel"},
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import fsb200
+
+    f = fsb200.femm
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    hbm_peak, peak_kind = peaks()
+
+    # host (pinned) inputs, as a Julia host would hold them
+    xyz_p, k1 = pin_copy(w["xyz"])
+    conn_p, k2 = pin_copy(np.ascontiguousarray(w["conn"]))
+    dof_p, k3 = pin_copy(w["dofnums"])
+    mat = f.MatDeforElastIso(w["E"], w["nu"], w["rho"])
+    femm = f.FEMMShellQ4RS(f.IntegDomain(conn_p, f.GaussRule2x2(), w["thickness"]), mat, device=local_rank)
+    stream = torch.cuda.Stream()
+    femm.ctx.set_stream(stream.cuda_stream)
+    geom0 = f.NodalField.__new__(f.NodalField)
+    geom0.values = xyz_p
+    dchi = f.NodalField.__new__(f.NodalField)
+    dchi.values, dchi.dofnums, dchi._nfree = None, dof_p, w["nfree"]
+    u0 = R0 = None
+
+    # --- setup (untimed): nodal normals, first symbolic phase -------------------------------
+    f.associategeometry(femm, geom0)
+    t0 = time.perf_counter()
+    femm._startassembly(f.SysmatAssemblerFFBlock(), dchi)
+    femm.ctx.sync()
+    symbolic_ms = (time.perf_counter() - t0) * 1e3
+    nr, nc, nnz = femm.ctx.symbolic(fsb200._lib.FFBLOCK)  # (second build, for a warm number)
+    t0 = time.perf_counter()
+    nr, nc, nnz = femm.ctx.symbolic(fsb200._lib.FFBLOCK)
+    femm.ctx.sync()
+    symbolic_warm_ms = (time.perf_counter() - t0) * 1e3
+    params = femm._params()
+    femm._sync_stab()
+    fp64_peak, copy_bw = femm.ctx.measure_peaks()
+
+    # --- device-resident numeric phase: `value` --------------------------------------------
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        femm.ctx.shell_op("q4rs_stiffness", params)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = femm.ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        femm.ctx.shell_op("q4rs_stiffness", params)
+        kms.append(femm.ctx.last_kernel_ms)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = femm.ctx.launch_count - l0
+    ms_total = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    value = nelem * world / (ms_per_step * 1e-3)
+    kernel_ms = float(np.mean(kms))
+
+    # --- end to end through the reference-facing operator API: `e2e` -------------------------
+    cp_p, k4 = pinned((nc + 1,), np.int64)
+    rv_p, k5 = pinned((nnz,), np.int64)
+    nz_p, k6 = pinned((nnz,), np.float64)
+    nrm_host, val_host = femm._normals, femm._normal_valid
+    h2d = conn_p.nbytes + xyz_p.nbytes + dof_p.nbytes + nrm_host.nbytes + val_host.size + 8
+    d2h = cp_p.nbytes + rv_p.nbytes + nz_p.nbytes
+
+    def e2e_step():
+        g = f.NodalField.__new__(f.NodalField)  # fresh field objects -> mesh, dofs, normals re-uploaded
+        g.values = xyz_p
+        d = f.NodalField.__new__(f.NodalField)
+        d.values, d.dofnums, d._nfree = None, dof_p, w["nfree"]
+        femm.reset_uploads()
+        return f.stiffness(femm, f.SysmatAssemblerFFBlock(), g, u0, R0, d, out=(cp_p, rv_p, nz_p))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        K = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = nelem * world / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # --- roofline of the dominant kernel ------------------------------------------------------
+    out_bytes = 8.0 * nnz / nelem  # values written once (pattern reused)
+    alg_bytes = Q4_IN_BYTES + out_bytes
+    achieved = alg_bytes * nelem / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "kernel": "k_q4_stiffness<false,EmitScatter>",
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_element": alg_bytes,
+                "kernel_share_of_step": kernel_ms / ms_per_step}
+    fl = Q4_FLOPS * nelem / (kernel_ms * 1e-3) / 1e12
+    fp64 = {"achieved_tflops": fl, "peak_tflops": fp64_peak, "frac": fl / fp64_peak, "flops_per_element": Q4_FLOPS,
+            "peak_source": "fsgpu_measure_peaks DFMA micro-kernel on this device", "copy_gbs_this_device": copy_bw}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        ncores = os.cpu_count() or 1
+        normals, valid = nrm_host, val_host
+        s1 = min(nelem, 20000)
+        v1, t1 = cpu_q4rs_assembly(w, s1, 1, normals, valid)
+        sN = min(nelem, max(40000, 8000 * ncores))
+        vN, tN = cpu_q4rs_assembly(w, sN, ncores, normals, valid)
+        cpu = {"value": vN, "unit": unit, "cores": ncores, "kind": "port",
+               "sample": f"first {sN} elements (all {ncores} threads, {tN:.1f} s); single-thread = reference behaviour: "
+                         f"{v1:.0f} elements/s on the first {s1} elements ({t1:.1f} s)",
+               "single_thread_value": v1}
+
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_s * 1e3, "includes": "H2D mesh+dofs+normals, symbolic phase, numeric phase, D2H colptr+rowval+nzval (Int64/f64)"},
+            "gpu_launches": int(launches), "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu,
+            "symbolic_ms": {"first": symbolic_ms, "warm": symbolic_warm_ms}, "nnz": int(nnz)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

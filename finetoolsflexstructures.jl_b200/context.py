@@ -128,6 +128,17 @@ class Context:
     def launch_count(self):
         return int(lib.fsgpu_launch_count(self._h))
 
+    @property
+    def last_kernel_ms(self):
+        ms = C.c_double()
+        check(lib.fsgpu_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def measure_peaks(self):
+        f, b = C.c_double(), C.c_double()
+        check(lib.fsgpu_measure_peaks(self._h, C.byref(f), C.byref(b)))
+        return f.value, b.value
+
     # ---- symbolic / numeric -------------------------------------------------------------
     def symbolic(self, target):
         nr, nc, nnz = C.c_int64(), C.c_int64(), C.c_int64()

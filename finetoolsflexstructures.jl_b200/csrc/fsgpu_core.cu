@@ -25,6 +25,20 @@ int check_ctx(fsgpu_ctx* c) {
   return FSGPU_OK;
 }
 
+int time_begin(fsgpu_ctx* c) {
+  if (!c->ev0) {
+    FS_CUDA(cudaEventCreate(&c->ev0));
+    FS_CUDA(cudaEventCreate(&c->ev1));
+  }
+  FS_CUDA(cudaEventRecord(c->ev0, c->stream));
+  return FSGPU_OK;
+}
+int time_end(fsgpu_ctx* c) {
+  FS_CUDA(cudaEventRecord(c->ev1, c->stream));
+  c->timed = true;
+  return FSGPU_OK;
+}
+
 int upload(fsgpu_ctx* c, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return FSGPU_OK;
   FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -172,6 +186,8 @@ extern "C" int fsgpu_destroy(fsgpu_ctx* c) {
   if (!c) return FSGPU_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
   return FSGPU_OK;
 }
@@ -195,6 +211,15 @@ extern "C" int fsgpu_sync(fsgpu_ctx* c) {
   return FSGPU_OK;
 }
 extern "C" int64_t fsgpu_launch_count(fsgpu_ctx* c) { return c ? c->launches : 0; }
+extern "C" int fsgpu_last_kernel_ms(fsgpu_ctx* c, double* ms) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(ms && c->timed, FSGPU_ERR_STATE, "no timed operator has run");
+  FS_CUDA(cudaEventSynchronize(c->ev1));
+  float f = 0;
+  FS_CUDA(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+  *ms = f;
+  return FSGPU_OK;
+}
 
 // ------------------------------------------------------------------------------------
 // data hand-over

@@ -740,10 +740,12 @@ int shell_stiffness(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool co
   ShellArgs A;
   FS_TRY(shell_args(c, p, nnpe, comp, true, A));
   FS_TRY(begin_matrix(c));
+  FS_TRY(time_begin(c));
   if (nnpe == 3)
     FS_TRY(launch_t3(c, A, comp, p->transv_shear_formulation == 1, scatter_of(c)));
   else
     FS_TRY(launch_q4(c, A, comp, scatter_of(c)));
+  FS_TRY(time_end(c));
   int32_t f = 0;
   FS_CUDA(cudaMemcpyAsync(&f, c->flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   FS_CUDA(cudaStreamSynchronize(c->stream));
@@ -800,10 +802,12 @@ int beam_matrix(fsgpu_ctx* c, const fsgpu_beam_params* p, int op) {
   FS_TRY(beam_args(c, p, B));
   FS_TRY(begin_matrix(c));
   const int64_t n = B.nelem * 4;
+  FS_TRY(time_begin(c));
   if (n > 0) {
     k_beam_matrix<EmitScatter><<<grid_for(n, 128), 128, 0, c->stream>>>(B, op, scatter_of(c));
     c->launches++;
   }
+  FS_TRY(time_end(c));
   FS_CUDA(cudaGetLastError());
   FS_CUDA(cudaStreamSynchronize(c->stream));
   return finalize_matrix(c);

@@ -373,3 +373,72 @@ extern "C" int fsgpu_explicit_kinetic_energy(fsgpu_explicit* h, double* ke) {
   *ke = 0.5 * s;
   return FSGPU_OK;
 }
+
+// ---- measurement support: FP64 FMA peak and copy bandwidth of this device ------------------
+namespace {
+__global__ void k_dfma_peak(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double x = 1.0000001, y = 1e-9 * threadIdx.x;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, x, y);
+    a1 = fma(a1, x, y);
+    a2 = fma(a2, x, y);
+    a3 = fma(a3, x, y);
+    a4 = fma(a4, x, y);
+    a5 = fma(a5, x, y);
+    a6 = fma(a6, x, y);
+    a7 = fma(a7, x, y);
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;  // keep the loop alive
+}
+__global__ void k_copy(const double2* __restrict__ a, double2* __restrict__ b, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+}  // namespace
+
+extern "C" int fsgpu_measure_peaks(fsgpu_ctx* c, double* fp64_tflops, double* copy_gbs) {
+  FS_TRY(check_ctx(c));
+  cudaEvent_t e0, e1;
+  FS_CUDA(cudaEventCreate(&e0));
+  FS_CUDA(cudaEventCreate(&e1));
+  DBuf<double> out;
+  FS_TRY(out.ensure(8));
+  int sms = 0;
+  FS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  float best = 1e30f;
+  const int iters = 1 << 15, blocks = sms * 8, threads = 256;
+  for (int rep = 0; rep < 5; ++rep) {
+    FS_CUDA(cudaEventRecord(e0, c->stream));
+    k_dfma_peak<<<blocks, threads, 0, c->stream>>>(out.p, iters, 1.0);
+    FS_CUDA(cudaEventRecord(e1, c->stream));
+    FS_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    FS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  c->launches += 5;
+  if (fp64_tflops) *fp64_tflops = (double)blocks * threads * iters * 8 * 2 / (best * 1e-3) / 1e12;
+  if (copy_gbs) {
+    const int64_t n = (int64_t)1 << 26;  // 2 x 1 GiB of double2
+    DBuf<double2> a, b;
+    FS_TRY(a.ensure((size_t)n));
+    FS_TRY(b.ensure((size_t)n));
+    FS_CUDA(cudaMemsetAsync(a.p, 0, (size_t)n * sizeof(double2), c->stream));
+    best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+      FS_CUDA(cudaEventRecord(e0, c->stream));
+      k_copy<<<sms * 16, 512, 0, c->stream>>>(a.p, b.p, n);
+      FS_CUDA(cudaEventRecord(e1, c->stream));
+      FS_CUDA(cudaEventSynchronize(e1));
+      float ms;
+      FS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    c->launches += 6;
+    *copy_gbs = 2.0 * (double)n * sizeof(double2) / (best * 1e-3) / 1e9;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return FSGPU_OK;
+}

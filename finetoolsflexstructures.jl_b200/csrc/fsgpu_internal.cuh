@@ -79,6 +79,9 @@ struct fsgpu_ctx {
   int device = 0;
   cudaStream_t stream = 0;
   int64_t launches = 0;
+  // device time of the dominant kernel of the last operator (CUDA events on `stream`)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
 
   // mesh
   int nnpe = 0;
@@ -142,6 +145,8 @@ int upload(fsgpu_ctx* c, void* dst, const void* src, size_t bytes);
 int download(fsgpu_ctx* c, void* dst, const void* src, size_t bytes);
 // after an operator has filled nzval: SPARSE_SYMM symmetrisation + zero dropping, bookkeeping
 int finalize_matrix(fsgpu_ctx* c);
+int time_begin(fsgpu_ctx* c);
+int time_end(fsgpu_ctx* c);
 // CSC (0-based, device) -> CSR of the same matrix, by sorting entries on (row, col)
 int csc_to_csr(fsgpu_ctx* c, const int32_t* colptr, const int32_t* rowval, const double* nz, int64_t nrows,
                int64_t ncols, int64_t nnz, DBuf<int32_t>& rowptr, DBuf<int32_t>& colval, DBuf<double>& val);

@@ -282,6 +282,10 @@ class _FEMMBase:
     def _after_mesh(self):
         pass
 
+    def reset_uploads(self):
+        """Forget what is resident on the device: the next operator re-uploads everything."""
+        self._mesh_key = self._dof_key = self._sym_key = None
+
     def _sync_dofs(self, dchi):
         key = id(dchi)
         if self._dof_key != key:
@@ -386,8 +390,9 @@ def _require_associated(femm):
         raise FsgpuError(L.ERR_STATE, "geometry not associated: call associategeometry(femm, geom0) first")
 
 
-def stiffness(femm, *args):
-    """stiffness(femm, [assembler,] geom0, u1, Rfield1, dchi)"""
+def stiffness(femm, *args, out=None):
+    """stiffness(femm, [assembler,] geom0, u1, Rfield1, dchi); `out`: optional caller-owned
+    (colptr, rowval, nzval) arrays (e.g. pinned) that receive the result."""
     if len(args) == 4:
         args = (SysmatAssemblerSparseSymm(),) + args
     assembler, geom0, u1, Rfield1, dchi = args
@@ -398,7 +403,7 @@ def stiffness(femm, *args):
     femm._startassembly(assembler, dchi)
     femm._sync_stab()
     femm.ctx.shell_op(femm._opname + "_stiffness", femm._params())
-    return femm.ctx.fetch_matrix()
+    return femm.ctx.fetch_matrix(out)
 
 
 def mass(femm, *args, mass_type=1):

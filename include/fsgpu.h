@@ -85,6 +85,12 @@ int fsgpu_set_stream(fsgpu_ctx* ctx, void* cuda_stream);
 int fsgpu_sync(fsgpu_ctx* ctx);
 /* number of kernels this context has launched so far */
 int64_t fsgpu_launch_count(fsgpu_ctx* ctx);
+/* device time (CUDA events on the context's stream) of the element kernel of the last
+ * matrix operator -- the number the roofline fraction is computed from */
+int fsgpu_last_kernel_ms(fsgpu_ctx* ctx, double* ms);
+/* measurement support: FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s, read+write) of the
+ * device, from micro-kernels -- the FP64 roofline denominator (not in MEASURED_PEAKS.json) */
+int fsgpu_measure_peaks(fsgpu_ctx* ctx, double* fp64_tflops, double* copy_gbs);
 
 /* ---- data hand-over (host pointers; copied to the device) ---------------------- */
 /* fes.conn + geom0.values.  nnpe: 2 (L2 beam), 3 (T3), 4 (Q4).
