@@ -671,6 +671,60 @@ __global__ void k_slot_map(const int32_t* __restrict__ conn, const int32_t* __re
     }
   }
 }
+// per node: masks of the included dofs in the free run (A) and the prescribed run (B);
+// flag[1] is raised when a run is not consecutive-ascending in the local dof order
+__global__ void k_node_info(const int32_t* __restrict__ dof, int64_t nnodes, int64_t nr, int64_t nfree,
+                            int32_t* __restrict__ info, int32_t* __restrict__ flag) {
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= nnodes) return;
+  int mA = 0, mB = 0, lastA = -2, lastB = -2, bad = 0;
+  for (int d = 0; d < 6; ++d) {
+    const int32_t v = dof[a * 6 + d];
+    if (v >= nr) continue;
+    if (v < nfree) {
+      if (mA && v != lastA + 1) bad = 1;
+      lastA = v;
+      mA |= 1 << d;
+    } else {
+      if (mB && v != lastB + 1) bad = 1;
+      lastB = v;
+      mB |= 1 << d;
+    }
+  }
+  info[a] = mA | (mB << 8);
+  if (bad) atomicExch(flag + 1, 1);
+}
+// pairoff[((i*2 + which) * nelem + e) * nnpe + j]: position, relative to the column start, of the
+// first run-A / run-B row of node i inside any included column of node j (-1: no such entries)
+__global__ void k_pair_offsets(const int32_t* __restrict__ conn, const int32_t* __restrict__ dof,
+                               const int32_t* __restrict__ info, const int32_t* __restrict__ colptr,
+                               const int32_t* __restrict__ rowval, int nnpe, int64_t nelem, int64_t nc,
+                               int32_t* __restrict__ pairoff) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // e*nnpe + j
+  if (t >= nelem * nnpe) return;
+  const int64_t e = t / nnpe;
+  const int j = (int)(t % nnpe);
+  const int32_t* cj = dof + (int64_t)conn[e * nnpe + j] * 6;
+  int col = -1;
+  for (int cc = 0; cc < 6; ++cc)
+    if (cj[cc] < nc) {
+      col = cj[cc];
+      break;
+    }
+  for (int i = 0; i < nnpe; ++i) {
+    const int ni = conn[e * nnpe + i];
+    const int inf = info[ni];
+    const int mA = inf & 63, mB = (inf >> 8) & 63;
+    int oA = -1, oB = -1;
+    if (col >= 0) {
+      const int lo = colptr[col], hi = colptr[col + 1];
+      if (mA) oA = find_row(rowval, lo, hi, dof[(int64_t)ni * 6 + (__ffs(mA) - 1)]) - lo;
+      if (mB) oB = find_row(rowval, lo, hi, dof[(int64_t)ni * 6 + (__ffs(mB) - 1)]) - lo;
+    }
+    pairoff[((int64_t)(i * 2 + 0) * nelem + e) * nnpe + j] = oA;
+    pairoff[((int64_t)(i * 2 + 1) * nelem + e) * nnpe + j] = oB;
+  }
+}
 __global__ void k_diag_slot(const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowval, int64_t nall,
                             int64_t nc, int32_t* __restrict__ diagslot) {
   int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -756,10 +810,25 @@ extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int6
   LAUNCH(c, k_fill_rowval, nn * 6, c->dof.p, adjptr.p, adj.p, c->colptr.p, nn, ti.nr, ti.nc, ti.diag_only ? 1 : 0,
          c->rowval.p);
 
-  // (4) slot maps
-  FS_TRY(c->slot.ensure((size_t)36 * nnpe * nnpe * ne + 1));
-  LAUNCH(c, k_slot_map, ne * nnpe, c->conn.p, c->dof.p, c->colptr.p, c->rowval.p, nnpe, ne, ti.nr, ti.nc,
-         ti.diag_only ? 1 : 0, c->slot.p);
+  // (4) addressing: run-structured fast path when every node's dofs form consecutive runs
+  //     (FinEtools numbering), generic per-entry slot map otherwise / for diagonal targets
+  FS_TRY(ensure_flag(c));
+  FS_TRY(c->nodeinfo.ensure((size_t)nn + 1));
+  LAUNCH(c, k_node_info, nn, c->dof.p, nn, ti.nr, c->nfree, c->nodeinfo.p, c->flag.p);
+  int32_t notruns = 0;
+  FS_TRY(read_flag(c, 1, &notruns));
+  c->fast = !ti.diag_only && !notruns && getenv("FSGPU_FORCE_GENERIC") == nullptr;
+  if (c->fast) {
+    FS_TRY(c->pairoff.ensure((size_t)2 * nnpe * nnpe * ne + 1));
+    LAUNCH(c, k_pair_offsets, ne * nnpe, c->conn.p, c->dof.p, c->nodeinfo.p, c->colptr.p, c->rowval.p, nnpe, ne, ti.nc,
+           c->pairoff.p);
+    c->slot.release();
+  } else {
+    c->pairoff.release();
+    FS_TRY(c->slot.ensure((size_t)36 * nnpe * nnpe * ne + 1));
+    LAUNCH(c, k_slot_map, ne * nnpe, c->conn.p, c->dof.p, c->colptr.p, c->rowval.p, nnpe, ne, ti.nr, ti.nc,
+           ti.diag_only ? 1 : 0, c->slot.p);
+  }
   FS_TRY(c->diagslot.ensure((size_t)c->nall + 1));
   LAUNCH(c, k_diag_slot, c->nall, c->colptr.p, c->rowval.p, c->nall, ti.nc, c->diagslot.p);
   FS_TRY(c->nzval.ensure((size_t)total + 1));

@@ -21,24 +21,71 @@ namespace {
 
 // ---- emitters -----------------------------------------------------------------------
 // t = e*nnpe + j (element-major, column node j), i = row node, r/c = local dof in the 6x6 block
-struct EmitScatter {
+// Every emitter takes one finished 6x6 block (row node i, column node j of element e).
+struct EmitScatter {  // generic path: per-entry slot map, any dof numbering
   double* nz;
   const int32_t* slot;
   int64_t plane;  // nelem * nnpe
   int nnpe;
-  __device__ __forceinline__ void operator()(int64_t t, int i, int r, int c, double v) const {
-    const int s = __ldg(slot + ((int64_t)((c * 6 + r) * nnpe + i)) * plane + t);
-    if (s >= 0) atomicAdd(nz + s, v);
+  __device__ __forceinline__ void block(int64_t e, int i, int j, int, int, const double (&a)[6][6]) const {
+    const int64_t t = e * nnpe + j;
+    int sl[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) sl[k] = __ldg(slot + ((int64_t)(k * nnpe + i)) * plane + t);
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+        if (sl[c * 6 + r] >= 0) atomicAdd(nz + sl[c * 6 + r], a[r][c]);
+  }
+};
+struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in every column
+  double* nz;
+  const int32_t* pairoff;
+  const int32_t* nodeinfo;
+  const int32_t* dof;
+  const int32_t* colptr;
+  int64_t nelem;
+  int64_t nc;
+  int nnpe;
+  __device__ __forceinline__ void block(int64_t e, int i, int j, int ni, int nj, const double (&a)[6][6]) const {
+    const int inf = __ldg(nodeinfo + ni);
+    const int mA = inf & 63, mB = (inf >> 8) & 63;
+    const int oA = __ldg(pairoff + ((int64_t)(i * 2 + 0) * nelem + e) * nnpe + j);
+    const int oB = __ldg(pairoff + ((int64_t)(i * 2 + 1) * nelem + e) * nnpe + j);
+    const int32_t* dj = dof + (int64_t)nj * 6;
+    int cd[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) cd[c] = __ldg(dj + c);
+    int base[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) base[c] = cd[c] < nc ? __ldg(colptr + cd[c]) : -1;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      if (base[c] < 0) continue;
+      double* pa = nz + base[c] + oA;
+      double* pb = nz + base[c] + oB;
+      int ka = 0, kb = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        if ((mA >> r) & 1)
+          atomicAdd(pa + ka++, a[r][c]);
+        else if ((mB >> r) & 1)
+          atomicAdd(pb + kb++, a[r][c]);
+      }
+    }
   }
 };
 struct EmitDense {
   double* out;  // [nelem][n][n] column-major per element
   int nnpe;
-  __device__ __forceinline__ void operator()(int64_t t, int i, int r, int c, double v) const {
-    const int64_t e = t / nnpe;
-    const int j = (int)(t % nnpe);
+  __device__ __forceinline__ void block(int64_t e, int i, int j, int, int, const double (&a)[6][6]) const {
     const int n = 6 * nnpe;
-    out[e * n * n + (int64_t)(j * 6 + c) * n + (i * 6 + r)] = v;
+    double* o = out + e * n * n;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) o[(int64_t)(j * 6 + c) * n + (i * 6 + r)] = a[r][c];
   }
 };
 
@@ -94,9 +141,13 @@ __global__ void __launch_bounds__(128) k_t3_stiffness(ShellArgs P, Emit emit) {
   double kpart = 0.0;  // this node's share of the nodal-basis bending diagonal
   V3 gdir = v3(0, 0, 0);
   bool validj = false;
+  int nn[3] = {0, 0, 0};
   if (active) {
     const int32_t* cn = P.conn + e * 3;
     const int n0 = __ldg(cn), n1 = __ldg(cn + 1), n2 = __ldg(cn + 2);
+    nn[0] = n0;
+    nn[1] = n1;
+    nn[2] = n2;
     const T3Geom g = t3_geometry(ld3(P.xyz, n0), ld3(P.xyz, n1), ld3(P.xyz, n2));
     ShellB<3> sb;
     sb.E = g.E;
@@ -104,7 +155,6 @@ __global__ void __launch_bounds__(128) k_t3_stiffness(ShellArgs P, Emit emit) {
       sb.gN[l][0] = g.gN[l][0];
       sb.gN[l][1] = g.gN[l][1];
     }
-    const int nn[3] = {n0, n1, n2};
     for (int l = 0; l < 3; ++l) {
       const double4 nv = ldg4(P.nrm + nn[l]);
       const bool vl = nv.w != 0.0;
@@ -182,7 +232,6 @@ __global__ void __launch_bounds__(128) k_t3_stiffness(ShellArgs P, Emit emit) {
   // pre-scale own strip by d_s
   for (int s = 0; s < NR; ++s)
     for (int cc = 0; cc < 6; ++cc) b[s][cc] *= dvec[s];
-  const int64_t t = e * 3 + j;
   for (int i = 0; i < 3; ++i) {
     double acc[6][6];
     for (int r = 0; r < 6; ++r)
@@ -201,8 +250,7 @@ __global__ void __launch_bounds__(128) k_t3_stiffness(ShellArgs P, Emit emit) {
       for (int r = 0; r < 3; ++r)
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * gg[r] * gg[cc];
     }
-    for (int cc = 0; cc < 6; ++cc)
-      for (int r = 0; r < 6; ++r) emit(t, i, r, cc, acc[r][cc]);
+    emit.block(e, i, j, nn[i], nn[j], acc);
   }
 }
 
@@ -346,9 +394,7 @@ __global__ void __launch_bounds__(128) k_q4_stiffness(ShellArgs P, Emit emit) {
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * (nvec[r] * nvec[cc]);
     }
   }
-  const int64_t t = e * 4 + bj;
-  for (int cc = 0; cc < 6; ++cc)
-    for (int r = 0; r < 6; ++r) emit(t, bi, r, cc, acc[r][cc]);
+  emit.block(e, bi, bj, nn[bi], nn[bj], acc);
 }
 
 // =====================================================================================
@@ -567,7 +613,7 @@ __global__ void k_beam_matrix(BeamArgs P, int op, Emit emit) {
   }
   // global block = Tb Kl Tb', Tb = blkdiag(Ft, Ft), Ft[r][a] = component r of e_a
   const double F[3][3] = {{k.Ft.e1.x, k.Ft.e2.x, k.Ft.e3.x}, {k.Ft.e1.y, k.Ft.e2.y, k.Ft.e3.y}, {k.Ft.e1.z, k.Ft.e2.z, k.Ft.e3.z}};
-  const int64_t t = e * 2 + bJ;
+  double Kg[6][6];
   for (int sp = 0; sp < 2; ++sp)
     for (int sq = 0; sq < 2; ++sq) {
       double tmp[3][3];
@@ -576,10 +622,11 @@ __global__ void k_beam_matrix(BeamArgs P, int op, Emit emit) {
           tmp[a][cc] = Kl[sp * 3 + a][sq * 3 + 0] * F[cc][0] + Kl[sp * 3 + a][sq * 3 + 1] * F[cc][1] + Kl[sp * 3 + a][sq * 3 + 2] * F[cc][2];
       for (int cc = 0; cc < 3; ++cc)
         for (int r = 0; r < 3; ++r) {
-          const double v = F[r][0] * tmp[0][cc] + F[r][1] * tmp[1][cc] + F[r][2] * tmp[2][cc];
-          emit(t, bI, sp * 3 + r, sq * 3 + cc, v);
+          Kg[sp * 3 + r][sq * 3 + cc] = F[r][0] * tmp[0][cc] + F[r][1] * tmp[1][cc] + F[r][2] * tmp[2][cc];
         }
     }
+  const int32_t* cn = P.conn + e * 2;
+  emit.block(e, bI, bJ, cn[bI], cn[bJ], Kg);
 }
 // restoring force: elvec = Te (-aN' DN dN)   (src/FEMMCorotBeamModule.jl:1132-1157)
 __global__ void k_beam_restoring(BeamArgs P, const int32_t* __restrict__ dof, double* __restrict__ out, int64_t limit,
@@ -734,6 +781,9 @@ int begin_matrix(fsgpu_ctx* c) {
   return FSGPU_OK;
 }
 EmitScatter scatter_of(fsgpu_ctx* c) { return EmitScatter{c->nzval.p, c->slot.p, c->nelem * c->nnpe, c->nnpe}; }
+EmitRuns runs_of(fsgpu_ctx* c) {
+  return EmitRuns{c->nzval.p, c->pairoff.p, c->nodeinfo.p, c->dof.p, c->colptr.p, c->nelem, c->pcols, c->nnpe};
+}
 
 int shell_stiffness(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp) {
   FS_TRY(check_ctx(c));
@@ -741,10 +791,17 @@ int shell_stiffness(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool co
   FS_TRY(shell_args(c, p, nnpe, comp, true, A));
   FS_TRY(begin_matrix(c));
   FS_TRY(time_begin(c));
-  if (nnpe == 3)
-    FS_TRY(launch_t3(c, A, comp, p->transv_shear_formulation == 1, scatter_of(c)));
-  else
-    FS_TRY(launch_q4(c, A, comp, scatter_of(c)));
+  if (nnpe == 3) {
+    if (c->fast)
+      FS_TRY(launch_t3(c, A, comp, p->transv_shear_formulation == 1, runs_of(c)));
+    else
+      FS_TRY(launch_t3(c, A, comp, p->transv_shear_formulation == 1, scatter_of(c)));
+  } else {
+    if (c->fast)
+      FS_TRY(launch_q4(c, A, comp, runs_of(c)));
+    else
+      FS_TRY(launch_q4(c, A, comp, scatter_of(c)));
+  }
   FS_TRY(time_end(c));
   int32_t f = 0;
   FS_CUDA(cudaMemcpyAsync(&f, c->flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -804,7 +861,10 @@ int beam_matrix(fsgpu_ctx* c, const fsgpu_beam_params* p, int op) {
   const int64_t n = B.nelem * 4;
   FS_TRY(time_begin(c));
   if (n > 0) {
-    k_beam_matrix<EmitScatter><<<grid_for(n, 128), 128, 0, c->stream>>>(B, op, scatter_of(c));
+    if (c->fast)
+      k_beam_matrix<EmitRuns><<<grid_for(n, 128), 128, 0, c->stream>>>(B, op, runs_of(c));
+    else
+      k_beam_matrix<EmitScatter><<<grid_for(n, 128), 128, 0, c->stream>>>(B, op, scatter_of(c));
     c->launches++;
   }
   FS_TRY(time_end(c));

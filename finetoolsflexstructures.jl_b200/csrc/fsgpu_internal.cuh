@@ -121,6 +121,11 @@ struct fsgpu_ctx {
   fs::DBuf<int32_t> rowval;   // [pnnz] 0-based
   fs::DBuf<int32_t> slot;     // [36][nnpe][nelem][nnpe]  (-1 = dropped)
   fs::DBuf<int32_t> diagslot; // [nall] slot of (d,d) or -1
+  // run-structured addressing (fast path): the included dofs of every node form <= 2
+  // consecutive ascending runs (free / prescribed), as FinEtools' numberdofs! produces
+  bool fast = false;
+  fs::DBuf<int32_t> nodeinfo; // [nnodes] bits 0-5 run-A mask, bits 8-13 run-B mask
+  fs::DBuf<int32_t> pairoff;  // [nnpe(i)][2][nelem][nnpe(j)] row offset of node i's runs in node j's columns
   // result matrix
   bool have_matrix = false;
   int64_t rrows = 0, rcols = 0, rnnz = 0;
