@@ -1,0 +1,222 @@
+"""Pins the CPU oracle against the reference's OWN known-answer tests.
+Runs without a GPU.  Golden numbers are copied from /root/reference/test/*.jl (file:line cited)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from oracle import beam as obeam
+from oracle import fe_external as fx
+from oracle import layup as oly
+from oracle import shells as osh
+
+INF = np.inf
+
+
+def _scordelis(n, quad):
+    """test/test_shell_statics.jl:15-93 (T3FF) / test/test_q4rs_shell_statics.jl:15-90 (Q4RS)."""
+    E, nu, th, R, L = 4.32e8, 0.0, 0.25, 25.0, 50.0
+    tol = R / n / 1000
+    xy, conn = (fx.q4block if quad else fx.t3block)(40 / 360 * 2 * np.pi, L / 2, n, n)
+    a, y = xy[:, 0], xy[:, 1]
+    xyz = np.column_stack([R * np.sin(a), y, R * (np.cos(a) - 1)])
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(E, nu))
+    d = fx.DofField(xyz.shape[0])
+    for box, comps in (([-INF, INF, 0, 0, -INF, INF], (1, 3, 5)), ([-INF, INF, L / 2, L / 2, -INF, INF], (2, 4, 6)), ([0, 0, -INF, INF, -INF, INF], (1, 5, 6))):
+        l1 = fx.selectnode_box(xyz, box, tol)
+        for c in comps:
+            d.setebc(l1, c)
+    d.numberdofs()
+    stab = osh.stab_lyly(0.2)
+    if quad:
+        nrm, val = osh.q4rs_associategeometry(xyz, conn)
+        Ke = osh.q4rs_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, th, stab_fun=stab)
+        F = fx.distribloads_q4(xyz, conn, [0, 0, -90, 0, 0, 0])
+    else:
+        nrm, val = osh.t3ff_associategeometry(xyz, conn)
+        Ke = osh.t3ff_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, th, stab_fun=stab)
+        F = fx.distribloads_t3(xyz, conn, [0, 0, -90, 0, 0, 0])
+    na = d.nalldofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, d.gatherdofnums(conn), na), na, na)
+    fx.solve_blocked(K, F, d)
+    nl = fx.selectnode_box(xyz, [np.sin(40 / 360 * 2 * np.pi) * 25] * 2 + [L / 2, L / 2, -INF, INF], tol)
+    return d.values[nl, 2][0] / (-0.3024) * 100
+
+
+# test/test_shell_statics.jl:97-104
+@pytest.mark.parametrize("n,ref", [(4, 66.54771615057949), (8, 85.54615143134853), (10, 89.85075281481419), (12, 92.50616661644985), (16, 95.40469210310079)])
+def test_t3ff_scordelis_lo(n, ref):
+    assert abs(_scordelis(n, False) - ref) / ref < 1e-9  # the reference test uses rtol 1e-4
+
+
+# test/test_q4rs_shell_statics.jl:95-102
+@pytest.mark.parametrize("n,ref", [(4, 97.88098976068304), (8, 98.766679964194), (10, 99.1305903792941), (12, 99.33597700449404), (16, 99.52904556664862)])
+def test_q4rs_scordelis_lo(n, ref):
+    assert abs(_scordelis(n, True) - ref) / ref < 1e-9
+
+
+def test_t3ff_fv12_frequencies():
+    """test/test_shell_dynamics.jl:26-133: K + lumped M, 8 non-rigid frequencies (:119-127)."""
+    E, nu, rho, th, L, n = 200e3 * 1e6, 0.3, 8000.0, 0.05, 10.0, 8
+    xy, conn = fx.t3block(L, L, n, n)
+    xyz = fx.xyz3(xy - L / 2)
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(E, nu))
+    d = fx.DofField(xyz.shape[0]).numberdofs()
+    nrm, val = osh.t3ff_associategeometry(xyz, conn)
+    Ke = osh.t3ff_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, th, stab_fun=osh.stab_lyly(0.2))
+    Me = osh.t3ff_mass_elmats(xyz, conn, rho, th)
+    dn, na = d.gatherdofnums(conn), d.nalldofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, dn, na), na, na).toarray()
+    M = fx.csc_to_scipy(*fx.assemble_matrix("symm", Me, dn, na), na, na).toarray()
+    sh = (0.5 * 2 * np.pi) ** 2
+    ev = sla.eigh(K + sh * M, M, eigvals_only=True)[:14] - sh
+    fs = np.real(np.sqrt(ev.astype(complex))) / (2 * np.pi)
+    ref = [1.572130183778014, 2.2424585076387427, 2.8079394352847316, 3.883763676656034, 4.039123204140305, 6.787320617260535, 6.920636670319986, 7.127888889722697]
+    assert np.max(np.abs(fs[6:] - ref) / np.array(ref)) < 1e-9  # reference: rtol 1e-6
+    assert np.all(np.abs(fs[:6]) < 1e-4)
+
+
+def _boundary_nodes(xyz, ax, ay, tol):
+    return np.nonzero((np.abs(xyz[:, 0]) < tol) | (np.abs(xyz[:, 0] - ax) < tol) | (np.abs(xyz[:, 1]) < tol) | (np.abs(xyz[:, 1] - ay) < tol))[0]
+
+
+@pytest.mark.parametrize("nplies,axes", [(10, (1, 2, 3)), (3, (2, -1, 3)), (5, (-1, -2, 3)), (4, (-2, 1, 3))])
+def test_t3ffcomp_nayak_frequencies(nplies, axes):
+    """test/test_composite_shell_dynamics.jl:354-460: 9 nondimensional frequencies, norm < 1e-13."""
+    ax = ay = 0.1
+    nx = ny = 9
+    E1, E2, G12, G13, nu12, G23, rho, C11 = 143.52e9, 75.38e9, 42.03e9, 25.56e9, 0.44, 42.65e9, 1500.0, 159.85e9
+    th, tol = ax / 10, ax / nx / 100
+    D6 = oly.lamina_moduli(E1, E2, nu12, G12, G13, G23)
+    lay = oly.CompositeLayup("nayak", [oly.Ply(f"p{i}", D6, th / nplies, 0, rho) for i in range(nplies)])
+    cs = oly.cartesian_csys(axes)
+    xy, conn = fx.t3block(ax, ay, nx, ny)
+    xyz = fx.xyz3(xy)
+    d = fx.DofField(xyz.shape[0])
+    for c in (1, 2, 3):
+        d.setebc(fx.selectnode_box(xyz, [ax, ax, 0, 0, -INF, INF], tol), c)
+    d.setebc(fx.selectnode_box(xyz, [0, 0, 0, 0, -INF, INF], tol), 2)
+    for c in (1, 2, 3):
+        d.setebc(_boundary_nodes(xyz, ax, ay, tol), c)
+    d.numberdofs()
+    nrm, val = osh.t3ff_associategeometry(xyz, conn, normal_dir=cs[:, 2])
+    A, B, D = lay.laminate_stiffnesses()
+    H = lay.laminate_transverse_stiffness()
+    Ke = osh.t3ffcomp_stiffness_elmats(xyz, conn, nrm, val, A, B, D, H, lay.thickness, cs)
+    Me = osh.t3ffcomp_mass_elmats(xyz, conn, *lay.laminate_inertia())
+    dn, na, nf = d.gatherdofnums(conn), d.nalldofs, d.nfreedofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, dn, na), na, na).toarray()[:nf, :nf]
+    M = fx.csc_to_scipy(*fx.assemble_matrix("symm", Me, dn, na), na, na).toarray()[:nf, :nf]
+    fs = np.sqrt(sla.eigh(K, M, eigvals_only=True)[:9]) / (2 * np.pi)
+    ref = np.array([0.04571652264814249, 0.10096323319412286, 0.11467782865238098, 0.16264669289730896, 0.18683613787902217, 0.20655080934826295, 0.23954509827380233, 0.2476225295798577, 0.2718218525817157])
+    assert np.linalg.norm(ref - th * np.sqrt(rho / C11) * (2 * np.pi * fs)) < 5e-13  # reference: 1e-13 with ARPACK
+
+
+@pytest.mark.parametrize("quad,ref", [(False, 0.22004349767718365), (True, 0.2278585006007462)])
+def test_composite_barbero_3_1(quad, ref):
+    """test/test_composite_shell_statics.jl:1-100 (T3FFComp) and test/test_composite_shell_statics_q4rs.jl:1-100."""
+    ax = ay = 2.0
+    nx = ny = 8
+    th, tol = 0.01, ax / nx / 100
+    D6 = oly.lamina_moduli(133860e6, 7706e6, 0.301, 4306e6, 4306e6, 2760e6)
+    lay = oly.CompositeLayup("ex31", [oly.Ply("0", D6, th / 2, 0), oly.Ply("90", D6, th / 2, 90)])
+    cs = oly.cartesian_csys((1, 2, 3))
+    xy, conn = (fx.q4block if quad else fx.t3block)(ax, ay, nx, ny)
+    xyz = fx.xyz3(xy)
+    d = fx.DofField(xyz.shape[0])
+    for c in (1, 2, 3):
+        d.setebc(fx.selectnode_box(xyz, [ax, ax, 0, 0, -INF, INF], tol), c)
+    d.setebc(fx.selectnode_box(xyz, [0, 0, 0, 0, -INF, INF], tol), 2)
+    d.setebc(_boundary_nodes(xyz, ax, ay, tol), 3)
+    d.numberdofs()
+    A, B, D = lay.laminate_stiffnesses()
+    H = lay.laminate_transverse_stiffness()
+    if quad:
+        nrm, val = osh.q4rs_associategeometry(xyz, conn, normal_dir=cs[:, 2])
+        Ke = osh.q4rscomp_stiffness_elmats(xyz, conn, nrm, val, A, B, D, H, lay.thickness, cs)
+    else:
+        nrm, val = osh.t3ff_associategeometry(xyz, conn, normal_dir=cs[:, 2])
+        Ke = osh.t3ffcomp_stiffness_elmats(xyz, conn, nrm, val, A, B, D, H, lay.thickness, cs)
+    na = d.nalldofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, d.gatherdofnums(conn), na), na, na)
+    F = np.zeros((xyz.shape[0], 6))
+    hx, q = ax / nx, 0.1e6 * th
+    for yy, sg in ((0.0, 1.0), (ay, -1.0)):
+        nodes = np.nonzero(np.abs(xyz[:, 1] - yy) < tol)[0]
+        nodes = nodes[np.argsort(xyz[nodes, 0])]
+        for a, b in zip(nodes[:-1], nodes[1:]):
+            F[a, 1] += sg * q * hx / 2
+            F[b, 1] += sg * q * hx / 2
+    fx.solve_blocked(K, F, d)
+    assert abs(d.values[:, 2].max() / 1e-3 - ref) / ref < 1e-9  # reference: `≈` (sqrt(eps))
+
+
+def test_layup_barbero_5_7():
+    """Ply plane-stress reduction pinned by test/test_composite_layup.jl:530-553 (Barbero Ex. 5.7 style):
+    Q11 = E1/(1-nu12 nu21), Q12 = nu12 E2/(1-nu12 nu21), Q66 = G12."""
+    E1, E2, nu12, G12 = 133860.0, 7706.0, 0.301, 4306.0
+    p = oly.Ply("x", oly.lamina_moduli(E1, E2, nu12, G12, G12, 2760.0), 1.0, 0.0)
+    nu21 = nu12 * E2 / E1
+    den = 1 - nu12 * nu21
+    ref = np.array([[E1 / den, nu12 * E2 / den, 0], [nu12 * E2 / den, E2 / den, 0], [0, 0, G12]])
+    assert np.abs(p.Dps - ref).max() < 1e-12 * E1
+    assert np.abs(p.Dts - np.diag([G12, 2760.0])).max() < 1e-12 * E1
+
+
+def test_beam_buckling_factors():
+    """test/test_beam_buckling.jl:19-85: stiffness + geostiffness + update_rotation_field!,
+    buckling factors [48.5475, 124.1839] (:30, tolerance 1e-3)."""
+    from scipy.interpolate import UnivariateSpline
+
+    E, nu, L, b, h, n, ms = 1e6, 0.3, 30.0, 0.5, 4.0, 32, 1000
+    magn = -0.2056167583560 * 1e4 / L**2
+    xs = [1, 1.5, 2.0, 2.5, 3.0, 4.0, 5.0, 6.0, 10, 20, 40, 80, 200, 2000]
+    ys = [0.141, 0.196, 0.229, 0.249, 0.263, 0.281, 0.291, 0.299, 0.312, 0.317, 0.325, 0.33, 1 / 3, 1 / 3]
+    c = float(UnivariateSpline(xs, ys, k=3, s=0)(max(b, h) / min(b, h)))  # = Dierckx Spline1D (src/CrossSectionModule.jl:139-158)
+    one = np.ones(n)
+    sec = dict(A=b * h * one, I1=(b * h**3 / 12 + b**3 * h / 12) * one, I2=b * h**3 / 12 * one, I3=b**3 * h / 12 * one,
+               J=c * max(b, h) * min(b, h) ** 3 * one, A2s=INF * one, A3s=INF * one, x1x2=np.tile([-1.0, 0, 0], (n, 1)))
+    xyz = np.zeros((n + 1, 3))
+    xyz[:, 2] = np.linspace(0, L, n + 1)
+    conn = np.column_stack([np.arange(1, n + 1), np.arange(2, n + 2)])
+    d = fx.DofField(n + 1)
+    for i in range(1, 7):
+        d.setebc([0], i)
+    d.numberdofs()
+    u0, R0 = np.zeros((n + 1, 3)), obeam.initial_Rfield(n + 1)
+    dn, na, nf = d.gatherdofnums(conn), d.nalldofs, d.nfreedofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", obeam.beam_stiffness_elmats(xyz, conn, u0, R0, sec, E, nu), dn, na), na, na)
+    F = np.zeros((n + 1, 6))
+    F[n, 1] = -magn * b * h / ms
+    fx.solve_blocked(K, F, d)
+    u0, R0 = d.values[:, :3].copy(), obeam.update_rotation_field(R0, d.values)
+    KG = fx.csc_to_scipy(*fx.assemble_matrix("symm", obeam.beam_geostiffness_elmats(xyz, conn, u0, R0, sec, E, nu), dn, na), na, na).toarray()[:nf, :nf]
+    dd = sla.eigh(-KG, K.toarray()[:nf, :nf], eigvals_only=True)
+    fs = np.abs(1 / dd[np.argsort(-np.abs(dd))][:4] / ms)
+    assert np.linalg.norm(np.array([48.5475, 124.1839]) - fs[1:3]) / np.linalg.norm([48.5475, 124.1839]) < 1e-5
+
+
+def test_assembler_equivalence():
+    """test/test_utilities.jl:12-47: SysmatAssemblerSparseCSRSymm == SysmatAssemblerSparseSymm."""
+    m1 = np.array([[0.24406, 0.599773, 0.833404, 0.0420141], [0.786024, 0.00206713, 0.995379, 0.780298], [0.845816, 0.198459, 0.355149, 0.224996]])
+    m2 = np.array([[0.146618, 0.53471, 0.614342, 0.737833], [0.479719, 0.41354, 0.00760941, 0.836455], [0.254868, 0.476189, 0.460794, 0.00919633], [0.159064, 0.261821, 0.317078, 0.77646], [0.643538, 0.429817, 0.59788, 0.958909]])
+    el = np.stack([m1.T @ m1, m2.T @ m2])
+    dn = np.array([[5, 2, 1, 4], [2, 3, 1, 5]])
+    rp, cv, nz = fx.assemble_matrix("csrsymm", el, dn, 7)
+    import scipy.sparse as sp
+
+    A = sp.csr_matrix((nz, cv - 1, rp - 1), shape=(7, 7)).toarray()
+    A1 = fx.csc_to_scipy(*fx.assemble_matrix("symm", el, dn, 7), 7, 7).toarray()
+    assert np.linalg.norm(A - A1) / np.linalg.norm(A1) < 1e-9
+
+
+def test_sparse_semantics():
+    """Julia `sparse`: rows ascending, duplicates summed, explicit zeros kept; SparseSymm drops exact zeros."""
+    I, J, V = [3, 1, 3, 2, 1], [1, 1, 1, 2, 3], [1.0, 2.0, 0.5, 0.0, -1.0]
+    cp, rv, nz = fx.sparse_csc(I, J, V, 3, 3)
+    assert cp.tolist() == [1, 3, 4, 5] and rv.tolist() == [1, 3, 2, 1] and nz.tolist() == [2.0, 1.5, 0.0, -1.0]
+    el = np.zeros((1, 2, 2))
+    el[0] = [[2.0, 0.0], [0.0, 3.0]]
+    cp, rv, nz = fx.assemble_matrix("symm", el, np.array([[1, 2]]), 2)
+    assert rv.tolist() == [1, 2] and nz.tolist() == [2.0, 3.0]
+    cp, rv, nz = fx.assemble_matrix("sparse", el, np.array([[1, 2]]), 2)
+    assert len(rv) == 4
