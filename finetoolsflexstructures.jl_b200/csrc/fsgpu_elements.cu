@@ -122,143 +122,249 @@ __device__ __forceinline__ V3 ld3(const double4* p, int i) {
 // =====================================================================================
 // T3FF / T3FFComp stiffness
 // =====================================================================================
-constexpr int T3_EPW = 10;  // elements per warp
+constexpr int T3_EPW = 10;  // elements per warp (3 lanes each; lanes 30, 31 idle)
+
+__device__ __forceinline__ void build_constit_t3(const ShellArgs& P, int64_t e, const Triad& E, double Ae, double shear_scale,
+                                                 bool comp, Constit& C) {
+  const double h = sqrt(2 * Ae);
+  if (comp) {
+    const double* gd = P.gdata + (size_t)__ldg(P.gof + e) * 34;
+    const double t = gd[31];
+    const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h * h);
+    double m, n;
+    layup_angle(E, P.cs + (P.ncs == 1 ? 0 : e * 9), m, n);
+    constit_laminate(gd, gd + 9, gd + 18, gd + 27, m, n, Ae, stab * Ae * shear_scale, C);
+  } else {
+    const double t = P.nthick == 1 ? __ldg(P.thick) : __ldg(P.thick + e);
+    const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h * h);
+    constit_homogeneous(P.Dps, P.Dt, t * Ae, (t * t * t) / 12 * Ae, t * stab * Ae * shear_scale, C);
+  }
+}
 
 template <bool COMP, bool SHEARK, class Emit>
-__global__ void __launch_bounds__(128) k_t3_stiffness(ShellArgs P, Emit emit) {
+__global__ void __launch_bounds__(128, 3) k_t3_stiffness(ShellArgs P, Emit emit) {
   constexpr int NR = SHEARK ? 12 : 8;
-  extern __shared__ double smem[];  // [warp][NR*6][32]
+  constexpr int WARP_DBL = NR * 6 * 32 + NR * T3_EPW;
+  extern __shared__ double smem[];  // per warp: strips [NR*6][32] + d [NR][T3_EPW]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  double* sw = smem + (size_t)wib * (NR * 6 * 32);
+  double* sw = smem + (size_t)wib * WARP_DBL;
+  double* sd = sw + NR * 6 * 32;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  const int64_t e = warp * T3_EPW + lane / 3;
-  const int j = lane % 3;
+  const int el = lane / 3, j = lane - 3 * el;
+  const int64_t e = warp * T3_EPW + el;
   const bool active = (lane < 3 * T3_EPW) && (e < P.nelem);
   const unsigned full = 0xffffffffu;
+  const int base = lane - j;
 
-  double b[NR][6];
-  double dvec[NR];
   double kpart = 0.0;  // this node's share of the nodal-basis bending diagonal
   V3 gdir = v3(0, 0, 0);
   bool validj = false;
   int nn[3] = {0, 0, 0};
+  T3Geom g;
+  M3 A;
+  Constit C;
   if (active) {
     const int32_t* cn = P.conn + e * 3;
-    const int n0 = __ldg(cn), n1 = __ldg(cn + 1), n2 = __ldg(cn + 2);
-    nn[0] = n0;
-    nn[1] = n1;
-    nn[2] = n2;
-    const T3Geom g = t3_geometry(ld3(P.xyz, n0), ld3(P.xyz, n1), ld3(P.xyz, n2));
-    ShellB<3> sb;
-    sb.E = g.E;
-    for (int l = 0; l < 3; ++l) {
-      sb.gN[l][0] = g.gN[l][0];
-      sb.gN[l][1] = g.gN[l][1];
-    }
-    for (int l = 0; l < 3; ++l) {
-      const double4 nv = ldg4(P.nrm + nn[l]);
-      const bool vl = nv.w != 0.0;
-      sb.A[l] = nodal_triad(g.E, v3(nv.x, nv.y, nv.z), vl);
-      if (l == j) validj = vl;
-    }
-    // thickness, stabilisation, constitutive factors
-    const double Ae = g.Ae, h = sqrt(2 * Ae);
-    Constit C;
-    if (COMP) {
-      const double* gd = P.gdata + (size_t)__ldg(P.gof + e) * 34;
-      const double t = gd[31];
-      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h * h);
-      double m, n;
-      layup_angle(g.E, P.cs + (P.ncs == 1 ? 0 : e * 9), m, n);
-      constit_laminate(gd, gd + 9, gd + 18, gd + 27, m, n, Ae, stab * Ae * (SHEARK ? (1.0 / 3) : 1.0), C);
+    nn[0] = __ldg(cn);
+    nn[1] = __ldg(cn + 1);
+    nn[2] = __ldg(cn + 2);
+    g = t3_geometry(ld3(P.xyz, nn[0]), ld3(P.xyz, nn[1]), ld3(P.xyz, nn[2]));
+    const double4 nv = ldg4(P.nrm + (j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2])));
+    validj = nv.w != 0.0;
+    A = nodal_triad(g.E, v3(nv.x, nv.y, nv.z), validj);
+    build_constit_t3(P, e, g.E, g.Ae, SHEARK ? (1.0 / 3) : 1.0, COMP, C);
+  }
+  constexpr int NSETS = SHEARK ? 3 : 1;
+#pragma unroll
+  for (int set = 0; set < NSETS; ++set) {
+    double bs[2][3];
+    double p1[5][3], p2[5][3];
+    double gx = 0.0, gy = 0.0;
+    if (active) {
+      gx = j == 0 ? g.gN[0][0] : (j == 1 ? g.gN[1][0] : g.gN[2][0]);
+      gy = j == 0 ? g.gN[0][1] : (j == 1 ? g.gN[1][1] : g.gN[2][1]);
+      t3_bs_node(g, j, SHEARK ? set : -1, bs);
+      node_coupling_contrib(A, gx, gy, bs, p1, p2);
     } else {
-      const double t = P.nthick == 1 ? __ldg(P.thick) : __ldg(P.thick + e);
-      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h * h);
-      constit_homogeneous(P.Dps, P.Dt, t * Ae, (t * t * t) / 12 * Ae, t * stab * Ae * (SHEARK ? (1.0 / 3) : 1.0), C);
-    }
-    constexpr int NSETS = SHEARK ? 3 : 1;
-    for (int set = 0; set < NSETS; ++set) {
+      for (int r = 0; r < 5; ++r)
+        for (int k = 0; k < 3; ++k) p1[r][k] = p2[r][k] = 0.0;
       for (int r = 0; r < 2; ++r)
-        for (int l = 0; l < 3; ++l)
-          for (int cc = 0; cc < 3; ++cc) sb.bs[r][l][cc] = 0.0;
-      if (SHEARK) {
-        t3_add_bs(g, set, (set + 1) % 3, (set + 2) % 3, sb.bs);
-      } else {
-        t3_add_bs(g, 0, 1, 2, sb.bs);
-        t3_add_bs(g, 1, 2, 0, sb.bs);
-        t3_add_bs(g, 2, 0, 1, sb.bs);
-        for (int r = 0; r < 2; ++r)
-          for (int l = 0; l < 3; ++l)
-            for (int cc = 0; cc < 3; ++cc) sb.bs[r][l][cc] *= (1.0 / 3);
+        for (int k = 0; k < 3; ++k) bs[r][k] = 0.0;
+    }
+    // sum the coupling matrices over the element's three lanes, in node order on every lane
+    double P1[5][3], P2[5][3];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          s1 += __shfl_sync(full, p1[r][k], (base + l) & 31);
+          s2 += __shfl_sync(full, p2[r][k], (base + l) & 31);
+        }
+        P1[r][k] = s1;
+        P2[r][k] = s2;
       }
-      sb.build_coupling();
-      // nodal-basis strip: bending-diagonal share for kavg (src/FEMMShellT3FFModule.jl:714-722)
-      double bt[8][6];
-      sb.node_bt(j, bt);
-      fold_constit(C, bt);
-      const int s0 = set == 0 ? 0 : 6;
-      for (int s = s0; s < 8; ++s) kpart += constit_d(C, s) * (bt[s][3] * bt[s][3] + bt[s][4] * bt[s][4]);
+    if (active) {
+      double R[2][2], brn[5][2];
+      node_R(A, R);
+      node_bt_rot(gx, gy, bs, R, brn);
+      kpart += node_kavg_part(C, brn, set > 0);
       double bg[8][6];
-      gdir = sb.node_bg(j, bg);
+      gdir = node_strip(g.E, A, gx, gy, bs, P1, P2, bg);
       fold_constit(C, bg);
       if (set == 0) {
-        for (int s = 0; s < 8; ++s) {
-          dvec[s] = constit_d(C, s);
-          for (int cc = 0; cc < 6; ++cc) b[s][cc] = bg[s][cc];
-        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) sw[(s * 6 + cc) * 32 + lane] = bg[s][cc];
+        if (j == 0)
+          for (int s = 0; s < 8; ++s) sd[s * T3_EPW + el] = constit_d(C, s);
       } else {
-        for (int s = 0; s < 2; ++s) {
-          dvec[6 + 2 * set + s] = constit_d(C, 6 + s);
-          for (int cc = 0; cc < 6; ++cc) b[6 + 2 * set + s][cc] = bg[6 + s][cc];
-        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) sw[((6 + 2 * set + s) * 6 + cc) * 32 + lane] = bg[6 + s][cc];
+        if (j == 0)
+          for (int s = 0; s < 2; ++s) sd[(6 + 2 * set + s) * T3_EPW + el] = constit_d(C, 6 + s);
       }
     }
-  } else {
-    for (int s = 0; s < NR; ++s) {
-      dvec[s] = 0.0;
-      for (int cc = 0; cc < 6; ++cc) b[s][cc] = 0.0;
-    }
   }
-  // publish the strip
-  for (int s = 0; s < NR; ++s)
-    for (int cc = 0; cc < 6; ++cc) sw[(s * 6 + cc) * 32 + lane] = b[s][cc];
-  // kavg = mean of the 6 bending diagonals * scale: sum the three lanes of the element
-  const int base = lane - j;
+  // kavg = mean of the 6 bending diagonals * scale (src/FEMMShellT3FFModule.jl:714-722)
   double ksum = 0.0;
+#pragma unroll
   for (int l = 0; l < 3; ++l) ksum += __shfl_sync(full, kpart, (base + l) & 31);
   const double kavg = ksum / 6 * P.drill;
   __syncwarp();
   if (!active) return;
-  // pre-scale own strip by d_s
-  for (int s = 0; s < NR; ++s)
-    for (int cc = 0; cc < 6; ++cc) b[s][cc] *= dvec[s];
+#pragma unroll 1
   for (int i = 0; i < 3; ++i) {
     double acc[6][6];
+#pragma unroll
     for (int r = 0; r < 6; ++r)
+#pragma unroll
       for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
     const int src = base + i;
 #pragma unroll
     for (int s = 0; s < NR; ++s) {
-      double bi[6];
+      const double d = sd[s * T3_EPW + el];
+      double bi[6], bj[6];
+#pragma unroll
       for (int r = 0; r < 6; ++r) bi[r] = sw[(s * 6 + r) * 32 + src];
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) bj[cc] = d * sw[(s * 6 + cc) * 32 + lane];
+#pragma unroll
       for (int r = 0; r < 6; ++r)
-        for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(bi[r], b[s][cc], acc[r][cc]);
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(bi[r], bj[cc], acc[r][cc]);
     }
     if (i == j && validj) {
       // drilling stiffness kavg on the nodal normal direction (nodal dof 6), rotated to global
       const double gg[3] = {gdir.x, gdir.y, gdir.z};
+#pragma unroll
       for (int r = 0; r < 3; ++r)
+#pragma unroll
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * gg[r] * gg[cc];
     }
-    emit.block(e, i, j, nn[i], nn[j], acc);
+    emit.block(e, i, j, i == 0 ? nn[0] : (i == 1 ? nn[1] : nn[2]), j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]), acc);
   }
 }
 
 // =====================================================================================
 // Q4RS / Q4RSComp stiffness
 // =====================================================================================
+// One setup pass: lane (g4, jn) builds the folded strip of node jn at integration point gp
+// (own triad / own shear entries only; the coupling matrices are summed over the four lanes of
+// the same point by a shuffle butterfly) and stores it in the half-warp's shared tile.
+template <bool COMP>
+__device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64_t e, int gp, int g4, int jn, const V3 (&X)[4],
+                                              const double4& nvown, double hq, const double* gd, double* sb_, double* sd_) {
+  const unsigned full = 0xffffffffu;
+  double p1[5][3], p2[5][3], bs[2][3];
+  Q4Geom g;
+  M3 A;
+  double xi = 0.0, eta = 0.0, w = 0.0, gx = 0.0, gy = 0.0;
+  if (on) {
+    xi = P.rule.xi[gp];
+    eta = P.rule.eta[gp];
+    w = P.rule.w[gp];
+    g = q4_geometry(X, xi, eta);
+    if (g.singular) atomicExch(P.flag, 1);
+    A = nodal_triad(g.E, v3(nvown.x, nvown.y, nvown.z), nvown.w != 0.0);
+    gx = jn == 0 ? g.gN[0][0] : (jn == 1 ? g.gN[1][0] : (jn == 2 ? g.gN[2][0] : g.gN[3][0]));
+    gy = jn == 0 ? g.gN[0][1] : (jn == 1 ? g.gN[1][1] : (jn == 2 ? g.gN[2][1] : g.gN[3][1]));
+    q4_mitc_bs_node(g, xi, eta, jn, bs);
+    node_coupling_contrib(A, gx, gy, bs, p1, p2);
+  } else {
+    for (int r = 0; r < 5; ++r)
+      for (int k = 0; k < 3; ++k) p1[r][k] = p2[r][k] = 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      p1[r][k] += __shfl_xor_sync(full, p1[r][k], 1);
+      p2[r][k] += __shfl_xor_sync(full, p2[r][k], 1);
+      p1[r][k] += __shfl_xor_sync(full, p1[r][k], 2);
+      p2[r][k] += __shfl_xor_sync(full, p2[r][k], 2);
+    }
+  double bg[8][6];
+  double dv[8];
+  if (on) {
+    Constit C;
+    const double jw = g.Jac * w;
+    const int npts = P.rule.npts;
+    if (COMP) {
+      const double t = gd[31];
+      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * hq * hq);
+      double m, n;
+      const int64_t ci = P.ncs == 1 ? 0 : (P.ncs == P.nelem ? e : e * npts + gp);
+      layup_angle(g.E, P.cs + ci * 9, m, n);
+      constit_laminate(gd, gd + 9, gd + 18, gd + 27, m, n, jw, stab * jw, C);
+    } else {
+      const double t = P.nthick == 1 ? __ldg(P.thick) : (P.nthick == P.nelem ? __ldg(P.thick + e) : __ldg(P.thick + e * npts + gp));
+      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * hq * hq);
+      constit_homogeneous(P.Dps, P.Dt, t * jw, (t * t * t / 12.0) * jw, t * stab * jw, C);
+    }
+    node_strip(g.E, A, gx, gy, bs, p1, p2, bg);
+    fold_constit(C, bg);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) dv[s] = constit_d(C, s);
+  } else {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      dv[s] = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) bg[s][cc] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = bg[s][cc];
+    if (jn == 0) sd_[g4 * 8 + s] = dv[s];
+  }
+}
+
+__device__ __forceinline__ void q4_product_pass(const double* sb_, const double* sd_, int bi, int bj, double (&acc)[6][6]) {
+#pragma unroll 8
+  for (int s = 0; s < 32; ++s) {
+    const double d = sd_[s];
+    double vi[6], vj[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) vi[r] = sb_[s * 24 + bi * 6 + r];
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) vj[cc] = d * sb_[s * 24 + bj * 6 + cc];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
+  }
+}
+
 template <bool COMP, class Emit>
-__global__ void __launch_bounds__(128) k_q4_stiffness(ShellArgs P, Emit emit) {
+__global__ void __launch_bounds__(128, 3) k_q4_stiffness(ShellArgs P, Emit emit) {
   // per half-warp: b[32][24] + d[32]
   extern __shared__ double smem[];
   constexpr int HW_DBL = 32 * 24 + 32;
@@ -274,16 +380,17 @@ __global__ void __launch_bounds__(128) k_q4_stiffness(ShellArgs P, Emit emit) {
 
   V3 X[4];
   int nn[4] = {0, 0, 0, 0};
-  double4 nv[4];
+  double4 nvown = make_double4(0, 0, 1, 0);
   double hq = 0.0;
   const double* gd = nullptr;
   if (active) {
     const int32_t* cn = P.conn + e * 4;
+#pragma unroll
     for (int a = 0; a < 4; ++a) {
       nn[a] = __ldg(cn + a);
       X[a] = ld3(P.xyz, nn[a]);
-      nv[a] = ldg4(P.nrm + nn[a]);
     }
+    nvown = ldg4(P.nrm + (jn == 0 ? nn[0] : (jn == 1 ? nn[1] : (jn == 2 ? nn[2] : nn[3]))));
     // quirk: "diameter" = max distance from node 1 (src/FEMMShellQ4RSModule.jl:861-870)
     double md = 0.0;
     for (int a = 1; a < 4; ++a) {
@@ -294,73 +401,36 @@ __global__ void __launch_bounds__(128) k_q4_stiffness(ShellArgs P, Emit emit) {
     if (COMP) gd = P.gdata + (size_t)__ldg(P.gof + e) * 34;
   }
   double acc[6][6];
-  for (int r = 0; r < 6; ++r)
-    for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-
   const int npts = P.rule.npts;
-  for (int chunk = 0; chunk * 4 < npts; ++chunk) {
-    const int gp = chunk * 4 + g4;
-    double bg[8][6];
-    double dv[8];
-    if (active && gp < npts) {
-      const double xi = P.rule.xi[gp], eta = P.rule.eta[gp], w = P.rule.w[gp];
-      const Q4Geom g = q4_geometry(X, xi, eta);
-      if (g.singular) atomicExch(P.flag, 1);
-      ShellB<4> sb;
-      sb.E = g.E;
-      for (int a = 0; a < 4; ++a) {
-        sb.gN[a][0] = g.gN[a][0];
-        sb.gN[a][1] = g.gN[a][1];
-        sb.A[a] = nodal_triad(g.E, v3(nv[a].x, nv[a].y, nv[a].z), nv[a].w != 0.0);
-      }
-      q4_mitc_bs(g, xi, eta, sb.bs);
-      sb.build_coupling();
-      Constit C;
-      const double jw = g.Jac * w;
-      if (COMP) {
-        const double t = gd[31];
-        const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * hq * hq);
-        double m, n;
-        const int64_t ci = P.ncs == 1 ? 0 : (P.ncs == P.nelem ? e : e * npts + gp);
-        layup_angle(g.E, P.cs + ci * 9, m, n);
-        constit_laminate(gd, gd + 9, gd + 18, gd + 27, m, n, jw, stab * jw, C);
-      } else {
-        const double t = P.nthick == 1 ? __ldg(P.thick) : (P.nthick == P.nelem ? __ldg(P.thick + e) : __ldg(P.thick + e * npts + gp));
-        const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * hq * hq);
-        constit_homogeneous(P.Dps, P.Dt, t * jw, (t * t * t / 12.0) * jw, t * stab * jw, C);
-      }
-      sb.node_bg(jn, bg);
-      fold_constit(C, bg);
-      for (int s = 0; s < 8; ++s) dv[s] = constit_d(C, s);
-    } else {
-      for (int s = 0; s < 8; ++s) {
-        dv[s] = 0.0;
-        for (int cc = 0; cc < 6; ++cc) bg[s][cc] = 0.0;
-      }
-    }
-    for (int s = 0; s < 8; ++s) {
-      for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = bg[s][cc];
-      if (jn == 0) sd_[g4 * 8 + s] = dv[s];
-    }
+  if (npts <= 4) {
+    q4_setup_pass<COMP>(P, active && g4 < npts, e, g4, g4, jn, X, nvown, hq, gd, sb_, sd_);
     __syncwarp();
-#pragma unroll 4
-    for (int s = 0; s < 32; ++s) {
-      const double d = sd_[s];
-      double vi[6], vj[6];
-      for (int r = 0; r < 6; ++r) vi[r] = sb_[s * 24 + bi * 6 + r];
-      for (int cc = 0; cc < 6; ++cc) vj[cc] = d * sb_[s * 24 + bj * 6 + cc];
-      for (int r = 0; r < 6; ++r)
-        for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
+    q4_product_pass(sb_, sd_, bi, bj, acc);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
+    for (int chunk = 0; chunk * 4 < npts; ++chunk) {
+      const int gp = chunk * 4 + g4;
+      q4_setup_pass<COMP>(P, active && gp < npts, e, gp, g4, jn, X, nvown, hq, gd, sb_, sd_);
+      __syncwarp();
+      q4_product_pass(sb_, sd_, bi, bj, acc);
+      __syncwarp();
     }
-    __syncwarp();
   }
 
-  // drilling stiffness (src/FEMMShellQ4RSModule.jl:807-859): lanes (k,k) hold the rotational blocks
+  // drilling stiffness (src/FEMMShellQ4RSModule.jl:807-859): lanes (k,k) hold the rotational blocks;
+  // for those lanes the setup-role node jn equals the block node, so `nvown` is its normal
   double tang = 0.0;
   int ok = 0;
   double nvec[3] = {0, 0, 0};
   if (active && bi == bj) {
-    const double4 n4 = nv[bi];
+    const double4 n4 = ldg4(P.nrm + (bi == 0 ? nn[0] : (bi == 1 ? nn[1] : (bi == 2 ? nn[2] : nn[3]))));
     const double nl = sqrt(n4.x * n4.x + n4.y * n4.y + n4.z * n4.z);
     if (n4.w != 0.0 && nl != 0.0) {
       ok = 1;
@@ -394,7 +464,8 @@ __global__ void __launch_bounds__(128) k_q4_stiffness(ShellArgs P, Emit emit) {
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * (nvec[r] * nvec[cc]);
     }
   }
-  emit.block(e, bi, bj, nn[bi], nn[bj], acc);
+  emit.block(e, bi, bj, bi == 0 ? nn[0] : (bi == 1 ? nn[1] : (bi == 2 ? nn[2] : nn[3])),
+             bj == 0 ? nn[0] : (bj == 1 ? nn[1] : (bj == 2 ? nn[2] : nn[3])), acc);
 }
 
 // =====================================================================================
@@ -736,7 +807,7 @@ int launch_t3(fsgpu_ctx* c, const ShellArgs& A, bool comp, bool sheark, Emit em)
   const int64_t nwarps = (A.nelem + T3_EPW - 1) / T3_EPW;
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
-  const size_t sm = (size_t)wpb * (sheark ? 12 : 8) * 6 * 32 * sizeof(double);
+  const size_t sm = (size_t)wpb * ((sheark ? 12 : 8) * 6 * 32 + (sheark ? 12 : 8) * T3_EPW) * sizeof(double);
 #define T3_GO(CO, SK)                                                                                         \
   do {                                                                                                        \
     FS_CUDA(cudaFuncSetAttribute(k_t3_stiffness<CO, SK, Emit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \

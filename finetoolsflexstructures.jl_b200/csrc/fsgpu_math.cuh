@@ -225,103 +225,87 @@ FS_HD void constit_laminate(const double A[9], const double B[9], const double D
 }
 
 // ---------------------------------------------------------------------------------
-// Generic "B in global dofs" builder shared by T3FF and Q4RS.
-//   NN        nodes per element
-//   gN[l][2]  shape-function gradients in the element basis
-//   bs[r][l][c] transverse-shear B entries for (w, theta_x, theta_y) of node l, r = 0,1
-//   A[l]      nodal triads, E element triad
-// Output for ONE node j: bg[8][6] = rows (3 membrane, 3 curvature, 2 shear) x global dofs
-// of node j, and (optionally) the nodal-basis rotation columns needed for T3FF's kavg.
+// "B in global dofs" for ONE node of a shell element (shared by T3FF and Q4RS).
+//
+// Element-basis B of node l (cols u v w tx ty tz; rows 3 membrane, 3 curvature, 2 shear):
+//   membrane  [gx 0 0 | 0 0 0; 0 gy 0 | 0 0 0; gy gx 0 | 0 0 0]
+//   curvature [0 0 0 | 0 gx 0; 0 0 0 | -gy 0 0; 0 0 0 | -gx gy 0]
+//   shear     [0 0 bs[r][0] | bs[r][1] bs[r][2] 0]
+// (src/FEMMShellT3FFModule.jl:539-561, src/FEMMShellQ4RSModule.jl:548-578).
+// With T_ae of src/FEMMShellT3FFModule.jl:421-463 and the block-diagonal T_ga = A'E' (:398-419):
+//  * translations: B_l[:,0:3] A_l (A_l' E') = B_l[:,0:3] E'   (A_l is a rotation), plus the
+//    drilling-consistency coupling  cpl_l = 1/2 (gx_l P2 - gy_l P1),  P1|2 = sum_m q_m (x) A_m[0|1,:],
+//    q_m = B_m[:,tx] A_m[0][2]/A_m[2][2] + B_m[:,ty] A_m[1][2]/A_m[2][2]   (rows 3..7 only);
+//  * rotations: B_l[:,tx:ty] R_l G_l[0:2,:],  R = A[0:2,0:2] - A[0:2,2] A[0:2,2]'/A[2][2].
 // ---------------------------------------------------------------------------------
-template <int NN>
-struct ShellB {
-  double gN[NN][2];
-  double bs[2][NN][3];
-  // coupling accumulators (rows 3..7 only; membrane rows are structurally zero)
-  double P1[5][3], P2[5][3];
-  M3 A[NN];
-  Triad E;
-
-  // rotation-dof columns (theta_x = 3, theta_y = 4) of the element-basis B for node l,
-  // rows 3..7 -> index 0..4
-  FS_HD void brot(int l, double (&c3)[5], double (&c4)[5]) const {
-    // curvature rows (src/FEMMShellT3FFModule.jl:550-561)
-    c3[0] = 0.0;
-    c4[0] = gN[l][0];
-    c3[1] = -gN[l][1];
-    c4[1] = 0.0;
-    c3[2] = -gN[l][0];
-    c4[2] = gN[l][1];
-    c3[3] = bs[0][l][1];
-    c4[3] = bs[0][l][2];
-    c3[4] = bs[1][l][1];
-    c4[4] = bs[1][l][2];
-  }
-
-  FS_HD void build_coupling() {
-    for (int r = 0; r < 5; ++r)
-      for (int k = 0; k < 3; ++k) P1[r][k] = P2[r][k] = 0.0;
-    for (int l = 0; l < NN; ++l) {
-      const double a33 = A[l].a[2][2];
-      const double m1 = (1.0 / a33) * A[l].a[0][2];
-      const double m2 = (1.0 / a33) * A[l].a[1][2];
-      double c3[5], c4[5];
-      brot(l, c3, c4);
-      for (int r = 0; r < 5; ++r) {
-        const double q = c3[r] * m1 + c4[r] * m2;
-        for (int k = 0; k < 3; ++k) {
-          P1[r][k] += q * A[l].a[0][k];
-          P2[r][k] += q * A[l].a[1][k];
-        }
-      }
-    }
-  }
-
-  // nodal-basis B for node j: bt[8][6] (column 5, the nodal drilling dof, is zero)
-  FS_HD void node_bt(int j, double (&bt)[8][6]) const {
-    const M3& Aj = A[j];
-    const double gx = gN[j][0], gy = gN[j][1];
-    // translations: B_j[:,0:3] * A_j + drilling-consistency coupling
+// rotation-dof columns of the element-basis B, rows 3..7 -> index 0..4
+FS_HD void node_brot(double gx, double gy, const double (&bs)[2][3], double (&c3)[5], double (&c4)[5]) {
+  c3[0] = 0.0;
+  c4[0] = gx;
+  c3[1] = -gy;
+  c4[1] = 0.0;
+  c3[2] = -gx;
+  c4[2] = gy;
+  c3[3] = bs[0][1];
+  c4[3] = bs[0][2];
+  c3[4] = bs[1][1];
+  c4[4] = bs[1][2];
+}
+// this node's contribution to P1, P2 (5 x 3 each)
+FS_HD void node_coupling_contrib(const M3& A, double gx, double gy, const double (&bs)[2][3], double (&p1)[5][3],
+                                 double (&p2)[5][3]) {
+  const double ia = 1.0 / A.a[2][2];
+  const double m1 = ia * A.a[0][2], m2 = ia * A.a[1][2];
+  double c3[5], c4[5];
+  node_brot(gx, gy, bs, c3, c4);
+  for (int r = 0; r < 5; ++r) {
+    const double q = c3[r] * m1 + c4[r] * m2;
     for (int k = 0; k < 3; ++k) {
-      bt[0][k] = gx * Aj.a[0][k];
-      bt[1][k] = gy * Aj.a[1][k];
-      bt[2][k] = gy * Aj.a[0][k] + gx * Aj.a[1][k];
-      const double hx = 0.5 * gx, hy = 0.5 * gy;
-      bt[3][k] = hx * P2[0][k] - hy * P1[0][k];
-      bt[4][k] = hx * P2[1][k] - hy * P1[1][k];
-      bt[5][k] = hx * P2[2][k] - hy * P1[2][k];
-      bt[6][k] = bs[0][j][0] * Aj.a[2][k] + hx * P2[3][k] - hy * P1[3][k];
-      bt[7][k] = bs[1][j][0] * Aj.a[2][k] + hx * P2[4][k] - hy * P1[4][k];
+      p1[r][k] = q * A.a[0][k];
+      p2[r][k] = q * A.a[1][k];
     }
-    // rotations: 2x2 reduced block R = A[rw][cl] - A[rw][2] A[cl][2] / A33
-    const double ia = 1.0 / Aj.a[2][2];
-    double R[2][2];
-    for (int rw = 0; rw < 2; ++rw)
-      for (int cl = 0; cl < 2; ++cl) R[rw][cl] = Aj.a[rw][cl] - ia * Aj.a[rw][2] * Aj.a[cl][2];
-    double c3[5], c4[5];
-    brot(j, c3, c4);
-    for (int cl = 0; cl < 2; ++cl) {
-      bt[0][3 + cl] = bt[1][3 + cl] = bt[2][3 + cl] = 0.0;
-      for (int r = 0; r < 5; ++r) bt[3 + r][3 + cl] = c3[r] * R[0][cl] + c4[r] * R[1][cl];
-    }
-    for (int r = 0; r < 8; ++r) bt[r][5] = 0.0;
   }
-
-  // global-dof B for node j: bg = bt * blkdiag(G_j, G_j); returns g = third row of G_j
-  // (the nodal normal direction in global components, used by the T3FF drilling term).
-  FS_HD V3 node_bg(int j, double (&bg)[8][6]) const {
-    double bt[8][6];
-    node_bt(j, bt);
-    const M3 G = global_to_nodal(A[j], E);
-    for (int r = 0; r < 8; ++r) {
-      for (int c = 0; c < 3; ++c) {
-        bg[r][c] = bt[r][0] * G.a[0][c] + bt[r][1] * G.a[1][c] + bt[r][2] * G.a[2][c];
-        bg[r][3 + c] = bt[r][3] * G.a[0][c] + bt[r][4] * G.a[1][c];
-      }
-    }
-    return v3(G.a[2][0], G.a[2][1], G.a[2][2]);
+}
+// 2x2 reduced rotation block
+FS_HD void node_R(const M3& A, double (&R)[2][2]) {
+  const double ia = 1.0 / A.a[2][2];
+  for (int rw = 0; rw < 2; ++rw)
+    for (int cl = 0; cl < 2; ++cl) R[rw][cl] = A.a[rw][cl] - ia * A.a[rw][2] * A.a[cl][2];
+}
+// nodal-basis rotation columns (theta_1, theta_2) of rows 3..7: brn[r][cl]
+FS_HD void node_bt_rot(double gx, double gy, const double (&bs)[2][3], const double (&R)[2][2], double (&brn)[5][2]) {
+  double c3[5], c4[5];
+  node_brot(gx, gy, bs, c3, c4);
+  for (int r = 0; r < 5; ++r)
+    for (int cl = 0; cl < 2; ++cl) brn[r][cl] = c3[r] * R[0][cl] + c4[r] * R[1][cl];
+}
+// Unfolded global-dof strip of one node: bg[8][6].  P1, P2 are the element's summed coupling
+// matrices.  Returns the nodal normal direction in global components (third row of G).
+FS_HD V3 node_strip(const Triad& E, const M3& A, double gx, double gy, const double (&bs)[2][3], const double (&P1)[5][3],
+                    const double (&P2)[5][3], double (&bg)[8][6]) {
+  const M3 G = global_to_nodal(A, E);
+  double R[2][2], brn[5][2];
+  node_R(A, R);
+  node_bt_rot(gx, gy, bs, R, brn);
+  const double e1[3] = {E.e1.x, E.e1.y, E.e1.z}, e2[3] = {E.e2.x, E.e2.y, E.e2.z}, e3[3] = {E.e3.x, E.e3.y, E.e3.z};
+  const double hx = 0.5 * gx, hy = 0.5 * gy;
+  for (int c = 0; c < 3; ++c) {
+    bg[0][c] = gx * e1[c];
+    bg[1][c] = gy * e2[c];
+    bg[2][c] = gy * e1[c] + gx * e2[c];
+    bg[0][3 + c] = bg[1][3 + c] = bg[2][3 + c] = 0.0;
   }
-};
+  for (int r = 0; r < 5; ++r) {
+    double cp[3];
+    for (int k = 0; k < 3; ++k) cp[k] = hx * P2[r][k] - hy * P1[r][k];
+    const double w = r >= 3 ? bs[r - 3][0] : 0.0;
+    for (int c = 0; c < 3; ++c) {
+      bg[3 + r][c] = w * e3[c] + cp[0] * G.a[0][c] + cp[1] * G.a[1][c] + cp[2] * G.a[2][c];
+      bg[3 + r][3 + c] = brn[r][0] * G.a[0][c] + brn[r][1] * G.a[1][c];
+    }
+  }
+  return v3(G.a[2][0], G.a[2][1], G.a[2][2]);
+}
 
 // b <- L' b (rows), so that K = sum_s d_s b_s (x) b_s.
 FS_HD void fold_constit(const Constit& C, double (&b)[8][6]) {
@@ -335,6 +319,25 @@ FS_HD void fold_constit(const Constit& C, double (&b)[8][6]) {
   }
 }
 FS_HD double constit_d(const Constit& C, int s) { return s < 6 ? C.d6[s] : C.d2[s - 6]; }
+// this node's share of T3FF's kavg numerator: sum_s d_s (bt'_s[theta1]^2 + bt'_s[theta2]^2) over the
+// folded nodal-basis rotation columns (membrane rows are zero) -- src/FEMMShellT3FFModule.jl:714-722.
+// shear_only: count only the two shear rows (extra AVERAGE_K orderings)
+FS_HD double node_kavg_part(const Constit& C, const double (&brn)[5][2], bool shear_only) {
+  double f[8][2];
+  for (int cl = 0; cl < 2; ++cl) {
+    f[0][cl] = f[1][cl] = f[2][cl] = 0.0;
+    for (int r = 0; r < 5; ++r) f[3 + r][cl] = brn[r][cl];
+    for (int s = 0; s < 6; ++s) {
+      double v = f[s][cl];
+      for (int t = s + 1; t < 6; ++t) v += C.L6[t][s] * f[t][cl];
+      f[s][cl] = v;
+    }
+    f[6][cl] += C.L2 * f[7][cl];
+  }
+  double k = 0.0;
+  for (int s = shear_only ? 6 : 0; s < 8; ++s) k += constit_d(C, s) * (f[s][0] * f[s][0] + f[s][1] * f[s][1]);
+  return k;
+}
 
 // ---------------------------------------------------------------------------------
 // T3FF geometry + DSG shear B (src/FEMMShellT3FFModule.jl:269-314,465-537)
@@ -385,6 +388,27 @@ FS_HD void t3_add_bs(const T3Geom& g, int s, int p, int q, double (&bs)[2][3][3]
   bs[1][q][0] += m * a;
   bs[1][q][1] += m * (-a * d / 2);
   bs[1][q][2] += m * (a * c / 2);
+}
+
+// DSG shear entries of ONE node l (averaged over the three cyclic orderings, or one ordering
+// `only` = 0,1,2 for the AVERAGE_K formulation): out[2][3] (cols w, theta_x, theta_y)
+FS_HD void t3_bs_node(const T3Geom& g, int l, int only, double (&out)[2][3]) {
+  double bs[2][3][3];
+  for (int r = 0; r < 2; ++r)
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) bs[r][a][c] = 0.0;
+  if (only >= 0) {
+    t3_add_bs(g, only, (only + 1) % 3, (only + 2) % 3, bs);
+  } else {
+    t3_add_bs(g, 0, 1, 2, bs);
+    t3_add_bs(g, 1, 2, 0, bs);
+    t3_add_bs(g, 2, 0, 1, bs);
+    for (int r = 0; r < 2; ++r)
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) bs[r][a][c] *= (1.0 / 3);
+  }
+  for (int r = 0; r < 2; ++r)
+    for (int c = 0; c < 3; ++c) out[r][c] = l == 0 ? bs[r][0][c] : (l == 1 ? bs[r][1][c] : bs[r][2][c]);
 }
 
 // ---------------------------------------------------------------------------------
@@ -488,6 +512,14 @@ FS_HD void q4_mitc_bs(const Q4Geom& g, double r, double s, double (&bs)[2][4][3]
       bs[0][a][c] = -(crz[a][c] * sb - csz[a][c] * sa);
       bs[1][a][c] = -(-crz[a][c] * cb + csz[a][c] * ca);
     }
+}
+
+// MITC shear entries of ONE node a: out[2][3]
+FS_HD void q4_mitc_bs_node(const Q4Geom& g, double r, double s, int a, double (&out)[2][3]) {
+  double bs[2][4][3];
+  q4_mitc_bs(g, r, s, bs);
+  for (int q = 0; q < 2; ++q)
+    for (int c = 0; c < 3; ++c) out[q][c] = a == 0 ? bs[q][0][c] : (a == 1 ? bs[q][1][c] : (a == 2 ? bs[q][2][c] : bs[q][3][c]));
 }
 
 // ---------------------------------------------------------------------------------

@@ -18,13 +18,8 @@ extern "C" {
 void hm_t3_elmat(const double* X, const double* nrm, const unsigned char* valid, const double* Dps, const double* Dt56,
                  double t, double alpha, double drill, int sheark, const double* group, const double* cs, double* out) {
   const T3Geom g = t3_geometry(v3(X[0], X[1], X[2]), v3(X[3], X[4], X[5]), v3(X[6], X[7], X[8]));
-  ShellB<3> sb;
-  sb.E = g.E;
-  for (int l = 0; l < 3; ++l) {
-    sb.gN[l][0] = g.gN[l][0];
-    sb.gN[l][1] = g.gN[l][1];
-    sb.A[l] = nodal_triad(g.E, v3(nrm[3 * l], nrm[3 * l + 1], nrm[3 * l + 2]), valid[l] != 0);
-  }
+  M3 A[3];
+  for (int l = 0; l < 3; ++l) A[l] = nodal_triad(g.E, v3(nrm[3 * l], nrm[3 * l + 1], nrm[3 * l + 2]), valid[l] != 0);
   const double Ae = g.Ae, h = sqrt(2 * Ae);
   const double sk = sheark ? 1.0 / 3 : 1.0;
   Constit C;
@@ -43,24 +38,23 @@ void hm_t3_elmat(const double* X, const double* nrm, const unsigned char* valid,
   double b[3][12][6], d[12], kpart[3] = {0, 0, 0};
   V3 gdir[3];
   for (int set = 0; set < nsets; ++set) {
-    memset(sb.bs, 0, sizeof sb.bs);
-    if (sheark) {
-      t3_add_bs(g, set, (set + 1) % 3, (set + 2) % 3, sb.bs);
-    } else {
-      t3_add_bs(g, 0, 1, 2, sb.bs);
-      t3_add_bs(g, 1, 2, 0, sb.bs);
-      t3_add_bs(g, 2, 0, 1, sb.bs);
-      for (int r = 0; r < 2; ++r)
-        for (int l = 0; l < 3; ++l)
-          for (int c = 0; c < 3; ++c) sb.bs[r][l][c] *= (1.0 / 3);
+    double bs[3][2][3], P1[5][3] = {}, P2[5][3] = {};
+    for (int l = 0; l < 3; ++l) {
+      t3_bs_node(g, l, sheark ? set : -1, bs[l]);
+      double p1[5][3], p2[5][3];
+      node_coupling_contrib(A[l], g.gN[l][0], g.gN[l][1], bs[l], p1, p2);
+      for (int r = 0; r < 5; ++r)
+        for (int k = 0; k < 3; ++k) {
+          P1[r][k] += p1[r][k];
+          P2[r][k] += p2[r][k];
+        }
     }
-    sb.build_coupling();
     for (int j = 0; j < 3; ++j) {
-      double bt[8][6], bg[8][6];
-      sb.node_bt(j, bt);
-      fold_constit(C, bt);
-      for (int s = (set == 0 ? 0 : 6); s < 8; ++s) kpart[j] += constit_d(C, s) * (bt[s][3] * bt[s][3] + bt[s][4] * bt[s][4]);
-      gdir[j] = sb.node_bg(j, bg);
+      double R[2][2], brn[5][2], bg[8][6];
+      node_R(A[j], R);
+      node_bt_rot(g.gN[j][0], g.gN[j][1], bs[j], R, brn);
+      kpart[j] += node_kavg_part(C, brn, set > 0);
+      gdir[j] = node_strip(g.E, A[j], g.gN[j][0], g.gN[j][1], bs[j], P1, P2, bg);
       fold_constit(C, bg);
       if (set == 0) {
         for (int s = 0; s < 8; ++s) {
@@ -108,15 +102,19 @@ int hm_q4_elmat(const double* Xin, const double* nrm, const unsigned char* valid
   for (int gp = 0; gp < npts; ++gp) {
     const Q4Geom g = q4_geometry(X, xi[gp], eta[gp]);
     singular |= g.singular;
-    ShellB<4> sb;
-    sb.E = g.E;
+    M3 A[4];
+    double bs[4][2][3], P1[5][3] = {}, P2[5][3] = {};
     for (int a = 0; a < 4; ++a) {
-      sb.gN[a][0] = g.gN[a][0];
-      sb.gN[a][1] = g.gN[a][1];
-      sb.A[a] = nodal_triad(g.E, v3(nrm[3 * a], nrm[3 * a + 1], nrm[3 * a + 2]), valid[a] != 0);
+      A[a] = nodal_triad(g.E, v3(nrm[3 * a], nrm[3 * a + 1], nrm[3 * a + 2]), valid[a] != 0);
+      q4_mitc_bs_node(g, xi[gp], eta[gp], a, bs[a]);
+      double p1[5][3], p2[5][3];
+      node_coupling_contrib(A[a], g.gN[a][0], g.gN[a][1], bs[a], p1, p2);
+      for (int r = 0; r < 5; ++r)
+        for (int k = 0; k < 3; ++k) {
+          P1[r][k] += p1[r][k];
+          P2[r][k] += p2[r][k];
+        }
     }
-    q4_mitc_bs(g, xi[gp], eta[gp], sb.bs);
-    sb.build_coupling();
     Constit C;
     const double jw = g.Jac * w[gp];
     if (group) {
@@ -132,7 +130,7 @@ int hm_q4_elmat(const double* Xin, const double* nrm, const unsigned char* valid
     }
     double b[4][8][6], d[8];
     for (int j = 0; j < 4; ++j) {
-      sb.node_bg(j, b[j]);
+      node_strip(g.E, A[j], g.gN[j][0], g.gN[j][1], bs[j], P1, P2, b[j]);
       fold_constit(C, b[j]);
     }
     for (int s = 0; s < 8; ++s) d[s] = constit_d(C, s);
