@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfsgpu.so")
+LIB_PATH = os.environ.get("FSGPU_LIB", os.path.join(_HERE, "libfsgpu.so"))
 
 
 class FsgpuError(RuntimeError):

@@ -17,21 +17,38 @@
 using namespace fs;
 using namespace fsm;
 
+#ifndef FS_T3_MINB
+#define FS_T3_MINB 3
+#endif
+#ifndef FS_Q4_MINB
+#define FS_Q4_MINB 3
+#endif
+
 namespace {
 
 // ---- emitters -----------------------------------------------------------------------
 // t = e*nnpe + j (element-major, column node j), i = row node, r/c = local dof in the 6x6 block
-// Every emitter takes one finished 6x6 block (row node i, column node j of element e).
+// Every emitter takes one finished 6x6 block (row node i, column node j of element e).  The
+// addressing data is split so that kernels can fetch it early (cols: once per column node,
+// rows: once per block) and overlap the load latency with arithmetic.
+struct BlockRef {
+  int64_t e;
+  int i, j;
+};
 struct EmitScatter {  // generic path: per-entry slot map, any dof numbering
   double* nz;
   const int32_t* slot;
   int64_t plane;  // nelem * nnpe
   int nnpe;
-  __device__ __forceinline__ void block(int64_t e, int i, int j, int, int, const double (&a)[6][6]) const {
-    const int64_t t = e * nnpe + j;
+  struct Cols {};
+  struct Rows {};
+  __device__ __forceinline__ Cols cols(int) const { return Cols{}; }
+  __device__ __forceinline__ Rows rows(int64_t, int, int, int) const { return Rows{}; }
+  __device__ __forceinline__ void block(const BlockRef& b, const Cols&, const Rows&, const double (&a)[6][6]) const {
+    const int64_t t = b.e * nnpe + b.j;
     int sl[36];
 #pragma unroll
-    for (int k = 0; k < 36; ++k) sl[k] = __ldg(slot + ((int64_t)(k * nnpe + i)) * plane + t);
+    for (int k = 0; k < 36; ++k) sl[k] = __ldg(slot + ((int64_t)(k * nnpe + b.i)) * plane + t);
 #pragma unroll
     for (int c = 0; c < 6; ++c)
 #pragma unroll
@@ -48,29 +65,43 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   int64_t nelem;
   int64_t nc;
   int nnpe;
-  __device__ __forceinline__ void block(int64_t e, int i, int j, int ni, int nj, const double (&a)[6][6]) const {
-    const int inf = __ldg(nodeinfo + ni);
-    const int mA = inf & 63, mB = (inf >> 8) & 63;
-    const int oA = __ldg(pairoff + ((int64_t)(i * 2 + 0) * nelem + e) * nnpe + j);
-    const int oB = __ldg(pairoff + ((int64_t)(i * 2 + 1) * nelem + e) * nnpe + j);
+  struct Cols {
+    int base[6];
+  };
+  struct Rows {
+    int mA, mB, oA, oB;
+  };
+  __device__ __forceinline__ Cols cols(int nj) const {
+    Cols c;
     const int32_t* dj = dof + (int64_t)nj * 6;
     int cd[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) cd[c] = __ldg(dj + c);
-    int base[6];
+    for (int k = 0; k < 6; ++k) cd[k] = __ldg(dj + k);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) base[c] = cd[c] < nc ? __ldg(colptr + cd[c]) : -1;
+    for (int k = 0; k < 6; ++k) c.base[k] = cd[k] < nc ? __ldg(colptr + cd[k]) : -1;
+    return c;
+  }
+  __device__ __forceinline__ Rows rows(int64_t e, int i, int j, int ni) const {
+    Rows r;
+    const int inf = __ldg(nodeinfo + ni);
+    r.mA = inf & 63;
+    r.mB = (inf >> 8) & 63;
+    r.oA = __ldg(pairoff + ((int64_t)(i * 2 + 0) * nelem + e) * nnpe + j);
+    r.oB = __ldg(pairoff + ((int64_t)(i * 2 + 1) * nelem + e) * nnpe + j);
+    return r;
+  }
+  __device__ __forceinline__ void block(const BlockRef&, const Cols& cb, const Rows& rw, const double (&a)[6][6]) const {
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      if (base[c] < 0) continue;
-      double* pa = nz + base[c] + oA;
-      double* pb = nz + base[c] + oB;
+      if (cb.base[c] < 0) continue;
+      double* pa = nz + cb.base[c] + rw.oA;
+      double* pb = nz + cb.base[c] + rw.oB;
       int ka = 0, kb = 0;
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
-        if ((mA >> r) & 1)
+        if ((rw.mA >> r) & 1)
           atomicAdd(pa + ka++, a[r][c]);
-        else if ((mB >> r) & 1)
+        else if ((rw.mB >> r) & 1)
           atomicAdd(pb + kb++, a[r][c]);
       }
     }
@@ -79,13 +110,17 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
 struct EmitDense {
   double* out;  // [nelem][n][n] column-major per element
   int nnpe;
-  __device__ __forceinline__ void block(int64_t e, int i, int j, int, int, const double (&a)[6][6]) const {
+  struct Cols {};
+  struct Rows {};
+  __device__ __forceinline__ Cols cols(int) const { return Cols{}; }
+  __device__ __forceinline__ Rows rows(int64_t, int, int, int) const { return Rows{}; }
+  __device__ __forceinline__ void block(const BlockRef& b, const Cols&, const Rows&, const double (&a)[6][6]) const {
     const int n = 6 * nnpe;
-    double* o = out + e * n * n;
+    double* o = out + b.e * n * n;
 #pragma unroll
     for (int c = 0; c < 6; ++c)
 #pragma unroll
-      for (int r = 0; r < 6; ++r) o[(int64_t)(j * 6 + c) * n + (i * 6 + r)] = a[r][c];
+      for (int r = 0; r < 6; ++r) o[(int64_t)(b.j * 6 + c) * n + (b.i * 6 + r)] = a[r][c];
   }
 };
 
@@ -99,6 +134,7 @@ struct ShellArgs {
   int64_t nstab;
   int64_t nelem;
   double Dps[9], Dt[4];  // Dt already x 5/6
+  HomogFactors hf;       // LDL' factors of Dps and Dt (host)
   double rho, alpha, drill;
   // composite
   const double* gdata;
@@ -142,7 +178,7 @@ __device__ __forceinline__ void build_constit_t3(const ShellArgs& P, int64_t e, 
 }
 
 template <bool COMP, bool SHEARK, class Emit>
-__global__ void __launch_bounds__(128, 3) k_t3_stiffness(ShellArgs P, Emit emit) {
+__global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, Emit emit) {
   constexpr int NR = SHEARK ? 12 : 8;
   constexpr int WARP_DBL = NR * 6 * 32 + NR * T3_EPW;
   extern __shared__ double smem[];  // per warp: strips [NR*6][32] + d [NR][T3_EPW]
@@ -238,7 +274,12 @@ __global__ void __launch_bounds__(128, 3) k_t3_stiffness(ShellArgs P, Emit emit)
   const double kavg = ksum / 6 * P.drill;
   __syncwarp();
   if (!active) return;
-#pragma unroll 1
+  const int nj = j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]);
+  const typename Emit::Cols ecols = emit.cols(nj);
+  typename Emit::Rows erows[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) erows[i] = emit.rows(e, i, j, nn[i]);
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     double acc[6][6];
 #pragma unroll
@@ -267,7 +308,7 @@ __global__ void __launch_bounds__(128, 3) k_t3_stiffness(ShellArgs P, Emit emit)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * gg[r] * gg[cc];
     }
-    emit.block(e, i, j, i == 0 ? nn[0] : (i == 1 ? nn[1] : nn[2]), j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]), acc);
+    emit.block(BlockRef{e, i, j}, ecols, erows[i], acc);
   }
 }
 
@@ -309,41 +350,81 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
       p1[r][k] += __shfl_xor_sync(full, p1[r][k], 2);
       p2[r][k] += __shfl_xor_sync(full, p2[r][k], 2);
     }
-  double bg[8][6];
-  double dv[8];
   if (on) {
-    Constit C;
     const double jw = g.Jac * w;
     const int npts = P.rule.npts;
     if (COMP) {
+      Constit C;
       const double t = gd[31];
       const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * hq * hq);
       double m, n;
       const int64_t ci = P.ncs == 1 ? 0 : (P.ncs == P.nelem ? e : e * npts + gp);
       layup_angle(g.E, P.cs + ci * 9, m, n);
       constit_laminate(gd, gd + 9, gd + 18, gd + 27, m, n, jw, stab * jw, C);
+      double bg[8][6];
+      node_strip(g.E, A, gx, gy, bs, p1, p2, bg);
+      fold_constit(C, bg);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = bg[s][cc];
+        if (jn == 0) sd_[g4 * 8 + s] = constit_d(C, s);
+      }
     } else {
       const double t = P.nthick == 1 ? __ldg(P.thick) : (P.nthick == P.nelem ? __ldg(P.thick + e) : __ldg(P.thick + e * npts + gp));
       const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * hq * hq);
-      constit_homogeneous(P.Dps, P.Dt, t * jw, (t * t * t / 12.0) * jw, t * stab * jw, C);
-    }
-    node_strip(g.E, A, gx, gy, bs, p1, p2, bg);
-    fold_constit(C, bg);
+      const double cm = t * jw, cb = (t * t * t / 12.0) * jw, cs = t * stab * jw;
+      if (jn == 0) {
 #pragma unroll
-    for (int s = 0; s < 8; ++s) dv[s] = constit_d(C, s);
+        for (int s = 0; s < 3; ++s) {
+          sd_[g4 * 8 + s] = cm * P.hf.dps[s];
+          sd_[g4 * 8 + 3 + s] = cb * P.hf.dps[s];
+        }
+        sd_[g4 * 8 + 6] = cs * P.hf.dts[0];
+        sd_[g4 * 8 + 7] = cs * P.hf.dts[1];
+      }
+      double* dst = sb_ + (g4 * 8) * 24 + jn * 6;
+      {
+        double m[3][6];
+        strip_membrane(g.E, gx, gy, m);
+        fold3(P.hf, m);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) dst[s * 24 + cc] = m[s][cc];
+      }
+      const M3 G = global_to_nodal(A, g.E);
+      double R[2][2], brn[5][2];
+      node_R(A, R);
+      node_bt_rot(gx, gy, bs, R, brn);
+      {
+        double m[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) strip_row(g.E, G, brn, gx, gy, 0.0, p1, p2, r, m[r]);
+        fold3(P.hf, m);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) dst[(3 + s) * 24 + cc] = m[s][cc];
+      }
+      {
+        double r6[6], r7[6];
+        strip_row(g.E, G, brn, gx, gy, bs[0][0], p1, p2, 3, r6);
+        strip_row(g.E, G, brn, gx, gy, bs[1][0], p1, p2, 4, r7);
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          dst[6 * 24 + cc] = r6[cc] + P.hf.Lt * r7[cc];
+          dst[7 * 24 + cc] = r7[cc];
+        }
+      }
+    }
   } else {
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
-      dv[s] = 0.0;
 #pragma unroll
-      for (int cc = 0; cc < 6; ++cc) bg[s][cc] = 0.0;
+      for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = 0.0;
+      if (jn == 0) sd_[g4 * 8 + s] = 0.0;
     }
-  }
-#pragma unroll
-  for (int s = 0; s < 8; ++s) {
-#pragma unroll
-    for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = bg[s][cc];
-    if (jn == 0) sd_[g4 * 8 + s] = dv[s];
   }
 }
 
@@ -364,7 +445,7 @@ __device__ __forceinline__ void q4_product_pass(const double* sb_, const double*
 }
 
 template <bool COMP, class Emit>
-__global__ void __launch_bounds__(128, 3) k_q4_stiffness(ShellArgs P, Emit emit) {
+__global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, Emit emit) {
   // per half-warp: b[32][24] + d[32]
   extern __shared__ double smem[];
   constexpr int HW_DBL = 32 * 24 + 32;
@@ -400,6 +481,14 @@ __global__ void __launch_bounds__(128, 3) k_q4_stiffness(ShellArgs P, Emit emit)
     hq = sqrt(md);
     if (COMP) gd = P.gdata + (size_t)__ldg(P.gof + e) * 34;
   }
+  const int nbi = bi == 0 ? nn[0] : (bi == 1 ? nn[1] : (bi == 2 ? nn[2] : nn[3]));
+  const int nbj = bj == 0 ? nn[0] : (bj == 1 ? nn[1] : (bj == 2 ? nn[2] : nn[3]));
+  typename Emit::Cols ecols;
+  typename Emit::Rows erows;
+  if (active) {
+    ecols = emit.cols(nbj);
+    erows = emit.rows(e, bi, bj, nbi);
+  }
   double acc[6][6];
   const int npts = P.rule.npts;
   if (npts <= 4) {
@@ -430,7 +519,7 @@ __global__ void __launch_bounds__(128, 3) k_q4_stiffness(ShellArgs P, Emit emit)
   int ok = 0;
   double nvec[3] = {0, 0, 0};
   if (active && bi == bj) {
-    const double4 n4 = ldg4(P.nrm + (bi == 0 ? nn[0] : (bi == 1 ? nn[1] : (bi == 2 ? nn[2] : nn[3]))));
+    const double4 n4 = ldg4(P.nrm + nbi);
     const double nl = sqrt(n4.x * n4.x + n4.y * n4.y + n4.z * n4.z);
     if (n4.w != 0.0 && nl != 0.0) {
       ok = 1;
@@ -464,8 +553,7 @@ __global__ void __launch_bounds__(128, 3) k_q4_stiffness(ShellArgs P, Emit emit)
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * (nvec[r] * nvec[cc]);
     }
   }
-  emit.block(e, bi, bj, bi == 0 ? nn[0] : (bi == 1 ? nn[1] : (bi == 2 ? nn[2] : nn[3])),
-             bj == 0 ? nn[0] : (bj == 1 ? nn[1] : (bj == 2 ? nn[2] : nn[3])), acc);
+  emit.block(BlockRef{e, bi, bj}, ecols, erows, acc);
 }
 
 // =====================================================================================
@@ -697,7 +785,7 @@ __global__ void k_beam_matrix(BeamArgs P, int op, Emit emit) {
         }
     }
   const int32_t* cn = P.conn + e * 2;
-  emit.block(e, bI, bJ, cn[bI], cn[bJ], Kg);
+  emit.block(BlockRef{e, bI, bJ}, emit.cols(cn[bJ]), emit.rows(e, bI, bJ, cn[bI]), Kg);
 }
 // restoring force: elvec = Te (-aN' DN dN)   (src/FEMMCorotBeamModule.jl:1132-1157)
 __global__ void k_beam_restoring(BeamArgs P, const int32_t* __restrict__ dof, double* __restrict__ out, int64_t limit,
@@ -787,6 +875,21 @@ int shell_args(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp, b
   A.nelem = c->nelem;
   for (int i = 0; i < 9; ++i) A.Dps[i] = p->Dps[i];
   for (int i = 0; i < 4; ++i) A.Dt[i] = p->Dt[i] * (5.0 / 6.0);  // shear correction (src/FEMMShellT3FFModule.jl:658-659)
+  {
+    double a[3][3], d[3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) a[i][j] = A.Dps[i * 3 + j];
+    ldlt<3>(a, d);
+    A.hf.L10 = a[1][0];
+    A.hf.L20 = a[2][0];
+    A.hf.L21 = a[2][1];
+    for (int i = 0; i < 3; ++i) A.hf.dps[i] = d[i];
+    double h[2][2] = {{A.Dt[0], A.Dt[1]}, {A.Dt[2], A.Dt[3]}}, dd[2];
+    ldlt<2>(h, dd);
+    A.hf.Lt = h[1][0];
+    A.hf.dts[0] = dd[0];
+    A.hf.dts[1] = dd[1];
+  }
   A.rho = p->rho;
   A.alpha = p->stab_alpha;
   A.drill = p->drilling_stiffness_scale;

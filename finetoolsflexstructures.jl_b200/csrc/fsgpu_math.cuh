@@ -279,32 +279,55 @@ FS_HD void node_bt_rot(double gx, double gy, const double (&bs)[2][3], const dou
   for (int r = 0; r < 5; ++r)
     for (int cl = 0; cl < 2; ++cl) brn[r][cl] = c3[r] * R[0][cl] + c4[r] * R[1][cl];
 }
-// Unfolded global-dof strip of one node: bg[8][6].  P1, P2 are the element's summed coupling
-// matrices.  Returns the nodal normal direction in global components (third row of G).
+// Unfolded global-dof strip of one node, by constitutive row group (the groups are
+// independent, so a kernel can build, fold and store them one after the other).
+FS_HD void strip_membrane(const Triad& E, double gx, double gy, double (&m)[3][6]) {
+  const double e1[3] = {E.e1.x, E.e1.y, E.e1.z}, e2[3] = {E.e2.x, E.e2.y, E.e2.z};
+  for (int c = 0; c < 3; ++c) {
+    m[0][c] = gx * e1[c];
+    m[1][c] = gy * e2[c];
+    m[2][c] = gy * e1[c] + gx * e2[c];
+    m[0][3 + c] = m[1][3 + c] = m[2][3 + c] = 0.0;
+  }
+}
+// one of the rows 3..7 (r = 0..4): w = shear w-entry (0 for the curvature rows)
+FS_HD void strip_row(const Triad& E, const M3& G, const double (&brn)[5][2], double gx, double gy, double w, const double (&P1)[5][3],
+                     const double (&P2)[5][3], int r, double (&row)[6]) {
+  const double e3[3] = {E.e3.x, E.e3.y, E.e3.z};
+  const double hx = 0.5 * gx, hy = 0.5 * gy;
+  double cp[3];
+  for (int k = 0; k < 3; ++k) cp[k] = hx * P2[r][k] - hy * P1[r][k];
+  for (int c = 0; c < 3; ++c) {
+    row[c] = w * e3[c] + cp[0] * G.a[0][c] + cp[1] * G.a[1][c] + cp[2] * G.a[2][c];
+    row[3 + c] = brn[r][0] * G.a[0][c] + brn[r][1] * G.a[1][c];
+  }
+}
+// Whole strip bg[8][6].  P1, P2 are the element's summed coupling matrices.  Returns the nodal
+// normal direction in global components (third row of G).
 FS_HD V3 node_strip(const Triad& E, const M3& A, double gx, double gy, const double (&bs)[2][3], const double (&P1)[5][3],
                     const double (&P2)[5][3], double (&bg)[8][6]) {
   const M3 G = global_to_nodal(A, E);
   double R[2][2], brn[5][2];
   node_R(A, R);
   node_bt_rot(gx, gy, bs, R, brn);
-  const double e1[3] = {E.e1.x, E.e1.y, E.e1.z}, e2[3] = {E.e2.x, E.e2.y, E.e2.z}, e3[3] = {E.e3.x, E.e3.y, E.e3.z};
-  const double hx = 0.5 * gx, hy = 0.5 * gy;
-  for (int c = 0; c < 3; ++c) {
-    bg[0][c] = gx * e1[c];
-    bg[1][c] = gy * e2[c];
-    bg[2][c] = gy * e1[c] + gx * e2[c];
-    bg[0][3 + c] = bg[1][3 + c] = bg[2][3 + c] = 0.0;
-  }
-  for (int r = 0; r < 5; ++r) {
-    double cp[3];
-    for (int k = 0; k < 3; ++k) cp[k] = hx * P2[r][k] - hy * P1[r][k];
-    const double w = r >= 3 ? bs[r - 3][0] : 0.0;
-    for (int c = 0; c < 3; ++c) {
-      bg[3 + r][c] = w * e3[c] + cp[0] * G.a[0][c] + cp[1] * G.a[1][c] + cp[2] * G.a[2][c];
-      bg[3 + r][3 + c] = brn[r][0] * G.a[0][c] + brn[r][1] * G.a[1][c];
-    }
-  }
+  double m[3][6];
+  strip_membrane(E, gx, gy, m);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 6; ++c) bg[r][c] = m[r][c];
+  for (int r = 0; r < 5; ++r) strip_row(E, G, brn, gx, gy, r >= 3 ? bs[r - 3][0] : 0.0, P1, P2, r, bg[3 + r]);
   return v3(G.a[2][0], G.a[2][1], G.a[2][2]);
+}
+
+// Host-factored homogeneous constitutive data: Dps = L diag(dps) L' (unit lower, entries
+// L10, L20, L21), Dt (x5/6) = Lt diag(dts) Lt'.
+struct HomogFactors {
+  double L10, L20, L21, dps[3], Lt, dts[2];
+};
+FS_HD void fold3(const HomogFactors& H, double (&m)[3][6]) {
+  for (int c = 0; c < 6; ++c) {
+    m[0][c] += H.L10 * m[1][c] + H.L20 * m[2][c];
+    m[1][c] += H.L21 * m[2][c];
+  }
 }
 
 // b <- L' b (rows), so that K = sum_s d_s b_s (x) b_s.
