@@ -159,6 +159,185 @@ def oracle_normals(w):
 
 
 # ---------------------------------------------------------------------------------------
+# Secondary workloads reported in the same JSON line ("other_workloads"): BASELINE configs[3]
+# (explicit T3FF shell, 4M-element panel, element-partitioned) -- assembly rate and steps/s.
+# ---------------------------------------------------------------------------------------
+T3_IN_BYTES, T3_FLOPS = 73.0, 9.0e3
+EXPL_FLOPS_PER_NNZ = 2.0
+
+
+def explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
+    import torch
+    import torch.distributed as dist
+
+    import fsb200
+    from fsb200 import partition as pt
+    from fsb200 import workloads as wl
+
+    f = fsb200.femm
+    nx, ny = args.c4_nx, args.c4_nx // 2
+    w = wl.c4_strip(rank, world, nx, ny)
+    nelem = w["conn"].shape[0]
+    femm = f.FEMMShellT3FF(f.IntegDomain(w["conn"], None, w["thickness"]), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]), device=local_rank)
+    femm.ctx.set_stream(stream.cuda_stream)
+    geom0 = f.NodalField.__new__(f.NodalField)
+    geom0.values = w["xyz"]
+    dchi = f.NodalField.__new__(f.NodalField)
+    dchi.values, dchi.dofnums, dchi._nfree = None, w["dofnums"], w["nfree"]
+    f.associategeometry(femm, geom0)
+    t0 = time.perf_counter()
+    femm._startassembly(f.SysmatAssemblerFFBlock(), dchi)
+    femm.ctx.sync()
+    sym_ms = (time.perf_counter() - t0) * 1e3
+    femm._sync_stab()
+    p = femm._params()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- T3FF stiffness assembly (numeric phase, device resident) ---
+    for _ in range(3):
+        femm.ctx.shell_op("t3ff_stiffness", p)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    e0.record(stream)
+    nrep = max(3, args.steps // 2)
+    for _ in range(nrep):
+        femm.ctx.shell_op("t3ff_stiffness", p)
+        kms.append(femm.ctx.last_kernel_ms)
+    e1.record(stream)
+    barrier()
+    tm = torch.tensor([e0.elapsed_time(e1) / nrep], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    asm_ms = float(tm.item())
+    nnz = femm.ctx.result_size()[2]
+    kernel_ms = float(np.mean(kms))
+    alg = T3_IN_BYTES + 8.0 * nnz / nelem
+    asm = {"workload": f"T3FF stiffness -> CSC (FFBlock), {nelem} elements per rank", "value": nelem * world / (asm_ms * 1e-3),
+           "unit": "elements/s", "ms_per_step": asm_ms, "kernel_ms": kernel_ms, "symbolic_ms": sym_ms, "nnz": int(nnz),
+           "roofline": {"bound": "hbm", "achieved": alg * nelem / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg * nelem / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_element": alg,
+                        "kernel": "k_t3_stiffness<false,false,EmitRuns>"},
+           "fp64": {"achieved_tflops": T3_FLOPS * nelem / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
+                    "frac": T3_FLOPS * nelem / (kernel_ms * 1e-3) / 1e12 / fp64_peak, "flops_per_element": T3_FLOPS}}
+
+    # --- explicit central differences: K = FF block (device resident), lumped M ---
+    femm.ctx.shell_mass_diag(p, 3, nfree_only=True)
+    nf = w["nfree"]
+    links = pt.strip_links(rank, world, w["lo_dofs"], w["hi_dofs"])
+    ex_if = pt.InterfaceExchange(links, torch.device("cuda", local_rank)) if world > 1 else None
+    with torch.cuda.stream(stream):
+        if world > 1:  # lumped mass of interface nodes: sum of both partitions' contributions
+            import ctypes as C
+
+            vp, vn = C.c_void_p(), C.c_int64()
+            fsb200._lib.check(fsb200._lib.lib.fsgpu_vector_device(femm.ctx._h, C.byref(vp), C.byref(vn)))
+            Mt = torch.as_tensor(pt.DevicePointer(vp.value, vn.value), device="cuda")
+            ex_if.exchange_sum(Mt)
+            torch.cuda.synchronize()
+        ex = fsb200.Explicit(femm.ctx, c_scale=100.0, dt=0.0)
+        lam = ex.omega_max_sq(args.power_its)
+        if world > 1:
+            lt = torch.tensor([lam], device="cuda", dtype=torch.float64)
+            dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+            lam = float(lt.item())
+        ex.close()
+        dt = 0.9 * 2 / np.sqrt(lam)
+        ex = fsb200.Explicit(femm.ctx, c_scale=100.0, dt=dt)
+        F0 = np.zeros(nf)
+        F0[2::6][: nf // 600] = 1.0  # a small pressure patch
+        ex.set_load(F0)
+        ex.start(1.0)
+        U, V, A, E = ex.device_state()
+        Et = torch.as_tensor(pt.DevicePointer(E, nf), device="cuda")
+        nsteps = args.expl_steps
+
+        def run(n):
+            if world == 1:
+                ex.step(n)
+            else:
+                for _ in range(n):
+                    ex.step_begin()
+                    ex_if.exchange_sum(Et)
+                    ex.step_end(1.0)
+
+        run(20)
+        barrier()
+        l0 = femm.ctx.launch_count
+        e0.record(stream)
+        run(nsteps)
+        e1.record(stream)
+        barrier()
+        launches = femm.ctx.launch_count - l0
+        tm = torch.tensor([e0.elapsed_time(e1) / nsteps], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        step_ms = float(tm.item())
+        Uh = ex.get_state()[0]
+        ke = ex.kinetic_energy()
+    knnz = nnz
+    alg_step = (12.0 * knnz + 10 * 8.0 * nf) / nelem  # f64 value + i32 column per entry, ~10 vector passes
+    expl = {"workload": f"explicit central differences, T3FF, {nelem} elements per rank x {world} rank(s), SpMV form (K_ff CSR, lumped M)",
+            "steps_per_s": 1e3 / step_ms, "element_steps_per_s": nelem * world * 1e3 / step_ms, "ms_per_step": step_ms, "dt": dt,
+            "omega_max": float(np.sqrt(lam)), "nsteps_timed": nsteps, "gpu_launches": int(launches), "max_abs_U": float(np.abs(Uh).max()),
+            "kinetic_energy": ke, "interface_exchange": "pairwise NCCL isend/irecv of packed interface E entries" if world > 1 else "none",
+            "roofline": {"bound": "hbm", "achieved": alg_step * nelem / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_step * nelem / (step_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_element_step": alg_step,
+                         "kernel": "k_spmv_step + k_update_u"}}
+    # CPU arm for the explicit loop (rank 0, bounded sample: a 1/100-size strip, all host threads)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_explicit(local_rank)
+        except Exception as ex_:  # never let the side measurement kill the bench line
+            cpu = {"error": repr(ex_)}
+    ex.close()
+    return {"t3ff_assembly_C4": asm, "explicit_C4": expl, "explicit_cpu_baseline": cpu}
+
+
+def cpu_explicit(local_rank, nx=400):
+    """Reference explicit loop (SpMV + vector updates) on the host cores: K of a nx x nx/2 x 2
+    T3FF strip (assembled on the GPU, fetched), oracle C port `ref_explicit_steps`."""
+    import scipy.sparse as sp
+
+    import fsb200
+    from fsb200 import workloads as wl
+
+    f = fsb200.femm
+    w = wl.c4_t3ff_panel(nx, nx // 2)
+    femm = f.FEMMShellT3FF(f.IntegDomain(w["conn"], None, w["thickness"]), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]), device=local_rank)
+    geom0 = f.NodalField.__new__(f.NodalField)
+    geom0.values = w["xyz"]
+    dchi = f.NodalField.__new__(f.NodalField)
+    dchi.values, dchi.dofnums, dchi._nfree = None, w["dofnums"], w["nfree"]
+    f.associategeometry(femm, geom0)
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, None, None, dchi)
+    femm.ctx.shell_mass_diag(femm._params(), 3, nfree_only=True)
+    M = femm.ctx.fetch_vector(w["nfree"])
+    Kc = K.to_scipy().tocsr()
+    Kc.sort_indices()
+    rp, cv, nz = (Kc.indptr + 1).astype(np.int64), (Kc.indices + 1).astype(np.int64), Kc.data
+    lib = load_refport()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = w["nfree"]
+    U, V, A, F0 = np.zeros(n), np.zeros(n), np.zeros(n), np.ones(n)
+    ncores = os.cpu_count() or 1
+    nst = 50
+    lib.ref_explicit_steps(C.c_int64(n), P(rp), P(cv), P(nz), P(M), C.c_double(100.0), C.c_double(1e-8), P(F0), None, C.c_int64(5), P(U), P(V), P(A), ncores)
+    t0 = time.perf_counter()
+    lib.ref_explicit_steps(C.c_int64(n), P(rp), P(cv), P(nz), P(M), C.c_double(100.0), C.c_double(1e-8), P(F0), None, C.c_int64(nst), P(U), P(V), P(A), ncores)
+    dt = time.perf_counter() - t0
+    ne = w["conn"].shape[0]
+    return {"value": ne * nst / dt, "unit": "element-steps/s", "cores": ncores, "kind": "port",
+            "sample": f"{ne}-element T3FF strip, {nst} steps, CSR SpMV (Int64 indices) + vector updates, OpenMP row-parallel"}
+
+
+# ---------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,6 +347,10 @@ def main():
     ap.add_argument("--n", type=int, default=1000, help="quads per side (1000 -> 1M elements, the BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (T3FF assembly / explicit loop on C4)")
+    ap.add_argument("--c4-nx", type=int, default=2000, help="C4 strip: nx x nx/2 cells x 2 triangles (2000 -> 4M elements per rank)")
+    ap.add_argument("--expl-steps", type=int, default=200)
+    ap.add_argument("--power-its", type=int, default=30)
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     metric, unit = "element matrices assembled/sec (Q4RS stiffness -> CSC)", "elements/s"
@@ -303,6 +486,13 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = nelem * world / float(te.item())
 
+    # free the C2 buffers before the 4M-element workload
+    del K, cp_p, rv_p, nz_p, k4, k5, k6
+    femm.ctx.close()
+    extras = None
+    if not args.no_extras:
+        extras = explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -339,7 +529,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3, "includes": "H2D mesh+dofs+normals, symbolic phase, numeric phase, D2H colptr+rowval+nzval (Int64/f64)"},
             "gpu_launches": int(launches), "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu,
-            "symbolic_ms": {"first": symbolic_ms, "warm": symbolic_warm_ms}, "nnz": int(nnz)}
+            "symbolic_ms": {"first": symbolic_ms, "warm": symbolic_warm_ms}, "nnz": int(nnz), "other_workloads": extras}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -88,6 +88,39 @@ def c4_t3ff_panel(nx=2000, ny=1000):
                 E=68e9, nu=0.33, rho=2660.0, thickness=1e-3)
 
 
+def c4_strip(rank, world, nx=2000, ny=1000, Ly=1.0):
+    """Element-partitioned C4: the global panel is `world` strips of ny cell rows stacked in y;
+    this returns rank `rank`'s strip in local numbering plus the local free-dof indices (0-based)
+    of the bottom / top interface rows, ordered along x (identical order on both sides)."""
+    Lx, R = 2.0, 5.0
+    xyz, conn = t3block(Lx, Ly, nx, ny)
+    x = xyz[:, 0].copy()
+    xyz[:, 0] = R * np.sin(x / R)
+    xyz[:, 1] += rank * Ly
+    xyz[:, 2] = R * (np.cos(x / R) - 1)
+    tol = 1e-9
+    yl = xyz[:, 1] - rank * Ly
+    b = (x < tol) | (x > Lx - tol)
+    if rank == 0:
+        b |= yl < tol
+    if rank == world - 1:
+        b |= yl > Ly - tol
+    fixed = np.zeros((xyz.shape[0], 6), dtype=bool)
+    fixed[b, :] = True
+    dof, nfree = number_dofs(fixed)
+    bottom = np.arange(0, nx + 1)
+    top = ny * (nx + 1) + np.arange(0, nx + 1)
+
+    def free_dofs(nodes):
+        d = dof[nodes].ravel()
+        return (d[d <= nfree] - 1).astype(np.int64)
+
+    return dict(name=f"C4 T3FF strip {rank}/{world} {nx}x{ny}x2", kind="t3", xyz=np.asfortranarray(xyz), conn=conn, dofnums=dof,
+                nfree=nfree, E=68e9, nu=0.33, rho=2660.0, thickness=1e-3,
+                lo_dofs=free_dofs(bottom) if rank > 0 else np.zeros(0, np.int64),
+                hi_dofs=free_dofs(top) if rank < world - 1 else np.zeros(0, np.int64))
+
+
 def c1_small_t3(n=64):
     """CPU-runnable small case (stand-in for C1's size class): curved T3 panel."""
     w = c4_t3ff_panel(n, n)
