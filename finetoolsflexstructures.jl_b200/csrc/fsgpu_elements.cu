@@ -180,11 +180,10 @@ __device__ __forceinline__ void build_constit_t3(const ShellArgs& P, int64_t e, 
 template <bool COMP, bool SHEARK, class Emit>
 __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, Emit emit) {
   constexpr int NR = SHEARK ? 12 : 8;
-  constexpr int WARP_DBL = NR * 6 * 32 + NR * T3_EPW;
-  extern __shared__ double smem[];  // per warp: strips [NR*6][32] + d [NR][T3_EPW]
+  constexpr int WARP_DBL = NR * 6 * 32;
+  extern __shared__ double smem[];  // per warp: strips [NR*6][32], rows pre-scaled by sqrt(d_s)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sw = smem + (size_t)wib * WARP_DBL;
-  double* sd = sw + NR * 6 * 32;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   const int el = lane / 3, j = lane - 3 * el;
   const int64_t e = warp * T3_EPW + el;
@@ -250,20 +249,24 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
       double bg[8][6];
       gdir = node_strip(g.E, A, gx, gy, bs, P1, P2, bg);
       fold_constit(C, bg);
+      // K = sum_s d_s b_s (x) b_s = sum_s (sqrt(d_s) b_s) (x) (sqrt(d_s) b_s): d_s > 0 for a positive
+      // definite constitutive matrix (a negative pivot raises flag[2] -> FSGPU_ERR_ARG)
       if (set == 0) {
 #pragma unroll
-        for (int s = 0; s < 8; ++s)
+        for (int s = 0; s < 8; ++s) {
+          const double d = constit_d(C, s);
+          if (d < 0.0) atomicExch(P.flag + 2, 1);
+          const double q = sqrt(d);
 #pragma unroll
-          for (int cc = 0; cc < 6; ++cc) sw[(s * 6 + cc) * 32 + lane] = bg[s][cc];
-        if (j == 0)
-          for (int s = 0; s < 8; ++s) sd[s * T3_EPW + el] = constit_d(C, s);
+          for (int cc = 0; cc < 6; ++cc) sw[(s * 6 + cc) * 32 + lane] = q * bg[s][cc];
+        }
       } else {
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < 2; ++s) {
+          const double q = sqrt(constit_d(C, 6 + s));
 #pragma unroll
-          for (int cc = 0; cc < 6; ++cc) sw[((6 + 2 * set + s) * 6 + cc) * 32 + lane] = bg[6 + s][cc];
-        if (j == 0)
-          for (int s = 0; s < 2; ++s) sd[(6 + 2 * set + s) * T3_EPW + el] = constit_d(C, 6 + s);
+          for (int cc = 0; cc < 6; ++cc) sw[((6 + 2 * set + s) * 6 + cc) * 32 + lane] = q * bg[6 + s][cc];
+        }
       }
     }
   }
@@ -289,12 +292,11 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
     const int src = base + i;
 #pragma unroll
     for (int s = 0; s < NR; ++s) {
-      const double d = sd[s * T3_EPW + el];
       double bi[6], bj[6];
 #pragma unroll
       for (int r = 0; r < 6; ++r) bi[r] = sw[(s * 6 + r) * 32 + src];
 #pragma unroll
-      for (int cc = 0; cc < 6; ++cc) bj[cc] = d * sw[(s * 6 + cc) * 32 + lane];
+      for (int cc = 0; cc < 6; ++cc) bj[cc] = sw[(s * 6 + cc) * 32 + lane];
 #pragma unroll
       for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -366,23 +368,17 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
       fold_constit(C, bg);
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
+        const double d = constit_d(C, s);
+        if (d < 0.0) atomicExch(P.flag + 2, 1);
+        const double q = sqrt(d);
 #pragma unroll
-        for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = bg[s][cc];
-        if (jn == 0) sd_[g4 * 8 + s] = constit_d(C, s);
+        for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = q * bg[s][cc];
       }
     } else {
       const double t = P.nthick == 1 ? __ldg(P.thick) : (P.nthick == P.nelem ? __ldg(P.thick + e) : __ldg(P.thick + e * npts + gp));
       const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * hq * hq);
-      const double cm = t * jw, cb = (t * t * t / 12.0) * jw, cs = t * stab * jw;
-      if (jn == 0) {
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          sd_[g4 * 8 + s] = cm * P.hf.dps[s];
-          sd_[g4 * 8 + 3 + s] = cb * P.hf.dps[s];
-        }
-        sd_[g4 * 8 + 6] = cs * P.hf.dts[0];
-        sd_[g4 * 8 + 7] = cs * P.hf.dts[1];
-      }
+      // rows are pre-scaled by sqrt(d_s): sqrt(c) * sqrt(dps) with sqrt(dps), sqrt(dts) from the host
+      const double qm = sqrt(t * jw), qb = sqrt((t * t * t / 12.0) * jw), qs = sqrt(t * stab * jw);
       double* dst = sb_ + (g4 * 8) * 24 + jn * 6;
       {
         double m[3][6];
@@ -391,7 +387,7 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
 #pragma unroll
         for (int s = 0; s < 3; ++s)
 #pragma unroll
-          for (int cc = 0; cc < 6; ++cc) dst[s * 24 + cc] = m[s][cc];
+          for (int cc = 0; cc < 6; ++cc) dst[s * 24 + cc] = (qm * P.hf.sdps[s]) * m[s][cc];
       }
       const M3 G = global_to_nodal(A, g.E);
       double R[2][2], brn[5][2];
@@ -405,7 +401,7 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
 #pragma unroll
         for (int s = 0; s < 3; ++s)
 #pragma unroll
-          for (int cc = 0; cc < 6; ++cc) dst[(3 + s) * 24 + cc] = m[s][cc];
+          for (int cc = 0; cc < 6; ++cc) dst[(3 + s) * 24 + cc] = (qb * P.hf.sdps[s]) * m[s][cc];
       }
       {
         double r6[6], r7[6];
@@ -413,30 +409,27 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
         strip_row(g.E, G, brn, gx, gy, bs[1][0], p1, p2, 4, r7);
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) {
-          dst[6 * 24 + cc] = r6[cc] + P.hf.Lt * r7[cc];
-          dst[7 * 24 + cc] = r7[cc];
+          dst[6 * 24 + cc] = (qs * P.hf.sdts[0]) * (r6[cc] + P.hf.Lt * r7[cc]);
+          dst[7 * 24 + cc] = (qs * P.hf.sdts[1]) * r7[cc];
         }
       }
     }
   } else {
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 0; s < 8; ++s)
 #pragma unroll
       for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = 0.0;
-      if (jn == 0) sd_[g4 * 8 + s] = 0.0;
-    }
   }
 }
 
 __device__ __forceinline__ void q4_product_pass(const double* sb_, const double* sd_, int bi, int bj, double (&acc)[6][6]) {
 #pragma unroll 8
   for (int s = 0; s < 32; ++s) {
-    const double d = sd_[s];
     double vi[6], vj[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) vi[r] = sb_[s * 24 + bi * 6 + r];
 #pragma unroll
-    for (int cc = 0; cc < 6; ++cc) vj[cc] = d * sb_[s * 24 + bj * 6 + cc];
+    for (int cc = 0; cc < 6; ++cc) vj[cc] = sb_[s * 24 + bj * 6 + cc];
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -883,12 +876,19 @@ int shell_args(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp, b
     A.hf.L10 = a[1][0];
     A.hf.L20 = a[2][0];
     A.hf.L21 = a[2][1];
-    for (int i = 0; i < 3; ++i) A.hf.dps[i] = d[i];
+    for (int i = 0; i < 3; ++i) {
+      A.hf.dps[i] = d[i];
+      A.hf.sdps[i] = sqrt(d[i]);
+    }
     double h[2][2] = {{A.Dt[0], A.Dt[1]}, {A.Dt[2], A.Dt[3]}}, dd[2];
     ldlt<2>(h, dd);
     A.hf.Lt = h[1][0];
     A.hf.dts[0] = dd[0];
     A.hf.dts[1] = dd[1];
+    A.hf.sdts[0] = sqrt(dd[0]);
+    A.hf.sdts[1] = sqrt(dd[1]);
+    if (!comp) FS_REQUIRE(d[0] > 0 && d[1] > 0 && d[2] > 0 && dd[0] > 0 && dd[1] > 0, FSGPU_ERR_ARG,
+                          "the plane-stress / transverse-shear moduli are not positive definite");
   }
   A.rho = p->rho;
   A.alpha = p->stab_alpha;
@@ -910,7 +910,7 @@ int launch_t3(fsgpu_ctx* c, const ShellArgs& A, bool comp, bool sheark, Emit em)
   const int64_t nwarps = (A.nelem + T3_EPW - 1) / T3_EPW;
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
-  const size_t sm = (size_t)wpb * ((sheark ? 12 : 8) * 6 * 32 + (sheark ? 12 : 8) * T3_EPW) * sizeof(double);
+  const size_t sm = (size_t)wpb * (sheark ? 12 : 8) * 6 * 32 * sizeof(double);
 #define T3_GO(CO, SK)                                                                                         \
   do {                                                                                                        \
     FS_CUDA(cudaFuncSetAttribute(k_t3_stiffness<CO, SK, Emit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
@@ -981,6 +981,9 @@ int shell_stiffness(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool co
   FS_CUDA(cudaMemcpyAsync(&f, c->flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   FS_CUDA(cudaStreamSynchronize(c->stream));
   FS_REQUIRE(f == 0, FSGPU_ERR_SINGULAR, "Singular metric matrix in _gradN_e!");
+  FS_CUDA(cudaMemcpyAsync(&f, c->flag.p + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  FS_REQUIRE(f == 0, FSGPU_ERR_ARG, "laminate constitutive matrix is not positive definite");
   return finalize_matrix(c);
 }
 

@@ -322,6 +322,7 @@ FS_HD V3 node_strip(const Triad& E, const M3& A, double gx, double gy, const dou
 // L10, L20, L21), Dt (x5/6) = Lt diag(dts) Lt'.
 struct HomogFactors {
   double L10, L20, L21, dps[3], Lt, dts[2];
+  double sdps[3], sdts[2];  // square roots of the pivots
 };
 FS_HD void fold3(const HomogFactors& H, double (&m)[3][6]) {
   for (int c = 0; c < 6; ++c) {
@@ -537,12 +538,39 @@ FS_HD void q4_mitc_bs(const Q4Geom& g, double r, double s, double (&bs)[2][4][3]
     }
 }
 
-// MITC shear entries of ONE node a: out[2][3]
+// MITC shear entries of ONE node a: out[2][3].  Same tying functionals as q4_mitc_bs, restricted
+// to the two edges that meet at node a (r-edges (0,1),(3,2); s-edges (0,3),(1,2)).
 FS_HD void q4_mitc_bs_node(const Q4Geom& g, double r, double s, int a, double (&out)[2][3]) {
-  double bs[2][4][3];
-  q4_mitc_bs(g, r, s, bs);
-  for (int q = 0; q < 2; ++q)
-    for (int c = 0; c < 3; ++c) out[q][c] = a == 0 ? bs[q][0][c] : (a == 1 ? bs[q][1][c] : (a == 2 ? bs[q][2][c] : bs[q][3][c]));
+  const double* X = g.ex;
+  const double* Y = g.ey;
+  const double J11 = (X[0] * (s - 1) - X[1] * (s - 1) + X[2] * (s + 1) - X[3] * (s + 1)) / 4;
+  const double J21 = (Y[0] * (s - 1) - Y[1] * (s - 1) + Y[2] * (s + 1) - Y[3] * (s + 1)) / 4;
+  const double J12 = (X[0] * (r - 1) - X[1] * (r + 1) + X[2] * (r + 1) - X[3] * (r - 1)) / 4;
+  const double J22 = (Y[0] * (r - 1) - Y[1] * (r + 1) + Y[2] * (r + 1) - Y[3] * (r - 1)) / 4;
+  const double iA = 1.0 / sqrt(J11 * J11 + J21 * J21), iB = 1.0 / sqrt(J12 * J12 + J22 * J22);
+  const double ca = J11 * iA, sa = J21 * iA, cb = J12 * iB, sb = J22 * iB;
+  const double i8d = 1.0 / (8 * (J11 * J22 - J12 * J21));
+  const double Ax = X[0] - X[1] - X[2] + X[3], Ay = Y[0] - Y[1] - Y[2] + Y[3];
+  const double Bx = X[0] - X[1] + X[2] - X[3], By = Y[0] - Y[1] + Y[2] - Y[3];
+  const double Cx = X[0] + X[1] - X[2] - X[3], Cy = Y[0] + Y[1] - Y[2] - Y[3];
+  const double SC = sqrt((Cx + r * Bx) * (Cx + r * Bx) + (Cy + r * By) * (Cy + r * By)) * i8d;
+  const double SA = sqrt((Ax + s * Bx) * (Ax + s * Bx) + (Ay + s * By) * (Ay + s * By)) * i8d;
+  // own coordinates and the partners across the r-edge / s-edge
+  const bool lo = a < 2, out03 = (a == 0) || (a == 3);
+  const double xa = a == 0 ? X[0] : (a == 1 ? X[1] : (a == 2 ? X[2] : X[3]));
+  const double ya = a == 0 ? Y[0] : (a == 1 ? Y[1] : (a == 2 ? Y[2] : Y[3]));
+  const double xr = a == 0 ? X[1] : (a == 1 ? X[0] : (a == 2 ? X[3] : X[2]));
+  const double yr = a == 0 ? Y[1] : (a == 1 ? Y[0] : (a == 2 ? Y[3] : Y[2]));
+  const double xs = a == 0 ? X[3] : (a == 1 ? X[2] : (a == 2 ? X[1] : X[0]));
+  const double ys = a == 0 ? Y[3] : (a == 1 ? Y[2] : (a == 2 ? Y[1] : Y[0]));
+  const double wr = SC * (lo ? (1 + s) : (1 - s)), sr = out03 ? 1.0 : -1.0;   // first node of (0,1) is 0, of (3,2) is 3
+  const double ws = SA * (out03 ? (1 + r) : (1 - r)), ss = lo ? 1.0 : -1.0;    // first node of (0,3) is 0, of (1,2) is 1
+  const double crz[3] = {sr * wr / 2, -(sr * (ya - yr)) / 4 * wr, (sr * (xa - xr)) / 4 * wr};
+  const double csz[3] = {ss * ws / 2, -(ss * (ya - ys)) / 4 * ws, (ss * (xa - xs)) / 4 * ws};
+  for (int c = 0; c < 3; ++c) {
+    out[0][c] = -(crz[c] * sb - csz[c] * sa);
+    out[1][c] = -(-crz[c] * cb + csz[c] * ca);
+  }
 }
 
 // ---------------------------------------------------------------------------------
