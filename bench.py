@@ -300,6 +300,89 @@ def explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
     return {"t3ff_assembly_C4": asm, "explicit_C4": expl, "explicit_cpu_baseline": cpu}
 
 
+def extras_c3_c5(args, rank, local_rank, world, stream):
+    """BASELINE configs[2] (T3FFComp laminated cylinder, 2M triangles: stiffness + mass) and configs[4]
+    (corotational beam lattice, 1.01M elements: restoringforce + stiffness + geostiffness = one Newton
+    iteration's assembly).  Numeric phase, device-resident, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    import fsb200
+    from fsb200 import workloads as wl
+
+    f = fsb200.femm
+    out = {}
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        tm = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm.item())
+
+    def field(values=None, dofnums=None, nfree=0):
+        x = f.NodalField.__new__(f.NodalField)
+        x.values, x.dofnums, x._nfree = values, dofnums, nfree
+        return x
+
+    # ---- C3 ----
+    w = wl.c3_t3ffcomp_cylinder(args.c3_n, args.c3_n)
+    mat = f.lamina_material(*w["lamina"])
+    t = w["thickness"]
+    plies = [f.Ply(f"p{k}", mat, t / 4, a) for k, a in enumerate(w["angles"])]
+    layup = f.CompositeLayup("C3", plies, w["csmat"])
+    femm = f.FEMMShellT3FFComp(f.IntegDomain(w["conn"], None, t), layup, device=local_rank)
+    femm.ctx.set_stream(stream.cuda_stream)
+    geom0, dchi = field(w["xyz"]), field(None, w["dofnums"], w["nfree"])
+    femm._sync_mesh(geom0)
+    femm._normals, femm._normal_valid = w["normals"], np.ones(w["xyz"].shape[0], bool)  # radial = layup csys normal
+    femm.ctx.set_normals(femm._normals, femm._normal_valid)
+    femm._associatedgeometry = True
+    femm._startassembly(f.SysmatAssemblerFFBlock(), dchi)
+    femm._sync_stab()
+    p = femm._params()
+    ne = w["conn"].shape[0]
+    ms_k = timed(lambda: femm.ctx.shell_op("t3ffcomp_stiffness", p))
+    kms = femm.ctx.last_kernel_ms
+    ms_m = timed(lambda: femm.ctx.shell_op("t3ffcomp_mass", p))
+    out["t3ffcomp_C3"] = {"workload": f"T3FFComp 4-ply [0/90/90/0] cylinder, {ne} triangles per rank, per-element layup csys: stiffness and lumped mass -> CSC (FFBlock)",
+                          "stiffness_elements_per_s": ne * world / (ms_k * 1e-3), "stiffness_ms": ms_k, "stiffness_kernel_ms": kms,
+                          "mass_elements_per_s": ne * world / (ms_m * 1e-3), "mass_ms": ms_m, "nnz": int(femm.ctx.result_size()[2])}
+    femm.ctx.close()
+
+    # ---- C5 ----
+    w = wl.c5_beam_lattice(args.c5_n)
+    sc = w["sections"]
+    secs = f.FESetL2Beam(sc["A"], sc["I1"], sc["I2"], sc["I3"], sc["J"], sc["A2s"], sc["A3s"], sc["x1x2"])
+    bf = f.FEMMCorotBeam(f.IntegDomain(w["conn"]), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]), secs, device=local_rank)
+    bf.ctx.set_stream(stream.cuda_stream)
+    geom0, dchi = field(w["xyz"]), field(None, w["dofnums"], w["nfree"])
+    bf._sync_mesh(geom0)
+    bf._startassembly(f.SysmatAssemblerFFBlock(), dchi)
+    bf.ctx.set_state(w["u1"], w["Rfield1"])
+    bp = bf._params()
+    ne = w["conn"].shape[0]
+    ms_r = timed(lambda: bf.ctx.beam_op("restoringforce", bp, 1))
+    ms_s = timed(lambda: bf.ctx.beam_op("stiffness", bp))
+    ms_g = timed(lambda: bf.ctx.beam_op("geostiffness", bp))
+    tot = ms_r + ms_s + ms_g
+    out["corotbeam_C5"] = {"workload": f"corotational beam lattice, {ne} elements per rank: restoringforce + stiffness + geostiffness (one Newton iteration's assembly, FFBlock)",
+                           "newton_assemblies_per_s": 1e3 / tot, "elements_per_s": ne * world / (tot * 1e-3), "restoringforce_ms": ms_r,
+                           "stiffness_ms": ms_s, "geostiffness_ms": ms_g, "nnz": int(bf.ctx.result_size()[2])}
+    bf.ctx.close()
+    return out
+
+
 def cpu_explicit(local_rank, nx=400):
     """Reference explicit loop (SpMV + vector updates) on the host cores: K of a nx x nx/2 x 2
     T3FF strip (assembled on the GPU, fetched), oracle C port `ref_explicit_steps`."""
@@ -351,6 +434,8 @@ def main():
     ap.add_argument("--c4-nx", type=int, default=2000, help="C4 strip: nx x nx/2 cells x 2 triangles (2000 -> 4M elements per rank)")
     ap.add_argument("--expl-steps", type=int, default=200)
     ap.add_argument("--power-its", type=int, default=30)
+    ap.add_argument("--c3-n", type=int, default=1000, help="C3 cylinder: n x n x 2 triangles (1000 -> 2M)")
+    ap.add_argument("--c5-n", type=int, default=69, help="C5 lattice cells per side (69 -> 1,014,300 beams)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     metric, unit = "element matrices assembled/sec (Q4RS stiffness -> CSC)", "elements/s"
@@ -492,6 +577,8 @@ def main():
     extras = None
     if not args.no_extras:
         extras = explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak)
+        with torch.cuda.stream(stream):
+            extras.update(extras_c3_c5(args, rank, local_rank, world, stream))
 
     if rank != 0:
         if world > 1:

@@ -126,3 +126,84 @@ def c1_small_t3(n=64):
     w = c4_t3ff_panel(n, n)
     w["name"] = f"small T3FF panel {n}x{n}x2"
     return w
+
+
+def c3_t3ffcomp_cylinder(ncirc=1000, nlen=1000):
+    """C3: laminated cylinder R = 0.1, L = 0.8 (examples/shells/dynamics/homogeneous/explicit/
+    clamp_cyl_expl_examples.jl:59-84), T3block(360 deg, L, ncirc, nlen) wrapped with the seam merged
+    -> 2*ncirc*nlen triangles; 4 plies [0/90/90/0] of t/4, t = R/100, lamina of
+    test/test_composite_shell_statics.jl:21-27, rho = 1500; layup csys = cylindrical (axial, hoop,
+    radial) evaluated per element centroid; one end clamped."""
+    R, L = 0.1, 0.8
+    xy, conn = t3block(2 * np.pi, L, ncirc, nlen)
+    nrow = ncirc + 1
+    # merge the seam: node (i = ncirc, j) -> node (i = 0, j); renumber compactly
+    ids = np.arange(xy.shape[0])
+    i = ids % nrow
+    j = ids // nrow
+    keep = i < ncirc
+    new = np.where(keep, j * ncirc + i, j * ncirc)  # 0-based new ids
+    conn = new[conn - 1] + 1
+    a = xy[keep, 0]
+    z = xy[keep, 1]
+    xyz = np.column_stack([R * np.cos(a), R * np.sin(a), z])
+    fixed = np.zeros((xyz.shape[0], 6), dtype=bool)
+    fixed[z < 1e-12, :] = True
+    dof, nfree = number_dofs(fixed)
+    # cylindrical csys at element centroids: e1 = axial (z), e3 = radial (outward), e2 = e3 x e1
+    c = xyz[conn - 1].mean(axis=1)
+    er = np.column_stack([c[:, 0], c[:, 1], np.zeros(len(c))])
+    er /= np.linalg.norm(er, axis=1)[:, None]
+    ez = np.tile([0.0, 0.0, 1.0], (len(c), 1))
+    e2 = np.cross(er, ez)
+    cs = np.stack([ez, e2, er], axis=2)  # columns = basis vectors
+    # nodal normals are radial for this geometry (the layup csys normal)
+    nrm = np.column_stack([xyz[:, 0], xyz[:, 1], np.zeros(xyz.shape[0])]) / R
+    return dict(name=f"C3 T3FFComp cylinder {ncirc}x{nlen}x2", kind="t3", xyz=np.asfortranarray(xyz), conn=conn, dofnums=dof,
+                nfree=nfree, csmat=cs, normals=np.asfortranarray(nrm), thickness=R / 100,
+                lamina=(1500.0, 133860e6, 7706e6, 0.301, 4306e6, 4306e6, 2760e6), angles=(0.0, 90.0, 90.0, 0.0))
+
+
+def c5_beam_lattice(ncell=69, seed=0):
+    """C5: cubic lattice of ncell^3 cells: (ncell+1)^3 nodes, 3*ncell*(ncell+1)^2 members; rectangular
+    section b = h = 0.02*cell (Bernoulli for x/y members, Timoshenko 5/6 for z members), x1x2 = z for x/y
+    members, x for z members; E = 71240, nu = 0.31, rho = 5e-9 (test/test_beam_modal.jl:19-21); displaced
+    state u1 ~ U(-1,1)*0.01*cell, Rfield1 = exp of rotation vectors ~ U(-1,1)*0.05."""
+    n1 = ncell + 1
+    cell = 1.0
+    g = np.arange(n1)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    nid = (X * n1 + Y) * n1 + Z + 1  # 1-based
+    xyz = np.column_stack([X.ravel(), Y.ravel(), Z.ravel()]).astype(np.float64) * cell
+    cx = np.column_stack([nid[:-1, :, :].ravel(), nid[1:, :, :].ravel()])
+    cy = np.column_stack([nid[:, :-1, :].ravel(), nid[:, 1:, :].ravel()])
+    cz = np.column_stack([nid[:, :, :-1].ravel(), nid[:, :, 1:].ravel()])
+    conn = np.concatenate([cx, cy, cz]).astype(np.int64)
+    ne = conn.shape[0]
+    b = 0.02 * cell
+    A = np.full(ne, b * b)
+    I2 = np.full(ne, b**4 / 12)
+    I3 = I2.copy()
+    I1 = I2 + I3
+    J = np.full(ne, 0.141 * b**4)
+    A2s = np.full(ne, np.inf)
+    A3s = np.full(ne, np.inf)
+    zmem = np.arange(ne) >= len(cx) + len(cy)
+    A2s[zmem] = A3s[zmem] = 5.0 / 6.0 * b * b
+    x1x2 = np.tile([0.0, 0.0, 1.0], (ne, 1))
+    x1x2[zmem] = [1.0, 0.0, 0.0]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u1 = (rng.random((xyz.shape[0], 3)) * 2 - 1) * 0.01 * cell
+    rv = (rng.random((xyz.shape[0], 3)) * 2 - 1) * 0.05
+    th = np.linalg.norm(rv, axis=1)
+    k = rv / th[:, None]
+    K = np.zeros((len(th), 3, 3))
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+    Rm = np.eye(3)[None] + np.sin(th)[:, None, None] * K + (1 - np.cos(th))[:, None, None] * (K @ K)
+    Rf = np.asfortranarray(Rm.transpose(0, 2, 1).reshape(-1, 9))  # each row a column-major 3x3
+    fixed = np.zeros((xyz.shape[0], 6), dtype=bool)
+    fixed[xyz[:, 2] < 1e-12, :] = True
+    dof, nfree = number_dofs(fixed)
+    return dict(name=f"C5 beam lattice {ncell}^3", kind="l2", xyz=np.asfortranarray(xyz), conn=conn, dofnums=dof, nfree=nfree,
+                sections=dict(A=A, I1=I1, I2=I2, I3=I3, J=J, A2s=A2s, A3s=A3s, x1x2=x1x2), u1=np.asfortranarray(u1), Rfield1=Rf,
+                E=71240.0, nu=0.31, rho=5e-9)

@@ -475,3 +475,64 @@ def test_explicit_loop(fs):
     ex2.start(0.0)
     ex2.step(nsteps, fsc)
     assert relfro(ex2.get_state()[0], Uo) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE configs[0]: modal check -- frequencies from GPU-assembled K, M vs oracle-assembled (1e-9)
+# and vs the reference's FV12 goldens (test/test_shell_dynamics.jl:113-133)
+# ---------------------------------------------------------------------------------------
+def test_modal_check_fv12(fs):
+    import scipy.linalg as sla
+
+    f = fs.femm
+    E, nu, rho, th, L, n = 200e3 * 1e6, 0.3, 8000.0, 0.05, 10.0, 8
+    xy, conn = fx.t3block(L, L, n, n)
+    xyz = fx.xyz3(xy - L / 2)
+    femm = f.FEMMShellT3FF(f.IntegDomain(conn, None, th), f.MatDeforElastIso(E, nu, rho), stab_alpha=0.2)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6))).numberdofs()
+    f.associategeometry(femm, geom0)
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    K = f.stiffness(femm, geom0, u0, R0, dchi).to_scipy().toarray()  # default SysmatAssemblerSparseSymm
+    M = f.mass(femm, geom0, dchi).to_scipy().toarray()
+    sh = (0.5 * 2 * np.pi) ** 2
+    fs_g = np.real(np.sqrt((sla.eigh(K + sh * M, M, eigvals_only=True)[:14] - sh).astype(complex))) / (2 * np.pi)
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(E, nu))
+    nrm, val = osh.t3ff_associategeometry(xyz, conn)
+    od = fx.DofField(xyz.shape[0]).numberdofs()
+    dn, na = od.gatherdofnums(conn), od.nalldofs
+    Ko = fx.csc_to_scipy(*fx.assemble_matrix("symm", osh.t3ff_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, th, stab_fun=osh.stab_lyly(0.2)), dn, na), na, na).toarray()
+    Mo = fx.csc_to_scipy(*fx.assemble_matrix("symm", osh.t3ff_mass_elmats(xyz, conn, rho, th), dn, na), na, na).toarray()
+    fs_o = np.real(np.sqrt((sla.eigh(Ko + sh * Mo, Mo, eigvals_only=True)[:14] - sh).astype(complex))) / (2 * np.pi)
+    assert np.max(np.abs(fs_g[6:] - fs_o[6:]) / fs_o[6:]) < 1e-9
+    ref = [1.572130183778014, 2.2424585076387427, 2.8079394352847316, 3.883763676656034, 4.039123204140305, 6.787320617260535, 6.920636670319986, 7.127888889722697]
+    assert np.max(np.abs(fs_g[6:] - ref) / np.array(ref)) < 1e-6  # the reference test's own tolerance
+
+
+def test_full_size_properties_t3(fs):
+    """Size-independent checks on a larger mesh (the oracle is too slow there): symmetry of the
+    assembled K, rigid-body translations in the null space, lumped mass sums to rho*t*area."""
+    f = fs.femm
+    from fsb200 import workloads as wl
+
+    w = wl.c4_t3ff_panel(400, 200)
+    femm = f.FEMMShellT3FF(f.IntegDomain(w["conn"], None, w["thickness"]), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]))
+    geom0 = f.NodalField(w["xyz"])
+    dchi = f.NodalField(np.zeros((w["xyz"].shape[0], 6))).numberdofs()  # free-free
+    f.associategeometry(femm, geom0)
+    K = f.stiffness(femm, f.SysmatAssemblerSparse(), geom0, None, None, dchi).to_scipy()
+    scale = abs(K).max()
+    assert abs(K - K.T).max() < 1e-9 * scale
+    for d in range(3):
+        u = np.zeros(dchi.dofnums.shape)
+        u[:, d] = 1.0
+        v = np.zeros(dchi.dofnums.size)
+        v[dchi.dofnums.ravel() - 1] = u.ravel()
+        assert np.abs(K @ v).max() < 1e-7 * scale
+    femm.ctx.shell_mass_diag(femm._params(), 3, nfree_only=False)
+    Md = femm.ctx.fetch_vector(dchi.dofnums.size)
+    c = w["conn"] - 1
+    X = np.asarray(w["xyz"])
+    area = 0.5 * np.linalg.norm(np.cross(X[c[:, 1]] - X[c[:, 0]], X[c[:, 2]] - X[c[:, 0]]), axis=1).sum()
+    tm = Md[dchi.dofnums[:, 0] - 1].sum()
+    assert abs(tm - w["rho"] * w["thickness"] * area) < 1e-10 * tm
