@@ -94,7 +94,11 @@ _SIGNATURES = {
     "fsgpu_corotbeam_geostiffness": [_vp, _P(BeamParams)],
     "fsgpu_corotbeam_mass": [_vp, _P(BeamParams)],
     "fsgpu_corotbeam_restoringforce": [_vp, _P(BeamParams), _i32],
+    "fsgpu_set_velocity": [_vp, _vp],
+    "fsgpu_corotbeam_gyroscopic": [_vp, _P(BeamParams)],
+    "fsgpu_corotbeam_distribloads": [_vp, _P(BeamParams), _vp, _i64, _i32],
     "fsgpu_shell_mass_diag": [_vp, _P(ShellParams), _i32, _i32],
+    "fsgpu_shell_resultants": [_vp, _P(ShellParams), _i32, _i32, _vp, _vp, _i64, _vp],
     "fsgpu_update_rotation_field": [_vp, _vp, _vp],
     "fsgpu_element_matrices": [_vp, _i32, _i32, _vp, _vp],
     "fsgpu_element_vectors": [_vp, _P(BeamParams), _vp],

@@ -118,6 +118,14 @@ class Context:
         R = f64(Rfield1, "F")
         check(lib.fsgpu_set_state(self._h, ptr(u), ptr(R)))
 
+    def set_velocity(self, v1):
+        v = f64(v1, "F")
+        check(lib.fsgpu_set_velocity(self._h, ptr(v)))
+
+    def beam_distribloads(self, params, force, nfree_only=False):
+        fo = np.ascontiguousarray(np.asarray(force, dtype=np.float64).reshape(-1, 3))
+        check(lib.fsgpu_corotbeam_distribloads(self._h, C.byref(params), ptr(fo), fo.shape[0], 1 if nfree_only else 0))
+
     def set_stream(self, cuda_stream):
         check(lib.fsgpu_set_stream(self._h, C.c_void_p(cuda_stream)))
 
@@ -191,6 +199,18 @@ class Context:
     def element_vectors(self, params):
         out = np.zeros((self.nelem, 12))
         check(lib.fsgpu_element_vectors(self._h, C.byref(params), ptr(out)))
+        return out
+
+    def shell_resultants(self, params, kind, quantity, u, outputcsys=None, npts=1):
+        uu = f64(u, "F")
+        out = np.zeros((self.nelem, npts, 3))
+        if outputcsys is None:
+            cs, ncs = None, 0
+        else:
+            cs = np.asarray(outputcsys, dtype=np.float64).reshape(-1, 3, 3)
+            ncs = cs.shape[0]
+            cs = np.ascontiguousarray(np.transpose(cs, (0, 2, 1)))
+        check(lib.fsgpu_shell_resultants(self._h, C.byref(params), kind, quantity, ptr(uu), ptr(cs), ncs, ptr(out)))
         return out
 
     def update_rotation_field(self, dchi_values):

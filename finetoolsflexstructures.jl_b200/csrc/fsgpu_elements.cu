@@ -676,6 +676,138 @@ __global__ void k_shell_mass_pairs(ShellArgs P, double* __restrict__ dvals) {
   dvals[t * 2 + 1] = rmass;
 }
 
+// =====================================================================================
+// inspectintegpoints, batched: stress resultants per element (T3) / per integration point (Q4)
+// in the output csys (src/FEMMShellT3FFModule.jl:850-962, src/FEMMShellQ4RSModule.jl:1061-1170).
+// strains = (B T_ae T_ga) u_e, i.e. the unfolded global-dof strips applied to the nodal dofs.
+// quant: 1 bending moment, 2 transverse shear, 3 membrane force.  out[(e*npts + gp)*3 + k].
+// =====================================================================================
+__device__ __forceinline__ void resultant_out(const ShellArgs& P, int quant, const double (&st)[8], double t, double stab,
+                                              const Triad& E, const double* ocs, double* out) {
+  double m = 1.0, n = 0.0;
+  double cs[9];
+  if (ocs) {
+    for (int q = 0; q < 9; ++q) cs[q] = ocs[q];
+  } else {  // default: the material csys = element triad itself (isoparametric!)
+    cs[0] = E.e1.x; cs[3] = E.e1.y; cs[6] = E.e1.z;
+    cs[1] = E.e2.x; cs[4] = E.e2.y; cs[7] = E.e2.z;
+    cs[2] = E.e3.x; cs[5] = E.e3.y; cs[8] = E.e3.z;
+  }
+  layup_angle(E, cs, m, n);
+  if (quant == 2) {
+    const double f0 = t * stab * (P.Dt[0] * st[6] + P.Dt[1] * st[7]);
+    const double f1 = t * stab * (P.Dt[2] * st[6] + P.Dt[3] * st[7]);
+    // fo = o2' * frc, o2 = [m n; -n m]
+    out[0] = m * f0 - n * f1;
+    out[1] = n * f0 + m * f1;
+    out[2] = 0.0;
+    return;
+  }
+  const int o = quant == 1 ? 3 : 0;
+  const double c = quant == 1 ? (t * t * t) / 12 : t;
+  double v[3];
+  for (int i = 0; i < 3; ++i) v[i] = c * (P.Dps[i * 3] * st[o] + P.Dps[i * 3 + 1] * st[o + 1] + P.Dps[i * 3 + 2] * st[o + 2]);
+  // mo = o2' [v0 v2; v2 v1] o2
+  const double M00 = v[0], M11 = v[1], M01 = v[2];
+  const double a00 = m * M00 - n * M01, a01 = m * M01 - n * M11;  // (o2' M) row 0
+  const double a10 = n * M00 + m * M01, a11 = n * M01 + m * M11;  // row 1
+  out[0] = a00 * m - a01 * n;
+  out[1] = a10 * n + a11 * m;
+  out[2] = a00 * n + a01 * m;
+}
+
+__global__ void k_t3_resultants(ShellArgs P, const double* __restrict__ u, int quant, const double* __restrict__ ocs, int64_t nocs,
+                                double* __restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= P.nelem) return;
+  const int32_t* cn = P.conn + e * 3;
+  const int nn[3] = {cn[0], cn[1], cn[2]};
+  const T3Geom g = t3_geometry(ld3(P.xyz, nn[0]), ld3(P.xyz, nn[1]), ld3(P.xyz, nn[2]));
+  double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double P1[5][3], P2[5][3];
+  for (int r = 0; r < 5; ++r)
+    for (int k = 0; k < 3; ++k) P1[r][k] = P2[r][k] = 0.0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int l = 0; l < 3; ++l) {
+      const double4 nv = ldg4(P.nrm + nn[l]);
+      const M3 A = nodal_triad(g.E, v3(nv.x, nv.y, nv.z), nv.w != 0.0);
+      double bs[2][3];
+      t3_bs_node(g, l, -1, bs);
+      if (pass == 0) {
+        double p1[5][3], p2[5][3];
+        node_coupling_contrib(A, g.gN[l][0], g.gN[l][1], bs, p1, p2);
+        for (int r = 0; r < 5; ++r)
+          for (int k = 0; k < 3; ++k) {
+            P1[r][k] += p1[r][k];
+            P2[r][k] += p2[r][k];
+          }
+      } else {
+        double bg[8][6];
+        node_strip(g.E, A, g.gN[l][0], g.gN[l][1], bs, P1, P2, bg);
+        const double* ul = u + (int64_t)nn[l] * 6;
+        for (int s = 0; s < 8; ++s)
+          for (int c = 0; c < 6; ++c) st[s] += bg[s][c] * ul[c];
+      }
+    }
+  }
+  const double t = P.nthick == 1 ? P.thick[0] : P.thick[e];
+  const double h = sqrt(2 * g.Ae);
+  const double stab = P.nstab ? P.stabf[e] : t * t / (t * t + P.alpha * h * h);
+  resultant_out(P, quant, st, t, stab, g.E, nocs == 0 ? nullptr : ocs + (nocs == 1 ? 0 : e * 9), out + e * 3);
+}
+
+__global__ void k_q4_resultants(ShellArgs P, const double* __restrict__ u, int quant, const double* __restrict__ ocs, int64_t nocs,
+                                double* __restrict__ out) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int npts = P.rule.npts;
+  if (tid >= P.nelem * npts) return;
+  const int64_t e = tid / npts;
+  const int gp = (int)(tid % npts);
+  const int32_t* cn = P.conn + e * 4;
+  const int nn[4] = {cn[0], cn[1], cn[2], cn[3]};
+  V3 X[4];
+  for (int a = 0; a < 4; ++a) X[a] = ld3(P.xyz, nn[a]);
+  double md = 0.0;
+  for (int a = 1; a < 4; ++a) {
+    const V3 d = X[a] - X[0];
+    md = fmax(md, dot(d, d));
+  }
+  const double hq = sqrt(md);
+  const double xi = P.rule.xi[gp], eta = P.rule.eta[gp];
+  const Q4Geom g = q4_geometry(X, xi, eta);
+  double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double P1[5][3], P2[5][3];
+  for (int r = 0; r < 5; ++r)
+    for (int k = 0; k < 3; ++k) P1[r][k] = P2[r][k] = 0.0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int l = 0; l < 4; ++l) {
+      const double4 nv = ldg4(P.nrm + nn[l]);
+      const M3 A = nodal_triad(g.E, v3(nv.x, nv.y, nv.z), nv.w != 0.0);
+      double bs[2][3];
+      q4_mitc_bs_node(g, xi, eta, l, bs);
+      if (pass == 0) {
+        double p1[5][3], p2[5][3];
+        node_coupling_contrib(A, g.gN[l][0], g.gN[l][1], bs, p1, p2);
+        for (int r = 0; r < 5; ++r)
+          for (int k = 0; k < 3; ++k) {
+            P1[r][k] += p1[r][k];
+            P2[r][k] += p2[r][k];
+          }
+      } else {
+        double bg[8][6];
+        node_strip(g.E, A, g.gN[l][0], g.gN[l][1], bs, P1, P2, bg);
+        const double* ul = u + (int64_t)nn[l] * 6;
+        for (int s = 0; s < 8; ++s)
+          for (int c = 0; c < 6; ++c) st[s] += bg[s][c] * ul[c];
+      }
+    }
+  }
+  const double t = P.nthick == 1 ? P.thick[0] : (P.nthick == P.nelem ? P.thick[e] : P.thick[e * npts + gp]);
+  const double stab = P.nstab ? P.stabf[e] : t * t / (t * t + P.alpha * hq * hq);
+  const double* oc = nocs == 0 ? nullptr : ocs + (nocs == 1 ? 0 : (nocs == P.nelem ? e : tid) * 9);
+  resultant_out(P, quant, st, t, stab, g.E, oc, out + tid * 3);
+}
+
 __global__ void k_element_sizes(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe, int64_t nelem,
                                 double* __restrict__ h) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -701,6 +833,9 @@ __global__ void k_element_sizes(const int32_t* __restrict__ conn, const double4*
 // corotational beam
 // =====================================================================================
 struct BeamArgs {
+  const double* v1;     // [nnodes][6] (gyroscopic only)
+  const double* force;  // distributed load: 3 values or [nelem][3]
+  int64_t nforce;
   const int32_t* conn;
   const double4* xyz;
   const double4* u1;
@@ -757,7 +892,7 @@ __global__ void k_beam_matrix(BeamArgs P, int op, Emit emit) {
     beam_local_geo(PN, k.L1, S);
     for (int p = 0; p < 6; ++p)
       for (int q = 0; q < 6; ++q) Kl[p][q] = S[bI * 6 + p][bJ * 6 + q];
-  } else {
+  } else {  // op 1 (mass) and op 3 (gyroscopic) start from the mass matrix
     double M[12][12];
     beam_local_mass(s, P.rho, k.L0, P.mass_type, M);
     for (int p = 0; p < 6; ++p)
@@ -778,23 +913,65 @@ __global__ void k_beam_matrix(BeamArgs P, int op, Emit emit) {
         }
     }
   const int32_t* cn = P.conn + e * 2;
+  if (op == 3) {
+    // gyroscopic: Ge = Omega~ M - M Omega~ with the block-diagonal skew matrix of the element spin
+    // (src/FEMMCorotBeamModule.jl:934-947); Kg holds the global mass block here
+    const double* vI = P.v1 + (int64_t)cn[0] * 6;
+    const double* vJ = P.v1 + (int64_t)cn[1] * 6;
+    // evel1f[n, a] = sum_k evel1[n, k] Ft[k, a]
+    auto loc = [&](const double* v, int off, int a) { return v[off] * F[0][a] + v[off + 1] * F[1][a] + v[off + 2] * F[2][a]; };
+    const double w1 = (loc(vI, 3, 0) + loc(vJ, 3, 0)) / 2;
+    const double w2 = (loc(vI, 0, 2) - loc(vJ, 0, 2)) / k.L1;
+    const double w3 = (loc(vJ, 0, 1) - loc(vI, 0, 1)) / k.L1;
+    const double Om[3] = {w1 * F[0][0] + w2 * F[0][1] + w3 * F[0][2], w1 * F[1][0] + w2 * F[1][1] + w3 * F[1][2],
+                          w1 * F[2][0] + w2 * F[2][1] + w3 * F[2][2]};
+    const double OS[3][3] = {{0, -Om[2], Om[1]}, {Om[2], 0, -Om[0]}, {-Om[1], Om[0], 0}};
+    double Gg[6][6];
+    for (int sp = 0; sp < 2; ++sp)
+      for (int sq = 0; sq < 2; ++sq)
+        for (int r = 0; r < 3; ++r)
+          for (int cc = 0; cc < 3; ++cc) {
+            double v = 0.0;
+            for (int m = 0; m < 3; ++m) v += OS[r][m] * Kg[sp * 3 + m][sq * 3 + cc] - Kg[sp * 3 + r][sq * 3 + m] * OS[m][cc];
+            Gg[sp * 3 + r][sq * 3 + cc] = v;
+          }
+    emit.block(BlockRef{e, bI, bJ}, emit.cols(cn[bJ]), emit.rows(e, bI, bJ, cn[bI]), Gg);
+    return;
+  }
   emit.block(BlockRef{e, bI, bJ}, emit.cols(cn[bJ]), emit.rows(e, bI, bJ, cn[bI]), Kg);
 }
 // restoring force: elvec = Te (-aN' DN dN)   (src/FEMMCorotBeamModule.jl:1132-1157)
+// mode 0: restoring force; mode 1: consistent nodal loads of a uniform global force per unit length
+// (distribloads_global, src/FEMMCorotBeamModule.jl:1186-1247)
 __global__ void k_beam_restoring(BeamArgs P, const int32_t* __restrict__ dof, double* __restrict__ out, int64_t limit,
-                                 double* __restrict__ elvec_out) {
+                                 double* __restrict__ elvec_out, int mode) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= P.nelem) return;
   BeamSec s;
   BeamKin k;
   beam_load(P, e, s, k);
-  double DN[6], aN[6][12], LF[12];
-  beam_natural_stiffness(P.E, P.G, s, k.L1, DN);
-  beam_aN(k.L1, aN);
-  for (int q = 0; q < 12; ++q) {
-    double v = 0.0;
-    for (int m = 0; m < 6; ++m) v += aN[m][q] * (DN[m] * k.dN[m]);
-    LF[q] = -v;
+  double LF[12];
+  if (mode == 0) {
+    double DN[6], aN[6][12];
+    beam_natural_stiffness(P.E, P.G, s, k.L1, DN);
+    beam_aN(k.L1, aN);
+    for (int q = 0; q < 12; ++q) {
+      double v = 0.0;
+      for (int m = 0; m < 6; ++m) v += aN[m][q] * (DN[m] * k.dN[m]);
+      LF[q] = -v;
+    }
+  } else {
+    const double* fp = P.force + (P.nforce == 1 ? 0 : e * 3);
+    const V3 fg = v3(fp[0], fp[1], fp[2]);
+    const double l1 = dot(k.Ft.e1, fg), l2 = dot(k.Ft.e2, fg), l3 = dot(k.Ft.e3, fg), L0 = k.L0;
+    LF[0] = LF[6] = l1 * L0 / 2;
+    LF[1] = LF[7] = l2 * L0 / 2;
+    LF[2] = LF[8] = l3 * L0 / 2;
+    LF[3] = LF[9] = 0.0;
+    LF[4] = -l3 * L0 * L0 / 12;
+    LF[5] = l2 * L0 * L0 / 12;
+    LF[10] = l3 * L0 * L0 / 12;
+    LF[11] = -l2 * L0 * L0 / 12;
   }
   const double F[3][3] = {{k.Ft.e1.x, k.Ft.e2.x, k.Ft.e3.x}, {k.Ft.e1.y, k.Ft.e2.y, k.Ft.e3.y}, {k.Ft.e1.z, k.Ft.e2.z, k.Ft.e3.z}};
   const int32_t* cn = P.conn + e * 2;
@@ -835,6 +1012,20 @@ __global__ void k_update_rotation(double* __restrict__ R, const double* __restri
   for (int q = 0; q < 9; ++q) Rp[q] = Ro[q];
 }
 
+__global__ void k_cm3_to_rm3(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * 9) return;
+  int64_t m = i / 9;
+  int k = (int)(i % 9), r = k / 3, cc = k % 3;
+  out[i] = in[m * 9 + cc * 3 + r];
+}
+__global__ void k_cols_to_rows(const double* __restrict__ in, double* __restrict__ out, int64_t nrows, int ncols) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nrows * ncols) return;
+  int64_t r = i / ncols;
+  int cc = (int)(i % ncols);
+  out[i] = in[(int64_t)cc * nrows + r];
+}
 __global__ void k_rows_to_colmajor(const double* __restrict__ in, double* __restrict__ out, int64_t nrows, int ncols) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nrows * ncols) return;
@@ -1028,12 +1219,16 @@ int beam_args(fsgpu_ctx* c, const fsgpu_beam_params* p, BeamArgs& B) {
   B.G = p->E / 2 / (1 + p->nu);
   B.rho = p->rho;
   B.mass_type = p->mass_type;
+  B.v1 = c->v1.p;
+  B.force = nullptr;
+  B.nforce = 0;
   return FSGPU_OK;
 }
 int beam_matrix(fsgpu_ctx* c, const fsgpu_beam_params* p, int op) {
   FS_TRY(check_ctx(c));
   BeamArgs B;
   FS_TRY(beam_args(c, p, B));
+  if (op == 3) FS_REQUIRE(c->have_velocity, FSGPU_ERR_STATE, "v1 not set (fsgpu_set_velocity)");
   FS_TRY(begin_matrix(c));
   const int64_t n = B.nelem * 4;
   FS_TRY(time_begin(c));
@@ -1064,6 +1259,47 @@ extern "C" int fsgpu_q4rscomp_mass(fsgpu_ctx* c, const fsgpu_shell_params* p) { 
 extern "C" int fsgpu_corotbeam_stiffness(fsgpu_ctx* c, const fsgpu_beam_params* p) { return beam_matrix(c, p, 0); }
 extern "C" int fsgpu_corotbeam_mass(fsgpu_ctx* c, const fsgpu_beam_params* p) { return beam_matrix(c, p, 1); }
 extern "C" int fsgpu_corotbeam_geostiffness(fsgpu_ctx* c, const fsgpu_beam_params* p) { return beam_matrix(c, p, 2); }
+extern "C" int fsgpu_corotbeam_gyroscopic(fsgpu_ctx* c, const fsgpu_beam_params* p) { return beam_matrix(c, p, 3); }
+
+extern "C" int fsgpu_set_velocity(fsgpu_ctx* c, const double* v1) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->nnpe > 0 && v1, FSGPU_ERR_ARG, "set the mesh first / null v1");
+  const int64_t n = c->nnodes;
+  FS_TRY(c->v1.ensure((size_t)n * 6 + 1));
+  FS_TRY(c->tmp.ensure((size_t)n * 6 * sizeof(double)));
+  FS_TRY(upload(c, c->tmp.p, v1, (size_t)n * 6 * sizeof(double)));
+  k_cols_to_rows<<<grid_for(n * 6, 256), 256, 0, c->stream>>>((const double*)c->tmp.p, c->v1.p, n, 6);
+  c->launches++;
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_velocity = true;
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_corotbeam_distribloads(fsgpu_ctx* c, const fsgpu_beam_params* p, const double* force, int64_t nforce,
+                                            int32_t nfree_only) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->have_dofs, FSGPU_ERR_STATE, "dofnums not set");
+  BeamArgs B;
+  FS_TRY(beam_args(c, p, B));
+  FS_REQUIRE(force && (nforce == 1 || nforce == B.nelem), FSGPU_ERR_ARG, "force must hold 3 or 3*nelem values");
+  DBuf<double> df;
+  FS_TRY(df.ensure((size_t)nforce * 3 + 1));
+  FS_TRY(upload(c, df.p, force, (size_t)nforce * 3 * sizeof(double)));
+  B.force = df.p;
+  B.nforce = nforce;
+  const int64_t n = nfree_only ? c->nfree : c->nall;
+  FS_TRY(c->vec.ensure((size_t)n + 1));
+  FS_CUDA(cudaMemsetAsync(c->vec.p, 0, ((size_t)n + 1) * sizeof(double), c->stream));
+  if (B.nelem > 0) {
+    k_beam_restoring<<<grid_for(B.nelem, 128), 128, 0, c->stream>>>(B, c->dof.p, c->vec.p, n, nullptr, 1);
+    c->launches++;
+  }
+  FS_CUDA(cudaGetLastError());
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_vector = true;
+  c->vlen = n;
+  return FSGPU_OK;
+}
 
 extern "C" int fsgpu_shell_mass_diag(fsgpu_ctx* c, const fsgpu_shell_params* p, int32_t kind, int32_t nfree_only) {
   FS_TRY(check_ctx(c));
@@ -1088,7 +1324,7 @@ extern "C" int fsgpu_corotbeam_restoringforce(fsgpu_ctx* c, const fsgpu_beam_par
   FS_TRY(c->vec.ensure((size_t)n + 1));
   FS_CUDA(cudaMemsetAsync(c->vec.p, 0, ((size_t)n + 1) * sizeof(double), c->stream));
   if (B.nelem > 0) {
-    k_beam_restoring<<<grid_for(B.nelem, 128), 128, 0, c->stream>>>(B, c->dof.p, c->vec.p, n, nullptr);
+    k_beam_restoring<<<grid_for(B.nelem, 128), 128, 0, c->stream>>>(B, c->dof.p, c->vec.p, n, nullptr, 0);
     c->launches++;
   }
   FS_CUDA(cudaGetLastError());
@@ -1106,7 +1342,7 @@ extern "C" int fsgpu_element_vectors(fsgpu_ctx* c, const fsgpu_beam_params* p, d
   DBuf<double> d;
   FS_TRY(d.ensure((size_t)B.nelem * 12 + 1));
   if (B.nelem > 0) {
-    k_beam_restoring<<<grid_for(B.nelem, 128), 128, 0, c->stream>>>(B, nullptr, nullptr, 0, d.p);
+    k_beam_restoring<<<grid_for(B.nelem, 128), 128, 0, c->stream>>>(B, nullptr, nullptr, 0, d.p, 0);
     c->launches++;
   }
   FS_CUDA(cudaGetLastError());
@@ -1129,7 +1365,8 @@ extern "C" int fsgpu_element_matrices(fsgpu_ctx* c, int32_t kind, int32_t op, co
   if (kind == 2) {
     BeamArgs B;
     FS_TRY(beam_args(c, (const fsgpu_beam_params*)params, B));
-    FS_REQUIRE(op >= 0 && op <= 2, FSGPU_ERR_ARG, "beam op must be 0, 1 or 2");
+    FS_REQUIRE(op >= 0 && op <= 3, FSGPU_ERR_ARG, "beam op must be 0 (stiffness), 1 (mass), 2 (geostiffness) or 3 (gyroscopic)");
+    if (op == 3) FS_REQUIRE(c->have_velocity, FSGPU_ERR_STATE, "v1 not set (fsgpu_set_velocity)");
     if (B.nelem > 0) {
       k_beam_matrix<EmitDense><<<grid_for(B.nelem * 4, 128), 128, 0, c->stream>>>(B, op, em);
       c->launches++;
@@ -1169,6 +1406,45 @@ extern "C" int fsgpu_element_matrices(fsgpu_ctx* c, int32_t kind, int32_t op, co
   }
   FS_CUDA(cudaGetLastError());
   FS_TRY(download(c, out, d.p, total * sizeof(double)));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_shell_resultants(fsgpu_ctx* c, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
+                                      const double* outputcsys, int64_t ncs, double* out) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(kind == 3 || kind == 4, FSGPU_ERR_ARG, "resultants are implemented for the homogeneous T3FF (3) and Q4RS (4) shells");
+  FS_REQUIRE(quantity >= 1 && quantity <= 3 && u && out, FSGPU_ERR_ARG, "quantity must be 1 (bending), 2 (shear) or 3 (membrane)");
+  ShellArgs A;
+  FS_TRY(shell_args(c, p, kind, false, true, A));
+  const int npts = kind == 3 ? 1 : c->rule.npts;
+  FS_REQUIRE(ncs == 0 || ncs == 1 || ncs == c->nelem || ncs == c->nelem * npts, FSGPU_ERR_ARG, "bad output csys count");
+  const int64_t n = c->nnodes, nout = c->nelem * npts * 3;
+  DBuf<double> du, dcs, dout, tmpc;
+  FS_TRY(du.ensure((size_t)n * 6 + 1));
+  FS_TRY(c->tmp.ensure((size_t)n * 6 * sizeof(double)));
+  FS_TRY(upload(c, c->tmp.p, u, (size_t)n * 6 * sizeof(double)));
+  k_cols_to_rows<<<grid_for(n * 6, 256), 256, 0, c->stream>>>((const double*)c->tmp.p, du.p, n, 6);
+  c->launches++;
+  if (ncs > 0) {
+    FS_REQUIRE(outputcsys, FSGPU_ERR_ARG, "null output csys");
+    FS_TRY(dcs.ensure((size_t)ncs * 9));
+    FS_TRY(tmpc.ensure((size_t)ncs * 9));
+    FS_TRY(upload(c, tmpc.p, outputcsys, (size_t)ncs * 9 * sizeof(double)));
+    // column-major 3x3 -> row-major
+    k_cm3_to_rm3<<<grid_for(ncs * 9, 256), 256, 0, c->stream>>>(tmpc.p, dcs.p, ncs);
+    c->launches++;
+  }
+  FS_TRY(dout.ensure((size_t)nout + 1));
+  if (c->nelem > 0) {
+    if (kind == 3)
+      k_t3_resultants<<<grid_for(c->nelem, 128), 128, 0, c->stream>>>(A, du.p, quantity, dcs.p, ncs, dout.p);
+    else
+      k_q4_resultants<<<grid_for(c->nelem * npts, 128), 128, 0, c->stream>>>(A, du.p, quantity, dcs.p, ncs, dout.p);
+    c->launches++;
+  }
+  FS_CUDA(cudaGetLastError());
+  FS_TRY(download(c, out, dout.p, (size_t)nout * sizeof(double)));
   FS_CUDA(cudaStreamSynchronize(c->stream));
   return FSGPU_OK;
 }

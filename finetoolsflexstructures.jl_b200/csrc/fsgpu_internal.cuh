@@ -113,6 +113,8 @@ struct fsgpu_ctx {
   bool have_state = false;
   fs::DBuf<double4> u1;         // (ux,uy,uz,0)
   fs::DBuf<double> R1;          // [nnodes][9] each column-major 3x3
+  bool have_velocity = false;
+  fs::DBuf<double> v1;          // [nnodes][6] generalized velocities (gyroscopic)
 
   // symbolic
   int target = -1;

@@ -428,6 +428,51 @@ def geostiffness(femm, *args):
     return femm._matrix_op("geostiffness", *args)
 
 
+_QUANTITY = {"bending": 1, "moment": 1, "bending_moment": 1, "transverse_shear": 2, "transverse": 2, "shear": 2,
+             "membrane_force": 3, "membrane": 3}
+
+
+def inspectintegpoints(femm, geom0, u, felist=None, quantity="moment", outputcsys=None):
+    """Batched `inspectintegpoints` (src/FEMMShellT3FFModule.jl:850-962): instead of calling a host
+    `inspector` closure per point, returns the array of resultants, shape (len(felist), npts, 3),
+    in the output csys (default: the material csys = element triad).  Homogeneous T3FF / Q4RS."""
+    _require_associated(femm)
+    if femm._comp:
+        raise FsgpuError(L.ERR_ARG, "batched resultants are implemented for the homogeneous shells only")
+    femm._sync_mesh(geom0)
+    femm._sync_stab()
+    npts = 1 if femm._nnpe == 3 else femm.ctx.npts
+    out = femm.ctx.shell_resultants(femm._params(), femm._nnpe, _QUANTITY[quantity], u.values, outputcsys, npts)
+    return out if felist is None else out[np.asarray(felist) - 1]
+
+
+def gyroscopic(femm, *args, mass_type=1):
+    """gyroscopic(femm, [assembler,] geom0, u1, Rfield1, v1, dchi; mass_type)
+    (src/FEMMCorotBeamModule.jl:883-952)"""
+    if len(args) == 5:
+        args = (SysmatAssemblerSparseSymm(),) + args
+    assembler, geom0, u1, Rfield1, v1, dchi = args
+    femm._sync_mesh(geom0)
+    femm._startassembly(assembler, dchi)
+    femm.ctx.set_state(u1.values, Rfield1.values)
+    femm.ctx.set_velocity(v1.values)
+    femm.ctx.beam_op("gyroscopic", femm._params(mass_type))
+    return femm.ctx.fetch_matrix()
+
+
+def distribloads_global(femm, *args):
+    """distribloads_global(femm, [assembler,] geom0, u1, Rfield1, dchi, fi); `fi`: force per unit
+    length in global components, (3,) or (nelem, 3) (src/FEMMCorotBeamModule.jl:1186-1247)"""
+    if len(args) == 5:
+        args = (SysvecAssembler(),) + args
+    assembler, geom0, u1, Rfield1, dchi, fi = args
+    femm._sync_mesh(geom0)
+    femm._sync_dofs(dchi)
+    femm.ctx.set_state(u1.values, Rfield1.values)
+    femm.ctx.beam_distribloads(femm._params(), fi, assembler.nfree_only)
+    return femm.ctx.fetch_vector(nfreedofs(dchi) if assembler.nfree_only else nalldofs(dchi))
+
+
 def restoringforce(femm, *args):
     if len(args) == 4:
         args = (SysvecAssembler(),) + args

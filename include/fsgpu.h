@@ -149,16 +149,32 @@ int fsgpu_q4rscomp_mass(fsgpu_ctx* ctx, const fsgpu_shell_params* p);      /* :9
 int fsgpu_corotbeam_stiffness(fsgpu_ctx* ctx, const fsgpu_beam_params* p);    /* src/FEMMCorotBeamModule.jl:972-1023 */
 int fsgpu_corotbeam_geostiffness(fsgpu_ctx* ctx, const fsgpu_beam_params* p); /* :1042-1094 */
 int fsgpu_corotbeam_mass(fsgpu_ctx* ctx, const fsgpu_beam_params* p);         /* :810-868 */
+/* v1.values (nnodes x 6 column-major), needed by gyroscopic only */
+int fsgpu_set_velocity(fsgpu_ctx* ctx, const double* v1);
+int fsgpu_corotbeam_gyroscopic(fsgpu_ctx* ctx, const fsgpu_beam_params* p);   /* :883-952 */
+/* distribloads_global (:1186-1247): uniform force per unit length in global components, 3 values
+ * (nforce = 1) or 3 x nelem (nforce = nelem); result is a vector like restoringforce */
+int fsgpu_corotbeam_distribloads(fsgpu_ctx* ctx, const fsgpu_beam_params* p, const double* force, int64_t nforce,
+                                 int32_t nfree_only);
 /* vector operators; nfree_only != 0: SysvecAssemblerFBlock(nfree), else SysvecAssembler */
 int fsgpu_corotbeam_restoringforce(fsgpu_ctx* ctx, const fsgpu_beam_params* p, int32_t nfree_only); /* :1112-1159 */
 /* lumped shell mass as a diagonal VECTOR over all dofs (the diag(M) the explicit loop uses,
  * examples/.../plate_expl_examples.jl:69-71); kind 3 = T3FF, 4 = Q4RS, 13 = T3FFComp, 14 = Q4RSComp */
 int fsgpu_shell_mass_diag(fsgpu_ctx* ctx, const fsgpu_shell_params* p, int32_t kind, int32_t nfree_only);
+/* inspectintegpoints, batched (no per-point host callback): stress resultants of the homogeneous
+ * T3FF (kind 3, one point per element) / Q4RS (kind 4, one per integration point) shells
+ * (src/FEMMShellT3FFModule.jl:850-962, src/FEMMShellQ4RSModule.jl:1061-1170).
+ * quantity: 1 = bending moments (m11, m22, m12), 2 = transverse shear forces (q1, q2, 0),
+ * 3 = membrane forces (n11, n22, n12), in the output csys: ncs = 0 -> the default material csys
+ * (element triad), else ncs = 1 | nelem | nelem*npts column-major 3x3 matrices.
+ * u: nnodes x 6 column-major (the displacement/rotation field); out: 3 x npts x nelem. */
+int fsgpu_shell_resultants(fsgpu_ctx* ctx, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
+                           const double* outputcsys, int64_t ncs, double* out);
 /* R <- exp(dtheta) R per node (src/RotUtilModule.jl:29-42); dchi_values nnodes x 6 column-major */
 int fsgpu_update_rotation_field(fsgpu_ctx* ctx, const double* dchi_values, double* Rfield_out);
 
 /* parity / debug: raw element matrices, n x n x nelem column-major (Julia elmat per element).
- * op: 0 stiffness, 1 mass, 2 geostiffness (beam).  kind as in fsgpu_shell_mass_diag, 2 = beam. */
+ * op: 0 stiffness, 1 mass, 2 geostiffness (beam), 3 gyroscopic (beam).  kind as in fsgpu_shell_mass_diag, 2 = beam. */
 int fsgpu_element_matrices(fsgpu_ctx* ctx, int32_t kind, int32_t op, const void* params, double* out);
 /* element vectors of restoringforce, 12 x nelem */
 int fsgpu_element_vectors(fsgpu_ctx* ctx, const fsgpu_beam_params* p, double* out);

@@ -246,3 +246,42 @@ def update_rotation_field(Rfield, dchi_values):
     Rd = fx.rotmat3(dchi_values[:, 3:6])
     Ru = np.einsum("nij,njk->nik", Rd, R)
     return Ru.transpose(0, 2, 1).reshape(-1, 9).copy()
+
+
+def beam_gyroscopic_elmats(xyz, conn, u1, Rfield1, v1, sec, rho, mass_type=1):
+    """Quadratic-inertial-term (gyroscopic) matrix Ge = Omega~ M - M Omega~.
+    src/FEMMCorotBeamModule.jl:883-952."""
+    c = np.asarray(conn) - 1
+    x0, x1, RI, RJ = _gather(xyz, conn, u1, Rfield1)
+    L1, Ft, dN, L0 = local_frame_and_def(x0, sec["x1x2"], x1, RI, RJ)
+    MM = local_mass(sec["A"], sec["I1"], sec["I2"], sec["I3"], rho, L0, mass_type)
+    Te = _Te(Ft)
+    M = np.einsum("eij,ejk,elk->eil", Te, MM, Te)
+    ev = v1[c]  # (ne, 2, 6)
+    evf = np.concatenate([np.einsum("enk,ekj->enj", ev[:, :, 0:3], Ft), np.einsum("enk,ekj->enj", ev[:, :, 3:6], Ft)], axis=2)
+    Om = (
+        ((evf[:, 0, 3] + evf[:, 1, 3]) / 2)[:, None] * Ft[:, :, 0]
+        + ((evf[:, 0, 2] - evf[:, 1, 2]) / L1)[:, None] * Ft[:, :, 1]
+        + ((evf[:, 1, 1] - evf[:, 0, 1]) / L1)[:, None] * Ft[:, :, 2]
+    )
+    OS = fx.skewmat(Om)
+    Ot = _Te(OS)
+    return np.einsum("eij,ejk->eik", Ot, M) - np.einsum("eij,ejk->eik", M, Ot)
+
+
+def beam_distribloads_elvecs(xyz, conn, u1, Rfield1, sec, force):
+    """Uniform global force per unit length (3,) or (ne,3) -> element vectors (ne,12).
+    src/FEMMCorotBeamModule.jl:1186-1247."""
+    x0, x1, RI, RJ = _gather(xyz, conn, u1, Rfield1)
+    L1, Ft, dN, L0 = local_frame_and_def(x0, sec["x1x2"], x1, RI, RJ)
+    f = np.broadcast_to(np.asarray(force, dtype=np.float64), (x0.shape[0], 3))
+    Lf = np.einsum("eji,ej->ei", Ft, f)
+    ev = np.zeros((x0.shape[0], 12))
+    for k in range(3):
+        ev[:, k] = Lf[:, k] * L0 / 2
+        ev[:, 6 + k] = Lf[:, k] * L0 / 2
+    ev[:, 4] = -Lf[:, 2] * L0**2 / 12
+    ev[:, 5] = +Lf[:, 1] * L0**2 / 12
+    ev[:, 10] = +Lf[:, 2] * L0**2 / 12
+    ev[:, 11] = -Lf[:, 1] * L0**2 / 12
+    return np.einsum("eij,ej->ei", _Te(Ft), ev)

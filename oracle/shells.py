@@ -732,3 +732,79 @@ def q4rscomp_mass_elmats(xyz, conn, mass_density, moi_density, rule=None):
         tmass += mass_density * Jac * w[j]
         rmass += moi_density * Jac * w[j]
     return lumped_elmats(tmass / 4, rmass / 4, 4)
+
+
+# ---------------------------------------------------------------------------
+# inspectintegpoints: stress resultants per element / integration point
+# ---------------------------------------------------------------------------
+BENDING_MOMENT, TRANSVERSE_SHEAR, MEMBRANE_FORCE = 1, 2, 3
+
+
+def _rotate_out(quant, vec, E_G, ocs):
+    """Rotate a resultant into the output csys (src/FEMMShellT3FFModule.jl:926-956)."""
+    ne = E_G.shape[0]
+    l = E_G if ocs is None else np.broadcast_to(np.asarray(ocs, dtype=np.float64), (ne, 3, 3))
+    m, n = layup2element_angle(E_G, l)
+    o2 = np.zeros((ne, 2, 2))
+    o2[:, 0, 0] = o2[:, 1, 1] = m
+    o2[:, 0, 1] = n
+    o2[:, 1, 0] = -n
+    out = np.zeros((ne, 3))
+    if quant == TRANSVERSE_SHEAR:
+        fo = np.einsum("eji,ej->ei", o2, vec)
+        out[:, 0:2] = fo
+    else:
+        M = np.zeros((ne, 2, 2))
+        M[:, 0, 0], M[:, 1, 1], M[:, 0, 1], M[:, 1, 0] = vec[:, 0], vec[:, 1], vec[:, 2], vec[:, 2]
+        mo = np.einsum("eji,ejk,ekl->eil", o2, M, o2)
+        out[:, 0], out[:, 1], out[:, 2] = mo[:, 0, 0], mo[:, 1, 1], mo[:, 0, 1]
+    return out
+
+
+def t3ff_resultants(xyz, conn, normals, normal_valid, Dps, Dt, thickness, u, quant, ocs=None, stab_fun=None):
+    """(ne,3) resultants of FEMMShellT3FF.  `u` (nnodes,6).  src/FEMMShellT3FFModule.jl:850-962."""
+    stab_fun = stab_fun or stab_lyly(T3_DEFAULT_ALPHA)
+    c = np.asarray(conn) - 1
+    ne = c.shape[0]
+    X = xyz[c]
+    J0, E_G, ec, g, Ae = t3_geometry(X)
+    t = np.broadcast_to(np.asarray(thickness, dtype=np.float64), (ne,))
+    edisp = u[c].reshape(ne, 18)
+    A_Es, nvalid = nodal_triads_e(E_G, normals, normal_valid, conn)
+    edisp_n = np.einsum("eij,ej->ei", transfmat_g_to_a(A_Es, E_G), edisp)
+    edisp_e = np.einsum("eij,ej->ei", transfmat_a_to_e(A_Es, g), edisp_n)
+    if quant == BENDING_MOMENT:
+        vec = ((t**3) / 12)[:, None] * np.einsum("ij,ej->ei", Dps, np.einsum("eij,ej->ei", _bb(g), edisp_e))
+    elif quant == MEMBRANE_FORCE:
+        vec = t[:, None] * np.einsum("ij,ej->ei", Dps, np.einsum("eij,ej->ei", _bm(g), edisp_e))
+    else:
+        h = np.sqrt(2 * Ae)
+        shr = np.einsum("eij,ej->ei", _t3_bs(ec, Ae), edisp_e)
+        vec = (t * stab_fun(t, h))[:, None] * np.einsum("ij,ej->ei", Dt * (5 / 6), shr)
+    return _rotate_out(quant, vec, E_G, ocs)
+
+
+def q4rs_resultants(xyz, conn, normals, normal_valid, Dps, Dt, thickness, u, quant, ocs=None, rule=None, stab_fun=None):
+    """(ne,npts,3) resultants of FEMMShellQ4RS.  src/FEMMShellQ4RSModule.jl:1061-1170."""
+    stab_fun = stab_fun or stab_lyly(Q4_DEFAULT_ALPHA)
+    pc, w = rule if rule is not None else fx.gauss_rule_2x2()
+    c = np.asarray(conn) - 1
+    ne = c.shape[0]
+    X = xyz[c]
+    h = q4_diameter(X)
+    t = np.broadcast_to(np.asarray(thickness, dtype=np.float64), (ne,))
+    edisp = u[c].reshape(ne, 24)
+    out = np.zeros((ne, len(w), 3))
+    for j in range(len(w)):
+        _, _, Jac, E_G, ec, g, T = _q4_gp_setup(X, normals, normal_valid, conn, *pc[j])
+        if quant == BENDING_MOMENT:
+            B = np.einsum("eij,ejk->eik", _bb(g), T)
+            vec = ((t**3) / 12)[:, None] * np.einsum("ij,ej->ei", Dps, np.einsum("eij,ej->ei", B, edisp))
+        elif quant == MEMBRANE_FORCE:
+            B = np.einsum("eij,ejk->eik", _bm(g), T)
+            vec = t[:, None] * np.einsum("ij,ej->ei", Dps, np.einsum("eij,ej->ei", B, edisp))
+        else:
+            B = np.einsum("eij,ejk->eik", _q4_mitc_bs(ec, *pc[j]), T)
+            vec = (t * stab_fun(t, h))[:, None] * np.einsum("ij,ej->ei", Dt * (5 / 6), np.einsum("eij,ej->ei", B, edisp))
+        out[:, j, :] = _rotate_out(quant, vec, E_G, ocs)
+    return out

@@ -140,6 +140,35 @@ def test_element_mass(fs, kind, comp):
 
 
 # ---------------------------------------------------------------------------------------
+# inspectintegpoints (batched resultants)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["t3", "q4"])
+def test_resultants(fs, kind):
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh(kind, n=7)
+    femm = _make_femm(fs, kind, conn)
+    geom0 = f.NodalField(xyz)
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals(kind, xyz, conn)
+    Dps, Dt = _iso()
+    rng = np.random.default_rng(13)
+    u = rng.standard_normal((xyz.shape[0], 6)) * 1e-3
+    th = np.deg2rad(25.0)
+    ocs = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    ofun = osh.t3ff_resultants if kind == "t3" else osh.q4rs_resultants
+    for q, name in ((1, "moment"), (2, "shear"), (3, "membrane")):
+        got = f.inspectintegpoints(femm, geom0, f.NodalField(u), None, name, outputcsys=ocs)
+        ref = ofun(xyz, conn, normals, valid, Dps, Dt, T_, u, q, ocs=ocs)
+        ref = ref.reshape(got.shape)
+        assert relfro(got, ref) < 1e-11, (name, relfro(got, ref))
+        # default output csys = element triad: the reference's sqrt(1 - m^2) with m ~ 1 amplifies
+        # round-off to ~1e-8, so this case is only comparable to that level
+        got = f.inspectintegpoints(femm, geom0, f.NodalField(u), None, name)
+        ref = ofun(xyz, conn, normals, valid, Dps, Dt, T_, u, q).reshape(got.shape)
+        assert relfro(got, ref) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------
 # assembled matrices, every assembler target: pattern bit-exact, values 1e-12
 # ---------------------------------------------------------------------------------------
 ASM = {"sparse": "SysmatAssemblerSparse", "symm": "SysmatAssemblerSparseSymm", "diag": "SysmatAssemblerSparseDiag", "ffblock": "ffblock", "ffblock_diag": "ffblock_diag", "csrsymm": "SysmatAssemblerSparseCSRSymm"}
@@ -322,6 +351,38 @@ def test_beam_operators(fs):
     assert relfro(Fr, fx.assemble_vector(ev, dn, od.nalldofs, od.nfreedofs)) < TOL
     Fa = f.restoringforce(femm, geom0, uf, Rf, dchi)
     assert relfro(Fa, fx.assemble_vector(ev, dn, od.nalldofs)) < TOL
+
+
+def test_beam_gyroscopic_and_distribloads(fs):
+    f, femm, xyz, conn, u1, R1, sec, od, dchi = _beam(fs)
+    geom0, uf, Rf = f.NodalField(xyz), f.NodalField(u1), f.NodalField(R1)
+    rng = np.random.default_rng(21)
+    v1 = rng.standard_normal((xyz.shape[0], 6))
+    dn = od.gatherdofnums(conn)
+    for mt in (1, 3):
+        Ge = obeam.beam_gyroscopic_elmats(xyz, conn, u1, R1, v1, sec, RHOB, mt)
+        femm._sync_mesh(geom0)
+        femm.ctx.set_state(u1, R1)
+        femm.ctx.set_velocity(v1)
+        got = femm.ctx.element_matrices(2, 3, femm._params(mt))
+        # Ge = Omega~ M - M Omega~ is a commutator: the two products nearly cancel, so round-off is
+        # relative to |Omega~ M| (>> |Ge|); measure the error on that scale
+        Me = obeam.beam_mass_elmats(xyz, conn, u1, R1, sec, RHOB, mt)
+        scale = [np.linalg.norm(Me[e]) * np.linalg.norm(v1) for e in range(len(conn))]
+        assert max(np.linalg.norm(got[e] - Ge[e]) / scale[e] for e in range(len(conn))) < TOL
+        assert max(relfro(got[e], Ge[e]) for e in range(len(conn))) < 1e-10
+        G = f.gyroscopic(femm, f.SysmatAssemblerSparse(), geom0, uf, Rf, f.NodalField(v1), dchi, mass_type=mt)
+        cp, rv, nz = fx.assemble_matrix("sparse", Ge, dn, od.nalldofs)
+        assert np.array_equal(G.colptr, cp) and np.array_equal(G.rowval, rv)
+        assert relfro(G.nzval, nz) < 1e-10
+    q = np.array([0.3, -1.2, 2.5])
+    ev = obeam.beam_distribloads_elvecs(xyz, conn, u1, R1, sec, q)
+    F = f.distribloads_global(femm, f.SysvecAssemblerFBlock(), geom0, uf, Rf, dchi, q)
+    assert relfro(F, fx.assemble_vector(ev, dn, od.nalldofs, od.nfreedofs)) < TOL
+    qe = rng.standard_normal((len(conn), 3))
+    ev = obeam.beam_distribloads_elvecs(xyz, conn, u1, R1, sec, qe)
+    F = f.distribloads_global(femm, geom0, uf, Rf, dchi, qe)
+    assert relfro(F, fx.assemble_vector(ev, dn, od.nalldofs)) < TOL
 
 
 def test_update_rotation_field(fs):

@@ -220,3 +220,68 @@ def test_sparse_semantics():
     assert rv.tolist() == [1, 2] and nz.tolist() == [2.0, 3.0]
     cp, rv, nz = fx.assemble_matrix("sparse", el, np.array([[1, 2]]), 2)
     assert len(rv) == 4
+
+
+def test_beam_fast_top_newmark():
+    """test/test_beam_dyn.jl:21-254: implicit Newmark run of the fast top (8 corotational beam elements,
+    1252 steps) -- pins restoringforce, mass, gyroscopic, stiffness, distribloads_global and
+    update_rotation_field! through the 27+27 stored tip coordinates (reference tolerance 1e-3)."""
+    import time
+    bm = obeam
+    E=71240.;nu=0.31;rho=2.7e-9;W=60.;Len=4*W
+    Omega0=313*np.pi; R0=fx.rotmat3(np.array([0.05,0,0])); g=9.81e3; q=np.array([0,0,-g*W*W*rho])
+    maxit=12; dt=min(2*np.pi/abs(Omega0)/10,0.005); tend=0.8; ng=0.5; nb=0.25*(0.5+ng)**2
+    spin=R0@np.array([0,0,Omega0]); X=np.array([[0,0,0],R0@np.array([0,0,Len])]); n=8
+    xyz=np.linspace(0,1,n+1)[:,None]*X[1][None,:]
+    conn=np.column_stack([np.arange(1,n+1),np.arange(2,n+2)])
+    one=np.ones(n); I=W**4/12
+    sec=dict(A=W*W*one,I1=2*I*one,I2=I*one,I3=I*one,J=0.141*W*W**3*one,A2s=np.inf*one,A3s=np.inf*one,x1x2=np.tile([1.,0,0],(n,1)))
+    d=fx.DofField(n+1)
+    for i in (1,2,3): d.setebc([0],i)
+    d.numberdofs(); nf=d.nfreedofs; na=d.nalldofs
+    dn=d.gatherdofnums(conn)
+    u0=np.zeros((n+1,3)); Rf0=bm.initial_Rfield(n+1)
+    v0=np.zeros((n+1,6)); v0[:,3:6]=spin; a0=np.zeros((n+1,6))
+    gather=lambda f: (lambda out: out)(np.array([f.ravel()[np.argsort(d.dofnums.ravel())]]).ravel()[:nf])
+    def gv(f):
+        v=np.zeros(na); v[d.dofnums.ravel()-1]=f.ravel(); return v[:nf]
+    def sc(vec):
+        out=np.zeros((n+1,6)); free=d.dofnums<=nf; out[free]=vec[d.dofnums[free]-1]; return out
+    def ff(elm):
+        return fx.csc_to_scipy(*fx.assemble_matrix('sparse',elm,dn,na),na,na).toarray()[:nf,:nf]
+    tipx=[X[1,0]]; tipy=[X[1,1]]
+    t=0.0; step=0; tt=time.time()
+    while t<=tend:
+        t+=dt
+        u1=u0.copy(); Rf1=Rf0.copy(); stepd=np.zeros((n+1,6))
+        a1=-(1/nb/dt)*v0-(1/2-nb)/nb*a0
+        v1=v0+dt*((1-ng)*a0+ng*a1)
+        v0v=gv(v0); a0v=gv(a0)
+        dchipv=dt*v0v+(dt**2/2*(1-2*nb))*a0v
+        vpv=v0v+(dt*(1-ng))*a0v
+        it=1
+        while True:
+            F=fx.assemble_vector(bm.beam_distribloads_elvecs(xyz,conn,u1,Rf1,sec,q),dn,na)[:nf]
+            Fr=fx.assemble_vector(bm.beam_restoringforce_elvecs(xyz,conn,u1,Rf1,sec,E,nu),dn,na)[:nf]
+            rhs=F+Fr
+            K=ff(bm.beam_stiffness_elmats(xyz,conn,u1,Rf1,sec,E,nu))
+            M=ff(bm.beam_mass_elmats(xyz,conn,u1,Rf1,sec,rho,1))
+            G=ff(bm.beam_gyroscopic_elmats(xyz,conn,u1,Rf1,v1,sec,rho,1))
+            sv=gv(stepd)
+            rhs=rhs+M@((-1/(nb*dt**2))*sv+(1/(nb*dt**2))*dchipv)
+            rhs=rhs+G@((-ng/nb/dt)*sv+(ng/nb/dt)*dchipv-vpv)
+            dch=sc(np.linalg.solve(K+(ng/nb/dt)*G+(1/(nb*dt**2))*M, rhs))
+            u1+=dch[:,:3]; stepd+=dch; v1+=(ng/nb/dt)*dch; a1+=(1/nb/dt**2)*dch
+            Rf1=bm.update_rotation_field(Rf1,dch)
+            if np.abs(dch).max()<1e-13*nf: break
+            if it>maxit: raise RuntimeError('no conv')
+            it+=1
+        u0=u1; Rf0=Rf1; v0=v1; a0=a1
+        if step%50==0:
+            tipx.append(X[1,0]+u1[n,0]); tipy.append(X[1,1]+u1[n,1])
+        step+=1
+    reftipx=[0.0,7.436031085824281e-7,0.11777019275816547,0.8203709506659435,2.241864039281919,3.9679895248072063,5.3454217754301885,5.971372979336259,5.994274006124595,5.998838219173172,6.562336269473291,7.816659235667364,9.346281101346545,10.499101141896105,10.875849911112233,10.628929261212697,10.345322488144156,10.602025422687818,11.529299245601559,12.710964257026657,13.496913529329909,13.492271339298975,12.854269845420365,12.172880227196368,12.025322964890227,12.540504127222404,13.301744975038586]
+    reftipy=[-11.995000624962799,-11.99507329138783,-12.34434321937684,-13.092699071921164,-13.606709453527161,-13.384277801594491,-12.433899377302394,-11.269034682594993,-10.521805428897146,-10.467440913151172,-10.818091285108137,-10.941387824929802,-10.338997425035933,-9.024387391352876,-7.51482956095552,-6.443555337060203,-6.084606620045228,-6.148711597765479,-6.004002866512018,-5.155146068191021,-3.6197117072489498,-1.9179359415572481,-0.6834506841073384,-0.18854220120395482,-0.1419789099985156,0.08825549466116911,0.9953416189668296]
+    assert np.linalg.norm(np.array(reftipx) - tipx) / np.linalg.norm(reftipx) < 1e-5
+    assert np.linalg.norm(np.array(reftipy) - tipy) / np.linalg.norm(reftipy) < 1e-5
+
