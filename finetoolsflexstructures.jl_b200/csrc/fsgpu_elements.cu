@@ -36,6 +36,7 @@ struct BlockRef {
   int i, j;
 };
 struct EmitScatter {  // generic path: per-entry slot map, any dof numbering
+  static constexpr bool kCoop = false;
   double* nz;
   const int32_t* slot;
   int64_t plane;  // nelem * nnpe
@@ -56,7 +57,14 @@ struct EmitScatter {  // generic path: per-entry slot map, any dof numbering
         if (sl[c * 6 + r] >= 0) atomicAdd(nz + sl[c * 6 + r], a[r][c]);
   }
 };
+// Cooperative (warp-transposed) emission: every lane publishes its 6x6 block and its addressing
+// in shared memory, then the warp walks the 32 x 36 entries so that consecutive lanes add
+// consecutive rows of one column -- RED.ADD.F64 requests that share 32 B sectors (measured:
+// 266 G RED/s coalesced vs 194 G RED/s one-lane-per-sector, scripts/micro/red_bench.cu).
+constexpr int COOP_STAGE_LD = 37;                                 // doubles per lane (36 + 1 pad)
+constexpr int COOP_DBL = 32 * COOP_STAGE_LD + (12 * 32) / 2;      // stage + colb[6][32] + rowp[6][32] (ints)
 struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in every column
+  static constexpr bool kCoop = true;
   double* nz;
   const int32_t* pairoff;
   const int32_t* nodeinfo;
@@ -90,6 +98,44 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     r.oB = __ldg(pairoff + ((int64_t)(i * 2 + 1) * nelem + e) * nnpe + j);
     return r;
   }
+  // coop scratch layout (per warp): double stage[32][37]; int colb[6][32]; int rowp[6][32]
+  __device__ __forceinline__ void coop_cols(double* scratch, int lane, const Cols& cb, bool on) const {
+    int* colb = reinterpret_cast<int*>(scratch + 32 * COOP_STAGE_LD);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) colb[c * 32 + lane] = on ? cb.base[c] : -1;
+  }
+  __device__ __forceinline__ void coop_block(double* scratch, int lane, const Rows& rw, bool on, const double (&a)[6][6]) const {
+    double* stage = scratch;
+    const int* colb = reinterpret_cast<const int*>(scratch + 32 * COOP_STAGE_LD);
+    int* rowp = reinterpret_cast<int*>(scratch + 32 * COOP_STAGE_LD) + 6 * 32;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) stage[lane * COOP_STAGE_LD + c * 6 + r] = a[r][c];
+    int ka = 0, kb = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      int p = -1;
+      if ((rw.mA >> r) & 1)
+        p = rw.oA + ka++;
+      else if ((rw.mB >> r) & 1)
+        p = rw.oB + kb++;
+      rowp[r * 32 + lane] = on ? p : -1;
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int it = 0; it < 36; ++it) {
+      const int q = it * 32 + lane;
+      const int o = q / 36;
+      const int k = q - o * 36;
+      const int c = k / 6;
+      const int r = k - c * 6;
+      const int b = colb[c * 32 + o];
+      const int rp = rowp[r * 32 + o];
+      if (b >= 0 && rp >= 0) atomicAdd(nz + b + rp, stage[o * COOP_STAGE_LD + k]);
+    }
+    __syncwarp();
+  }
   __device__ __forceinline__ void block(const BlockRef&, const Cols& cb, const Rows& rw, const double (&a)[6][6]) const {
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
@@ -108,6 +154,7 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   }
 };
 struct EmitDense {
+  static constexpr bool kCoop = false;
   double* out;  // [nelem][n][n] column-major per element
   int nnpe;
   struct Cols {};
@@ -180,8 +227,8 @@ __device__ __forceinline__ void build_constit_t3(const ShellArgs& P, int64_t e, 
 template <bool COMP, bool SHEARK, class Emit>
 __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, Emit emit) {
   constexpr int NR = SHEARK ? 12 : 8;
-  constexpr int WARP_DBL = NR * 6 * 32;
-  extern __shared__ double smem[];  // per warp: strips [NR*6][32], rows pre-scaled by sqrt(d_s)
+  constexpr int WARP_DBL = NR * 6 * 32 + (Emit::kCoop ? COOP_DBL : 0);
+  extern __shared__ double smem[];  // per warp: strips [NR*6][32], rows pre-scaled by sqrt(d_s) (+ coop scratch)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sw = smem + (size_t)wib * WARP_DBL;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -276,12 +323,17 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
   for (int l = 0; l < 3; ++l) ksum += __shfl_sync(full, kpart, (base + l) & 31);
   const double kavg = ksum / 6 * P.drill;
   __syncwarp();
-  if (!active) return;
+  if (!Emit::kCoop && !active) return;
   const int nj = j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]);
-  const typename Emit::Cols ecols = emit.cols(nj);
+  typename Emit::Cols ecols;
   typename Emit::Rows erows[3];
+  if (active) {
+    ecols = emit.cols(nj);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) erows[i] = emit.rows(e, i, j, nn[i]);
+    for (int i = 0; i < 3; ++i) erows[i] = emit.rows(e, i, j, nn[i]);
+  }
+  double* coop = sw + NR * 6 * 32;
+  if constexpr (Emit::kCoop) emit.coop_cols(coop, lane, ecols, active);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     double acc[6][6];
@@ -310,7 +362,10 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * gg[r] * gg[cc];
     }
-    emit.block(BlockRef{e, i, j}, ecols, erows[i], acc);
+    if constexpr (Emit::kCoop)
+      emit.coop_block(coop, lane, erows[i], active, acc);
+    else
+      emit.block(BlockRef{e, i, j}, ecols, erows[i], acc);
   }
 }
 
@@ -1101,7 +1156,7 @@ int launch_t3(fsgpu_ctx* c, const ShellArgs& A, bool comp, bool sheark, Emit em)
   const int64_t nwarps = (A.nelem + T3_EPW - 1) / T3_EPW;
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
-  const size_t sm = (size_t)wpb * (sheark ? 12 : 8) * 6 * 32 * sizeof(double);
+  const size_t sm = (size_t)wpb * ((sheark ? 12 : 8) * 6 * 32 + (Emit::kCoop ? COOP_DBL : 0)) * sizeof(double);
 #define T3_GO(CO, SK)                                                                                         \
   do {                                                                                                        \
     FS_CUDA(cudaFuncSetAttribute(k_t3_stiffness<CO, SK, Emit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
