@@ -61,7 +61,7 @@ struct EmitScatter {  // generic path: per-entry slot map, any dof numbering
 // in shared memory, then the warp walks the 32 x 36 entries so that consecutive lanes add
 // consecutive rows of one column -- RED.ADD.F64 requests that share 32 B sectors (measured:
 // 266 G RED/s coalesced vs 194 G RED/s one-lane-per-sector, scripts/micro/red_bench.cu).
-constexpr int COOP_STAGE_LD = 37;                                 // doubles per lane (36 + 1 pad)
+constexpr int COOP_STAGE_LD = 19;                                 // doubles per lane: half a block (18) + 1 pad
 constexpr int COOP_DBL = 32 * COOP_STAGE_LD + (12 * 32) / 2;      // stage + colb[6][32] + rowp[6][32] (ints)
 struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in every column
   static constexpr bool kCoop = true;
@@ -108,10 +108,6 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     double* stage = scratch;
     const int* colb = reinterpret_cast<const int*>(scratch + 32 * COOP_STAGE_LD);
     int* rowp = reinterpret_cast<int*>(scratch + 32 * COOP_STAGE_LD) + 6 * 32;
-#pragma unroll
-    for (int c = 0; c < 6; ++c)
-#pragma unroll
-      for (int r = 0; r < 6; ++r) stage[lane * COOP_STAGE_LD + c * 6 + r] = a[r][c];
     int ka = 0, kb = 0;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
@@ -122,19 +118,27 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
         p = rw.oB + kb++;
       rowp[r * 32 + lane] = on ? p : -1;
     }
-    __syncwarp();
-#pragma unroll 4
-    for (int it = 0; it < 36; ++it) {
-      const int q = it * 32 + lane;
-      const int o = q / 36;
-      const int k = q - o * 36;
-      const int c = k / 6;
-      const int r = k - c * 6;
-      const int b = colb[c * 32 + o];
-      const int rp = rowp[r * 32 + o];
-      if (b >= 0 && rp >= 0) atomicAdd(nz + b + rp, stage[o * COOP_STAGE_LD + k]);
+    // the block goes out in two halves (columns 0-2, 3-5) to keep the staging area small
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) stage[lane * COOP_STAGE_LD + c * 6 + r] = a[r][half * 3 + c];
+      __syncwarp();
+#pragma unroll 6
+      for (int it = 0; it < 18; ++it) {
+        const int q = it * 32 + lane;
+        const int o = q / 18;
+        const int k = q - o * 18;
+        const int c = k / 6;
+        const int r = k - c * 6;
+        const int b = colb[(half * 3 + c) * 32 + o];
+        const int rp = rowp[r * 32 + o];
+        if (b >= 0 && rp >= 0) atomicAdd(nz + b + rp, stage[o * COOP_STAGE_LD + k]);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   __device__ __forceinline__ void block(const BlockRef&, const Cols& cb, const Rows& rw, const double (&a)[6][6]) const {
 #pragma unroll
@@ -593,7 +597,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
     tsum += __shfl_sync(full, tang, hb + 5 * k);
     cnt += __shfl_sync(full, ok, hb + 5 * k);
   }
-  if (!active) return;
+  if (!Emit::kCoop && !active) return;
   if (P.drill != 0.0 && cnt > 0) {
     const double kavg = tsum / cnt * P.drill;
     if (kavg != 0.0 && ok) {
@@ -601,7 +605,15 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * (nvec[r] * nvec[cc]);
     }
   }
-  emit.block(BlockRef{e, bi, bj}, ecols, erows, acc);
+  if constexpr (Emit::kCoop) {
+    // the strips are dead: reuse the warp's tile as the staging area of the cooperative emission
+    __syncwarp();
+    double* coop = smem + (size_t)wib * 2 * HW_DBL;
+    emit.coop_cols(coop, lane, ecols, active);
+    emit.coop_block(coop, lane, erows, active, acc);
+  } else {
+    emit.block(BlockRef{e, bi, bj}, ecols, erows, acc);
+  }
 }
 
 // =====================================================================================
