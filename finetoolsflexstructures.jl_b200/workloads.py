@@ -207,3 +207,49 @@ def c5_beam_lattice(ncell=69, seed=0):
     return dict(name=f"C5 beam lattice {ncell}^3", kind="l2", xyz=np.asfortranarray(xyz), conn=conn, dofnums=dof, nfree=nfree,
                 sections=dict(A=A, I1=I1, I2=I2, I3=I3, J=J, A2s=A2s, A3s=A3s, x1x2=x1x2), u1=np.asfortranarray(u1), Rfield1=Rf,
                 E=71240.0, nu=0.31, rho=5e-9)
+
+
+def t3refine(xyz, conn):
+    """`T3refine`: split every triangle into four through the edge midpoints (shared per edge)."""
+    c = conn - 1
+    edges = np.concatenate([c[:, [0, 1]], c[:, [1, 2]], c[:, [2, 0]]])
+    es = np.sort(edges, axis=1)
+    key = es[:, 0].astype(np.int64) * (xyz.shape[0] + 1) + es[:, 1]
+    uk, inv = np.unique(key, return_inverse=True)
+    a, b = uk // (xyz.shape[0] + 1), uk % (xyz.shape[0] + 1)
+    mid = 0.5 * (xyz[a] + xyz[b])
+    nn = xyz.shape[0]
+    ne = c.shape[0]
+    m01, m12, m20 = nn + inv[:ne], nn + inv[ne : 2 * ne], nn + inv[2 * ne :]
+    new = np.concatenate([
+        np.column_stack([c[:, 0], m01, m20]),
+        np.column_stack([m01, c[:, 1], m12]),
+        np.column_stack([m20, m12, c[:, 2]]),
+        np.column_stack([m01, m12, m20]),
+    ])
+    return np.vstack([xyz, mid]), new + 1
+
+
+def c1_double_cell_box(nref=4):
+    """C1: double-cell box of examples/shells/dynamics/homogeneous/free_vibration/dcbs_vibration_examples.jl:21-59
+    (6-node cross-section, 7 L2 segments, Q4extrudeL2 with 5 layers, Q4toT3, T3refine x nref; nref = 4 gives
+    17 920 T3 / 8 991 nodes), E = 207 GPa, nu = 0.3, rho = 7850, t = 12.7 mm, clamped at z = 0.  The junction
+    nodes of the middle wall have invalid nodal normals."""
+    L0, B0 = 2.54, 1.27
+    X = np.array([[0.0, 0, 0], [B0, 0, 0], [B0, B0, 0], [B0, 2 * B0, 0], [0, 2 * B0, 0], [0, B0, 0]])
+    segs = np.array([[1, 2], [6, 3], [5, 4], [2, 3], [3, 4], [5, 6], [6, 1]])
+    nl, nn1 = 5, 6
+    xyz = np.vstack([X + np.array([0, 0, k * L0 / nl]) for k in range(nl + 1)])
+    quads = []
+    for k in range(1, nl + 1):
+        for a, b in segs:
+            quads.append([a + (k - 1) * nn1, b + (k - 1) * nn1, b + k * nn1, a + k * nn1])
+    q = np.array(quads, dtype=np.int64)
+    conn = np.concatenate([q[:, [0, 1, 2]], q[:, [0, 2, 3]]])  # Q4toT3
+    for _ in range(nref):
+        xyz, conn = t3refine(xyz, conn)
+    fixed = np.zeros((xyz.shape[0], 6), dtype=bool)
+    fixed[np.abs(xyz[:, 2]) < B0 / max(nref, 1) / 1000, :] = True
+    dof, nfree = number_dofs(fixed)
+    return dict(name=f"C1 double-cell box, T3refine x{nref}", kind="t3", xyz=np.asfortranarray(xyz), conn=conn.astype(np.int64), dofnums=dof,
+                nfree=nfree, fixed=fixed, E=207e9, nu=0.3, rho=7850.0, thickness=12.7e-3)
