@@ -537,15 +537,15 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   const int nbj = bj == 0 ? nn[0] : (bj == 1 ? nn[1] : (bj == 2 ? nn[2] : nn[3]));
   typename Emit::Cols ecols;
   typename Emit::Rows erows;
-  if (active) {
-    ecols = emit.cols(nbj);
-    erows = emit.rows(e, bi, bj, nbi);
-  }
   double acc[6][6];
   const int npts = P.rule.npts;
   if (npts <= 4) {
     q4_setup_pass<COMP>(P, active && g4 < npts, e, g4, g4, jn, X, nvown, hq, gd, sb_, sd_);
     __syncwarp();
+    if (active) {  // addressing data: fetched here so the loads overlap the product loop
+      ecols = emit.cols(nbj);
+      erows = emit.rows(e, bi, bj, nbi);
+    }
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -556,6 +556,10 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
     for (int r = 0; r < 6; ++r)
 #pragma unroll
       for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
+    if (active) {
+      ecols = emit.cols(nbj);
+      erows = emit.rows(e, bi, bj, nbi);
+    }
     for (int chunk = 0; chunk * 4 < npts; ++chunk) {
       const int gp = chunk * 4 + g4;
       q4_setup_pass<COMP>(P, active && gp < npts, e, gp, g4, jn, X, nvown, hq, gd, sb_, sd_);
