@@ -70,6 +70,18 @@ class Context:
         fd = None if fixed_dir is None else f64(fixed_dir)
         check(lib.fsgpu_associategeometry(self._h, float(threshold_angle), ptr(fd), 1 if accumulate else 0))
 
+    def normals_accumulate(self, fixed_dir=None, accumulate=False):
+        fd = None if fixed_dir is None else f64(fixed_dir)
+        p = C.c_void_p()
+        check(lib.fsgpu_normals_accumulate(self._h, ptr(fd), 1 if accumulate else 0, C.byref(p)))
+        return p.value  # device address of the [nnodes][3] sums
+
+    def normals_finish(self, threshold_angle=30.0, fixed_dir=None):
+        fd = None if fixed_dir is None else f64(fixed_dir)
+        p = C.c_void_p()
+        check(lib.fsgpu_normals_finish(self._h, float(threshold_angle), ptr(fd), C.byref(p)))
+        return p.value  # device address of the packed [nnodes][4] normals (4th = valid flag)
+
     def get_normals(self):
         n = np.zeros((self.nnodes, 3), order="F")
         v = np.zeros(self.nnodes, dtype=np.uint8)

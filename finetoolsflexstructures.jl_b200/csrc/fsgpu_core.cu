@@ -377,17 +377,20 @@ __global__ void k_unpack_acc(const double4* __restrict__ nrm, double* __restrict
   acc[3 * i + 2] = v.z;
 }
 
-extern "C" int fsgpu_associategeometry(fsgpu_ctx* c, double threshold_angle_deg, const double* fixed_dir,
-                                       int32_t accumulate) {
+// Split form for element-partitioned runs: (1) accumulate the (weighted) element normals at the
+// nodes of THIS partition, (2) the host sums the interface-node entries across ranks (device
+// pointer handed out), (3) normalise + validity pass; the host then min-combines the validity
+// flags of interface nodes (the 4th component of the packed normals).
+extern "C" int fsgpu_normals_accumulate(fsgpu_ctx* c, const double* fixed_dir, int32_t accumulate, double** dev_sums) {
   FS_TRY(check_ctx(c));
   FS_REQUIRE(c->nnpe == 3 || c->nnpe == 4, FSGPU_ERR_STATE, "associategeometry needs a T3 or Q4 mesh");
   const int64_t n = c->nnodes;
   const bool had = c->associated && c->nrm.p != nullptr;
   FS_TRY(c->nrm.ensure((size_t)n));
-  FS_TRY(c->tmp.ensure((size_t)n * 3 * sizeof(double)));
-  double* acc = (double*)c->tmp.p;
-  const int keep = (accumulate && had) ? 1 : 0;
-  if (keep) {
+  FS_TRY(c->nacc.ensure((size_t)n * 3 + 1));
+  double* acc = c->nacc.p;
+  c->nacc_keep = accumulate && had;
+  if (c->nacc_keep) {
     LAUNCH(c, k_unpack_acc, n, c->nrm.p, acc, n);
   } else {
     FS_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * 3 * sizeof(double), c->stream));
@@ -395,7 +398,17 @@ extern "C" int fsgpu_associategeometry(fsgpu_ctx* c, double threshold_angle_deg,
   const int uf = fixed_dir ? 1 : 0;
   const double fx = uf ? fixed_dir[0] : 0, fy = uf ? fixed_dir[1] : 0, fz = uf ? fixed_dir[2] : 0;
   LAUNCH(c, k_normals_accumulate, c->nelem * c->nnpe, c->conn.p, c->xyz.p, c->nnpe, c->nelem, acc, uf, fx, fy, fz);
-  LAUNCH(c, k_normals_normalize, n, acc, c->nrm.p, n, keep);
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  if (dev_sums) *dev_sums = acc;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_normals_finish(fsgpu_ctx* c, double threshold_angle_deg, const double* fixed_dir, double** dev_normals4) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->nacc.p != nullptr, FSGPU_ERR_STATE, "call fsgpu_normals_accumulate first");
+  const int64_t n = c->nnodes;
+  const int uf = fixed_dir ? 1 : 0;
+  const double fx = uf ? fixed_dir[0] : 0, fy = uf ? fixed_dir[1] : 0, fz = uf ? fixed_dir[2] : 0;
+  LAUNCH(c, k_normals_normalize, n, c->nacc.p, c->nrm.p, n, c->nacc_keep ? 1 : 0);
   const double s = sin(threshold_angle_deg / 180 * M_PI);
   const double ntol = 1 - sqrt(1 - s * s);
   // T3 (homogeneous and composite) checks against the ELEMENT normal (src/FEMMShellT3FFModule.jl:601-611,
@@ -405,7 +418,13 @@ extern "C" int fsgpu_associategeometry(fsgpu_ctx* c, double threshold_angle_deg,
          fy, fz, fixed_in_check);
   FS_CUDA(cudaStreamSynchronize(c->stream));
   c->associated = true;
+  if (dev_normals4) *dev_normals4 = reinterpret_cast<double*>(c->nrm.p);
   return FSGPU_OK;
+}
+extern "C" int fsgpu_associategeometry(fsgpu_ctx* c, double threshold_angle_deg, const double* fixed_dir,
+                                       int32_t accumulate) {
+  FS_TRY(fsgpu_normals_accumulate(c, fixed_dir, accumulate, nullptr));
+  return fsgpu_normals_finish(c, threshold_angle_deg, fixed_dir, nullptr);
 }
 
 extern "C" int fsgpu_set_thickness(fsgpu_ctx* c, const double* t, int64_t n) {

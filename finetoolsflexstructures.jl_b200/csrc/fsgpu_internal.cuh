@@ -95,6 +95,8 @@ struct fsgpu_ctx {
   // normals
   bool associated = false;
   fs::DBuf<double4> nrm;      // (nx, ny, nz, valid ? 1 : 0)
+  fs::DBuf<double> nacc;      // [nnodes][3] unnormalised normal sums (associategeometry, split form)
+  bool nacc_keep = false;
   // thickness / stab factor
   int64_t nthick = 0;
   fs::DBuf<double> thick;

@@ -369,16 +369,36 @@ class _FEMMShell(_FEMMBase):
             self.ctx.set_stab_factor(None)
 
 
-def associategeometry(femm, geom0):
+def associategeometry(femm, geom0, interface=None):
     """`associategeometry!(femm, geom0)`: nodal normals + validity, computed on the device
-    with the default csys (isoparametric) or the layup's cartesian csys for composites."""
+    with the default csys (isoparametric) or the layup's cartesian csys for composites.
+    `interface`: (InterfaceExchange over node indices, device) for element-partitioned runs -- the
+    normal sums and the validity flags of interface nodes are combined across ranks."""
     femm._sync_mesh(geom0)
     fixed = None
     if femm._comp:
         fixed = np.asarray(femm.layup_groups[0][0].csys, dtype=np.float64)[:, 2].copy()
     # homogeneous T3FF never resets its arrays (SURVEY App. B.6)
     accumulate = (femm._nnpe == 3) and (not femm._comp)
-    femm.ctx.associategeometry(femm.threshold_angle, fixed, accumulate)
+    if interface is None:
+        femm.ctx.associategeometry(femm.threshold_angle, fixed, accumulate)
+    else:
+        import torch
+
+        from .partition import DevicePointer, InterfaceExchange
+
+        nn = femm.ctx.nnodes
+        node_links, device = interface  # [(peer, local node indices)], torch device
+        ex3 = InterfaceExchange([(p, (np.asarray(ix)[:, None] * 3 + np.arange(3)[None, :]).ravel()) for p, ix in node_links], device)
+        ex4 = InterfaceExchange([(p, np.asarray(ix) * 4 + 3) for p, ix in node_links], device)
+        sums = torch.as_tensor(DevicePointer(femm.ctx.normals_accumulate(fixed, accumulate), nn * 3), device=device)
+        ex3.exchange_sum(sums)
+        torch.cuda.synchronize()
+        n4 = torch.as_tensor(DevicePointer(femm.ctx.normals_finish(femm.threshold_angle, fixed), nn * 4), device=device)
+        inval = 1.0 - n4  # only the 4th components are exchanged
+        ex4.exchange_sum(inval)
+        n4[3::4] = (inval[3::4] == 0.0).to(torch.float64)
+        torch.cuda.synchronize()
     femm._normals, femm._normal_valid = femm.ctx.get_normals()
     femm._associatedgeometry = True
     return femm

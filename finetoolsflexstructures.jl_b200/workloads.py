@@ -118,7 +118,8 @@ def c4_strip(rank, world, nx=2000, ny=1000, Ly=1.0):
     return dict(name=f"C4 T3FF strip {rank}/{world} {nx}x{ny}x2", kind="t3", xyz=np.asfortranarray(xyz), conn=conn, dofnums=dof,
                 nfree=nfree, E=68e9, nu=0.33, rho=2660.0, thickness=1e-3,
                 lo_dofs=free_dofs(bottom) if rank > 0 else np.zeros(0, np.int64),
-                hi_dofs=free_dofs(top) if rank < world - 1 else np.zeros(0, np.int64))
+                hi_dofs=free_dofs(top) if rank < world - 1 else np.zeros(0, np.int64),
+                lo_nodes=bottom if rank > 0 else np.zeros(0, np.int64), hi_nodes=top if rank < world - 1 else np.zeros(0, np.int64))
 
 
 def c1_small_t3(n=64):

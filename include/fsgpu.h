@@ -107,6 +107,11 @@ int fsgpu_set_normals(fsgpu_ctx* ctx, const double* normals, const uint8_t* vali
  * src/FEMMShellT3FFCompModule.jl:489-543).  accumulate != 0 reproduces the homogeneous T3FF
  * quirk of not resetting the arrays. */
 int fsgpu_associategeometry(fsgpu_ctx* ctx, double threshold_angle_deg, const double* fixed_dir, int32_t accumulate);
+/* the same in two halves for element-partitioned runs: after _accumulate the host sums the
+ * interface-node entries of *dev_sums ([nnodes][3] doubles, device) across ranks; after _finish it
+ * min-combines the validity flags, 4th component of *dev_normals4 ([nnodes][4] doubles, device) */
+int fsgpu_normals_accumulate(fsgpu_ctx* ctx, const double* fixed_dir, int32_t accumulate, double** dev_sums);
+int fsgpu_normals_finish(fsgpu_ctx* ctx, double threshold_angle_deg, const double* fixed_dir, double** dev_normals4);
 int fsgpu_get_normals(fsgpu_ctx* ctx, double* normals, uint8_t* valid);
 /* integdomain.otherdimension evaluated by the host glue: n = 1 (uniform), nelem (T3: at the
  * centroid) or nelem*npts (Q4: per integration point, element-major).

@@ -39,10 +39,16 @@ lo_node = rank * NY * nodes_per_row
 w = wl.c4_strip(rank, world, NX, NY)
 nloc = w["xyz"].shape[0]
 assert np.allclose(wg["xyz"][lo_node : lo_node + nloc], w["xyz"])
-femm, g, d = setup(w, rank)
-femm._normals = fg._normals[lo_node : lo_node + nloc].copy()
-femm._normal_valid = fg._normal_valid[lo_node : lo_node + nloc].copy()
-femm.ctx.set_normals(femm._normals, femm._normal_valid)
+femm = f.FEMMShellT3FF(f.IntegDomain(w["conn"], None, w["thickness"]), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]), device=rank)
+g = f.NodalField.__new__(f.NodalField)
+g.values = w["xyz"]
+d = f.NodalField.__new__(f.NodalField)
+d.values, d.dofnums, d._nfree = None, w["dofnums"], w["nfree"]
+# partitioned associategeometry!: interface-node normal sums and validity flags combined over NCCL
+node_links = pt.strip_links(rank, world, w["lo_nodes"], w["hi_nodes"])
+f.associategeometry(femm, g, interface=(node_links, torch.device("cuda", rank)))
+assert np.abs(femm._normals - fg._normals[lo_node : lo_node + nloc]).max() < 1e-14, "partitioned nodal normals differ from the global ones"
+assert np.array_equal(femm._normal_valid, fg._normal_valid[lo_node : lo_node + nloc])
 
 stream = torch.cuda.Stream()
 femm.ctx.set_stream(stream.cuda_stream)
