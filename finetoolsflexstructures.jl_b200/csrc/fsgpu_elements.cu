@@ -481,18 +481,38 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
   }
 }
 
+// Product pass over the 32 strain rows of one chunk.  Homogeneous shells: the membrane rows
+// (0..2 of every point) have no rotation columns in global dofs, so they only touch the
+// translation 3x3 sub-block (9 instead of 36 FMAs per row); laminates with B-coupling are dense.
+template <bool COMP>
 __device__ __forceinline__ void q4_product_pass(const double* sb_, const double* sd_, int bi, int bj, double (&acc)[6][6]) {
-#pragma unroll 8
-  for (int s = 0; s < 32; ++s) {
-    double vi[6], vj[6];
+#pragma unroll 2
+  for (int g = 0; g < 4; ++g) {
 #pragma unroll
-    for (int r = 0; r < 6; ++r) vi[r] = sb_[s * 24 + bi * 6 + r];
+    for (int q = 0; q < 8; ++q) {
+      const int s = g * 8 + q;
+      if (!COMP && q < 3) {
+        double vi[3], vj[3];
 #pragma unroll
-    for (int cc = 0; cc < 6; ++cc) vj[cc] = sb_[s * 24 + bj * 6 + cc];
+        for (int r = 0; r < 3; ++r) vi[r] = sb_[s * 24 + bi * 6 + r];
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
+        for (int cc = 0; cc < 3; ++cc) vj[cc] = sb_[s * 24 + bj * 6 + cc];
 #pragma unroll
-      for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
+      } else {
+        double vi[6], vj[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) vi[r] = sb_[s * 24 + bi * 6 + r];
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) vj[cc] = sb_[s * 24 + bj * 6 + cc];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
+      }
+    }
   }
 }
 
@@ -550,7 +570,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
     for (int r = 0; r < 6; ++r)
 #pragma unroll
       for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-    q4_product_pass(sb_, sd_, bi, bj, acc);
+    q4_product_pass<COMP>(sb_, sd_, bi, bj, acc);
   } else {
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -564,7 +584,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
       const int gp = chunk * 4 + g4;
       q4_setup_pass<COMP>(P, active && gp < npts, e, gp, g4, jn, X, nvown, hq, gd, sb_, sd_);
       __syncwarp();
-      q4_product_pass(sb_, sd_, bi, bj, acc);
+      q4_product_pass<COMP>(sb_, sd_, bi, bj, acc);
       __syncwarp();
     }
   }
