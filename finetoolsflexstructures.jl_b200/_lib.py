@@ -68,6 +68,8 @@ _SIGNATURES = {
     "fsgpu_sync": [_vp],
     "fsgpu_launch_count": [_vp],
     "fsgpu_last_kernel_ms": [_vp, _P(_dbl)],
+    "fsgpu_set_deterministic": [_vp, C.c_int],
+    "fsgpu_scatter_path": [_vp, _P(C.c_int)],
     "fsgpu_measure_peaks": [_vp, _P(_dbl), _P(_dbl)],
     "fsgpu_set_mesh": [_vp, _i32, _i64, _vp, _i64, _vp],
     "fsgpu_set_dofnums": [_vp, _vp, _i64, _i64],

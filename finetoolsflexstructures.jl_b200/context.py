@@ -154,6 +154,17 @@ class Context:
         check(lib.fsgpu_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def set_deterministic(self, on=True):
+        """Prefer the atomics-free T3 tile kernel (bitwise reproducible); effective at the next symbolic phase."""
+        check(lib.fsgpu_set_deterministic(self._h, 1 if on else 0))
+
+    @property
+    def scatter_path(self):
+        """0 slot map + RED, 1 run-structured + RED, 2 owner-computes tile, -1 none yet."""
+        v = C.c_int(-1)
+        check(lib.fsgpu_scatter_path(self._h, C.byref(v)))
+        return v.value
+
     def measure_peaks(self):
         f, b = C.c_double(), C.c_double()
         check(lib.fsgpu_measure_peaks(self._h, C.byref(f), C.byref(b)))

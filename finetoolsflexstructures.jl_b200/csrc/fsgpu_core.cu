@@ -6,6 +6,7 @@
 
 #include "fsgpu_internal.cuh"
 #include "fsgpu_math.cuh"
+#include "fsgpu_shell.cuh"
 
 namespace fs {
 
@@ -179,6 +180,8 @@ extern "C" int fsgpu_create(fsgpu_ctx** out, int device) {
   FS_CUDA(cudaSetDevice(device));
   fsgpu_ctx* c = new fsgpu_ctx();
   c->device = device;
+  const char* tl = getenv("FSGPU_TILE");
+  c->want_tile = tl && tl[0] && tl[0] != '0';
   *out = c;
   return FSGPU_OK;
 }
@@ -211,6 +214,16 @@ extern "C" int fsgpu_sync(fsgpu_ctx* c) {
   return FSGPU_OK;
 }
 extern "C" int64_t fsgpu_launch_count(fsgpu_ctx* c) { return c ? c->launches : 0; }
+extern "C" int fsgpu_set_deterministic(fsgpu_ctx* c, int on) {
+  FS_REQUIRE(c != nullptr, FSGPU_ERR_ARG, "null context");
+  c->want_tile = on != 0;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_scatter_path(fsgpu_ctx* c, int* path) {
+  FS_REQUIRE(c != nullptr && path != nullptr, FSGPU_ERR_ARG, "null argument");
+  *path = c->last_path;
+  return FSGPU_OK;
+}
 extern "C" int fsgpu_last_kernel_ms(fsgpu_ctx* c, double* ms) {
   FS_TRY(check_ctx(c));
   FS_REQUIRE(ms && c->timed, FSGPU_ERR_STATE, "no timed operator has run");
@@ -771,7 +784,10 @@ extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int6
   // (1) node adjacency from unique (a,b) pairs
   const int64_t npairs = ne * nnpe * nnpe;
   DBuf<uint64_t> keys, keys2;
-  DBuf<int32_t> deg, adjptr, adj, nodecnt;
+  DBuf<int32_t> deg, nodecnt;
+  DBuf<int32_t>& adjptr = c->adjptr;
+  DBuf<int32_t>& adj = c->adj;
+  c->tile_ok = false;
   DBuf<int64_t> colcnt, nsel;
   FS_TRY(keys.ensure((size_t)npairs + 1));
   FS_TRY(keys2.ensure((size_t)npairs + 1));
@@ -857,6 +873,8 @@ extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int6
   c->prows = ti.nr;
   c->pcols = ti.nc;
   c->pnnz = total;
+  // T3 meshes: data of the atomics-free owner-computes tile kernel (fsgpu_tile.cu)
+  FS_TRY(fsk::tile_symbolic(c));
   c->have_matrix = false;
   c->compacted = false;
   if (nrows) *nrows = ti.nr;

@@ -13,9 +13,11 @@
 // All arithmetic is FP64 on the CUDA cores; the scatter uses RED.ADD.F64 into L2.
 #include "fsgpu_internal.cuh"
 #include "fsgpu_math.cuh"
+#include "fsgpu_shell.cuh"
 
 using namespace fs;
 using namespace fsm;
+using namespace fsk;
 
 #ifndef FS_T3_MINB
 #define FS_T3_MINB 3
@@ -175,58 +177,10 @@ struct EmitDense {
   }
 };
 
-struct ShellArgs {
-  const int32_t* conn;
-  const double4* xyz;
-  const double4* nrm;
-  const double* thick;
-  int64_t nthick;
-  const double* stabf;
-  int64_t nstab;
-  int64_t nelem;
-  double Dps[9], Dt[4];  // Dt already x 5/6
-  HomogFactors hf;       // LDL' factors of Dps and Dt (host)
-  double rho, alpha, drill;
-  // composite
-  const double* gdata;
-  const int32_t* gof;
-  const double* cs;
-  int64_t ncs;
-  Rule rule;
-  int32_t* flag;
-};
-
-__device__ __forceinline__ double4 ldg4(const double4* p) {
-  const double2* q = reinterpret_cast<const double2*>(p);
-  const double2 a = __ldg(q), b = __ldg(q + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
-}
-__device__ __forceinline__ V3 ld3(const double4* p, int i) {
-  const double4 v = ldg4(p + i);
-  return v3(v.x, v.y, v.z);
-}
-
 // =====================================================================================
 // T3FF / T3FFComp stiffness
 // =====================================================================================
 constexpr int T3_EPW = 10;  // elements per warp (3 lanes each; lanes 30, 31 idle)
-
-__device__ __forceinline__ void build_constit_t3(const ShellArgs& P, int64_t e, const Triad& E, double Ae, double shear_scale,
-                                                 bool comp, Constit& C) {
-  const double h = sqrt(2 * Ae);
-  if (comp) {
-    const double* gd = P.gdata + (size_t)__ldg(P.gof + e) * 34;
-    const double t = gd[31];
-    const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h * h);
-    double m, n;
-    layup_angle(E, P.cs + (P.ncs == 1 ? 0 : e * 9), m, n);
-    constit_laminate(gd, gd + 9, gd + 18, gd + 27, m, n, Ae, stab * Ae * shear_scale, C);
-  } else {
-    const double t = P.nthick == 1 ? __ldg(P.thick) : __ldg(P.thick + e);
-    const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h * h);
-    constit_homogeneous(P.Dps, P.Dt, t * Ae, (t * t * t) / 12 * Ae, t * stab * Ae * shear_scale, C);
-  }
-}
 
 template <bool COMP, bool SHEARK, class Emit>
 __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, Emit emit) {
@@ -1126,6 +1080,8 @@ __global__ void k_rows_to_colmajor(const double* __restrict__ in, double* __rest
 }
 
 // ---- host helpers -------------------------------------------------------------------
+}  // namespace
+namespace fsk {
 int shell_args(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp, bool need_normals, ShellArgs& A) {
   FS_REQUIRE(p != nullptr, FSGPU_ERR_ARG, "null parameter block");
   FS_REQUIRE(c->nnpe == nnpe, FSGPU_ERR_STATE, "mesh has %d nodes per element, operator needs %d", c->nnpe, nnpe);
@@ -1186,6 +1142,8 @@ int shell_args(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp, b
   return FSGPU_OK;
 }
 
+}  // namespace fsk
+namespace {
 template <class Emit>
 int launch_t3(fsgpu_ctx* c, const ShellArgs& A, bool comp, bool sheark, Emit em) {
   const int wpb = 4;
@@ -1245,9 +1203,19 @@ int shell_stiffness(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool co
   FS_TRY(check_ctx(c));
   ShellArgs A;
   FS_TRY(shell_args(c, p, nnpe, comp, true, A));
-  FS_TRY(begin_matrix(c));
+  const bool tile = nnpe == 3 && c->tile_ok && c->want_tile && p->transv_shear_formulation != 1;
+  if (tile) {
+    // owner-computes: every stored entry is written exactly once, no clearing needed
+    FS_REQUIRE(c->target >= 0, FSGPU_ERR_STATE, "run fsgpu_symbolic before an operator (startassembly!)");
+    c->have_matrix = false;
+  } else {
+    FS_TRY(begin_matrix(c));
+  }
+  c->last_path = tile ? 2 : (c->fast ? 1 : 0);
   FS_TRY(time_begin(c));
-  if (nnpe == 3) {
+  if (tile) {
+    FS_TRY(launch_t3_tile(c, A, comp));
+  } else if (nnpe == 3) {
     if (c->fast)
       FS_TRY(launch_t3(c, A, comp, p->transv_shear_formulation == 1, runs_of(c)));
     else
@@ -1259,13 +1227,11 @@ int shell_stiffness(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool co
       FS_TRY(launch_q4(c, A, comp, scatter_of(c)));
   }
   FS_TRY(time_end(c));
-  int32_t f = 0;
-  FS_CUDA(cudaMemcpyAsync(&f, c->flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  int32_t f[3] = {0, 0, 0};
+  FS_CUDA(cudaMemcpyAsync(f, c->flag.p, sizeof f, cudaMemcpyDeviceToHost, c->stream));
   FS_CUDA(cudaStreamSynchronize(c->stream));
-  FS_REQUIRE(f == 0, FSGPU_ERR_SINGULAR, "Singular metric matrix in _gradN_e!");
-  FS_CUDA(cudaMemcpyAsync(&f, c->flag.p + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  FS_CUDA(cudaStreamSynchronize(c->stream));
-  FS_REQUIRE(f == 0, FSGPU_ERR_ARG, "laminate constitutive matrix is not positive definite");
+  FS_REQUIRE(f[0] == 0, FSGPU_ERR_SINGULAR, "Singular metric matrix in _gradN_e!");
+  FS_REQUIRE(f[2] == 0, FSGPU_ERR_ARG, "laminate constitutive matrix is not positive definite");
   return finalize_matrix(c);
 }
 

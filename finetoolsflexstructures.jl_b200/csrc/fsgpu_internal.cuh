@@ -130,6 +130,18 @@ struct fsgpu_ctx {
   bool fast = false;
   fs::DBuf<int32_t> nodeinfo; // [nnodes] bits 0-5 run-A mask, bits 8-13 run-B mask
   fs::DBuf<int32_t> pairoff;  // [nnpe(i)][2][nelem][nnpe(j)] row offset of node i's runs in node j's columns
+  // node adjacency (kept from the symbolic phase) and the T3 tile (owner-computes) data
+  fs::DBuf<int32_t> adjptr, adj;  // CSR over nodes, neighbours ascending by node id
+  bool tile_ok = false;
+  bool want_tile = false;         // fsgpu_set_deterministic / FSGPU_TILE=1: prefer the tile kernel
+  int last_path = -1;             // scatter path of the last matrix operator (fsgpu_scatter_path)
+  int64_t nadj = 0;               // entries of adj
+  int tile_no = 0, tile_cap = 0;  // owned nodes per tile, max elements per tile
+  int64_t ntiles = 0;
+  fs::DBuf<int32_t> morder;       // [nnodes] node ids in Morton order
+  fs::DBuf<int32_t> nel_ptr, nel; // node -> incident elements (ascending)
+  fs::DBuf<int32_t> tel_ptr, tel; // tile -> elements touching its owned nodes (ascending)
+  fs::DBuf<int32_t> adjoff;       // [2][nadj]: row offsets of the neighbour's runs in the node's columns
   // result matrix
   bool have_matrix = false;
   int64_t rrows = 0, rcols = 0, rnnz = 0;

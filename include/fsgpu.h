@@ -88,6 +88,15 @@ int64_t fsgpu_launch_count(fsgpu_ctx* ctx);
 /* device time (CUDA events on the context's stream) of the element kernel of the last
  * matrix operator -- the number the roofline fraction is computed from */
 int fsgpu_last_kernel_ms(fsgpu_ctx* ctx, double* ms);
+/* on != 0: T3FF / T3FFComp stiffness uses the owner-computes tile kernel when the mesh allows it
+ * (no atomics: bitwise reproducible values, every entry written once; ~2.8x slower than the
+ * RED.ADD scatter on B200).  Takes effect at the next fsgpu_symbolic.  Default: off, or the
+ * environment variable FSGPU_TILE=1 at fsgpu_create.  The reference's serial loop is
+ * deterministic by construction (src/FEMMShellT3FFModule.jl:664-733). */
+int fsgpu_set_deterministic(fsgpu_ctx* ctx, int on);
+/* scatter path of the last shell stiffness operator: 0 = per-entry slot map + RED.ADD,
+ * 1 = run-structured addressing + RED.ADD, 2 = owner-computes tile kernel, -1 = none yet */
+int fsgpu_scatter_path(fsgpu_ctx* ctx, int* path);
 /* measurement support: FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s, read+write) of the
  * device, from micro-kernels -- the FP64 roofline denominator (not in MEASURED_PEAKS.json) */
 int fsgpu_measure_peaks(fsgpu_ctx* ctx, double* fp64_tflops, double* copy_gbs);

@@ -277,6 +277,35 @@ def test_assembled_composite(fs, kind):
     _check_matrix(K, fx.assemble_matrix("sparse", _oracle_K(kind, True, xyz, conn, normals, valid, cs), dn, od.nalldofs), od.nalldofs)
     _check_matrix(M, fx.assemble_matrix("diag", _oracle_M(kind, True, xyz, conn), dn, od.nalldofs), od.nalldofs)
 
+@pytest.mark.parametrize("comp", [False, True])
+def test_deterministic_tile_path(fs, comp):
+    """fsgpu_set_deterministic: the owner-computes T3 kernel (no atomics) gives the same pattern, values
+    within 1e-12 of the oracle, and bitwise identical values from run to run."""
+    xyz, conn = meshes.shell_mesh("t3", n=12)
+    lay, cs = _layup()
+    od = meshes.clamp_edge_dofs(xyz)
+    f = fs.femm
+    femm = _make_femm(fs, "t3", conn, comp, cs)
+    femm.ctx.set_deterministic(True)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs()
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals("t3", xyz, conn, fixed=cs[:, 2] if comp else None)
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    for asm in ("ffblock", "sparse"):
+        K1 = f.stiffness(femm, _assembler(fs, asm), geom0, u0, R0, dchi)
+        assert femm.ctx.scatter_path == 2, "tile kernel did not engage"
+        K2 = f.stiffness(femm, _assembler(fs, asm), geom0, u0, R0, dchi)
+        assert np.array_equal(K1.nzval, K2.nzval), "deterministic path must be bitwise reproducible"
+        Ko = _oracle_K("t3", comp, xyz, conn, normals, valid, cs)
+        n = od.nfreedofs if asm == "ffblock" else od.nalldofs
+        _check_matrix(K1, fx.assemble_matrix(asm, Ko, od.gatherdofnums(conn), od.nalldofs, od.nfreedofs), n)
+    femm.ctx.set_deterministic(False)
+    K3 = f.stiffness(femm, _assembler(fs, "ffblock"), geom0, u0, R0, dchi)
+    assert femm.ctx.scatter_path == 1
+
 
 def test_rcm_like_permuted_numbering(fs):
     """numberdofs!(dchi, perm): dofs of a node are no longer monotone in the node index."""
