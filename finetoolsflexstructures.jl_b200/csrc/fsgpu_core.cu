@@ -726,6 +726,18 @@ __global__ void k_node_info(const int32_t* __restrict__ dof, int64_t nnodes, int
   info[a] = mA | (mB << 8);
   if (bad) atomicExch(flag + 1, 1);
 }
+// nodecol[a*8 + k], k < 6: colptr of the node's k-th dof (-1: not a column); [6] = nodeinfo; [7] = 0
+__global__ void k_node_cols(const int32_t* __restrict__ dof, const int32_t* __restrict__ info,
+                            const int32_t* __restrict__ colptr, int64_t nnodes, int64_t nc, int32_t* __restrict__ nodecol) {
+  int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= nnodes) return;
+  for (int k = 0; k < 6; ++k) {
+    const int32_t d = dof[a * 6 + k];
+    nodecol[a * 8 + k] = d < nc ? colptr[d] : -1;
+  }
+  nodecol[a * 8 + 6] = info[a];
+  nodecol[a * 8 + 7] = 0;
+}
 // pairoff[((i*2 + which) * nelem + e) * nnpe + j]: position, relative to the column start, of the
 // first run-A / run-B row of node i inside any included column of node j (-1: no such entries)
 __global__ void k_pair_offsets(const int32_t* __restrict__ conn, const int32_t* __restrict__ dof,
@@ -783,12 +795,12 @@ extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int6
 
   // (1) node adjacency from unique (a,b) pairs
   const int64_t npairs = ne * nnpe * nnpe;
-  DBuf<uint64_t> keys, keys2;
-  DBuf<int32_t> deg, nodecnt;
+  DBuf<uint64_t>&keys = c->scr_keys, &keys2 = c->scr_keys2;
+  DBuf<int32_t>&deg = c->scr_deg, &nodecnt = c->scr_nodecnt;
   DBuf<int32_t>& adjptr = c->adjptr;
   DBuf<int32_t>& adj = c->adj;
   c->tile_ok = false;
-  DBuf<int64_t> colcnt, nsel;
+  DBuf<int64_t>&colcnt = c->scr_colcnt, &nsel = c->scr_nsel;
   FS_TRY(keys.ensure((size_t)npairs + 1));
   FS_TRY(keys2.ensure((size_t)npairs + 1));
   FS_TRY(nsel.ensure(1));
@@ -826,7 +838,7 @@ extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int6
   FS_TRY(colcnt.ensure((size_t)ti.nc + 1));
   FS_CUDA(cudaMemsetAsync(colcnt.p, 0, ((size_t)ti.nc + 1) * sizeof(int64_t), st));
   LAUNCH(c, k_col_count, nn, c->dof.p, adjptr.p, adj.p, nodecnt.p, nn, ti.nc, ti.diag_only ? 1 : 0, colcnt.p);
-  DBuf<int64_t> colptr64;
+  DBuf<int64_t>& colptr64 = c->scr_colptr64;
   FS_TRY(colptr64.ensure((size_t)ti.nc + 1));
   FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, colcnt.p, colptr64.p, ti.nc + 1, st));
   FS_TRY(c->tmp.ensure(tb));
@@ -857,6 +869,8 @@ extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int6
     FS_TRY(c->pairoff.ensure((size_t)2 * nnpe * nnpe * ne + 1));
     LAUNCH(c, k_pair_offsets, ne * nnpe, c->conn.p, c->dof.p, c->nodeinfo.p, c->colptr.p, c->rowval.p, nnpe, ne, ti.nc,
            c->pairoff.p);
+    FS_TRY(c->nodecol.ensure((size_t)8 * nn + 8));
+    LAUNCH(c, k_node_cols, nn, c->dof.p, c->nodeinfo.p, c->colptr.p, nn, ti.nc, c->nodecol.p);
     c->slot.release();
   } else {
     c->pairoff.release();
@@ -986,17 +1000,18 @@ extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval
     rv = cv2.p;
     nz = v2.p;
   }
-  DBuf<int64_t> wide;
+  DBuf<int64_t>& wide = c->scr_wide;
+  const int64_t chunk = (int64_t)1 << 26;  // widen in chunks to bound the scratch
+  {
+    const int64_t need = nnz < chunk ? nnz : chunk;
+    FS_TRY(wide.ensure((size_t)(need > nc + 1 ? need : nc + 1)));
+  }
   if (colptr) {
-    FS_TRY(wide.ensure((size_t)nc + 1));
     LAUNCH(c, k_i32_plus1_to_i64, nc + 1, cp, wide.p, nc + 1);
     FS_TRY(download(c, colptr, wide.p, ((size_t)nc + 1) * sizeof(int64_t)));
     FS_CUDA(cudaStreamSynchronize(c->stream));
   }
   if (rowval && nnz > 0) {
-    // widen in chunks to bound the scratch
-    const int64_t chunk = (int64_t)1 << 26;
-    FS_TRY(wide.ensure((size_t)(nnz < chunk ? nnz : chunk)));
     for (int64_t o = 0; o < nnz; o += chunk) {
       int64_t m = nnz - o < chunk ? nnz - o : chunk;
       LAUNCH(c, k_i32_plus1_to_i64, m, rv + o, wide.p, m);

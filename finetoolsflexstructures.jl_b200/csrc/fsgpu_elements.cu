@@ -23,7 +23,7 @@ using namespace fsk;
 #define FS_T3_MINB 3
 #endif
 #ifndef FS_Q4_MINB
-#define FS_Q4_MINB 3
+#define FS_Q4_MINB 4
 #endif
 
 namespace {
@@ -75,12 +75,82 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   int64_t nelem;
   int64_t nc;
   int nnpe;
+  const int32_t* nodecol;  // [nnodes][8]: column starts of the node's 6 dofs (-1: not a column), nodeinfo, 0
   struct Cols {
     int base[6];
   };
   struct Rows {
     int mA, mB, oA, oB;
   };
+  // ---- Q4 path: addressing data travels global -> shared with cp.async while the product loop runs (no
+  // registers held, no exposed load latency); layout per warp: colb[32][8], raw[32][4] = (nodeinfo, oA, oB, -)
+  static constexpr int kAddrInts = 32 * 8 + 32 * 4;
+  static constexpr int kStageLd = 38;  // doubles per staged 6x6 block: 36 + 2 (conflict-free reads, 16 B aligned)
+  __device__ __forceinline__ void async_addr(int* addr, int lane, bool on, int nj, int ni, int64_t e, int i, int j) const {
+    int* colb = addr + lane * 8;
+    int* raw = addr + 32 * 8 + lane * 4;
+    if (on) {
+      const unsigned dc = (unsigned)__cvta_generic_to_shared(colb);
+      const unsigned dr = (unsigned)__cvta_generic_to_shared(raw);
+      const int32_t* sc = nodecol + (int64_t)nj * 8;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dc), "l"(sc) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dc + 16), "l"(sc + 4) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr), "l"(nodecol + (int64_t)ni * 8 + 6) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr + 4),
+                   "l"(pairoff + ((int64_t)(i * 2 + 0) * nelem + e) * nnpe + j)
+                   : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr + 8),
+                   "l"(pairoff + ((int64_t)(i * 2 + 1) * nelem + e) * nnpe + j)
+                   : "memory");
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) colb[k] = -1;
+      raw[0] = 0;
+      raw[1] = raw[2] = -1;
+    }
+  }
+  // stage every lane's full block in `scratch` (>= 32*kStageLd doubles + 6*32 ints, the dead strip area), then walk
+  // the 32 x 36 entries with lane = (block sub-index, row): 6 consecutive lanes add 6 consecutive rows of one column
+  __device__ __forceinline__ void coop_emit_full(double* scratch, const int* addr, int lane, const double (&a)[6][6]) const {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    double* stage = scratch;
+    int* rowp = reinterpret_cast<int*>(scratch + 32 * kStageLd);
+    const int* raw = addr + 32 * 8 + lane * 4;
+    const int inf = raw[0], oA = raw[1], oB = raw[2];
+    const int mA = inf & 63, mB = (inf >> 8) & 63;
+    __syncwarp();  // every lane is done with the strips
+    int ka = 0, kb = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      int p = -1;
+      if ((mA >> r) & 1)
+        p = oA >= 0 ? oA + ka++ : -1;
+      else if ((mB >> r) & 1)
+        p = oB >= 0 ? oB + kb++ : -1;
+      rowp[r * 32 + lane] = p;
+    }
+    double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int r = 0; r < 6; r += 2) st2[(c * 6 + r) >> 1] = make_double2(a[r][c], a[r + 1][c]);
+    __syncwarp();
+    const int sub = lane / 6, r = lane - sub * 6;
+#pragma unroll 1
+    for (int g = 0; g < 7; ++g) {
+      const int o = g * 5 + sub;
+      if (lane >= 30 || o >= 32) continue;
+      const int rp = rowp[r * 32 + o];
+      if (rp < 0) continue;
+      const int4 c0 = *reinterpret_cast<const int4*>(addr + o * 8);
+      const int2 c1 = *reinterpret_cast<const int2*>(addr + o * 8 + 4);
+      const int cb[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
+      const double* sv = stage + o * kStageLd + r;
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        if (cb[c] >= 0) atomicAdd(nz + cb[c] + rp, sv[c * 6]);
+    }
+  }
   __device__ __forceinline__ Cols cols(int nj) const {
     Cols c;
     const int32_t* dj = dof + (int64_t)nj * 6;
@@ -335,7 +405,7 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
 // the same point by a shuffle butterfly) and stores it in the half-warp's shared tile.
 template <bool COMP>
 __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64_t e, int gp, int g4, int jn, const V3 (&X)[4],
-                                              const double4& nvown, double hq, const double* gd, double* sb_, double* sd_) {
+                                              const double4& nvown, double hq, const double* gd, double* sb_) {
   const unsigned full = 0xffffffffu;
   double p1[5][3], p2[5][3], bs[2][3];
   Q4Geom g;
@@ -439,7 +509,7 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
 // (0..2 of every point) have no rotation columns in global dofs, so they only touch the
 // translation 3x3 sub-block (9 instead of 36 FMAs per row); laminates with B-coupling are dense.
 template <bool COMP>
-__device__ __forceinline__ void q4_product_pass(const double* sb_, const double* sd_, int bi, int bj, double (&acc)[6][6]) {
+__device__ __forceinline__ void q4_product_pass(const double* sb_, int bi, int bj, double (&acc)[6][6]) {
 #pragma unroll 2
   for (int g = 0; g < 4; ++g) {
 #pragma unroll
@@ -470,15 +540,20 @@ __device__ __forceinline__ void q4_product_pass(const double* sb_, const double*
   }
 }
 
+constexpr int Q4_WARP_DBL = 2 * 32 * 24 + (32 * 8 + 32 * 4) / 2;  // strips + addressing area (doubles)
+
 template <bool COMP, class Emit>
 __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, Emit emit) {
-  // per half-warp: b[32][24] + d[32]
+  // per warp: strips b[32][24] of its two elements (one per half-warp) + the addressing area of the
+  // cooperative emission (EmitRuns::kAddrInts ints)
   extern __shared__ double smem[];
-  constexpr int HW_DBL = 32 * 24 + 32;
+  constexpr int HW_DBL = 32 * 24;
+  constexpr int WARP_DBL = Q4_WARP_DBL;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int half = lane >> 4, l16 = lane & 15;
-  double* sb_ = smem + ((size_t)wib * 2 + half) * HW_DBL;
-  double* sd_ = sb_ + 32 * 24;
+  double* wbase = smem + (size_t)wib * WARP_DBL;
+  double* sb_ = wbase + half * HW_DBL;
+  int* addr = reinterpret_cast<int*>(wbase + 2 * HW_DBL);
   const int64_t e = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wib) * 2 + half;
   const bool active = e < P.nelem;
   const int g4 = l16 >> 2, jn = l16 & 3;  // setup role
@@ -514,9 +589,12 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   double acc[6][6];
   const int npts = P.rule.npts;
   if (npts <= 4) {
-    q4_setup_pass<COMP>(P, active && g4 < npts, e, g4, g4, jn, X, nvown, hq, gd, sb_, sd_);
+    q4_setup_pass<COMP>(P, active && g4 < npts, e, g4, g4, jn, X, nvown, hq, gd, sb_);
     __syncwarp();
-    if (active) {  // addressing data: fetched here so the loads overlap the product loop
+    // addressing data: requested here so the loads overlap the product loop
+    if constexpr (Emit::kCoop) {
+      emit.async_addr(addr, lane, active, nbj, nbi, e, bi, bj);
+    } else if (active) {
       ecols = emit.cols(nbj);
       erows = emit.rows(e, bi, bj, nbi);
     }
@@ -524,21 +602,23 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
     for (int r = 0; r < 6; ++r)
 #pragma unroll
       for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-    q4_product_pass<COMP>(sb_, sd_, bi, bj, acc);
+    q4_product_pass<COMP>(sb_, bi, bj, acc);
   } else {
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
       for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-    if (active) {
+    if constexpr (Emit::kCoop) {
+      emit.async_addr(addr, lane, active, nbj, nbi, e, bi, bj);
+    } else if (active) {
       ecols = emit.cols(nbj);
       erows = emit.rows(e, bi, bj, nbi);
     }
     for (int chunk = 0; chunk * 4 < npts; ++chunk) {
       const int gp = chunk * 4 + g4;
-      q4_setup_pass<COMP>(P, active && gp < npts, e, gp, g4, jn, X, nvown, hq, gd, sb_, sd_);
+      q4_setup_pass<COMP>(P, active && gp < npts, e, gp, g4, jn, X, nvown, hq, gd, sb_);
       __syncwarp();
-      q4_product_pass<COMP>(sb_, sd_, bi, bj, acc);
+      q4_product_pass<COMP>(sb_, bi, bj, acc);
       __syncwarp();
     }
   }
@@ -584,11 +664,8 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
     }
   }
   if constexpr (Emit::kCoop) {
-    // the strips are dead: reuse the warp's tile as the staging area of the cooperative emission
-    __syncwarp();
-    double* coop = smem + (size_t)wib * 2 * HW_DBL;
-    emit.coop_cols(coop, lane, ecols, active);
-    emit.coop_block(coop, lane, erows, active, acc);
+    // the strips are dead: the warp's tile becomes the staging area of the cooperative emission
+    emit.coop_emit_full(wbase, addr, lane, acc);
   } else {
     emit.block(BlockRef{e, bi, bj}, ecols, erows, acc);
   }
@@ -1175,7 +1252,7 @@ int launch_q4(fsgpu_ctx* c, const ShellArgs& A, bool comp, Emit em) {
   const int64_t nwarps = (A.nelem + 1) / 2;
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
-  const size_t sm = (size_t)wpb * 2 * (32 * 24 + 32) * sizeof(double);
+  const size_t sm = (size_t)wpb * Q4_WARP_DBL * sizeof(double);
   if (comp) {
     FS_CUDA(cudaFuncSetAttribute(k_q4_stiffness<true, Emit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_q4_stiffness<true, Emit><<<grid, wpb * 32, sm, c->stream>>>(A, em);
@@ -1196,7 +1273,7 @@ int begin_matrix(fsgpu_ctx* c) {
 }
 EmitScatter scatter_of(fsgpu_ctx* c) { return EmitScatter{c->nzval.p, c->slot.p, c->nelem * c->nnpe, c->nnpe}; }
 EmitRuns runs_of(fsgpu_ctx* c) {
-  return EmitRuns{c->nzval.p, c->pairoff.p, c->nodeinfo.p, c->dof.p, c->colptr.p, c->nelem, c->pcols, c->nnpe};
+  return EmitRuns{c->nzval.p, c->pairoff.p, c->nodeinfo.p, c->dof.p, c->colptr.p, c->nelem, c->pcols, c->nnpe, c->nodecol.p};
 }
 
 int shell_stiffness(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp) {

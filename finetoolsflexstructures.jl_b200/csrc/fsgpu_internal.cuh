@@ -128,10 +128,16 @@ struct fsgpu_ctx {
   // run-structured addressing (fast path): the included dofs of every node form <= 2
   // consecutive ascending runs (free / prescribed), as FinEtools' numberdofs! produces
   bool fast = false;
+  fs::DBuf<int32_t> nodecol;  // fast path: [nnodes][8] column starts of the node's dofs (-1 none), nodeinfo, 0
   fs::DBuf<int32_t> nodeinfo; // [nnodes] bits 0-5 run-A mask, bits 8-13 run-B mask
   fs::DBuf<int32_t> pairoff;  // [nnpe(i)][2][nelem][nnpe(j)] row offset of node i's runs in node j's columns
   // node adjacency (kept from the symbolic phase) and the T3 tile (owner-computes) data
   fs::DBuf<int32_t> adjptr, adj;  // CSR over nodes, neighbours ascending by node id
+  // scratch of the symbolic phase and of fetch_matrix, kept between calls: cudaMalloc/cudaFree of
+  // 100+ MB blocks costs milliseconds and made the end-to-end time vary from call to call
+  fs::DBuf<uint64_t> scr_keys, scr_keys2;
+  fs::DBuf<int32_t> scr_deg, scr_nodecnt;
+  fs::DBuf<int64_t> scr_colcnt, scr_colptr64, scr_nsel, scr_wide;
   bool tile_ok = false;
   bool want_tile = false;         // fsgpu_set_deterministic / FSGPU_TILE=1: prefer the tile kernel
   int last_path = -1;             // scatter path of the last matrix operator (fsgpu_scatter_path)
