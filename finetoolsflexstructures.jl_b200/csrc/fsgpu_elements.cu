@@ -26,6 +26,14 @@ using namespace fsk;
 #define FS_Q4_MINB 4
 #endif
 
+// measurement aid (never defined in the shipped build): -DFS_NO_RED keeps all the arithmetic and addressing
+// but issues no RED, which gives the compute-side time of the scatter kernels
+#ifdef FS_NO_RED
+#define FS_RED_GUARD &&(nelem < 0)
+#else
+#define FS_RED_GUARD
+#endif
+
 namespace {
 
 // ---- emitters -----------------------------------------------------------------------
@@ -148,7 +156,7 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
       const double* sv = stage + o * kStageLd + r;
 #pragma unroll
       for (int c = 0; c < 6; ++c)
-        if (cb[c] >= 0) atomicAdd(nz + cb[c] + rp, sv[c * 6]);
+        if (cb[c] >= 0 FS_RED_GUARD) atomicAdd(nz + cb[c] + rp, sv[c * 6]);
     }
   }
   __device__ __forceinline__ Cols cols(int nj) const {
@@ -207,7 +215,7 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
         const int r = k - c * 6;
         const int b = colb[(half * 3 + c) * 32 + o];
         const int rp = rowp[r * 32 + o];
-        if (b >= 0 && rp >= 0) atomicAdd(nz + b + rp, stage[o * COOP_STAGE_LD + k]);
+        if (b >= 0 && rp >= 0 FS_RED_GUARD) atomicAdd(nz + b + rp, stage[o * COOP_STAGE_LD + k]);
       }
       __syncwarp();
     }
@@ -542,7 +550,10 @@ __device__ __forceinline__ void q4_product_pass(const double* sb_, int bi, int b
 
 constexpr int Q4_WARP_DBL = 2 * 32 * 24 + (32 * 8 + 32 * 4) / 2;  // strips + addressing area (doubles)
 
-template <bool COMP, class Emit>
+// CHUNKED = false: rules with <= 4 points (GaussRule(2,2)), one setup + one product pass.  CHUNKED = true: any
+// rule, chunks of 4 points with the accumulators carried through the setup passes.  Two kernels rather than
+// two branches of one: the second copy of setup + product doubled the code and the instruction-cache misses.
+template <bool COMP, bool CHUNKED, class Emit>
 __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, Emit emit) {
   // per warp: strips b[32][24] of its two elements (one per half-warp) + the addressing area of the
   // cooperative emission (EmitRuns::kAddrInts ints)
@@ -588,7 +599,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   typename Emit::Rows erows;
   double acc[6][6];
   const int npts = P.rule.npts;
-  if (npts <= 4) {
+  if constexpr (!CHUNKED) {
     q4_setup_pass<COMP>(P, active && g4 < npts, e, g4, g4, jn, X, nvown, hq, gd, sb_);
     __syncwarp();
     // addressing data: requested here so the loads overlap the product loop
@@ -1253,13 +1264,21 @@ int launch_q4(fsgpu_ctx* c, const ShellArgs& A, bool comp, Emit em) {
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
   const size_t sm = (size_t)wpb * Q4_WARP_DBL * sizeof(double);
-  if (comp) {
-    FS_CUDA(cudaFuncSetAttribute(k_q4_stiffness<true, Emit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_q4_stiffness<true, Emit><<<grid, wpb * 32, sm, c->stream>>>(A, em);
-  } else {
-    FS_CUDA(cudaFuncSetAttribute(k_q4_stiffness<false, Emit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_q4_stiffness<false, Emit><<<grid, wpb * 32, sm, c->stream>>>(A, em);
-  }
+#define Q4_GO(CO, CH)                                                                                          \
+  do {                                                                                                         \
+    FS_CUDA(cudaFuncSetAttribute(k_q4_stiffness<CO, CH, Emit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    k_q4_stiffness<CO, CH, Emit><<<grid, wpb * 32, sm, c->stream>>>(A, em);                                    \
+  } while (0)
+  const bool chunked = A.rule.npts > 4;
+  if (comp && chunked)
+    Q4_GO(true, true);
+  else if (comp)
+    Q4_GO(true, false);
+  else if (chunked)
+    Q4_GO(false, true);
+  else
+    Q4_GO(false, false);
+#undef Q4_GO
   c->launches++;
   FS_CUDA(cudaGetLastError());
   return FSGPU_OK;

@@ -197,6 +197,20 @@ def GaussRule2x2():
     return np.array([[-g, -g], [-g, g], [g, -g], [g, g]]), np.ones(4)
 
 
+def Simpson13Rule2():
+    """Simpson13Rule(2): 3x3 tensor product, first coordinate outer loop, 1-D weights (1/3, 4/3, 1/3)
+    (used by examples/shells/statics/homogeneous/plates/clamped_square_plate_udl_examples.jl)."""
+    p1 = np.array([-1.0, 0.0, 1.0])
+    w1 = np.array([1.0, 4.0, 1.0]) / 3.0
+    pc = np.array([[p1[i], p1[j]] for i in range(3) for j in range(3)])
+    w = np.array([w1[i] * w1[j] for i in range(3) for j in range(3)])
+    return pc, w
+
+
+def GaussRule1x1():
+    return np.array([[0.0, 0.0]]), np.array([4.0])
+
+
 # ---- assemblers: the plugin point (a new assembler type selects the GPU path) ----------------
 
 

@@ -126,6 +126,45 @@ def test_element_stiffness(fs, kind, comp, sheark):
     assert worst < TOL, worst
 
 
+@pytest.mark.parametrize("comp", [False, True])
+@pytest.mark.parametrize("rule", ["simpson13", "gauss1"])
+def test_q4_other_integration_rules(fs, comp, rule):
+    """9-point Simpson rule (chunks of 4 points: the CHUNKED kernel) and a 1-point rule (idle point lanes):
+    element matrices, assembled stiffness and lumped mass against the oracle."""
+    xyz, conn = meshes.shell_mesh("q4", n=6)
+    lay, cs = _layup()
+    f = fs.femm
+    orule = fx.simpson13_rule_2d() if rule == "simpson13" else fx.gauss_rule_1x1()
+    grule = f.Simpson13Rule2() if rule == "simpson13" else f.GaussRule1x1()
+    assert np.array_equal(orule[0], grule[0]) and np.array_equal(orule[1], grule[1])
+    idom = f.IntegDomain(conn, grule, T_)
+    femm = f.FEMMShellQ4RSComp(idom, _fs_layup(fs, cs)) if comp else f.FEMMShellQ4RS(idom, f.MatDeforElastIso(E_, NU_, RHO_))
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6))).numberdofs()
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals("q4", xyz, conn, fixed=cs[:, 2] if comp else None)
+    if comp:
+        A, B, D = lay.laminate_stiffnesses()
+        H = lay.laminate_transverse_stiffness()
+        Ko = osh.q4rscomp_stiffness_elmats(xyz, conn, normals, valid, A, B, D, H, lay.thickness, cs, rule=orule)
+        md, mi = lay.laminate_inertia()
+        Mo = osh.q4rscomp_mass_elmats(xyz, conn, md, mi, rule=orule)
+    else:
+        Dps, Dt = _iso()
+        Ko = osh.q4rs_stiffness_elmats(xyz, conn, normals, valid, Dps, Dt, T_, rule=orule)
+        Mo = osh.q4rs_mass_elmats(xyz, conn, RHO_, T_, rule=orule)
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    worst = max(relfro(Kg[e], Ko[e]) for e in range(conn.shape[0]))
+    assert worst < TOL, worst
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    od = fx.DofField(xyz.shape[0]).numberdofs()
+    dn = od.gatherdofnums(conn)
+    K = f.stiffness(femm, f.SysmatAssemblerSparse(), geom0, u0, R0, dchi)
+    _check_matrix(K, fx.assemble_matrix("sparse", Ko, dn, od.nalldofs), od.nalldofs)
+    M = f.mass(femm, f.SysmatAssemblerSparseDiag(), geom0, dchi)
+    _check_matrix(M, fx.assemble_matrix("diag", Mo, dn, od.nalldofs), od.nalldofs)
+
+
 @pytest.mark.parametrize("kind,comp", [("t3", False), ("t3", True), ("q4", False), ("q4", True)])
 def test_element_mass(fs, kind, comp):
     xyz, conn = meshes.shell_mesh(kind, n=5)
