@@ -143,6 +143,8 @@ struct fsgpu_ctx {
   int last_path = -1;             // scatter path of the last matrix operator (fsgpu_scatter_path)
   int64_t nadj = 0;               // entries of adj
   int tile_no = 0, tile_cap = 0;  // owned nodes per tile, max elements per tile
+  int tile_cfg = 0;               // index into fsk::kTileCfg
+  fs::DBuf<unsigned char> tile_items;  // [ntiles][nw*32] fsk::TileItem: phase-2 schedule of the tile kernel
   int64_t ntiles = 0;
   fs::DBuf<int32_t> morder;       // [nnodes] node ids in Morton order
   fs::DBuf<int32_t> nel_ptr, nel; // node -> incident elements (ascending)

@@ -4,14 +4,18 @@
 // Why: the scatter kernels are capped by the L2 atomic unit (RED.ADD.F64: ~266 G elements/s
 // measured, scripts/micro/red_bench.cu) -- 324 REDs per T3 element put a 4.9 ms floor under the
 // 4M-element mesh whereas HBM needs 0.7 ms.  Here a CTA owns a compact patch of NODES (consecutive
-// in Morton order of the coordinates).  Phase 1 builds the folded global-dof strips of every element
-// touching an owned node (halo elements are recomputed by the neighbouring tiles, ~1.3x setup work)
-// into shared memory.  Phase 2 forms, for every owned column node a and every neighbour b, the
-// complete 6x6 block K[b,a] = sum over the elements containing both -- all of them are in the tile --
-// and stores it with plain stores through the run-structured addressing (fsgpu_core.cu).
+// in Morton order of the coordinates).
+//   phase 1  builds the folded global-dof strips of every element touching an owned node (halo
+//            elements are recomputed by the neighbouring tiles, ~1.5x setup work) in shared memory;
+//   phase 2  runs a SCHEDULE built once per mesh by the symbolic phase: one lane per work item
+//            (<= 2 element contributions to one block K[b, a], a owned), 32 items per warp, the
+//            items of a block adjacent and never split between warps -> perfectly regular products;
+//   phase 3  stages the partial blocks in shared memory (over the dead strips), sums the items of
+//            every block in a fixed order and writes the block with plain stores, six consecutive
+//            lanes covering six consecutive rows of a column (run-structured addressing, fsgpu_core.cu).
 //
 // Requirements (checked in tile_symbolic, otherwise the RED kernel is used): T3 mesh, fast-path
-// numbering, non-diagonal target, AVERAGE_B shear, every tile fits the shared-memory capacity.
+// numbering, non-diagonal target, AVERAGE_B shear, every tile fits the shared-memory / item capacity.
 #include <cub/cub.cuh>
 
 #include "fsgpu_shell.cuh"
@@ -21,11 +25,27 @@ using namespace fsm;
 
 namespace fsk {
 
-constexpr int TILE_NO = 32;        // owned nodes per tile
-constexpr int TILE_CAP = 144;      // max elements per tile
-constexpr int TILE_THREADS = 512;  // 16 warps
-constexpr int STRIP_LD = 49;       // doubles per (element, node) strip: 48 + 1 pad (odd: conflict-free)
-constexpr int TILE_MAXDEG = 24;    // max node valence handled
+struct TileCfg {
+  int no;   // owned nodes per tile
+  int cap;  // max elements per tile
+  int nw;   // warps per CTA (= 32-item chunks of the schedule per tile)
+};
+// cfg 0: two CTAs per SM (2 x 105 KB); cfg 1: one CTA per SM (207 KB), less halo recomputation
+constexpr TileCfg kTileCfg[2] = {{16, 80, 6}, {32, 160, 12}};
+constexpr int STRIP_LD = 50;     // doubles per (element, node) strip: 48 + 2 (16 B aligned rows; 8 consecutive strips
+                                 // are conflict-free for 128-bit loads: 400 B = 100 banks = 4 mod 32)
+constexpr int STAGE_LD = 38;     // doubles per staged 6x6 block (16 B aligned, conflict-free 128-bit stores)
+constexpr int WARP_STAGE = 32 * STAGE_LD + 64 + 16;  // + info[32] (int4) + plist[32] (int), in doubles
+constexpr int TILE_MAXDEG = 24;  // max node valence handled
+
+// one work item of the phase-2 schedule (24 B).  Strip indices are 1 + (slot * 3 + local node), 0 = none.
+struct TileItem {
+  uint16_t s[4];  // (row strip, column strip) of contribution 0, of contribution 1
+  int32_t oA, oB; // first item of a block: row offsets of node b's runs inside node a's columns
+  int32_t inf;    // first item of a block: nodeinfo[b] | number of items << 16; 0 otherwise
+  int32_t a;      // first item of a block: column node
+};
+static_assert(sizeof(TileItem) == 24, "TileItem layout");
 
 // ------------------------------------------------------------------------------------
 // symbolic part
@@ -160,6 +180,91 @@ __global__ void k_max_i32(const int32_t* __restrict__ v, int64_t n, int32_t* __r
   if (i < n) atomicMax(out, v[i]);
 }
 
+// ---- phase-2 schedule --------------------------------------------------------------------------
+// pcnt[p]: number of elements shared by node a and its neighbour adj[p] (all elements of a for p = a itself)
+__global__ void k_pair_counts(const int32_t* __restrict__ adjptr, const int32_t* __restrict__ adj,
+                              const int32_t* __restrict__ nel_ptr, const int32_t* __restrict__ nel,
+                              const int32_t* __restrict__ conn, int64_t nnodes, int32_t* __restrict__ pcnt) {
+  const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= nnodes) return;
+  for (int p = adjptr[a]; p < adjptr[a + 1]; ++p) {
+    const int b = adj[p];
+    int n = 0;
+    for (int q = nel_ptr[a]; q < nel_ptr[a + 1]; ++q) {
+      const int32_t* cn = conn + (int64_t)nel[q] * 3;
+      n += (cn[0] == b || cn[1] == b || cn[2] == b) ? 1 : 0;
+    }
+    pcnt[p] = n;
+  }
+}
+// one thread per tile: lay the blocks (a owned, b neighbour) out in 32-item chunks; a block's items
+// (ceil(shared elements / 2)) are adjacent and never straddle a chunk.  itemoff[p]: tile-relative first item.
+__global__ void k_tile_layout(const int32_t* __restrict__ morder, const int32_t* __restrict__ adjptr,
+                              const int32_t* __restrict__ pcnt, int64_t nnodes, int no, int64_t ntiles,
+                              int32_t* __restrict__ itemoff, int32_t* __restrict__ tile_items) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  int pos = 0;
+  for (int l = 0; l < no; ++l) {
+    const int64_t m = t * no + l;
+    if (m >= nnodes) break;
+    const int a = morder[m];
+    for (int p = adjptr[a]; p < adjptr[a + 1]; ++p) {
+      const int n = (pcnt[p] + 1) >> 1;
+      if (n == 0) {
+        itemoff[p] = -1;
+        continue;
+      }
+      if ((pos & 31) + n > 32) pos = (pos + 31) & ~31;
+      itemoff[p] = pos;
+      pos += n;
+    }
+  }
+  tile_items[t] = pos;
+}
+// one thread per node a: write the items of its blocks into its tile's schedule
+__global__ void k_fill_items(const int32_t* __restrict__ mrank, const int32_t* __restrict__ adjptr,
+                             const int32_t* __restrict__ adj, const int32_t* __restrict__ adjoff, int64_t nadj,
+                             const int32_t* __restrict__ nodeinfo, const int32_t* __restrict__ nel_ptr,
+                             const int32_t* __restrict__ nel, const int32_t* __restrict__ conn,
+                             const int32_t* __restrict__ tel_ptr, const int32_t* __restrict__ tel,
+                             const int32_t* __restrict__ itemoff, const int32_t* __restrict__ pcnt, int64_t nnodes, int no,
+                             int cap_items, TileItem* __restrict__ items) {
+  const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (a >= nnodes) return;
+  const int64_t t = mrank[a] / no;
+  const int e0 = tel_ptr[t], net = tel_ptr[t + 1] - e0;
+  TileItem* base = items + t * cap_items;
+  for (int p = adjptr[a]; p < adjptr[a + 1]; ++p) {
+    if (itemoff[p] < 0) continue;
+    const int b = adj[p];
+    TileItem* it = base + itemoff[p];
+    int k = 0;
+    for (int q = nel_ptr[a]; q < nel_ptr[a + 1]; ++q) {
+      const int e = nel[q];
+      const int32_t* cn = conn + (int64_t)e * 3;
+      const int jj = cn[0] == a ? 0 : (cn[1] == a ? 1 : 2);
+      const int ii = cn[0] == b ? 0 : (cn[1] == b ? 1 : (cn[2] == b ? 2 : -1));
+      if (ii < 0) continue;
+      int lo = 0, hi = net;  // slot of e in the tile's element list (ascending)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tel[e0 + mid] < e)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      it[k >> 1].s[(k & 1) * 2] = (uint16_t)(1 + lo * 3 + ii);
+      it[k >> 1].s[(k & 1) * 2 + 1] = (uint16_t)(1 + lo * 3 + jj);
+      ++k;
+    }
+    it[0].oA = adjoff[p];
+    it[0].oB = adjoff[nadj + p];
+    it[0].inf = (nodeinfo[b] & 0xffff) | (((pcnt[p] + 1) >> 1) << 16);
+    it[0].a = (int32_t)a;
+  }
+}
+
 #define TLAUNCH(ctx, kern, n, ...)                                             \
   do {                                                                         \
     if ((n) > 0) {                                                             \
@@ -191,7 +296,10 @@ int tile_symbolic(fsgpu_ctx* c) {
   if (!c->want_tile) return FSGPU_OK;
   cudaStream_t st = c->stream;
   const int64_t nn = c->nnodes, ne = c->nelem, ninc = ne * 3;
-  const int NO = TILE_NO;
+  int cfg = 0;
+  if (const char* ev = getenv("FSGPU_TILE_CFG")) cfg = ev[0] == '1' ? 1 : 0;
+  const TileCfg tc = kTileCfg[cfg];
+  const int NO = tc.no;
   const int64_t ntiles = (nn + NO - 1) / NO;
   // (1) Morton order of the nodes
   DBuf<double> mm;
@@ -264,7 +372,7 @@ int tile_symbolic(fsgpu_ctx* c) {
   FS_CUDA(cudaMemcpyAsync(&maxel, tmax.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   FS_CUDA(cudaMemcpyAsync(&maxdeg, dmax.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   FS_CUDA(cudaStreamSynchronize(st));
-  if (maxel > TILE_CAP || maxdeg + 1 > TILE_MAXDEG) return FSGPU_OK;  // keep the RED kernel
+  if (maxel > tc.cap || maxdeg + 1 > TILE_MAXDEG) return FSGPU_OK;  // keep the RED kernel
   // (4) per-adjacency row offsets
   int32_t nadj32 = 0;
   FS_CUDA(cudaMemcpyAsync(&nadj32, c->adjptr.p + nn, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -273,10 +381,30 @@ int tile_symbolic(fsgpu_ctx* c) {
   FS_TRY(c->adjoff.ensure((size_t)2 * nadj + 1));
   TLAUNCH(c, k_adj_offsets, nn, c->adjptr.p, c->adj.p, c->dof.p, c->nodeinfo.p, c->colptr.p, c->rowval.p, nn, c->pcols, nadj,
           c->adjoff.p);
+  // (5) phase-2 schedule
+  const int cap_items = tc.nw * 32;
+  DBuf<int32_t> pcnt, itemoff, titems, imax;
+  FS_TRY(pcnt.ensure((size_t)nadj + 1));
+  FS_TRY(itemoff.ensure((size_t)nadj + 1));
+  FS_TRY(titems.ensure((size_t)ntiles + 1));
+  FS_TRY(imax.ensure(1));
+  TLAUNCH(c, k_pair_counts, nn, c->adjptr.p, c->adj.p, c->nel_ptr.p, c->nel.p, c->conn.p, nn, pcnt.p);
+  TLAUNCH(c, k_tile_layout, ntiles, c->morder.p, c->adjptr.p, pcnt.p, nn, NO, ntiles, itemoff.p, titems.p);
+  FS_CUDA(cudaMemsetAsync(imax.p, 0, sizeof(int32_t), st));
+  TLAUNCH(c, k_max_i32, ntiles, titems.p, ntiles, imax.p);
+  int32_t maxitems = 0;
+  FS_CUDA(cudaMemcpyAsync(&maxitems, imax.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  FS_CUDA(cudaStreamSynchronize(st));
+  if (maxitems > cap_items) return FSGPU_OK;  // keep the RED kernel
+  FS_TRY(c->tile_items.ensure((size_t)ntiles * cap_items * sizeof(TileItem) + 16));
+  FS_CUDA(cudaMemsetAsync(c->tile_items.p, 0, (size_t)ntiles * cap_items * sizeof(TileItem), st));
+  TLAUNCH(c, k_fill_items, nn, mrank.p, c->adjptr.p, c->adj.p, c->adjoff.p, nadj, c->nodeinfo.p, c->nel_ptr.p, c->nel.p,
+          c->conn.p, c->tel_ptr.p, c->tel.p, itemoff.p, pcnt.p, nn, NO, cap_items, reinterpret_cast<TileItem*>(c->tile_items.p));
   FS_CUDA(cudaStreamSynchronize(st));
   c->nadj = nadj;
   c->tile_no = NO;
-  c->tile_cap = TILE_CAP;
+  c->tile_cap = tc.cap;
+  c->tile_cfg = cfg;
   c->ntiles = ntiles;
   c->tile_ok = true;
   return FSGPU_OK;
@@ -286,308 +414,257 @@ int tile_symbolic(fsgpu_ctx* c) {
 // numeric kernel
 // ------------------------------------------------------------------------------------
 struct TileArgs {
-  const int32_t* morder;
   const int32_t* tel_ptr;
   const int32_t* tel;
-  const int32_t* nel_ptr;
-  const int32_t* nel;
-  const int32_t* adjptr;
-  const int32_t* adj;
-  const int32_t* adjoff;
-  const int32_t* nodeinfo;
-  const int32_t* dof;
-  const int32_t* colptr;
-  int64_t nnodes, nadj, nc;
+  const TileItem* items;
+  const int32_t* nodecol;
+  int cap;  // element capacity of the shared-memory layout
   double* nz;
 };
 
-template <bool COMP>
-__global__ void __launch_bounds__(TILE_THREADS, 1) k_t3_tile(ShellArgs P, TileArgs T) {
-  extern __shared__ double smem[];
-  double* strips = smem;                                   // [cap][3][STRIP_LD]
-  double* kd = strips + TILE_CAP * 3 * STRIP_LD;           // [cap][3][4]: kavg*valid*scale, g
-  int* sel = reinterpret_cast<int*>(kd + TILE_CAP * 3 * 4);  // [cap] tile elements (ascending)
-  int* scon = sel + TILE_CAP;                              // [cap][3]
-  int* own = scon + TILE_CAP * 3;                          // [NO] owned node ids
-  int* pfx = own + TILE_NO;                                // [NO+1] prefix of off-diagonal pair counts
+// position (relative to the column start) of dof r of a node with run masks `inf` and run offsets oA / oB
+__device__ __forceinline__ int tile_row_pos(int inf, int oA, int oB, int r) {
+  const int mA = inf & 63, mB = (inf >> 8) & 63, below = (1 << r) - 1;
+  if ((mA >> r) & 1) return oA >= 0 ? oA + __popc(mA & below) : -1;
+  if ((mB >> r) & 1) return oB >= 0 ? oB + __popc(mB & below) : -1;
+  return -1;
+}
+
+template <int NW, bool COMP>
+__global__ void __launch_bounds__(NW * 32, NW <= 6 ? 2 : 1) k_t3_tile(ShellArgs P, TileArgs T) {
+  extern __shared__ __align__(16) double smem[];
+  const int cap = T.cap;
+  double* strips = smem;                                   // [cap][3][STRIP_LD]; phase 3: per-warp staging
+  double* kd = strips + cap * 3 * STRIP_LD;                // [cap][3][4]: kavg*valid*scale, g
+  int* sel = reinterpret_cast<int*>(kd + cap * 3 * 4);     // [cap] tile elements (ascending)
+  int* scon = sel + cap;                                   // [cap][3]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nwarps = TILE_THREADS / 32;
   const int64_t tile = blockIdx.x;
   const int e0 = T.tel_ptr[tile], nelt = T.tel_ptr[tile + 1] - e0;
-  const int64_t n0 = tile * TILE_NO;
-  const int nown = (int)((T.nnodes - n0) < TILE_NO ? (T.nnodes - n0) : TILE_NO);
-  for (int k = tid; k < nelt; k += TILE_THREADS) {
+  for (int k = tid; k < nelt; k += NW * 32) {
     const int e = T.tel[e0 + k];
     sel[k] = e;
     scon[k * 3] = P.conn[(int64_t)e * 3];
     scon[k * 3 + 1] = P.conn[(int64_t)e * 3 + 1];
     scon[k * 3 + 2] = P.conn[(int64_t)e * 3 + 2];
   }
-  if (tid < TILE_NO) own[tid] = tid < nown ? T.morder[n0 + tid] : -1;
-  __syncthreads();
-  if (warp == 0) {
-    // exclusive prefix of (deg - 1) over the owned nodes (deg counts the node itself)
-    int run = 0;
-    for (int b0 = 0; b0 < TILE_NO; b0 += 32) {
-      const int l = b0 + lane;
-      int v = 0;
-      if (l < nown) {
-        const int a = own[l];
-        const int dg = T.adjptr[a + 1] - T.adjptr[a];
-        v = dg > 0 ? dg - 1 : 0;
-      }
-      int inc = v;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (l < TILE_NO) pfx[l] = run + inc - v;
-      run += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) pfx[TILE_NO] = run;
+  // this lane's work item (consumed after phase 1)
+  TileItem it;
+  {
+    const int2* src = reinterpret_cast<const int2*>(T.items + (tile * NW + warp) * 32 + lane);
+    const int2 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    it.s[0] = (uint16_t)(w0.x & 0xffff);
+    it.s[1] = (uint16_t)((unsigned)w0.x >> 16);
+    it.s[2] = (uint16_t)(w0.y & 0xffff);
+    it.s[3] = (uint16_t)((unsigned)w0.y >> 16);
+    it.oA = w1.x;
+    it.oB = w1.y;
+    it.inf = w2.x;
+    it.a = w2.y;
   }
+  __syncthreads();
 
   // ---------------- phase 1: strips of every tile element (3 lanes per element) ----------------
   const unsigned full = 0xffffffffu;
-  const int el = lane / 3, j = lane - 3 * el;
-  const int base = lane - j;
-  for (int s0 = warp * 10; s0 < nelt; s0 += nwarps * 10) {
-    const int slot = s0 + el;
-    const bool active = (lane < 30) && (slot < nelt);
-    double kpart = 0.0;
-    V3 gdir = v3(0, 0, 0);
-    bool validj = false;
-    double p1[5][3], p2[5][3], bs[2][3];
-    double gx = 0.0, gy = 0.0;
-    T3Geom g;
-    M3 A;
-    Constit C;
-    int64_t e = 0;
-    if (active) {
-      e = sel[slot];
-      const int n0_ = scon[slot * 3], n1_ = scon[slot * 3 + 1], n2_ = scon[slot * 3 + 2];
-      g = t3_geometry(ld3(P.xyz, n0_), ld3(P.xyz, n1_), ld3(P.xyz, n2_));
-      const double4 nv = ldg4(P.nrm + (j == 0 ? n0_ : (j == 1 ? n1_ : n2_)));
-      validj = nv.w != 0.0;
-      A = nodal_triad(g.E, v3(nv.x, nv.y, nv.z), validj);
-      build_constit_t3(P, e, g.E, g.Ae, 1.0, COMP, C);
-      gx = j == 0 ? g.gN[0][0] : (j == 1 ? g.gN[1][0] : g.gN[2][0]);
-      gy = j == 0 ? g.gN[0][1] : (j == 1 ? g.gN[1][1] : g.gN[2][1]);
-      t3_bs_node(g, j, -1, bs);
-      node_coupling_contrib(A, gx, gy, bs, p1, p2);
-    } else {
+  {
+    const int el = lane / 3, j = lane - 3 * el;
+    const int base = lane - j;
+    for (int s0 = warp * 10; s0 < nelt; s0 += NW * 10) {
+      const int slot = s0 + el;
+      const bool active = (lane < 30) && (slot < nelt);
+      double kpart = 0.0;
+      V3 gdir = v3(0, 0, 0);
+      bool validj = false;
+      double p1[5][3], p2[5][3], bs[2][3];
+      double gx = 0.0, gy = 0.0;
+      T3Geom g;
+      M3 A;
+      Constit C;
+      if (active) {
+        const int64_t e = sel[slot];
+        const int n0_ = scon[slot * 3], n1_ = scon[slot * 3 + 1], n2_ = scon[slot * 3 + 2];
+        g = t3_geometry(ld3(P.xyz, n0_), ld3(P.xyz, n1_), ld3(P.xyz, n2_));
+        const double4 nv = ldg4(P.nrm + (j == 0 ? n0_ : (j == 1 ? n1_ : n2_)));
+        validj = nv.w != 0.0;
+        A = nodal_triad(g.E, v3(nv.x, nv.y, nv.z), validj);
+        build_constit_t3(P, e, g.E, g.Ae, 1.0, COMP, C);
+        gx = j == 0 ? g.gN[0][0] : (j == 1 ? g.gN[1][0] : g.gN[2][0]);
+        gy = j == 0 ? g.gN[0][1] : (j == 1 ? g.gN[1][1] : g.gN[2][1]);
+        t3_bs_node(g, j, -1, bs);
+        node_coupling_contrib(A, gx, gy, bs, p1, p2);
+      } else {
+        for (int r = 0; r < 5; ++r)
+          for (int k = 0; k < 3; ++k) p1[r][k] = p2[r][k] = 0.0;
+      }
+      double P1[5][3], P2[5][3];
+#pragma unroll
       for (int r = 0; r < 5; ++r)
-        for (int k = 0; k < 3; ++k) p1[r][k] = p2[r][k] = 0.0;
-    }
-    double P1[5][3], P2[5][3];
 #pragma unroll
-    for (int r = 0; r < 5; ++r)
+        for (int k = 0; k < 3; ++k) {
+          double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-          s1 += __shfl_sync(full, p1[r][k], (base + l) & 31);
-          s2 += __shfl_sync(full, p2[r][k], (base + l) & 31);
+          for (int l = 0; l < 3; ++l) {
+            s1 += __shfl_sync(full, p1[r][k], (base + l) & 31);
+            s2 += __shfl_sync(full, p2[r][k], (base + l) & 31);
+          }
+          P1[r][k] = s1;
+          P2[r][k] = s2;
         }
-        P1[r][k] = s1;
-        P2[r][k] = s2;
+      if (active) {
+        double R[2][2], brn[5][2];
+        node_R(A, R);
+        node_bt_rot(gx, gy, bs, R, brn);
+        kpart = node_kavg_part(C, brn, false);
+        double bg[8][6];
+        gdir = node_strip(g.E, A, gx, gy, bs, P1, P2, bg);
+        fold_constit(C, bg);
+        double* dst = strips + (slot * 3 + j) * STRIP_LD;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          const double d = constit_d(C, s);
+          if (d < 0.0) atomicExch(P.flag + 2, 1);
+          const double q = sqrt(d);
+#pragma unroll
+          for (int cc = 0; cc < 6; cc += 2)
+            *reinterpret_cast<double2*>(dst + s * 6 + cc) = make_double2(q * bg[s][cc], q * bg[s][cc + 1]);
+        }
       }
-    if (active) {
-      double R[2][2], brn[5][2];
-      node_R(A, R);
-      node_bt_rot(gx, gy, bs, R, brn);
-      kpart = node_kavg_part(C, brn, false);
-      double bg[8][6];
-      gdir = node_strip(g.E, A, gx, gy, bs, P1, P2, bg);
-      fold_constit(C, bg);
-      double* dst = strips + (slot * 3 + j) * STRIP_LD;
+      double ksum = 0.0;
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const double d = constit_d(C, s);
-        if (d < 0.0) atomicExch(P.flag + 2, 1);
-        const double q = sqrt(d);
-#pragma unroll
-        for (int cc = 0; cc < 6; ++cc) dst[s * 6 + cc] = q * bg[s][cc];
+      for (int l = 0; l < 3; ++l) ksum += __shfl_sync(full, kpart, (base + l) & 31);
+      if (active) {
+        double* k4 = kd + (slot * 3 + j) * 4;
+        *reinterpret_cast<double2*>(k4) = make_double2(validj ? ksum / 6 * P.drill : 0.0, gdir.x);
+        *reinterpret_cast<double2*>(k4 + 2) = make_double2(gdir.y, gdir.z);
       }
-    }
-    double ksum = 0.0;
-#pragma unroll
-    for (int l = 0; l < 3; ++l) ksum += __shfl_sync(full, kpart, (base + l) & 31);
-    if (active) {
-      double* k4 = kd + (slot * 3 + j) * 4;
-      k4[0] = validj ? ksum / 6 * P.drill : 0.0;
-      k4[1] = gdir.x;
-      k4[2] = gdir.y;
-      k4[3] = gdir.z;
     }
   }
   __syncthreads();
 
-  // ---------------- phase 2: complete blocks K[b, a], a owned; 2 lanes per pair ----------------
-  // pair list: [diagonal pairs (one per owned node) padded to a multiple of 16] [off-diagonal pairs]
-  const int ndiag = (nown + 15) & ~15;
-  const int noff = pfx[TILE_NO];
-  const int npairs = ndiag + noff;
-  for (int w0 = 0; w0 < 2 * npairs; w0 += TILE_THREADS) {
-    const int item = w0 + tid;
-    const int pair = item >> 1, part = item & 1;
-    int l = -1, a = -1, b = -1, p = -1;  // owned index, column node, row node, adjacency entry
-    if (pair < ndiag) {
-      if (pair < nown) {
-        l = pair;
-        a = own[l];
-        b = a;
-      }
-    } else if (pair < npairs) {
-      const int q = pair - ndiag;
-      int lo = 0, hi = nown;  // last l with pfx[l] <= q
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (pfx[mid] <= q)
-          lo = mid;
-        else
-          hi = mid;
-      }
-      l = lo;
-      a = own[l];
-      int k = q - pfx[l];  // k-th off-diagonal neighbour: skip the diagonal entry
-      const int p0 = T.adjptr[a], p1_ = T.adjptr[a + 1];
-      // adjacency is ascending and contains a itself: entries before a keep their index
-      int pa = p0;
-      {
-        int lo2 = p0, hi2 = p1_;
-        while (lo2 < hi2) {
-          const int mid = (lo2 + hi2) >> 1;
-          if (T.adj[mid] < a)
-            lo2 = mid + 1;
-          else
-            hi2 = mid;
-        }
-        pa = lo2;
-      }
-      p = p0 + k;
-      if (p >= pa) ++p;
-      b = T.adj[p];
-    }
-    if (a >= 0 && b == a) {
-      int lo2 = T.adjptr[a], hi2 = T.adjptr[a + 1];
-      if (hi2 == lo2) {
-        a = -1;  // node without elements: nothing stored
+  // ---------------- phase 2: this lane's item = up to two contributions b_i' b_j to one block ----------------
+  double acc[6][6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
+#pragma unroll 1
+  for (int t = 0; t < 2; ++t) {
+    const int si = it.s[2 * t], sj = it.s[2 * t + 1];
+    if (si == 0) break;
+    const double* bi = strips + (si - 1) * STRIP_LD;
+    const double* bj = strips + (sj - 1) * STRIP_LD;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      if (!COMP && s < 3) {
+        // membrane rows of a homogeneous shell have no rotation columns in global dofs
+        const double2 i01 = *reinterpret_cast<const double2*>(bi + s * 6);
+        const double2 j01 = *reinterpret_cast<const double2*>(bj + s * 6);
+        const double vi[3] = {i01.x, i01.y, bi[s * 6 + 2]};
+        const double vj[3] = {j01.x, j01.y, bj[s * 6 + 2]};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
       } else {
-        while (lo2 < hi2) {
-          const int mid = (lo2 + hi2) >> 1;
-          if (T.adj[mid] < a)
-            lo2 = mid + 1;
-          else
-            hi2 = mid;
+        double vi[6], vj[6];
+#pragma unroll
+        for (int r = 0; r < 6; r += 2) {
+          const double2 a2 = *reinterpret_cast<const double2*>(bi + s * 6 + r);
+          const double2 b2 = *reinterpret_cast<const double2*>(bj + s * 6 + r);
+          vi[r] = a2.x;
+          vi[r + 1] = a2.y;
+          vj[r] = b2.x;
+          vj[r + 1] = b2.y;
         }
-        p = lo2;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
       }
     }
-    double acc[6][6];
+    if (si == sj) {
+      // drilling stiffness kavg on the nodal normal direction (nodal dof 6), rotated to global
+      const double2 k01 = *reinterpret_cast<const double2*>(kd + (sj - 1) * 4);
+      const double2 k23 = *reinterpret_cast<const double2*>(kd + (sj - 1) * 4 + 2);
+      const double gg[3] = {k01.y, k23.x, k23.y};
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-    if (a >= 0) {
-      int hit = 0;
-      for (int q = T.nel_ptr[a]; q < T.nel_ptr[a + 1]; ++q) {
-        const int e = T.nel[q];
-        // slot of e in the tile list (ascending)
-        int lo2 = 0, hi2 = nelt;
-        while (lo2 < hi2) {
-          const int mid = (lo2 + hi2) >> 1;
-          if (sel[mid] < e)
-            lo2 = mid + 1;
-          else
-            hi2 = mid;
-        }
-        const int slot = lo2;
-        const int c0 = scon[slot * 3], c1 = scon[slot * 3 + 1], c2 = scon[slot * 3 + 2];
-        const int jj = c0 == a ? 0 : (c1 == a ? 1 : 2);
-        const int ii = c0 == b ? 0 : (c1 == b ? 1 : (c2 == b ? 2 : -1));
-        if (ii < 0) continue;
-        if (((hit++) & 1) != part) continue;
-        const double* bi = strips + (slot * 3 + ii) * STRIP_LD;
-        const double* bj = strips + (slot * 3 + jj) * STRIP_LD;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          double vi[6], vj[6];
-#pragma unroll
-          for (int r = 0; r < 6; ++r) vi[r] = bi[s * 6 + r];
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) vj[cc] = bj[s * 6 + cc];
-#pragma unroll
-          for (int r = 0; r < 6; ++r)
-#pragma unroll
-            for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
-        }
-        if (b == a) {
-          const double* k4 = kd + (slot * 3 + jj) * 4;
-          const double kv = k4[0];
-          const double gg[3] = {k4[1], k4[2], k4[3]};
-#pragma unroll
-          for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kv * gg[r] * gg[cc];
-        }
-      }
+        for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += k01.x * gg[r] * gg[cc];
     }
-    // combine the two lanes of the pair
+  }
+  __syncthreads();  // every warp is done with the strips
+
+  // ---------------- phase 3: stage, sum the items of each block, store ----------------
+  double* stage = smem + (size_t)warp * WARP_STAGE;
+  int4* info = reinterpret_cast<int4*>(stage + 32 * STAGE_LD);
+  int* plist = reinterpret_cast<int*>(stage + 32 * STAGE_LD + 64);
+  {
+    double2* st2 = reinterpret_cast<double2*>(stage + lane * STAGE_LD);
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
+    for (int cc = 0; cc < 6; ++cc)
 #pragma unroll
-      for (int cc = 0; cc < 6; ++cc) acc[r][cc] += __shfl_xor_sync(full, acc[r][cc], 1);
-    if (a >= 0 && part == 0) {
-      const int inf = T.nodeinfo[b];
-      const int mA = inf & 63, mB = (inf >> 8) & 63;
-      const int oA = T.adjoff[p], oB = T.adjoff[T.nadj + p];
-      const int32_t* da = T.dof + (int64_t)a * 6;
+      for (int r = 0; r < 6; r += 2) st2[(cc * 6 + r) >> 1] = make_double2(acc[r][cc], acc[r + 1][cc]);
+  }
+  info[lane] = make_int4(it.oA, it.oB, it.inf, it.a);
+  const bool first = ((it.inf >> 16) & 15) > 0;
+  const unsigned firsts = __ballot_sync(full, first);
+  if (first) plist[__popc(firsts & ((1u << lane) - 1))] = lane;
+  const int npairs = __popc(firsts);
+  __syncwarp();
+  const int sub = lane / 6, r = lane - sub * 6;
+#pragma unroll 1
+  for (int g = 0; g * 5 < npairs; ++g) {
+    const int k = g * 5 + sub;
+    if (lane >= 30 || k >= npairs) continue;
+    const int o = plist[k];
+    const int4 I = info[o];
+    const int rp = tile_row_pos(I.z, I.x, I.y, r);
+    if (rp < 0) continue;
+    const int nit = (I.z >> 16) & 15;
+    const int4 c0 = __ldg(reinterpret_cast<const int4*>(T.nodecol + (int64_t)I.w * 8));
+    const int2 c1 = __ldg(reinterpret_cast<const int2*>(T.nodecol + (int64_t)I.w * 8 + 4));
+    const int cb[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
+    const double* sv = stage + o * STAGE_LD + r;
 #pragma unroll
-      for (int cc = 0; cc < 6; ++cc) {
-        const int cd = da[cc];
-        if (cd >= T.nc) continue;
-        double* col = T.nz + T.colptr[cd];
-        int ka = 0, kb = 0;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          if ((mA >> r) & 1)
-            col[oA + ka++] = acc[r][cc];
-          else if ((mB >> r) & 1)
-            col[oB + kb++] = acc[r][cc];
-        }
-      }
+    for (int cc = 0; cc < 6; ++cc) {
+      if (cb[cc] < 0) continue;
+      double v = sv[cc * 6];
+      for (int t = 1; t < nit; ++t) v += sv[t * STAGE_LD + cc * 6];
+      T.nz[cb[cc] + rp] = v;
     }
   }
 }
 
+template <int NW>
+static int launch_tile_nw(fsgpu_ctx* c, const ShellArgs& A, const TileArgs& T, bool comp, size_t sm) {
+  if (comp) {
+    FS_CUDA(cudaFuncSetAttribute(k_t3_tile<NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_t3_tile<NW, true><<<(unsigned)c->ntiles, NW * 32, sm, c->stream>>>(A, T);
+  } else {
+    FS_CUDA(cudaFuncSetAttribute(k_t3_tile<NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_t3_tile<NW, false><<<(unsigned)c->ntiles, NW * 32, sm, c->stream>>>(A, T);
+  }
+  return FSGPU_OK;
+}
+
 int launch_t3_tile(fsgpu_ctx* c, const ShellArgs& A, bool comp) {
+  const TileCfg tc = kTileCfg[c->tile_cfg];
   TileArgs T;
-  T.morder = c->morder.p;
   T.tel_ptr = c->tel_ptr.p;
   T.tel = c->tel.p;
-  T.nel_ptr = c->nel_ptr.p;
-  T.nel = c->nel.p;
-  T.adjptr = c->adjptr.p;
-  T.adj = c->adj.p;
-  T.adjoff = c->adjoff.p;
-  T.nodeinfo = c->nodeinfo.p;
-  T.dof = c->dof.p;
-  T.colptr = c->colptr.p;
-  T.nnodes = c->nnodes;
-  T.nadj = c->nadj;
-  T.nc = c->pcols;
+  T.items = reinterpret_cast<const TileItem*>(c->tile_items.p);
+  T.nodecol = c->nodecol.p;
+  T.cap = tc.cap;
   T.nz = c->nzval.p;
-  const size_t sm = (size_t)(TILE_CAP * 3 * STRIP_LD + TILE_CAP * 3 * 4) * sizeof(double) +
-                    (size_t)(TILE_CAP + TILE_CAP * 3 + TILE_NO + TILE_NO + 1 + 3) * sizeof(int);
-  if (comp) {
-    FS_CUDA(cudaFuncSetAttribute(k_t3_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_t3_tile<true><<<(unsigned)c->ntiles, TILE_THREADS, sm, c->stream>>>(A, T);
-  } else {
-    FS_CUDA(cudaFuncSetAttribute(k_t3_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_t3_tile<false><<<(unsigned)c->ntiles, TILE_THREADS, sm, c->stream>>>(A, T);
-  }
+  const size_t sm = (size_t)(tc.cap * 3 * STRIP_LD + tc.cap * 3 * 4) * sizeof(double) + (size_t)(tc.cap * 4) * sizeof(int);
+  // the per-warp staging areas of phase 3 live inside the (dead) strip area
+  static_assert(kTileCfg[0].nw * WARP_STAGE <= kTileCfg[0].cap * 3 * STRIP_LD, "stage does not fit (cfg 0)");
+  static_assert(kTileCfg[1].nw * WARP_STAGE <= kTileCfg[1].cap * 3 * STRIP_LD, "stage does not fit (cfg 1)");
+  if (c->tile_cfg == 0)
+    FS_TRY(launch_tile_nw<kTileCfg[0].nw>(c, A, T, comp, sm));
+  else
+    FS_TRY(launch_tile_nw<kTileCfg[1].nw>(c, A, T, comp, sm));
   c->launches++;
   FS_CUDA(cudaGetLastError());
   return FSGPU_OK;

@@ -89,7 +89,7 @@ int64_t fsgpu_launch_count(fsgpu_ctx* ctx);
  * matrix operator -- the number the roofline fraction is computed from */
 int fsgpu_last_kernel_ms(fsgpu_ctx* ctx, double* ms);
 /* on != 0: T3FF / T3FFComp stiffness uses the owner-computes tile kernel when the mesh allows it
- * (no atomics: bitwise reproducible values, every entry written once; ~2.8x slower than the
+ * (no atomics: bitwise reproducible values, every entry written once; schedule-driven, ~1.5x slower than the
  * RED.ADD scatter on B200).  Takes effect at the next fsgpu_symbolic.  Default: off, or the
  * environment variable FSGPU_TILE=1 at fsgpu_create.  The reference's serial loop is
  * deterministic by construction (src/FEMMShellT3FFModule.jl:664-733). */

@@ -109,3 +109,19 @@ print("--- fsgpu_elements.cu by source line (samples% instr%)")
 for line in sorted(byline_s):
     if byline_s[line] / ts > 0.004 or byline_i[line] / ti > 0.004:
         print(f"  line {line:5d}: {100 * byline_s[line] / ts:6.2f}% {100 * byline_i[line] / ti:6.2f}%")
+
+# optional: --ranges=NAME:a-b,NAME:c-d  sums the kernel file's lines by range; everything attributed to
+# other files (inlined math, intrinsics) is reported as "callees"
+rng = [a for a in sys.argv[1:] if a.startswith("--ranges=")]
+if rng:
+    spec = [(x.split(":")[0], *map(int, x.split(":")[1].split("-"))) for x in rng[0][9:].split(",")]
+    acc_s, acc_i = Counter(), Counter()
+    for line in byline_s:
+        name = next((n for n, a, b in spec if a <= line <= b), "other-lines")
+        acc_s[name] += byline_s[line]
+        acc_i[name] += byline_i[line]
+    acc_s["callees"] = ts - sum(byline_s.values())
+    acc_i["callees"] = ti - sum(byline_i.values())
+    print("--- by line range (samples% instr%)")
+    for n in acc_s:
+        print(f"  {n:>12}: {100 * acc_s[n] / ts:6.2f}% {100 * acc_i[n] / ti:6.2f}%")

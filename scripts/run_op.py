@@ -1,5 +1,5 @@
 """Run one operator a few times on a named synthetic workload (driver for ncu captures).
-usage: python scripts/run_op.py {q4rs|t3ff|explicit} [n] [reps]"""
+usage: python scripts/run_op.py {q4rs|t3ff|explicit} [n] [reps] [det]"""
 import os
 import sys
 import time
@@ -14,6 +14,7 @@ f = fsb200.femm
 which = sys.argv[1] if len(sys.argv) > 1 else "q4rs"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+det = len(sys.argv) > 4 and sys.argv[4] == "det"
 if which == "q4rs":
     w = wl.c2_q4rs_plate(n)
     femm = f.FEMMShellQ4RS(f.IntegDomain(w["conn"], f.GaussRule2x2(), w["thickness"]), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]))
@@ -24,6 +25,8 @@ geom0 = f.NodalField.__new__(f.NodalField)
 geom0.values = w["xyz"]
 dchi = f.NodalField.__new__(f.NodalField)
 dchi.values, dchi.dofnums, dchi._nfree = None, w["dofnums"], w["nfree"]
+if det:
+    femm.ctx.set_deterministic(True)
 f.associategeometry(femm, geom0)
 femm._startassembly(f.SysmatAssemblerFFBlock(), dchi)
 femm._sync_stab()
@@ -31,7 +34,7 @@ p = femm._params()
 op = femm._opname + "_stiffness"
 for _ in range(reps):
     femm.ctx.shell_op(op, p)
-    print(which, "nelem", w["conn"].shape[0], "kernel ms", femm.ctx.last_kernel_ms, flush=True)
+    print(which, "nelem", w["conn"].shape[0], "kernel ms", femm.ctx.last_kernel_ms, "path", femm.ctx.scatter_path, flush=True)
 if which == "explicit":
     femm.ctx.shell_mass_diag(p, 3, nfree_only=True)
     ex = fsb200.Explicit(femm.ctx, c_scale=100.0, dt=1e-7)
