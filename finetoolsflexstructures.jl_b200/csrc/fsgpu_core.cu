@@ -1,6 +1,13 @@
 // libfsgpu core: context, data hand-over, nodal normals, symbolic phase (CSC pattern
 // bit-exact to Julia `sparse` + element-entry slot map), result hand-back, COO->CSC.
 #include <stdarg.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
+#include <atomic>
+#include <thread>
+#include <vector>
 
 #include <cub/cub.cuh>
 
@@ -191,6 +198,12 @@ extern "C" int fsgpu_destroy(fsgpu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int k = 0; k < 4; ++k) {
+    if (c->ring[k]) cudaFreeHost(c->ring[k]);
+    if (c->ring_ev[k]) cudaEventDestroy(c->ring_ev[k]);
+  }
+  if (c->ev_x) cudaEventDestroy(c->ev_x);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
   return FSGPU_OK;
 }
@@ -984,6 +997,92 @@ extern "C" int fsgpu_result_size(fsgpu_ctx* c, int64_t* nrows, int64_t* ncols, i
 }
 
 
+// ------------------------------------------------------------------------------------
+// fetch of a large pattern: int32 rows over PCIe, widened on the host
+// ------------------------------------------------------------------------------------
+namespace fs {
+static void widen_plus1(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+#if defined(__x86_64__)
+  // non-temporal stores: the destination is written once and not read here (no read-for-ownership traffic)
+  for (int64_t i = 0; i < n; ++i) _mm_stream_si64(reinterpret_cast<long long*>(out + i), (long long)in[i] + 1);
+  _mm_sfence();
+#else
+  for (int64_t i = 0; i < n; ++i) out[i] = (int64_t)in[i] + 1;
+#endif
+}
+
+constexpr int kRing = 4;
+constexpr int64_t kRingEntries = (int64_t)1 << 23;  // 32 MB of int32 per ring buffer
+
+static int fetch_rows_narrow(fsgpu_ctx* c, const int32_t* rv, int64_t nnz, int64_t* rowval, const double* nz, double* nzval) {
+  if (!c->ring[0]) {
+    for (int k = 0; k < kRing; ++k) {
+      FS_CUDA(cudaMallocHost(&c->ring[k], (size_t)kRingEntries * sizeof(int32_t)));
+      FS_CUDA(cudaEventCreateWithFlags(&c->ring_ev[k], cudaEventDisableTiming));
+    }
+    FS_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    FS_CUDA(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+  }
+  // values: second stream, after everything already queued on the context's stream
+  cudaError_t nz_err = cudaSuccess;
+  std::thread nz_thread;
+  FS_CUDA(cudaEventRecord(c->ev_x, c->stream));
+  FS_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_x, 0));
+  if (nzval) {
+    // from a helper thread: with a pageable destination the copy call blocks its caller
+    nz_thread = std::thread([&] {
+      cudaSetDevice(c->device);
+      nz_err = cudaMemcpyAsync(nzval, nz, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream2);
+      if (nz_err == cudaSuccess) nz_err = cudaStreamSynchronize(c->stream2);
+    });
+  }
+  int nth = (int)std::thread::hardware_concurrency();
+  if (const char* ev = getenv("FSGPU_HOST_THREADS")) nth = atoi(ev);
+  nth = nth < 1 ? 1 : (nth > 32 ? 32 : nth);
+  const int64_t nchunks = (nnz + kRingEntries - 1) / kRingEntries;
+  std::vector<std::atomic<int>> arrived(nchunks), done(nchunks);
+  for (int64_t k = 0; k < nchunks; ++k) {
+    arrived[k].store(0);
+    done[k].store(0);
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nth; ++t)
+    pool.emplace_back([&, t] {
+      for (int64_t k = 0; k < nchunks; ++k) {
+        while (arrived[k].load(std::memory_order_acquire) == 0) std::this_thread::yield();
+        if (arrived[k].load(std::memory_order_acquire) < 0) return;  // aborted
+        const int64_t o = k * kRingEntries, m = nnz - o < kRingEntries ? nnz - o : kRingEntries;
+        const int64_t lo = m * t / nth, hi = m * (t + 1) / nth;
+        widen_plus1(static_cast<const int32_t*>(c->ring[k % kRing]) + lo, rowval + o + lo, hi - lo);
+        done[k].fetch_add(1, std::memory_order_release);
+      }
+    });
+  cudaError_t err = cudaSuccess;
+  int64_t issued = 0;
+  for (int64_t k = 0; k < nchunks && err == cudaSuccess; ++k) {
+    // keep the ring full: issue copies up to kRing chunks ahead of the chunk being handed to the workers
+    while (issued < nchunks && issued < k + kRing && err == cudaSuccess) {
+      if (issued >= kRing)
+        while (done[issued - kRing].load(std::memory_order_acquire) < nth) std::this_thread::yield();
+      const int64_t o = issued * kRingEntries, m = nnz - o < kRingEntries ? nnz - o : kRingEntries;
+      err = cudaMemcpyAsync(c->ring[issued % kRing], rv + o, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+      if (err == cudaSuccess) err = cudaEventRecord(c->ring_ev[issued % kRing], c->stream);
+      ++issued;
+    }
+    if (err == cudaSuccess) err = cudaEventSynchronize(c->ring_ev[k % kRing]);
+    arrived[k].store(err == cudaSuccess ? 1 : -1, std::memory_order_release);
+  }
+  if (err != cudaSuccess)
+    for (int64_t k = 0; k < nchunks; ++k)
+      if (arrived[k].load() == 0) arrived[k].store(-1, std::memory_order_release);
+  for (auto& th : pool) th.join();
+  if (nz_thread.joinable()) nz_thread.join();
+  FS_CUDA(err);
+  FS_CUDA(nz_err);
+  return FSGPU_OK;
+}
+}  // namespace fs
+
 extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval, double* nzval) {
   FS_TRY(check_ctx(c));
   FS_REQUIRE(c->have_matrix, FSGPU_ERR_STATE, "no matrix result available");
@@ -1011,17 +1110,27 @@ extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval
     FS_TRY(download(c, colptr, wide.p, ((size_t)nc + 1) * sizeof(int64_t)));
     FS_CUDA(cudaStreamSynchronize(c->stream));
   }
-  if (rowval && nnz > 0) {
-    for (int64_t o = 0; o < nnz; o += chunk) {
-      int64_t m = nnz - o < chunk ? nnz - o : chunk;
-      LAUNCH(c, k_i32_plus1_to_i64, m, rv + o, wide.p, m);
-      FS_TRY(download(c, rowval + o, wide.p, (size_t)m * sizeof(int64_t)));
+  // Large results: the PCIe link (not the GPU) bounds this call, so the row indices cross it as the
+  // device's int32 0-based array and are widened to Int64 1-based by host threads out of a pinned ring,
+  // while the values travel on a second stream.  Small results: widen on the device (no thread start-up).
+  int64_t narrow_min = (int64_t)1 << 22;
+  if (const char* ev = getenv("FSGPU_FETCH_NARROW_MIN")) narrow_min = atoll(ev);  // < 0: never (tests)
+  const bool narrow = rowval && narrow_min >= 0 && nnz >= narrow_min && nnz > 0;
+  if (narrow) {
+    FS_TRY(fetch_rows_narrow(c, rv, nnz, rowval, nzval ? nz : nullptr, nzval));
+  } else {
+    if (rowval && nnz > 0) {
+      for (int64_t o = 0; o < nnz; o += chunk) {
+        int64_t m = nnz - o < chunk ? nnz - o : chunk;
+        LAUNCH(c, k_i32_plus1_to_i64, m, rv + o, wide.p, m);
+        FS_TRY(download(c, rowval + o, wide.p, (size_t)m * sizeof(int64_t)));
+        FS_CUDA(cudaStreamSynchronize(c->stream));
+      }
+    }
+    if (nzval && nnz > 0) {
+      FS_TRY(download(c, nzval, nz, (size_t)nnz * sizeof(double)));
       FS_CUDA(cudaStreamSynchronize(c->stream));
     }
-  }
-  if (nzval && nnz > 0) {
-    FS_TRY(download(c, nzval, nz, (size_t)nnz * sizeof(double)));
-    FS_CUDA(cudaStreamSynchronize(c->stream));
   }
   return FSGPU_OK;
 }

@@ -82,6 +82,11 @@ struct fsgpu_ctx {
   // device time of the dominant kernel of the last operator (CUDA events on `stream`)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  // fetch of large results: pinned ring for the int32 row indices, second stream for the values
+  void* ring[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_x = nullptr;
 
   // mesh
   int nnpe = 0;

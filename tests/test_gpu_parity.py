@@ -465,6 +465,35 @@ def test_update_rotation_field(fs):
 
 
 # ---------------------------------------------------------------------------------------
+# fetch paths
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("asm", ["ffblock", "sparse", "csrsymm"])
+def test_fetch_narrow_rows_match_wide(fs, asm, monkeypatch):
+    """fsgpu_fetch_matrix: large results move the row indices as int32 and widen them with host threads
+    (multi-chunk ring, values on a second stream); the arrays must equal the device-widened path bit for bit."""
+    xyz, conn = meshes.shell_mesh("q4", n=170)  # nnz ~ 9.3 M: more than one ring chunk (8 Mi entries)
+    od = meshes.clamp_edge_dofs(xyz)
+    f = fs.femm
+    femm = _make_femm(fs, "q4", conn)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs()
+    f.associategeometry(femm, geom0)
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    monkeypatch.setenv("FSGPU_FETCH_NARROW_MIN", "-1")
+    Kw = f.stiffness(femm, _assembler(fs, asm), geom0, u0, R0, dchi)
+    for nth in ("3", "16"):
+        monkeypatch.setenv("FSGPU_FETCH_NARROW_MIN", "1")
+        monkeypatch.setenv("FSGPU_HOST_THREADS", nth)
+        Kn = femm.ctx.fetch_matrix()
+        assert np.array_equal(Kn.colptr, Kw.colptr)
+        assert np.array_equal(Kn.rowval, Kw.rowval)
+        assert np.array_equal(Kn.nzval, Kw.nzval)
+    assert Kw.rowval.size > (1 << 23), "mesh too small to exercise a second ring chunk"
+
+
+# ---------------------------------------------------------------------------------------
 # COO -> CSC, error paths
 # ---------------------------------------------------------------------------------------
 def test_coo_to_csc(fs):
