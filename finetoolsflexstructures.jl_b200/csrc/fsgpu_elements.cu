@@ -71,8 +71,8 @@ struct EmitScatter {  // generic path: per-entry slot map, any dof numbering
 // in shared memory, then the warp walks the 32 x 36 entries so that consecutive lanes add
 // consecutive rows of one column -- RED.ADD.F64 requests that share 32 B sectors (measured:
 // 266 G RED/s coalesced vs 194 G RED/s one-lane-per-sector, scripts/micro/red_bench.cu).
-constexpr int COOP_STAGE_LD = 19;                                 // doubles per lane: half a block (18) + 1 pad
-constexpr int COOP_DBL = 32 * COOP_STAGE_LD + (12 * 32) / 2;      // stage + colb[6][32] + rowp[6][32] (ints)
+constexpr int COOP_STAGE_LD = 13;                                 // doubles per lane: a third of a block (2 columns) + 1 pad
+constexpr int COOP_DBL = 32 * COOP_STAGE_LD + (2 * 32 * 8) / 2;   // T3: diagonal stage + colb[32][8] + raw[32][8] (ints)
 struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in every column
   static constexpr bool kCoop = true;
   double* nz;
@@ -178,46 +178,137 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     r.oB = __ldg(pairoff + ((int64_t)(i * 2 + 1) * nelem + e) * nnpe + j);
     return r;
   }
-  // coop scratch layout (per warp): double stage[32][37]; int colb[6][32]; int rowp[6][32]
-  __device__ __forceinline__ void coop_cols(double* scratch, int lane, const Cols& cb, bool on) const {
-    int* colb = reinterpret_cast<int*>(scratch + 32 * COOP_STAGE_LD);
+  // ---- T3 path: cooperative emission with IN-WARP MERGING.  A lane (element, own node j) forms only two
+  // products: D = K_e[j, j] and X = K_e[next(j), j]; K_e[j, next(j)] = X' by symmetry.  Blocks of different elements
+  // of the warp that land on the same matrix block (same node on the diagonal; same edge, either orientation) are
+  // summed in shared memory and added once: the RED unit (266 G RED/s on B200, the scatter's bound) sees 194 instead
+  // of 324 requests per element for a strip of 5 quads.
+  //   addr area per warp: colb[32][8] = nodecol row of the own node ([6] = nodeinfo, [7] = list of group leaders);
+  //   raw[32][8] = (oA, oB) of the three targets (j,j), (next,j), (j,next); [6] = merge group mask; [7] = row node
+  __device__ __forceinline__ void t3_async_addr(int* addr, int lane, bool on, int nj, int64_t e, int j, int jn) const {
+    int* colb = addr + lane * 8;
+    int* raw = addr + 32 * 8 + lane * 8;
+    if (on) {
+      const unsigned dc = (unsigned)__cvta_generic_to_shared(colb);
+      const unsigned dr = (unsigned)__cvta_generic_to_shared(raw);
+      const int32_t* sc = nodecol + (int64_t)nj * 8;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dc), "l"(sc) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dc + 16), "l"(sc + 4) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dc + 24), "l"(sc + 6) : "memory");
+      const int ii[3] = {j, jn, j}, jj[3] = {j, j, jn};
 #pragma unroll
-    for (int c = 0; c < 6; ++c) colb[c * 32 + lane] = on ? cb.base[c] : -1;
-  }
-  __device__ __forceinline__ void coop_block(double* scratch, int lane, const Rows& rw, bool on, const double (&a)[6][6]) const {
-    double* stage = scratch;
-    const int* colb = reinterpret_cast<const int*>(scratch + 32 * COOP_STAGE_LD);
-    int* rowp = reinterpret_cast<int*>(scratch + 32 * COOP_STAGE_LD) + 6 * 32;
-    int ka = 0, kb = 0;
+      for (int t = 0; t < 3; ++t)
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      int p = -1;
-      if ((rw.mA >> r) & 1)
-        p = rw.oA + ka++;
-      else if ((rw.mB >> r) & 1)
-        p = rw.oB + kb++;
-      rowp[r * 32 + lane] = on ? p : -1;
+        for (int w = 0; w < 2; ++w)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr + (t * 2 + w) * 4),
+                       "l"(pairoff + ((int64_t)(ii[t] * 2 + w) * nelem + e) * 3 + jj[t])
+                       : "memory");
+    } else {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        colb[k] = k < 6 ? -1 : 0;
+        raw[k] = -1;
+      }
     }
-    // the block goes out in two halves (columns 0-2, 3-5) to keep the staging area small
+  }
+  // position (relative to the column start) of dof r of a node with run masks `inf` and run offsets oA / oB
+  static __device__ __forceinline__ int row_pos(int inf, int oA, int oB, int r) {
+    const int mA = inf & 63, mB = (inf >> 8) & 63, below = (1 << r) - 1;
+    if ((mA >> r) & 1) return oA >= 0 ? oA + __popc(mA & below) : -1;
+    if ((mB >> r) & 1) return oB >= 0 ? oB + __popc(mB & below) : -1;
+    return -1;
+  }
+  // merge groups of the warp: lanes with equal keys; the lowest lane of a group is its leader.  Writes the group
+  // mask to raw[lane][6] and the compact leader list to colb[k][7]; returns the number of leaders.
+  __device__ __forceinline__ int t3_groups(int* addr, int lane, bool on, unsigned long long key) const {
+    const unsigned full = 0xffffffffu;
+    const unsigned grp = __match_any_sync(full, on ? key : (0xffffffff00000000ull | (unsigned)lane));
+    const bool leader = on && (__ffs(grp) - 1 == lane);
+    const unsigned leaders = __ballot_sync(full, leader);
+    addr[32 * 8 + lane * 8 + 6] = (int)grp;
+    if (leader) addr[__popc(leaders & ((1u << lane) - 1)) * 8 + 7] = lane;
+    return __popc(leaders);
+  }
+  // diagonal pass: `a` = K_e[j, j]; lanes with the same own node are merged.  `stage`: 32 x COOP_STAGE_LD doubles,
+  // the block goes through it two columns at a time.
+  __device__ __forceinline__ void t3_emit_diag(double* stage, int* addr, int lane, bool on, int nj, const double (&a)[6][6]) const {
+    const int nlead = t3_groups(addr, lane, on, (unsigned long long)(unsigned)nj);
+    const int* raw = addr + 32 * 8;
+    const int sub = lane / 6, r = lane - sub * 6;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int third = 0; third < 3; ++third) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int r = 0; r < 6; ++r) stage[lane * COOP_STAGE_LD + c * 6 + r] = a[r][half * 3 + c];
+        for (int q = 0; q < 6; ++q) stage[lane * COOP_STAGE_LD + c * 6 + q] = a[q][third * 2 + c];
       __syncwarp();
-#pragma unroll 6
-      for (int it = 0; it < 18; ++it) {
-        const int q = it * 32 + lane;
-        const int o = q / 18;
-        const int k = q - o * 18;
-        const int c = k / 6;
-        const int r = k - c * 6;
-        const int b = colb[(half * 3 + c) * 32 + o];
-        const int rp = rowp[r * 32 + o];
-        if (b >= 0 && rp >= 0 FS_RED_GUARD) atomicAdd(nz + b + rp, stage[o * COOP_STAGE_LD + k]);
+#pragma unroll 1
+      for (int g = 0; g * 5 < nlead; ++g) {
+        const int k = g * 5 + sub;
+        if (lane >= 30 || k >= nlead) continue;
+        const int o = addr[k * 8 + 7];
+        const int rp = row_pos(addr[o * 8 + 6], raw[o * 8 + 0], raw[o * 8 + 1], r);
+        if (rp < 0) continue;
+        const int cb0 = addr[o * 8 + third * 2], cb1 = addr[o * 8 + third * 2 + 1];
+        double v0 = 0.0, v1 = 0.0;
+        for (unsigned mm = (unsigned)raw[o * 8 + 6]; mm; mm &= mm - 1) {
+          const double* sp = stage + (__ffs(mm) - 1) * COOP_STAGE_LD + r;
+          v0 += sp[0];
+          v1 += sp[6];
+        }
+        if (cb0 >= 0 FS_RED_GUARD) atomicAdd(nz + cb0 + rp, v0);
+        if (cb1 >= 0 FS_RED_GUARD) atomicAdd(nz + cb1 + rp, v1);
       }
       __syncwarp();
+    }
+  }
+  // edge pass: `a` = K_e[next(j), j] (rows: node nnext, columns: own node nj).  Lanes on the same edge are merged,
+  // the sum S goes to block (row, col) and S' to block (col, row).  `stage`: 32 x kStageLd doubles (the dead strips).
+  __device__ __forceinline__ void t3_emit_edge(double* stage, int* addr, int lane, bool on, int nj, int nnext,
+                                               const double (&a)[6][6]) const {
+    const unsigned lo = (unsigned)min(nj, nnext), hi = (unsigned)max(nj, nnext);
+    __syncwarp();  // every lane is done with the strips and with the diagonal pass
+    int* raw = addr + 32 * 8;
+    raw[lane * 8 + 7] = nnext;
+    const int nlead = t3_groups(addr, lane, on, ((unsigned long long)lo << 32) | hi);
+    double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int q = 0; q < 6; q += 2) st2[(c * 6 + q) >> 1] = make_double2(a[q][c], a[q + 1][c]);
+    __syncwarp();
+    const int sub = lane / 6, r = lane - sub * 6;
+#pragma unroll 1
+    for (int g = 0; g * 5 < nlead; ++g) {
+      const int k = g * 5 + sub;
+      if (lane >= 30 || k >= nlead) continue;
+      const int o = addr[k * 8 + 7];
+      const int eo = o / 3, jo = o - 3 * eo;
+      const int ln = 3 * eo + (jo == 2 ? 0 : jo + 1);  // lane whose own node is this block's row node
+      const int rowO = raw[o * 8 + 7];
+      // direct target (row node, own node) and transposed target (own node, row node)
+      const int rpd = row_pos(addr[ln * 8 + 6], raw[o * 8 + 2], raw[o * 8 + 3], r);
+      const int rpt = row_pos(addr[o * 8 + 6], raw[o * 8 + 4], raw[o * 8 + 5], r);
+      double vd[6], vt[6];  // S[r][c] and S[c][r]
+#pragma unroll
+      for (int c = 0; c < 6; ++c) vd[c] = vt[c] = 0.0;
+      for (unsigned mm = (unsigned)raw[o * 8 + 6]; mm; mm &= mm - 1) {
+        const int p = __ffs(mm) - 1;
+        const bool same = raw[p * 8 + 7] == rowO;
+        const double* sp = stage + p * kStageLd;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const double x = sp[c * 6 + r], y = sp[r * 6 + c];
+          vd[c] += same ? x : y;
+          vt[c] += same ? y : x;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int cbd = addr[o * 8 + c], cbt = addr[ln * 8 + c];
+        if (cbd >= 0 && rpd >= 0 FS_RED_GUARD) atomicAdd(nz + cbd + rpd, vd[c]);
+        if (cbt >= 0 && rpt >= 0 FS_RED_GUARD) atomicAdd(nz + cbt + rpt, vt[c]);
+      }
     }
   }
   __device__ __forceinline__ void block(const BlockRef&, const Cols& cb, const Rows& rw, const double (&a)[6][6]) const {
@@ -359,38 +450,41 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
   for (int l = 0; l < 3; ++l) ksum += __shfl_sync(full, kpart, (base + l) & 31);
   const double kavg = ksum / 6 * P.drill;
   __syncwarp();
-  if (!Emit::kCoop && !active) return;
   const int nj = j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]);
-  typename Emit::Cols ecols;
-  typename Emit::Rows erows[3];
-  if (active) {
-    ecols = emit.cols(nj);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) erows[i] = emit.rows(e, i, j, nn[i]);
-  }
-  double* coop = sw + NR * 6 * 32;
-  if constexpr (Emit::kCoop) emit.coop_cols(coop, lane, ecols, active);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  if constexpr (Emit::kCoop) {
+    // Symmetric form with in-warp merging: this lane forms D = K_e[j, j] and X = K_e[next(j), j] only.
+    const int jn = j == 2 ? 0 : j + 1;
+    const int nnext = jn == 0 ? nn[0] : (jn == 1 ? nn[1] : nn[2]);
+    double* coop = sw + NR * 6 * 32;
+    int* addr = reinterpret_cast<int*>(coop + 32 * COOP_STAGE_LD);
+    emit.t3_async_addr(addr, lane, active, nj, e, j, jn);
     double acc[6][6];
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
       for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-    const int src = base + i;
 #pragma unroll
     for (int s = 0; s < NR; ++s) {
-      double bi[6], bj[6];
+      if (!COMP && s < 3) {
+        // membrane rows of a homogeneous shell have no rotation columns in global dofs
+        double b[3];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) bi[r] = sw[(s * 6 + r) * 32 + src];
+        for (int r = 0; r < 3; ++r) b[r] = sw[(s * 6 + r) * 32 + lane];
 #pragma unroll
-      for (int cc = 0; cc < 6; ++cc) bj[cc] = sw[(s * 6 + cc) * 32 + lane];
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
+          for (int cc = 0; cc < 3; ++cc) acc[r][cc] = fma(b[r], b[cc], acc[r][cc]);
+      } else {
+        double b[6];
 #pragma unroll
-        for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(bi[r], bj[cc], acc[r][cc]);
+        for (int r = 0; r < 6; ++r) b[r] = sw[(s * 6 + r) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(b[r], b[cc], acc[r][cc]);
+      }
     }
-    if (i == j && validj) {
+    if (validj) {
       // drilling stiffness kavg on the nodal normal direction (nodal dof 6), rotated to global
       const double gg[3] = {gdir.x, gdir.y, gdir.z};
 #pragma unroll
@@ -398,10 +492,73 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * gg[r] * gg[cc];
     }
-    if constexpr (Emit::kCoop)
-      emit.coop_block(coop, lane, erows[i], active, acc);
-    else
-      emit.block(BlockRef{e, i, j}, ecols, erows[i], acc);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    emit.t3_emit_diag(coop, addr, lane, active, nj, acc);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
+    const int src = (base + jn) & 31;
+#pragma unroll
+    for (int s = 0; s < NR; ++s) {
+      if (!COMP && s < 3) {
+        double bi[3], bj[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) bi[r] = sw[(s * 6 + r) * 32 + src];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) bj[cc] = sw[(s * 6 + cc) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) acc[r][cc] = fma(bi[r], bj[cc], acc[r][cc]);
+      } else {
+        double bi[6], bj[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) bi[r] = sw[(s * 6 + r) * 32 + src];
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) bj[cc] = sw[(s * 6 + cc) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(bi[r], bj[cc], acc[r][cc]);
+      }
+    }
+    emit.t3_emit_edge(sw, addr, lane, active, nj, nnext, acc);
+  } else {
+    if (!active) return;
+    typename Emit::Cols ecols = emit.cols(nj);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      typename Emit::Rows erows = emit.rows(e, i, j, nn[i]);
+      double acc[6][6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
+      const int src = base + i;
+#pragma unroll
+      for (int s = 0; s < NR; ++s) {
+        double bi[6], bj[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) bi[r] = sw[(s * 6 + r) * 32 + src];
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) bj[cc] = sw[(s * 6 + cc) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(bi[r], bj[cc], acc[r][cc]);
+      }
+      if (i == j && validj) {
+        // drilling stiffness kavg on the nodal normal direction (nodal dof 6), rotated to global
+        const double gg[3] = {gdir.x, gdir.y, gdir.z};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * gg[r] * gg[cc];
+      }
+      emit.block(BlockRef{e, i, j}, ecols, erows, acc);
+    }
   }
 }
 
