@@ -71,8 +71,7 @@ struct EmitScatter {  // generic path: per-entry slot map, any dof numbering
 // in shared memory, then the warp walks the 32 x 36 entries so that consecutive lanes add
 // consecutive rows of one column -- RED.ADD.F64 requests that share 32 B sectors (measured:
 // 266 G RED/s coalesced vs 194 G RED/s one-lane-per-sector, scripts/micro/red_bench.cu).
-constexpr int COOP_STAGE_LD = 13;                                 // doubles per lane: a third of a block (2 columns) + 1 pad
-constexpr int COOP_DBL = 32 * COOP_STAGE_LD + (2 * 32 * 8) / 2;   // T3: diagonal stage + colb[32][8] + raw[32][8] (ints)
+constexpr int COOP_DBL = (2 * 32 * 8) / 2;   // T3: colb[32][8] + raw[32][8] (ints); blocks are staged over the dead strips
 struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in every column
   static constexpr bool kCoop = true;
   double* nz;
@@ -229,38 +228,49 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     if (leader) addr[__popc(leaders & ((1u << lane) - 1)) * 8 + 7] = lane;
     return __popc(leaders);
   }
-  // diagonal pass: `a` = K_e[j, j]; lanes with the same own node are merged.  `stage`: 32 x COOP_STAGE_LD doubles,
-  // the block goes through it two columns at a time.
-  __device__ __forceinline__ void t3_emit_diag(double* stage, int* addr, int lane, bool on, int nj, const double (&a)[6][6]) const {
+  // diagonal pass: `d` = upper triangle of the symmetric K_e[j, j] (row-major, r <= c); lanes with the same own node
+  // are merged.  `stage`: 32 x kStageLd doubles (the dead strips).
+  __device__ __forceinline__ void t3_emit_diag(double* stage, int* addr, int lane, bool on, int nj, const double (&d)[21]) const {
     const int nlead = t3_groups(addr, lane, on, (unsigned long long)(unsigned)nj);
     const int* raw = addr + 32 * 8;
-    const int sub = lane / 6, r = lane - sub * 6;
+    {
+      double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
 #pragma unroll
-    for (int third = 0; third < 3; ++third) {
+      for (int c = 0; c < 6; ++c)
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int q = 0; q < 6; ++q) stage[lane * COOP_STAGE_LD + c * 6 + q] = a[q][third * 2 + c];
-      __syncwarp();
-#pragma unroll 1
-      for (int g = 0; g * 5 < nlead; ++g) {
-        const int k = g * 5 + sub;
-        if (lane >= 30 || k >= nlead) continue;
-        const int o = addr[k * 8 + 7];
-        const int rp = row_pos(addr[o * 8 + 6], raw[o * 8 + 0], raw[o * 8 + 1], r);
-        if (rp < 0) continue;
-        const int cb0 = addr[o * 8 + third * 2], cb1 = addr[o * 8 + third * 2 + 1];
-        double v0 = 0.0, v1 = 0.0;
-        for (unsigned mm = (unsigned)raw[o * 8 + 6]; mm; mm &= mm - 1) {
-          const double* sp = stage + (__ffs(mm) - 1) * COOP_STAGE_LD + r;
-          v0 += sp[0];
-          v1 += sp[6];
-        }
-        if (cb0 >= 0 FS_RED_GUARD) atomicAdd(nz + cb0 + rp, v0);
-        if (cb1 >= 0 FS_RED_GUARD) atomicAdd(nz + cb1 + rp, v1);
-      }
-      __syncwarp();
+        for (int q = 0; q < 6; q += 2) st2[(c * 6 + q) >> 1] = make_double2(d[tri(q, c)], d[tri(q + 1, c)]);
     }
+    __syncwarp();
+    const int sub = lane / 6, r = lane - sub * 6;
+#pragma unroll 1
+    for (int g = 0; g * 5 < nlead; ++g) {
+      const int k = g * 5 + sub;
+      if (lane >= 30 || k >= nlead) continue;
+      const int o = addr[k * 8 + 7];
+      const int4 c0 = *reinterpret_cast<const int4*>(addr + o * 8);
+      const int4 c1 = *reinterpret_cast<const int4*>(addr + o * 8 + 4);
+      const int4 r0 = *reinterpret_cast<const int4*>(raw + o * 8);
+      const int rp = row_pos(c1.z, r0.x, r0.y, r);
+      if (rp < 0) continue;
+      const int cb[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
+      unsigned mm = (unsigned)raw[o * 8 + 6];
+      const double* sp = stage + o * kStageLd + r;
+      double v[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v[c] = sp[c * 6];
+      for (mm &= mm - 1; mm; mm &= mm - 1) {
+        const double* sq = stage + (__ffs(mm) - 1) * kStageLd + r;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v[c] += sq[c * 6];
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        if (cb[c] >= 0 FS_RED_GUARD) atomicAdd(nz + cb[c] + rp, v[c]);
+    }
+  }
+  // index of (r, c) in the row-major upper triangle of a symmetric 6x6 block
+  static __host__ __device__ constexpr int tri(int r, int c) {
+    return r <= c ? r * 6 - r * (r - 1) / 2 + (c - r) : c * 6 - c * (c - 1) / 2 + (r - c);
   }
   // edge pass: `a` = K_e[next(j), j] (rows: node nnext, columns: own node nj).  Lanes on the same edge are merged,
   // the sum S goes to block (row, col) and S' to block (col, row).  `stage`: 32 x kStageLd doubles (the dead strips).
@@ -285,14 +295,25 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
       const int o = addr[k * 8 + 7];
       const int eo = o / 3, jo = o - 3 * eo;
       const int ln = 3 * eo + (jo == 2 ? 0 : jo + 1);  // lane whose own node is this block's row node
-      const int rowO = raw[o * 8 + 7];
+      const int4 co0 = *reinterpret_cast<const int4*>(addr + o * 8);
+      const int4 co1 = *reinterpret_cast<const int4*>(addr + o * 8 + 4);
+      const int4 cl0 = *reinterpret_cast<const int4*>(addr + ln * 8);
+      const int4 cl1 = *reinterpret_cast<const int4*>(addr + ln * 8 + 4);
+      const int4 r0 = *reinterpret_cast<const int4*>(raw + o * 8);
+      const int4 r1 = *reinterpret_cast<const int4*>(raw + o * 8 + 4);
       // direct target (row node, own node) and transposed target (own node, row node)
-      const int rpd = row_pos(addr[ln * 8 + 6], raw[o * 8 + 2], raw[o * 8 + 3], r);
-      const int rpt = row_pos(addr[o * 8 + 6], raw[o * 8 + 4], raw[o * 8 + 5], r);
+      const int rpd = row_pos(cl1.z, r0.z, r0.w, r);
+      const int rpt = row_pos(co1.z, r1.x, r1.y, r);
+      const int rowO = r1.w;
+      const double* so = stage + o * kStageLd;
       double vd[6], vt[6];  // S[r][c] and S[c][r]
 #pragma unroll
-      for (int c = 0; c < 6; ++c) vd[c] = vt[c] = 0.0;
-      for (unsigned mm = (unsigned)raw[o * 8 + 6]; mm; mm &= mm - 1) {
+      for (int c = 0; c < 6; ++c) {
+        vd[c] = so[c * 6 + r];
+        vt[c] = so[r * 6 + c];
+      }
+      unsigned mm = (unsigned)r1.z;
+      for (mm &= mm - 1; mm; mm &= mm - 1) {
         const int p = __ffs(mm) - 1;
         const bool same = raw[p * 8 + 7] == rowO;
         const double* sp = stage + p * kStageLd;
@@ -303,11 +324,12 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
           vt[c] += same ? y : x;
         }
       }
+      const int cbd[6] = {co0.x, co0.y, co0.z, co0.w, co1.x, co1.y};
+      const int cbt[6] = {cl0.x, cl0.y, cl0.z, cl0.w, cl1.x, cl1.y};
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        const int cbd = addr[o * 8 + c], cbt = addr[ln * 8 + c];
-        if (cbd >= 0 && rpd >= 0 FS_RED_GUARD) atomicAdd(nz + cbd + rpd, vd[c]);
-        if (cbt >= 0 && rpt >= 0 FS_RED_GUARD) atomicAdd(nz + cbt + rpt, vt[c]);
+        if (cbd[c] >= 0 && rpd >= 0 FS_RED_GUARD) atomicAdd(nz + cbd[c] + rpd, vd[c]);
+        if (cbt[c] >= 0 && rpt >= 0 FS_RED_GUARD) atomicAdd(nz + cbt[c] + rpt, vt[c]);
       }
     }
   }
@@ -455,46 +477,13 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
     // Symmetric form with in-warp merging: this lane forms D = K_e[j, j] and X = K_e[next(j), j] only.
     const int jn = j == 2 ? 0 : j + 1;
     const int nnext = jn == 0 ? nn[0] : (jn == 1 ? nn[1] : nn[2]);
-    double* coop = sw + NR * 6 * 32;
-    int* addr = reinterpret_cast<int*>(coop + 32 * COOP_STAGE_LD);
+    int* addr = reinterpret_cast<int*>(sw + NR * 6 * 32);
     emit.t3_async_addr(addr, lane, active, nj, e, j, jn);
-    double acc[6][6];
+    // D is symmetric: 21 accumulators (row-major upper triangle); X is a full block.  One pass over the strain
+    // rows feeds both (the own row b_j is loaded once).
+    double dd[21], acc[6][6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-#pragma unroll
-    for (int s = 0; s < NR; ++s) {
-      if (!COMP && s < 3) {
-        // membrane rows of a homogeneous shell have no rotation columns in global dofs
-        double b[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) b[r] = sw[(s * 6 + r) * 32 + lane];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc) acc[r][cc] = fma(b[r], b[cc], acc[r][cc]);
-      } else {
-        double b[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) b[r] = sw[(s * 6 + r) * 32 + lane];
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(b[r], b[cc], acc[r][cc]);
-      }
-    }
-    if (validj) {
-      // drilling stiffness kavg on the nodal normal direction (nodal dof 6), rotated to global
-      const double gg[3] = {gdir.x, gdir.y, gdir.z};
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * gg[r] * gg[cc];
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
-    emit.t3_emit_diag(coop, addr, lane, active, nj, acc);
+    for (int k = 0; k < 21; ++k) dd[k] = 0.0;
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -502,28 +491,36 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
     const int src = (base + jn) & 31;
 #pragma unroll
     for (int s = 0; s < NR; ++s) {
-      if (!COMP && s < 3) {
-        double bi[3], bj[3];
+      // membrane rows of a homogeneous shell have no rotation columns in global dofs
+      constexpr int kMemb = COMP ? 0 : 3;
+      const int w = s < kMemb ? 3 : 6;
+      double bi[6], bj[6];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) bi[r] = sw[(s * 6 + r) * 32 + src];
+      for (int r = 0; r < 6; ++r)
+        if (r < w) bi[r] = sw[(s * 6 + r) * 32 + src];
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) bj[cc] = sw[(s * 6 + cc) * 32 + lane];
+      for (int cc = 0; cc < 6; ++cc)
+        if (cc < w) bj[cc] = sw[(s * 6 + cc) * 32 + lane];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 6; ++r)
 #pragma unroll
-          for (int cc = 0; cc < 3; ++cc) acc[r][cc] = fma(bi[r], bj[cc], acc[r][cc]);
-      } else {
-        double bi[6], bj[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) bi[r] = sw[(s * 6 + r) * 32 + src];
-#pragma unroll
-        for (int cc = 0; cc < 6; ++cc) bj[cc] = sw[(s * 6 + cc) * 32 + lane];
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(bi[r], bj[cc], acc[r][cc]);
-      }
+        for (int cc = 0; cc < 6; ++cc)
+          if (r < w && cc < w) {
+            acc[r][cc] = fma(bi[r], bj[cc], acc[r][cc]);
+            if (r <= cc) dd[Emit::tri(r, cc)] = fma(bj[r], bj[cc], dd[Emit::tri(r, cc)]);
+          }
     }
+    if (validj) {
+      // drilling stiffness kavg on the nodal normal direction (nodal dof 6), rotated to global
+      const double gg[3] = {gdir.x, gdir.y, gdir.z};
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = r; cc < 3; ++cc) dd[Emit::tri(3 + r, 3 + cc)] += kavg * gg[r] * gg[cc];
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();  // every lane is done with the strips; the addressing data has landed
+    emit.t3_emit_diag(sw, addr, lane, active, nj, dd);
     emit.t3_emit_edge(sw, addr, lane, active, nj, nnext, acc);
   } else {
     if (!active) return;
