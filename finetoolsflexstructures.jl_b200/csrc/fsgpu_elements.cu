@@ -1227,6 +1227,139 @@ __global__ void k_beam_matrix(BeamArgs P, int op, Emit emit) {
   }
   emit.block(BlockRef{e, bI, bJ}, emit.cols(cn[bJ]), emit.rows(e, bI, bJ, cn[bI]), Kg);
 }
+// Fast-path variant: ONE lane per element forms the four 6x6 blocks one after the other with compile-time block
+// indices (the sparse local matrices fold into registers, the kinematics are evaluated once instead of four times),
+// and every block leaves through the warp-cooperative emission (coalesced RED rows).
+template <int OP, int BI, int BJ>
+__device__ __forceinline__ void beam_block_global(const BeamArgs& P, const BeamSec& s, const BeamKin& k, const double (&F)[3][3],
+                                                  const double (&Om)[3], double (&Kg)[6][6]) {
+  double Kl[6][6];
+  if (OP == 0) {
+    double DN[6], aN[6][12];
+    beam_natural_stiffness(P.E, P.G, s, k.L1, DN);
+    beam_aN(k.L1, aN);
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double v = 0.0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) v += aN[m][BI * 6 + p] * DN[m] * aN[m][BJ * 6 + q];
+        Kl[p][q] = v;
+      }
+  } else if (OP == 2) {
+    double DN[6], PN[6], S[12][12];
+    beam_natural_stiffness(P.E, P.G, s, k.L1, DN);
+#pragma unroll
+    for (int m = 0; m < 6; ++m) PN[m] = DN[m] * k.dN[m];
+    beam_local_geo(PN, k.L1, S);
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) Kl[p][q] = S[BI * 6 + p][BJ * 6 + q];
+  } else {
+    double M[12][12];
+    beam_local_mass(s, P.rho, k.L0, P.mass_type, M);
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) Kl[p][q] = M[BI * 6 + p][BJ * 6 + q];
+  }
+  double T[6][6];
+#pragma unroll
+  for (int sp = 0; sp < 2; ++sp)
+#pragma unroll
+    for (int sq = 0; sq < 2; ++sq) {
+      double tmp[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          tmp[a][cc] = Kl[sp * 3 + a][sq * 3 + 0] * F[cc][0] + Kl[sp * 3 + a][sq * 3 + 1] * F[cc][1] + Kl[sp * 3 + a][sq * 3 + 2] * F[cc][2];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) T[sp * 3 + r][sq * 3 + cc] = F[r][0] * tmp[0][cc] + F[r][1] * tmp[1][cc] + F[r][2] * tmp[2][cc];
+    }
+  if (OP == 3) {
+    const double OS[3][3] = {{0, -Om[2], Om[1]}, {Om[2], 0, -Om[0]}, {-Om[1], Om[0], 0}};
+#pragma unroll
+    for (int sp = 0; sp < 2; ++sp)
+#pragma unroll
+      for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) v += OS[r][m] * T[sp * 3 + m][sq * 3 + cc] - T[sp * 3 + r][sq * 3 + m] * OS[m][cc];
+            Kg[sp * 3 + r][sq * 3 + cc] = v;
+          }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) Kg[r][cc] = T[r][cc];
+  }
+}
+constexpr int BEAM_WARP_DBL = 32 * EmitRuns::kStageLd + (6 * 32) / 2 + 4 * (EmitRuns::kAddrInts / 2);
+template <int OP>
+__global__ void __launch_bounds__(128) k_beam_matrix_coop(BeamArgs P, EmitRuns emit) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* wbase = smem + (size_t)wib * BEAM_WARP_DBL;  // stage[32][kStageLd], rowp[6][32], 4 addressing areas
+  int* addr0 = reinterpret_cast<int*>(wbase + 32 * EmitRuns::kStageLd + (6 * 32) / 2);
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool active = e < P.nelem;
+  int cn[2] = {0, 0};
+  if (active) {
+    cn[0] = __ldg(P.conn + e * 2);
+    cn[1] = __ldg(P.conn + e * 2 + 1);
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+    emit.async_addr(addr0 + b * EmitRuns::kAddrInts, lane, active, cn[b & 1], cn[b >> 1], e, b >> 1, b & 1);
+  BeamSec s;
+  BeamKin k;
+  double F[3][3], Om[3] = {0, 0, 0};
+  if (active) {
+    beam_load(P, e, s, k);
+    const double Fi[3][3] = {{k.Ft.e1.x, k.Ft.e2.x, k.Ft.e3.x}, {k.Ft.e1.y, k.Ft.e2.y, k.Ft.e3.y}, {k.Ft.e1.z, k.Ft.e2.z, k.Ft.e3.z}};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) F[r][cc] = Fi[r][cc];
+    if (OP == 3) {
+      // element spin (src/FEMMCorotBeamModule.jl:934-947)
+      const double* vI = P.v1 + (int64_t)cn[0] * 6;
+      const double* vJ = P.v1 + (int64_t)cn[1] * 6;
+      auto loc = [&](const double* v, int off, int a) { return v[off] * F[0][a] + v[off + 1] * F[1][a] + v[off + 2] * F[2][a]; };
+      const double w1 = (loc(vI, 3, 0) + loc(vJ, 3, 0)) / 2;
+      const double w2 = (loc(vI, 0, 2) - loc(vJ, 0, 2)) / k.L1;
+      const double w3 = (loc(vJ, 0, 1) - loc(vI, 0, 1)) / k.L1;
+      Om[0] = w1 * F[0][0] + w2 * F[0][1] + w3 * F[0][2];
+      Om[1] = w1 * F[1][0] + w2 * F[1][1] + w3 * F[1][2];
+      Om[2] = w1 * F[2][0] + w2 * F[2][1] + w3 * F[2][2];
+    }
+  }
+  double Kg[6][6];
+#define BEAM_ROUND(BI, BJ)                                                                  \
+  do {                                                                                      \
+    if (active) {                                                                           \
+      beam_block_global<OP, BI, BJ>(P, s, k, F, Om, Kg);                                     \
+    } else {                                                                                \
+      for (int r = 0; r < 6; ++r)                                                           \
+        for (int cc = 0; cc < 6; ++cc) Kg[r][cc] = 0.0;                                     \
+    }                                                                                       \
+    emit.coop_emit_full(wbase, addr0 + (BI * 2 + BJ) * EmitRuns::kAddrInts, lane, Kg);      \
+  } while (0)
+  BEAM_ROUND(0, 0);
+  BEAM_ROUND(0, 1);
+  BEAM_ROUND(1, 0);
+  BEAM_ROUND(1, 1);
+#undef BEAM_ROUND
+}
 // restoring force: elvec = Te (-aN' DN dN)   (src/FEMMCorotBeamModule.jl:1132-1157)
 // mode 0: restoring force; mode 1: consistent nodal loads of a uniform global force per unit length
 // (distribloads_global, src/FEMMCorotBeamModule.jl:1186-1247)
@@ -1540,9 +1673,24 @@ int beam_matrix(fsgpu_ctx* c, const fsgpu_beam_params* p, int op) {
   const int64_t n = B.nelem * 4;
   FS_TRY(time_begin(c));
   if (n > 0) {
-    if (c->fast)
-      k_beam_matrix<EmitRuns><<<grid_for(n, 128), 128, 0, c->stream>>>(B, op, runs_of(c));
-    else
+    if (c->fast) {
+      const size_t sm = (size_t)4 * BEAM_WARP_DBL * sizeof(double);
+      const int grid = grid_for(B.nelem, 128);
+#define BEAM_GO(OPV)                                                                                                   \
+  do {                                                                                                                 \
+    FS_CUDA(cudaFuncSetAttribute(k_beam_matrix_coop<OPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));      \
+    k_beam_matrix_coop<OPV><<<grid, 128, sm, c->stream>>>(B, runs_of(c));                                              \
+  } while (0)
+      if (op == 0)
+        BEAM_GO(0);
+      else if (op == 1)
+        BEAM_GO(1);
+      else if (op == 2)
+        BEAM_GO(2);
+      else
+        BEAM_GO(3);
+#undef BEAM_GO
+    } else
       k_beam_matrix<EmitScatter><<<grid_for(n, 128), 128, 0, c->stream>>>(B, op, scatter_of(c));
     c->launches++;
   }

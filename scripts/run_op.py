@@ -15,6 +15,24 @@ which = sys.argv[1] if len(sys.argv) > 1 else "q4rs"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 det = len(sys.argv) > 4 and sys.argv[4] == "det"
+if which == "beam":
+    w = wl.c5_beam_lattice(n if n < 200 else 69)
+    sc = w["sections"]
+    secs = f.FESetL2Beam(sc["A"], sc["I1"], sc["I2"], sc["I3"], sc["J"], sc["A2s"], sc["A3s"], sc["x1x2"])
+    bf = f.FEMMCorotBeam(f.IntegDomain(w["conn"]), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]), secs)
+    geom0 = f.NodalField.__new__(f.NodalField)
+    geom0.values = w["xyz"]
+    dchi = f.NodalField.__new__(f.NodalField)
+    dchi.values, dchi.dofnums, dchi._nfree = None, w["dofnums"], w["nfree"]
+    bf._sync_mesh(geom0)
+    bf._startassembly(f.SysmatAssemblerFFBlock(), dchi)
+    bf.ctx.set_state(w["u1"], w["Rfield1"])
+    bp = bf._params()
+    for op in ("stiffness", "geostiffness", "mass"):
+        for _ in range(reps):
+            bf.ctx.beam_op(op, bp)
+            print("beam", op, "nelem", w["conn"].shape[0], "kernel ms", bf.ctx.last_kernel_ms, flush=True)
+    sys.exit(0)
 if which == "q4rs":
     w = wl.c2_q4rs_plate(n)
     femm = f.FEMMShellQ4RS(f.IntegDomain(w["conn"], f.GaussRule2x2(), w["thickness"]), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]))
