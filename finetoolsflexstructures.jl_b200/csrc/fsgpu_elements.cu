@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
   T3Geom g;
   M3 A;
   Constit C;
+  double wm = 0.0, wb = 0.0, ws = 0.0;  // homogeneous weights
   if (active) {
     const int32_t* cn = P.conn + e * 3;
     nn[0] = __ldg(cn);
@@ -403,7 +404,18 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
     const double4 nv = ldg4(P.nrm + (j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2])));
     validj = nv.w != 0.0;
     A = nodal_triad(g.E, v3(nv.x, nv.y, nv.z), validj);
-    build_constit_t3(P, e, g.E, g.Ae, SHEARK ? (1.0 / 3) : 1.0, COMP, C);
+    if constexpr (COMP) {
+      build_constit_t3(P, e, g.E, g.Ae, SHEARK ? (1.0 / 3) : 1.0, true, C);
+    } else {
+      // homogeneous shell: the LDL' factors of Dps and Dt come from the host (P.hf), only the three
+      // weights (membrane, bending, shear) depend on the element
+      const double t = P.nthick == 1 ? __ldg(P.thick) : __ldg(P.thick + e);
+      const double h2 = 2 * g.Ae;  // h^2, h = sqrt(2 Ae)
+      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h2);
+      wm = t * g.Ae;
+      wb = (t * t * t) / 12 * g.Ae;
+      ws = t * stab * g.Ae * (SHEARK ? (1.0 / 3) : 1.0);
+    }
   }
   constexpr int NSETS = SHEARK ? 3 : 1;
 #pragma unroll
@@ -441,28 +453,42 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
       double R[2][2], brn[5][2];
       node_R(A, R);
       node_bt_rot(gx, gy, bs, R, brn);
-      kpart += node_kavg_part(C, brn, set > 0);
       double bg[8][6];
       gdir = node_strip(g.E, A, gx, gy, bs, P1, P2, bg);
-      fold_constit(C, bg);
       // K = sum_s d_s b_s (x) b_s = sum_s (sqrt(d_s) b_s) (x) (sqrt(d_s) b_s): d_s > 0 for a positive
       // definite constitutive matrix (a negative pivot raises flag[2] -> FSGPU_ERR_ARG)
-      if (set == 0) {
+      double q[8];
+      if constexpr (COMP) {
+        kpart += node_kavg_part(C, brn, set > 0);
+        fold_constit(C, bg);
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
           const double d = constit_d(C, s);
           if (d < 0.0) atomicExch(P.flag + 2, 1);
-          const double q = sqrt(d);
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) sw[(s * 6 + cc) * 32 + lane] = q * bg[s][cc];
+          q[s] = sqrt(d);
         }
       } else {
+        kpart += node_kavg_part_h(P.hf, wb, ws, brn, set > 0);
+        fold_homogeneous(P.hf, bg);
+        const double qm = sqrt(wm), qb = sqrt(wb), qs = sqrt(ws);
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const double q = sqrt(constit_d(C, 6 + s));
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) sw[((6 + 2 * set + s) * 6 + cc) * 32 + lane] = q * bg[6 + s][cc];
+        for (int s = 0; s < 3; ++s) {
+          q[s] = qm * P.hf.sdps[s];
+          q[3 + s] = qb * P.hf.sdps[s];
         }
+        q[6] = qs * P.hf.sdts[0];
+        q[7] = qs * P.hf.sdts[1];
+      }
+      if (set == 0) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) sw[(s * 6 + cc) * 32 + lane] = q[s] * bg[s][cc];
+      } else {
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) sw[((6 + 2 * set + s) * 6 + cc) * 32 + lane] = q[6 + s] * bg[6 + s][cc];
       }
     }
   }

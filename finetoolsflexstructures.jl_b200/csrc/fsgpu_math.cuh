@@ -331,6 +331,33 @@ FS_HD void fold3(const HomogFactors& H, double (&m)[3][6]) {
   }
 }
 
+// homogeneous shell: b <- L' b with the host-factored block-diagonal L (membrane | bending | shear)
+FS_HD void fold_homogeneous(const HomogFactors& H, double (&b)[8][6]) {
+  for (int c = 0; c < 6; ++c) {
+    b[0][c] += H.L10 * b[1][c] + H.L20 * b[2][c];
+    b[1][c] += H.L21 * b[2][c];
+    b[3][c] += H.L10 * b[4][c] + H.L20 * b[5][c];
+    b[4][c] += H.L21 * b[5][c];
+    b[6][c] += H.Lt * b[7][c];
+  }
+}
+// node_kavg_part for a homogeneous shell: wb, ws = bending and shear weights of the element
+FS_HD double node_kavg_part_h(const HomogFactors& H, double wb, double ws, const double (&brn)[5][2], bool shear_only) {
+  double kb = 0.0, ks0 = 0.0, ks1 = 0.0;
+  for (int cl = 0; cl < 2; ++cl) {
+    const double f3 = brn[0][cl] + H.L10 * brn[1][cl] + H.L20 * brn[2][cl];
+    const double f4 = brn[1][cl] + H.L21 * brn[2][cl];
+    const double f5 = brn[2][cl];
+    const double f6 = brn[3][cl] + H.Lt * brn[4][cl];
+    const double f7 = brn[4][cl];
+    kb += H.dps[0] * f3 * f3 + H.dps[1] * f4 * f4 + H.dps[2] * f5 * f5;
+    ks0 += f6 * f6;
+    ks1 += f7 * f7;
+  }
+  const double k = ws * (H.dts[0] * ks0 + H.dts[1] * ks1);
+  return shear_only ? k : k + wb * kb;
+}
+
 // b <- L' b (rows), so that K = sum_s d_s b_s (x) b_s.
 FS_HD void fold_constit(const Constit& C, double (&b)[8][6]) {
   for (int c = 0; c < 6; ++c) {
