@@ -285,13 +285,18 @@ def explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
         Uh = ex.get_state()[0]
         ke = ex.kinetic_energy()
     knnz = nnz
-    alg_step = (12.0 * knnz + 10 * 8.0 * nf) / nelem  # f64 value + i32 column per entry, ~10 vector passes
+    _, _, nruns, idx_entries = ex.layout()
+    # f64 value per entry + one i32 column index per entry of every distinct row pattern (runs of <= 6 rows share
+    # one), ~10 vector passes.  SURVEY 8(d)'s figure for the plain Int32 CSR form is 12 B per entry.
+    alg_step = (8.0 * knnz + 4.0 * idx_entries + 10 * 8.0 * nf) / nelem
+    alg_step_csr = (12.0 * knnz + 10 * 8.0 * nf) / nelem
     expl = {"workload": f"explicit central differences, T3FF, {nelem} elements per rank x {world} rank(s), SpMV form (K_ff CSR, lumped M)",
             "steps_per_s": 1e3 / step_ms, "element_steps_per_s": nelem * world * 1e3 / step_ms, "ms_per_step": step_ms, "dt": dt,
             "omega_max": float(np.sqrt(lam)), "nsteps_timed": nsteps, "gpu_launches": int(launches), "max_abs_U": float(np.abs(Uh).max()),
             "kinetic_energy": ke, "interface_exchange": "pairwise NCCL isend/irecv of packed interface E entries" if world > 1 else "none",
             "roofline": {"bound": "hbm", "achieved": alg_step * nelem / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg_step * nelem / (step_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_element_step": alg_step,
+                         "plain_csr_bytes_per_element_step": alg_step_csr, "row_runs": int(nruns), "index_entries_read": int(idx_entries),
                          "kernel": "k_spmv_step + k_update_u"}}
     # CPU arm for the explicit loop (rank 0, bounded sample: a 1/100-size strip, all host threads)
     cpu = None
@@ -611,10 +616,26 @@ def main():
     out_bytes = 8.0 * nnz / nelem  # values written once (pattern reused)
     alg_bytes = Q4_IN_BYTES + out_bytes
     achieved = alg_bytes * nelem / (kernel_ms * 1e-3) / 1e9
+    # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture (same workload size)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_q4_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if int(tj.get("nelem", -1)) == int(nelem):
+                traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source")
+        except (OSError, ValueError, KeyError):
+            pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "kernel": "k_q4_stiffness<false,EmitScatter>",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "kernel": "k_q4_stiffness<false,false,EmitRuns>",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_element": alg_bytes,
                 "kernel_share_of_step": kernel_ms / ms_per_step}
+    # north_star: "the slower of FP64 peak and HBM bytes at peak bandwidth"
+    t_hbm = alg_bytes * nelem / (hbm_peak * 1e9)
+    t_fp64 = Q4_FLOPS * nelem / (fp64_peak * 1e12)
+    roofline["north_star"] = {"binding": "fp64" if t_fp64 >= t_hbm else "hbm", "t_roof_ms": max(t_hbm, t_fp64) * 1e3,
+                              "frac": max(t_hbm, t_fp64) * 1e3 / kernel_ms}
     fl = Q4_FLOPS * nelem / (kernel_ms * 1e-3) / 1e12
     fp64 = {"achieved_tflops": fl, "peak_tflops": fp64_peak, "frac": fl / fp64_peak, "flops_per_element": Q4_FLOPS,
             "peak_source": "fsgpu_measure_peaks DFMA micro-kernel on this device", "copy_gbs_this_device": copy_bw}

@@ -319,6 +319,12 @@ class Explicit:
         check(lib.fsgpu_explicit_omega_max(self._h, int(maxit), C.byref(lam)))
         return lam.value
 
+    def layout(self):
+        """(rows, stored entries, runs of rows sharing one column pattern, column indices read per SpMV)."""
+        v = [C.c_int64() for _ in range(4)]
+        check(lib.fsgpu_explicit_layout(self._h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
     def kinetic_energy(self):
         ke = C.c_double()
         check(lib.fsgpu_explicit_kinetic_energy(self._h, C.byref(ke)))

@@ -20,6 +20,7 @@ struct fsgpu_explicit {
   DBuf<int32_t> rowptr, colval;
   DBuf<int32_t> runs;   // [nruns + 1] first rows of the runs of <= 6 consecutive rows with one column pattern
   int64_t nruns = 0;
+  int64_t index_entries = 0;  // column indices actually read per SpMV (one pattern per run)
   DBuf<double> val;
   DBuf<double> M, C, invMC, U, V, A, F0, E, X, Y;
   double dt = 0, c_scale = 0;
@@ -105,6 +106,14 @@ __global__ void k_run_flags(const int32_t* __restrict__ same, int64_t n, int32_t
   while (back <= 8 * SNR && r - back >= 0 && same[r - back]) ++back;
   // rows with a longer history of equal patterns are rare (isolated elements): they start their own run
   flag[r] = (back > 8 * SNR) ? 1 : (back % SNR == 0 ? 1 : 0);
+}
+__global__ void k_run_entries(const int32_t* __restrict__ runs, int64_t nruns, const int32_t* __restrict__ rowptr,
+                              unsigned long long* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  unsigned long long v = 0;
+  if (i < nruns) v = (unsigned long long)(rowptr[runs[i] + 1] - rowptr[runs[i]]);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
 }
 __global__ void k_iota(int32_t* __restrict__ v, int64_t n) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -273,6 +282,9 @@ int alloc_vectors(fsgpu_explicit* h) {
       FS_CUDA(cudaStreamSynchronize(st));
       const int32_t last = (int32_t)h->n;
       FS_CUDA(cudaMemcpyAsync(h->runs.p + h->nruns, &last, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      FS_CUDA(cudaMemsetAsync(nsel.p, 0, sizeof(int64_t), st));
+      XL(h, k_run_entries, h->nruns, h->runs.p, h->nruns, h->rowptr.p, reinterpret_cast<unsigned long long*>(nsel.p));
+      FS_CUDA(cudaMemcpyAsync(&h->index_entries, nsel.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
     FS_CUDA(cudaStreamSynchronize(st));
   }
@@ -351,6 +363,15 @@ extern "C" int fsgpu_explicit_create_from_ctx(fsgpu_explicit** out, fsgpu_ctx* c
     return rc;
   }
   *out = h;
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_explicit_layout(fsgpu_explicit* h, int64_t* nrows, int64_t* nnz, int64_t* nruns, int64_t* index_entries) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  if (nrows) *nrows = h->n;
+  if (nnz) *nnz = h->nnz;
+  if (nruns) *nruns = h->nruns;
+  if (index_entries) *index_entries = h->index_entries;
   return FSGPU_OK;
 }
 

@@ -216,6 +216,10 @@ int fsgpu_explicit_create(fsgpu_explicit** h, fsgpu_ctx* ctx, int64_t n, const i
 /* same, adopting device-resident results: K = last matrix result of `ctx` (must be FFBLOCK),
  * M = last vector result (fsgpu_shell_mass_diag with nfree_only) */
 int fsgpu_explicit_create_from_ctx(fsgpu_explicit** h, fsgpu_ctx* ctx, double c_scale, double dt);
+/* storage layout of the loop's stiffness (measurement support): rows, stored entries, the number of runs of
+ * consecutive rows that share one column pattern (the 6 dofs of a shell node), and the column indices one SpMV
+ * actually reads (one pattern per run): traffic per step = 8 nnz + 4 index_entries + vector passes */
+int fsgpu_explicit_layout(fsgpu_explicit* h, int64_t* nrows, int64_t* nnz, int64_t* nruns, int64_t* index_entries);
 int fsgpu_explicit_destroy(fsgpu_explicit* h);
 int fsgpu_explicit_set_state(fsgpu_explicit* h, const double* U0, const double* V0);
 /* constant load vector F0 scaled by a per-step factor table (force!(F,t) closures of the
