@@ -262,6 +262,50 @@ def test_assembled_stiffness_and_mass(fs, kind, asm):
         assert abs(A - A.T).max() == 0.0, "SparseSymm result must be exactly symmetric"
 
 
+@pytest.mark.parametrize("kind,comp", [("t3", False), ("t3", True), ("q4", False)])
+@pytest.mark.parametrize("variant", ["shuffled", "duplicated", "reversed"])
+def test_element_order_and_duplicates(fs, kind, comp, variant):
+    """The fast-path kernels merge, inside a warp, the blocks of different elements that land on the same
+    matrix block.  The result must not depend on which elements share a warp: random element order (hardly any
+    merging), reversed order, and repeated elements (the same three nodes twice in one warp, also with the
+    opposite edge orientation) are all checked against the oracle."""
+    xyz, conn = meshes.shell_mesh(kind, n=9)
+    rng = np.random.default_rng(5)
+    if variant == "shuffled":
+        conn = conn[rng.permutation(conn.shape[0])]
+    elif variant == "reversed":
+        conn = conn[::-1].copy()
+    else:
+        # every 7th element twice in a row; T3 copies start from another node (same triangle, rotated connectivity)
+        rep = conn[::7]
+        if kind == "t3":
+            rep = np.roll(rep, 1, axis=1)
+        parts = []
+        for k in range(0, conn.shape[0], 7):
+            parts.append(conn[k:k + 1])
+            parts.append(rep[k // 7:k // 7 + 1])
+            parts.append(conn[k + 1:k + 7])
+        conn = np.ascontiguousarray(np.concatenate(parts))
+    lay, cs_all = _layup()
+    cs = cs_all if comp else None
+    od = meshes.clamp_edge_dofs(xyz)
+    f = fs.femm
+    femm = _make_femm(fs, kind, conn, comp, cs)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs()
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals(kind, xyz, conn, fixed=cs[:, 2] if comp else None)
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    Ko = _oracle_K(kind, comp, xyz, conn, normals, valid, cs)
+    dn = od.gatherdofnums(conn)
+    for asm in ("ffblock", "sparse"):
+        K = f.stiffness(femm, _assembler(fs, asm), geom0, u0, R0, dchi)
+        n = od.nfreedofs if asm == "ffblock" else od.nalldofs
+        _check_matrix(K, fx.assemble_matrix(asm, Ko, dn, od.nalldofs, od.nfreedofs), n)
+
+
 def test_symm_drops_exact_zeros_flat_plate(fs):
     """Flat axis-aligned plate: membrane/bending cross terms are exact zeros that
     SysmatAssemblerSparseSymm drops (value-dependent pattern)."""
