@@ -126,6 +126,7 @@ _SIGNATURES = {
     "fsgpu_explicit_device_state": [_vp, _P(_vp), _P(_vp), _P(_vp), _P(_vp)],
     "fsgpu_explicit_step_begin": [_vp],
     "fsgpu_explicit_step_end": [_vp, _dbl],
+    "fsgpu_d2h_bytes": [_vp, _P(_i64)],
     "fsgpu_explicit_layout": [_vp, _P(_i64), _P(_i64), _P(_i64), _P(_i64)],
 }
 _RESTYPE = {"fsgpu_last_error": C.c_char_p, "fsgpu_launch_count": _i64}

@@ -154,6 +154,12 @@ class Context:
         check(lib.fsgpu_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
+    @property
+    def d2h_bytes(self):
+        v = C.c_int64()
+        check(lib.fsgpu_d2h_bytes(self._h, C.byref(v)))
+        return v.value
+
     def set_deterministic(self, on=True):
         """Prefer the atomics-free T3 tile kernel (bitwise reproducible); effective at the next symbolic phase."""
         check(lib.fsgpu_set_deterministic(self._h, 1 if on else 0))

@@ -5,7 +5,6 @@
 #include <emmintrin.h>
 #endif
 
-#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -54,6 +53,7 @@ int upload(fsgpu_ctx* c, void* dst, const void* src, size_t bytes) {
 }
 int download(fsgpu_ctx* c, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return FSGPU_OK;
+  c->d2h_bytes += (int64_t)bytes;
   FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   return FSGPU_OK;
 }
@@ -897,6 +897,7 @@ extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int6
   FS_CUDA(cudaStreamSynchronize(st));
 
   c->target = target;
+  c->rle_for = nullptr;  // the cached run-length form belongs to the previous pattern
   c->prows = ti.nr;
   c->pcols = ti.nc;
   c->pnnz = total;
@@ -998,37 +999,154 @@ extern "C" int fsgpu_result_size(fsgpu_ctx* c, int64_t* nrows, int64_t* ncols, i
 
 
 // ------------------------------------------------------------------------------------
-// fetch of a large pattern: int32 rows over PCIe, widened on the host
+// fetch of a large pattern: compact row indices over PCIe, expanded to Int64 1-based on the host
 // ------------------------------------------------------------------------------------
 namespace fs {
-static void widen_plus1(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+// Destination arrays are written once and not read here: non-temporal stores (no read-for-ownership traffic),
+// 16 bytes at a time where the address allows it.
 #if defined(__x86_64__)
-  // non-temporal stores: the destination is written once and not read here (no read-for-ownership traffic)
-  for (int64_t i = 0; i < n; ++i) _mm_stream_si64(reinterpret_cast<long long*>(out + i), (long long)in[i] + 1);
-  _mm_sfence();
+static inline void store_nt(int64_t* __restrict__ dst, const int64_t* __restrict__ src, int64_t n) {
+  int64_t i = 0;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) && n > 0) {
+    _mm_stream_si64(reinterpret_cast<long long*>(dst), (long long)src[0]);
+    i = 1;
+  }
+  for (; i + 1 < n; i += 2)
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i)));
+  if (i < n) _mm_stream_si64(reinterpret_cast<long long*>(dst + i), (long long)src[i]);
+}
 #else
-  for (int64_t i = 0; i < n; ++i) out[i] = (int64_t)in[i] + 1;
+static inline void store_nt(int64_t* __restrict__ dst, const int64_t* __restrict__ src, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+#endif
+constexpr int kStageEntries = 1024;  // 8 KB per thread: stays in L1
+
+static void widen_plus1(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+  alignas(64) int64_t buf[kStageEntries];
+  for (int64_t o = 0; o < n; o += kStageEntries) {
+    const int64_t m = n - o < kStageEntries ? n - o : kStageEntries;
+    for (int64_t i = 0; i < m; ++i) buf[i] = (int64_t)in[o + i] + 1;
+    store_nt(out + o, buf, m);
+  }
+#if defined(__x86_64__)
+  _mm_sfence();
+#endif
+}
+// runs [k0, k1) of (position, first row) pairs; run k covers positions [runs[k].x, runs[k+1].x)
+static void expand_runs(const int2* __restrict__ runs, int64_t k0, int64_t k1, int64_t* __restrict__ out) {
+  alignas(64) int64_t buf[kStageEntries + 64];
+  if (k0 >= k1) return;
+  int64_t base = runs[k0].x;  // output position of buf[0]
+  int64_t fill = 0;
+  for (int64_t k = k0; k < k1; ++k) {
+    int64_t len = (int64_t)runs[k + 1].x - runs[k].x;
+    int64_t v = (int64_t)runs[k].y + 1;
+    while (len > 0) {
+      const int64_t room = kStageEntries - fill;
+      const int64_t m = len < room ? len : room;
+      for (int64_t i = 0; i < m; ++i) buf[fill + i] = v + i;
+      fill += m;
+      v += m;
+      len -= m;
+      if (fill == kStageEntries) {
+        store_nt(out + base, buf, fill);
+        base += fill;
+        fill = 0;
+      }
+    }
+  }
+  if (fill) store_nt(out + base, buf, fill);
+#if defined(__x86_64__)
+  _mm_sfence();
 #endif
 }
 
-constexpr int kRing = 4;
-constexpr int64_t kRingEntries = (int64_t)1 << 23;  // 32 MB of int32 per ring buffer
+// rows of a pattern as runs of consecutive indices: flag[i] = 1 where rv[i] != rv[i-1] + 1
+__global__ void k_run_starts(const int32_t* __restrict__ rv, int64_t n, uint8_t* __restrict__ flag) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || rv[i] != rv[i - 1] + 1) ? 1 : 0;
+}
+__global__ void k_run_pairs(const int32_t* __restrict__ rv, const int32_t* __restrict__ pos, int64_t nruns, int64_t n,
+                            int2* __restrict__ runs) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < nruns) runs[k] = make_int2(pos[k], rv[pos[k]]);
+  if (k == nruns) runs[k] = make_int2((int)n, 0);  // sentinel
+}
 
-static int fetch_rows_narrow(fsgpu_ctx* c, const int32_t* rv, int64_t nnz, int64_t* rowval, const double* nz, double* nzval) {
+constexpr int kRing = 2;                            // double buffer
+constexpr int64_t kRingBytes = (int64_t)128 << 20;  // per staging buffer (pinned)
+
+// Builds (once per pattern) the run-length form of the row indices when it is the smaller one.
+static int ensure_row_runs(fsgpu_ctx* c, const int32_t* rv, int64_t nnz) {
+  if (c->rle_for == rv && c->rle_nnz == nnz) return FSGPU_OK;
+  c->rle_for = nullptr;
+  c->rle_nruns = 0;
+  DBuf<uint8_t> flag;
+  DBuf<int32_t> pos;
+  DBuf<int64_t> nsel;
+  FS_TRY(flag.ensure((size_t)nnz + 1));
+  FS_TRY(nsel.ensure(1));
+  LAUNCH(c, k_run_starts, nnz, rv, nnz, flag.p);
+  // count first (cheap), then materialise only when the run form wins
+  size_t tb = 0;
+  FS_CUDA(cub::DeviceReduce::Sum(nullptr, tb, flag.p, nsel.p, nnz, c->stream));
+  FS_TRY(c->tmp.ensure(tb));
+  FS_CUDA(cub::DeviceReduce::Sum(c->tmp.p, tb, flag.p, nsel.p, nnz, c->stream));
+  c->launches += 2;
+  int64_t nruns = 0;
+  FS_CUDA(cudaMemcpyAsync(&nruns, nsel.p, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->rle_for = rv;
+  c->rle_nnz = nnz;
+  if (nruns * 8 > nnz * 4 * 6 / 10) return FSGPU_OK;  // int32 entries are (nearly) as compact: rle_nruns stays 0
+  FS_TRY(pos.ensure((size_t)nruns + 1));
+  FS_TRY(c->rle_runs.ensure((size_t)(nruns + 1) * sizeof(int2) + 16));
+  cub::CountingInputIterator<int32_t> iota(0);
+  tb = 0;
+  FS_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, iota, flag.p, pos.p, nsel.p, nnz, c->stream));
+  FS_TRY(c->tmp.ensure(tb));
+  FS_CUDA(cub::DeviceSelect::Flagged(c->tmp.p, tb, iota, flag.p, pos.p, nsel.p, nnz, c->stream));
+  c->launches += 2;
+  LAUNCH(c, k_run_pairs, nruns + 1, rv, pos.p, nruns, nnz, reinterpret_cast<int2*>(c->rle_runs.p));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->rle_nruns = nruns;
+  return FSGPU_OK;
+}
+
+// mode 1: int32 entries widened by host threads; mode 2: (position, first row) runs expanded by host threads.
+// The compact indices arrive in two alternating pinned staging buffers; while the host threads expand one piece the
+// next one is in flight, and the values travel on a second stream the whole time.  No spinning: the threads of a
+// piece are started when its data has arrived and joined before its buffer is reused.
+static int fetch_rows_narrow(fsgpu_ctx* c, const int32_t* rv, int64_t nnz, int64_t* rowval, const double* nz, double* nzval,
+                             int mode) {
   if (!c->ring[0]) {
     for (int k = 0; k < kRing; ++k) {
-      FS_CUDA(cudaMallocHost(&c->ring[k], (size_t)kRingEntries * sizeof(int32_t)));
+      FS_CUDA(cudaMallocHost(&c->ring[k], (size_t)kRingBytes + 64));
       FS_CUDA(cudaEventCreateWithFlags(&c->ring_ev[k], cudaEventDisableTiming));
     }
     FS_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     FS_CUDA(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
   }
+  const bool rle = mode == 2;
+  if (rle) FS_TRY(ensure_row_runs(c, rv, nnz));
+  const bool use_rle = rle && c->rle_nruns > 0;
+  // units: int32 entries, or runs (int2)
+  const int64_t nunits = use_rle ? c->rle_nruns : nnz;
+  const int64_t unit_bytes = use_rle ? (int64_t)sizeof(int2) : (int64_t)sizeof(int32_t);
+  int64_t per_chunk = kRingBytes / unit_bytes;
+  if (const char* ev = getenv("FSGPU_FETCH_CHUNK_UNITS")) {  // tests: force many pieces
+    const int64_t v = atoll(ev);
+    if (v >= 16 && v < per_chunk) per_chunk = v;
+  }
+  const char* src = use_rle ? reinterpret_cast<const char*>(c->rle_runs.p) : reinterpret_cast<const char*>(rv);
   // values: second stream, after everything already queued on the context's stream
   cudaError_t nz_err = cudaSuccess;
   std::thread nz_thread;
   FS_CUDA(cudaEventRecord(c->ev_x, c->stream));
   FS_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_x, 0));
   if (nzval) {
+    c->d2h_bytes += nnz * (int64_t)sizeof(double);
     // from a helper thread: with a pageable destination the copy call blocks its caller
     nz_thread = std::thread([&] {
       cudaSetDevice(c->device);
@@ -1036,46 +1154,41 @@ static int fetch_rows_narrow(fsgpu_ctx* c, const int32_t* rv, int64_t nnz, int64
       if (nz_err == cudaSuccess) nz_err = cudaStreamSynchronize(c->stream2);
     });
   }
-  int nth = (int)std::thread::hardware_concurrency();
+  // measured on a 16-core host: 8 threads keep up with the PCIe link; more only compete with the copy-issuing
+  // threads for cores (occasional 4x outliers at 16)
+  int nth = (int)std::thread::hardware_concurrency() - 2;
+  if (nth > 8) nth = 8;
   if (const char* ev = getenv("FSGPU_HOST_THREADS")) nth = atoi(ev);
   nth = nth < 1 ? 1 : (nth > 32 ? 32 : nth);
-  const int64_t nchunks = (nnz + kRingEntries - 1) / kRingEntries;
-  std::vector<std::atomic<int>> arrived(nchunks), done(nchunks);
-  for (int64_t k = 0; k < nchunks; ++k) {
-    arrived[k].store(0);
-    done[k].store(0);
-  }
-  std::vector<std::thread> pool;
-  for (int t = 0; t < nth; ++t)
-    pool.emplace_back([&, t] {
-      for (int64_t k = 0; k < nchunks; ++k) {
-        while (arrived[k].load(std::memory_order_acquire) == 0) std::this_thread::yield();
-        if (arrived[k].load(std::memory_order_acquire) < 0) return;  // aborted
-        const int64_t o = k * kRingEntries, m = nnz - o < kRingEntries ? nnz - o : kRingEntries;
-        const int64_t lo = m * t / nth, hi = m * (t + 1) / nth;
-        widen_plus1(static_cast<const int32_t*>(c->ring[k % kRing]) + lo, rowval + o + lo, hi - lo);
-        done[k].fetch_add(1, std::memory_order_release);
-      }
-    });
+  const int64_t nchunks = (nunits + per_chunk - 1) / per_chunk;
   cudaError_t err = cudaSuccess;
-  int64_t issued = 0;
+  auto issue = [&](int64_t k) {
+    const int64_t o = k * per_chunk, m = nunits - o < per_chunk ? nunits - o : per_chunk;
+    // runs: one extra entry (the next run's position, or the sentinel) closes the piece's last run
+    const size_t bytes = (size_t)(m + (use_rle ? 1 : 0)) * unit_bytes;
+    c->d2h_bytes += (int64_t)bytes;
+    err = cudaMemcpyAsync(c->ring[k % kRing], src + o * unit_bytes, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (err == cudaSuccess) err = cudaEventRecord(c->ring_ev[k % kRing], c->stream);
+  };
+  if (nchunks > 0) issue(0);
   for (int64_t k = 0; k < nchunks && err == cudaSuccess; ++k) {
-    // keep the ring full: issue copies up to kRing chunks ahead of the chunk being handed to the workers
-    while (issued < nchunks && issued < k + kRing && err == cudaSuccess) {
-      if (issued >= kRing)
-        while (done[issued - kRing].load(std::memory_order_acquire) < nth) std::this_thread::yield();
-      const int64_t o = issued * kRingEntries, m = nnz - o < kRingEntries ? nnz - o : kRingEntries;
-      err = cudaMemcpyAsync(c->ring[issued % kRing], rv + o, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-      if (err == cudaSuccess) err = cudaEventRecord(c->ring_ev[issued % kRing], c->stream);
-      ++issued;
-    }
+    if (k + 1 < nchunks) issue(k + 1);  // its buffer was released when piece k - 1 was joined
     if (err == cudaSuccess) err = cudaEventSynchronize(c->ring_ev[k % kRing]);
-    arrived[k].store(err == cudaSuccess ? 1 : -1, std::memory_order_release);
+    if (err != cudaSuccess) break;
+    const int64_t o = k * per_chunk, m = nunits - o < per_chunk ? nunits - o : per_chunk;
+    const void* buf = c->ring[k % kRing];
+    auto work = [&, o, m, buf](int t) {
+      const int64_t lo = m * t / nth, hi = m * (t + 1) / nth;
+      if (use_rle)
+        expand_runs(static_cast<const int2*>(buf), lo, hi, rowval);  // positions are absolute
+      else
+        widen_plus1(static_cast<const int32_t*>(buf) + lo, rowval + o + lo, hi - lo);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nth; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
   }
-  if (err != cudaSuccess)
-    for (int64_t k = 0; k < nchunks; ++k)
-      if (arrived[k].load() == 0) arrived[k].store(-1, std::memory_order_release);
-  for (auto& th : pool) th.join();
   if (nz_thread.joinable()) nz_thread.join();
   FS_CUDA(err);
   FS_CUDA(nz_err);
@@ -1083,6 +1196,11 @@ static int fetch_rows_narrow(fsgpu_ctx* c, const int32_t* rv, int64_t nnz, int64
 }
 }  // namespace fs
 
+extern "C" int fsgpu_d2h_bytes(fsgpu_ctx* c, int64_t* bytes) {
+  FS_REQUIRE(c != nullptr && bytes != nullptr, FSGPU_ERR_ARG, "null argument");
+  *bytes = c->d2h_bytes;
+  return FSGPU_OK;
+}
 extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval, double* nzval) {
   FS_TRY(check_ctx(c));
   FS_REQUIRE(c->have_matrix, FSGPU_ERR_STATE, "no matrix result available");
@@ -1117,7 +1235,13 @@ extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval
   if (const char* ev = getenv("FSGPU_FETCH_NARROW_MIN")) narrow_min = atoll(ev);  // < 0: never (tests)
   const bool narrow = rowval && narrow_min >= 0 && nnz >= narrow_min && nnz > 0;
   if (narrow) {
-    FS_TRY(fetch_rows_narrow(c, rv, nnz, rowval, nzval ? nz : nullptr, nzval));
+    // FSGPU_FETCH_MODE=entries: int32 entries; default: run-length form when it is the smaller one
+    const char* fm = getenv("FSGPU_FETCH_MODE");
+    const int mode = (fm && fm[0] == 'e') ? 1 : 2;
+    // the compacted (SparseSymm) and CSR index arrays change from call to call: no caching of their run form
+    if (c->compacted || c->target == FSGPU_CSR_SYMM) c->rle_for = nullptr;
+    FS_TRY(fetch_rows_narrow(c, rv, nnz, rowval, nzval ? nz : nullptr, nzval, mode));
+    if (c->compacted || c->target == FSGPU_CSR_SYMM) c->rle_for = nullptr;
   } else {
     if (rowval && nnz > 0) {
       for (int64_t o = 0; o < nnz; o += chunk) {

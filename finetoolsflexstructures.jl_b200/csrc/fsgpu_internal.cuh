@@ -79,14 +79,19 @@ struct fsgpu_ctx {
   int device = 0;
   cudaStream_t stream = 0;
   int64_t launches = 0;
+  int64_t d2h_bytes = 0;  // bytes moved device -> host by this context so far (measurement support)
   // device time of the dominant kernel of the last operator (CUDA events on `stream`)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
-  // fetch of large results: pinned ring for the int32 row indices, second stream for the values
+  // fetch of large results: two pinned staging buffers for the compact row indices, second stream for the values
   void* ring[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_x = nullptr;
+  // run-length form of the row indices of the current pattern (fetch of large results)
+  const int32_t* rle_for = nullptr;  // device array it was built from
+  int64_t rle_nnz = 0, rle_nruns = 0;  // rle_nruns == 0: not smaller than int32 entries
+  fs::DBuf<unsigned char> rle_runs;  // [nruns + 1] int2 (position, first row), sentinel (nnz, 0)
 
   // mesh
   int nnpe = 0;

@@ -85,6 +85,9 @@ int fsgpu_set_stream(fsgpu_ctx* ctx, void* cuda_stream);
 int fsgpu_sync(fsgpu_ctx* ctx);
 /* number of kernels this context has launched so far */
 int64_t fsgpu_launch_count(fsgpu_ctx* ctx);
+/* bytes this context has moved device -> host so far (large patterns cross PCIe in compact form, so this is
+ * less than the size of the host arrays fsgpu_fetch_matrix fills) */
+int fsgpu_d2h_bytes(fsgpu_ctx* ctx, int64_t* bytes);
 /* device time (CUDA events on the context's stream) of the element kernel of the last
  * matrix operator -- the number the roofline fraction is computed from */
 int fsgpu_last_kernel_ms(fsgpu_ctx* ctx, double* ms);

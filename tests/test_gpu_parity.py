@@ -531,12 +531,15 @@ def test_fetch_narrow_rows_match_wide(fs, asm, monkeypatch):
     u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
     monkeypatch.setenv("FSGPU_FETCH_NARROW_MIN", "-1")
     Kw = f.stiffness(femm, _assembler(fs, asm), geom0, u0, R0, dchi)
-    for nth in ("3", "16"):
+    for nth, mode, chunk in (("3", "entries", None), ("16", "entries", None), ("16", "runs", None), ("5", "runs", "100003")):
         monkeypatch.setenv("FSGPU_FETCH_NARROW_MIN", "1")
         monkeypatch.setenv("FSGPU_HOST_THREADS", nth)
+        monkeypatch.setenv("FSGPU_FETCH_MODE", mode)  # int32 entries | run-length (position, first row) pairs
+        if chunk:
+            monkeypatch.setenv("FSGPU_FETCH_CHUNK_UNITS", chunk)  # many ring chunks, runs straddling chunk ends
         Kn = femm.ctx.fetch_matrix()
         assert np.array_equal(Kn.colptr, Kw.colptr)
-        assert np.array_equal(Kn.rowval, Kw.rowval)
+        assert np.array_equal(Kn.rowval, Kw.rowval), (nth, mode, chunk)
         assert np.array_equal(Kn.nzval, Kw.nzval)
     assert Kw.rowval.size > (1 << 23), "mesh too small to exercise a second ring chunk"
 
