@@ -1157,6 +1157,10 @@ static int fetch_rows_narrow(fsgpu_ctx* c, const int32_t* rv, int64_t nnz, int64
   // measured on a 16-core host: 8 threads keep up with the PCIe link; more only compete with the copy-issuing
   // threads for cores (occasional 4x outliers at 16)
   int nth = (int)std::thread::hardware_concurrency() - 2;
+  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU on this host: share the cores
+    const int w = atoi(lw);
+    if (w > 1) nth /= w;
+  }
   if (nth > 8) nth = 8;
   if (const char* ev = getenv("FSGPU_HOST_THREADS")) nth = atoi(ev);
   nth = nth < 1 ? 1 : (nth > 32 ? 32 : nth);

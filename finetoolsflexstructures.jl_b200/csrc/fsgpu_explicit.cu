@@ -10,6 +10,8 @@
 // cuts the index traffic ~6x (12 -> ~8.7 B per entry).
 #include <cub/cub.cuh>
 
+#include <utility>
+
 #include "fsgpu_internal.cuh"
 
 using namespace fs;
@@ -23,6 +25,8 @@ struct fsgpu_explicit {
   int64_t index_entries = 0;  // column indices actually read per SpMV (one pattern per run)
   DBuf<double> val;
   DBuf<double> M, C, invMC, U, V, A, F0, E, X, Y;
+  DBuf<double> Un;       // displacements of the NEXT step, written by the fused step's epilogue
+  bool u_ahead = false;  // Un holds U + dt V + dt^2/2 A of the current (V, A): the next step swaps instead of updating
   double dt = 0, c_scale = 0;
   bool have_load = false;
 };
@@ -140,7 +144,8 @@ __global__ void k_spmv_step(const int32_t* __restrict__ runs, int64_t nruns, con
                             const int32_t* __restrict__ colval, const double* __restrict__ val,
                             const double* __restrict__ U, const double* __restrict__ F0, double fs,
                             const double* __restrict__ C, const double* __restrict__ invMC, double* __restrict__ V,
-                            double* __restrict__ A, double* __restrict__ E, double dt_2) {
+                            double* __restrict__ A, double* __restrict__ E, double dt_2, double dt, double dt2_2,
+                            double* __restrict__ Unext) {
   const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t run = g / LPR;
   const int sub = (int)(g % LPR);
@@ -164,6 +169,9 @@ __global__ void k_spmv_step(const int32_t* __restrict__ runs, int64_t nruns, con
     V[row] = v;
     A[row] = a1;
     E[row] = e;
+    // the next step's first statement (:85, U += dt V + dt^2/2 A) for this row, into the other buffer: this
+    // kernel still reads U of other rows
+    Unext[row] = U[row] + dt * v + dt2_2 * a1;
   }
 }
 // second half alone (element-partitioned runs: E already summed across ranks)
@@ -387,6 +395,7 @@ extern "C" int fsgpu_explicit_set_state(fsgpu_explicit* h, const double* U0, con
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
   const size_t b = (size_t)h->n * sizeof(double);
+  h->u_ahead = false;
   if (U0) FS_TRY(upload(h->ctx, h->U.p, U0, b));
   if (V0) FS_TRY(upload(h->ctx, h->V.p, V0, b));
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
@@ -405,6 +414,7 @@ extern "C" int fsgpu_explicit_set_load(fsgpu_explicit* h, const double* F0) {
 extern "C" int fsgpu_explicit_start(fsgpu_explicit* h, double fscale0) {
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
+  h->u_ahead = false;  // the acceleration changes
   XL(h, k_start, h->n, h->have_load ? h->F0.p : nullptr, fscale0, h->invMC.p, h->A.p, h->n);
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
   return FSGPU_OK;
@@ -413,10 +423,18 @@ extern "C" int fsgpu_explicit_step(fsgpu_explicit* h, int64_t nsteps, const doub
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
   const double dt = h->dt;
+  FS_TRY(h->Un.ensure((size_t)h->n + 1));
   for (int64_t s = 0; s < nsteps; ++s) {
-    XL(h, k_update_u, h->n, h->U.p, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
+    if (h->u_ahead) {
+      std::swap(h->U.p, h->Un.p);
+      std::swap(h->U.n, h->Un.n);
+    } else {
+      XL(h, k_update_u, h->n, h->U.p, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
+    }
     XL(h, k_spmv_step, h->nruns * LPR, h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, h->U.p,
-       h->have_load ? h->F0.p : nullptr, fscale ? fscale[s] : 1.0, h->C.p, h->invMC.p, h->V.p, h->A.p, h->E.p, dt / 2);
+       h->have_load ? h->F0.p : nullptr, fscale ? fscale[s] : 1.0, h->C.p, h->invMC.p, h->V.p, h->A.p, h->E.p, dt / 2, dt,
+       (dt * dt) / 2, h->Un.p);
+    h->u_ahead = true;
   }
   FS_CUDA(cudaGetLastError());
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
@@ -426,7 +444,13 @@ extern "C" int fsgpu_explicit_step_begin(fsgpu_explicit* h) {
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
   const double dt = h->dt;
-  XL(h, k_update_u, h->n, h->U.p, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
+  if (h->u_ahead) {
+    std::swap(h->U.p, h->Un.p);
+    std::swap(h->U.n, h->Un.n);
+    h->u_ahead = false;
+  } else {
+    XL(h, k_update_u, h->n, h->U.p, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
+  }
   XL(h, k_spmv, h->nruns * LPR, h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, h->U.p, h->E.p);
   FS_CUDA(cudaGetLastError());
   return FSGPU_OK;  // asynchronous: the host's exchange is enqueued on the same stream

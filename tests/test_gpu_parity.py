@@ -684,6 +684,20 @@ def test_explicit_loop(fs):
     ex2.start(0.0)
     ex2.step(nsteps, fsc)
     assert relfro(ex2.get_state()[0], Uo) < 1e-9
+    # the fused step precomputes the next step's displacements: the state must not depend on how the steps
+    # are grouped into calls, nor on mixing the fused step with the two-halves (multi-rank) form
+    ex3 = fs.Explicit(femm.ctx, c_scale=cs, dt=dt)
+    ex3.set_load(F0)
+    ex3.start(0.0)
+    ex3.step(37, fsc[:37])
+    assert relfro(ex3.get_state()[0], oexp.cd_loop(Mo, Ko, cs, np.zeros(nf), np.zeros(nf), 37, dt, tt)[0]) < 1e-9
+    for k in range(37, 40):
+        ex3.step_begin()
+        ex3.step_end(fsc[k])
+    ex3.step(1, fsc[40:41])
+    ex3.step(nsteps - 41, fsc[41:])
+    U3, V3, _ = ex3.get_state()
+    assert relfro(U3, Uo) < 1e-9 and relfro(V3, Vo) < 1e-9
 
 
 # ---------------------------------------------------------------------------------------
