@@ -337,7 +337,10 @@ function state(e::ExplicitGPU)
     return U, V, A
 end
 
-export SysmatAssemblerGPU, SysvecAssemblerGPU, Context, ExplicitGPU, sparse_gpu, set_load!, start!, step!, state
+"bitwise reproducible T3FF/T3FFComp stiffness (atomics-free owner-computes kernel); takes effect at the next symbolic phase"
+set_deterministic!(c::Context, on::Bool = true) = _check(ccall((:fsgpu_set_deterministic, libfsgpu), Cint, (Ptr{Cvoid}, Cint), c.h, on ? 1 : 0))
+
+export SysmatAssemblerGPU, SysvecAssemblerGPU, Context, ExplicitGPU, sparse_gpu, set_load!, start!, step!, state, set_deterministic!
 export SPARSE, SPARSE_SYMM, SPARSE_DIAG, FFBLOCK, FFBLOCK_DIAG, CSR_SYMM
 
 end # module
