@@ -1063,7 +1063,7 @@ static void expand_runs(const int2* __restrict__ runs, int64_t k0, int64_t k1, i
 }
 
 // rows of a pattern as runs of consecutive indices: flag[i] = 1 where rv[i] != rv[i-1] + 1
-__global__ void k_run_starts(const int32_t* __restrict__ rv, int64_t n, uint8_t* __restrict__ flag) {
+__global__ void k_run_starts(const int32_t* __restrict__ rv, int64_t n, unsigned char* __restrict__ flag) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) flag[i] = (i == 0 || rv[i] != rv[i - 1] + 1) ? 1 : 0;
 }
@@ -1082,9 +1082,10 @@ static int ensure_row_runs(fsgpu_ctx* c, const int32_t* rv, int64_t nnz) {
   if (c->rle_for == rv && c->rle_nnz == nnz) return FSGPU_OK;
   c->rle_for = nullptr;
   c->rle_nruns = 0;
-  DBuf<uint8_t> flag;
-  DBuf<int32_t> pos;
-  DBuf<int64_t> nsel;
+  // scratch kept between calls: cudaMalloc/cudaFree of 200-300 MB blocks costs 1-10 ms, at times far more
+  DBuf<unsigned char>& flag = c->scr_rle_flag;
+  DBuf<int32_t>& pos = c->scr_rle_pos;
+  DBuf<int64_t>& nsel = c->scr_nsel;
   FS_TRY(flag.ensure((size_t)nnz + 1));
   FS_TRY(nsel.ensure(1));
   LAUNCH(c, k_run_starts, nnz, rv, nnz, flag.p);

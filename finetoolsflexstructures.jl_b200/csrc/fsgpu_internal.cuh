@@ -92,6 +92,8 @@ struct fsgpu_ctx {
   const int32_t* rle_for = nullptr;  // device array it was built from
   int64_t rle_nnz = 0, rle_nruns = 0;  // rle_nruns == 0: not smaller than int32 entries
   fs::DBuf<unsigned char> rle_runs;  // [nruns + 1] int2 (position, first row), sentinel (nnz, 0)
+  fs::DBuf<unsigned char> scr_rle_flag;
+  fs::DBuf<int32_t> scr_rle_pos;
 
   // mesh
   int nnpe = 0;
