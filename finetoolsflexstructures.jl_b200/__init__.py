@@ -10,3 +10,4 @@ from . import _lib
 from ._lib import FsgpuError, BeamParams, ShellParams, EXPORTED_SYMBOLS, LIB_PATH
 from .context import Context, Explicit, SparseMatrixCSC
 from . import femm
+from . import partition

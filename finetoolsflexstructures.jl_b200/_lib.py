@@ -111,6 +111,7 @@ _SIGNATURES = {
     "fsgpu_fetch_vector": [_vp, _vp, _i64],
     "fsgpu_result_device": [_vp, _P(_vp), _P(_vp), _P(_vp)],
     "fsgpu_vector_device": [_vp, _P(_vp), _P(_i64)],
+    "fsgpu_result_block": [_vp, _i64, _i64, _vp, _P(_i64), _vp, _vp, _vp],
     "fsgpu_coo_to_csc": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _P(_i64), _vp, _vp, _vp],
     "fsgpu_explicit_create": [_P(_vp), _vp, _i64, _vp, _vp, _vp, _vp, _dbl, _dbl],
     "fsgpu_explicit_create_from_ctx": [_P(_vp), _vp, _dbl, _dbl],

@@ -210,6 +210,19 @@ class Context:
         check(lib.fsgpu_fetch_matrix(self._h, ptr(colptr), ptr(rowval), ptr(nzval)))
         return SparseMatrixCSC(m, n, colptr, rowval, nzval, csr=(self.target == L.CSR_SYMM))
 
+    def result_block(self, col_lo, col_hi, row_map=None, colcount=None, rowval=None, nzval=None):
+        """Columns [col_lo, col_hi) of the device-resident result as pieces of the global CSC, written into
+        DEVICE buffers (torch tensors or raw addresses; None skips); returns the number of stored entries."""
+        nb = C.c_int64()
+        check(lib.fsgpu_result_block(self._h, int(col_lo), int(col_hi), ptr(row_map), C.byref(nb), ptr(colcount), ptr(rowval), ptr(nzval)))
+        return nb.value
+
+    def vector_device(self):
+        """(device address, length) of the last vector result."""
+        vp, vn = C.c_void_p(), C.c_int64()
+        check(lib.fsgpu_vector_device(self._h, C.byref(vp), C.byref(vn)))
+        return vp.value, vn.value
+
     def fetch_values(self, nzval):
         check(lib.fsgpu_fetch_matrix(self._h, None, None, ptr(nzval)))
         return nzval

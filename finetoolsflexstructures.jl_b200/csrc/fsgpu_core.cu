@@ -1281,6 +1281,53 @@ extern "C" int fsgpu_result_device(fsgpu_ctx* c, const int32_t** colptr0, const 
   if (nzval) *nzval = c->compacted ? c->c_nzval.p : c->nzval.p;
   return FSGPU_OK;
 }
+// ------------------------------------------------------------------------------------
+// column blocks of the result for multi-GPU gathering (owner computes the columns of its
+// nodes): Julia-layout pieces (Int64, 1-based GLOBAL rows) written straight into the caller's device
+// buffers -- normally this rank's slice of the gathered global arrays, so the collective runs in place.
+// ------------------------------------------------------------------------------------
+namespace fs {
+__global__ void k_block_counts(const int32_t* __restrict__ colptr, int64_t lo, int64_t n, int64_t* __restrict__ cnt) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cnt[i] = (int64_t)colptr[lo + i + 1] - (int64_t)colptr[lo + i];
+}
+__global__ void k_block_rows(const int32_t* __restrict__ rv, const int64_t* __restrict__ row_map, int64_t n,
+                             int64_t* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t r = rv[i];
+  out[i] = row_map ? row_map[r] : (int64_t)r + 1;
+}
+}  // namespace fs
+
+extern "C" int fsgpu_result_block(fsgpu_ctx* c, int64_t col_lo, int64_t col_hi, const int64_t* row_map_dev,
+                                  int64_t* nnz_block, int64_t* colcount_dev, int64_t* rowval_dev, double* nzval_dev) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->have_matrix, FSGPU_ERR_STATE, "no matrix result available");
+  FS_REQUIRE(c->target != FSGPU_SPARSE_SYMM && c->target != FSGPU_CSR_SYMM, FSGPU_ERR_ARG,
+             "column blocks are defined for the SPARSE / FFBLOCK / DIAG targets (SPARSE_SYMM needs the mirror "
+             "columns of other ranks, CSR_SYMM is row-major)");
+  FS_REQUIRE(col_lo >= 0 && col_lo <= col_hi && col_hi <= c->rcols, FSGPU_ERR_ARG,
+             "column range [%lld, %lld) outside the result's %lld columns", (long long)col_lo, (long long)col_hi,
+             (long long)c->rcols);
+  const int32_t* cp = c->colptr.p;
+  int32_t ends[2] = {0, 0};
+  if (col_hi > col_lo) {
+    FS_CUDA(cudaMemcpyAsync(&ends[0], cp + col_lo, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(cudaMemcpyAsync(&ends[1], cp + col_hi, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    FS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  const int64_t nb = (int64_t)ends[1] - (int64_t)ends[0];
+  if (nnz_block) *nnz_block = nb;
+  if (colcount_dev) LAUNCH(c, k_block_counts, col_hi - col_lo, cp, col_lo, col_hi - col_lo, colcount_dev);
+  if (rowval_dev) LAUNCH(c, k_block_rows, nb, c->rowval.p + ends[0], row_map_dev, nb, rowval_dev);
+  if (nzval_dev && nb > 0)
+    FS_CUDA(cudaMemcpyAsync(nzval_dev, c->nzval.p + ends[0], (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  return FSGPU_OK;
+}
+
 extern "C" int fsgpu_vector_device(fsgpu_ctx* c, const double** v, int64_t* n) {
   FS_TRY(check_ctx(c));
   FS_REQUIRE(c->have_vector, FSGPU_ERR_STATE, "no vector result available");

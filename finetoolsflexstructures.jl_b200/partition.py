@@ -86,3 +86,161 @@ def strip_links(rank, world, lo_dofs, hi_dofs):
     if rank < world - 1:
         links.append((rank + 1, hi_dofs))
     return links
+
+
+# ---- gathering assembled blocks into ONE global CSC (option A) ---------------
+#
+# Rank r owns a contiguous range of COLUMNS of the global matrix (aligned on node boundaries) and
+# assembles every element that touches a node holding one of those columns, on a local mesh whose
+# dofs are renumbered by an order-preserving map.  Its owned columns are then complete -- interface
+# elements are computed by both neighbours instead of exchanging partial sums -- rows stay ascending
+# after mapping back, and the global CSC is the concatenation of the blocks: one in-place broadcast
+# (NCCL over NVLink on GPUs, gloo in the CPU tests) of each rank's slice of the global arrays.
+
+_FF_KINDS = ("ffblock", "ffblock_diag")
+
+
+class ColumnBlockPlan:
+    """What rank `rank` of `world` assembles and which columns of the global matrix it owns.
+
+    Attributes (all host numpy arrays):
+      col_lo, col_hi    owned columns [col_lo, col_hi) of the global matrix, 0-based
+      elems             global 0-based ids of the elements assembled here (ascending)
+      nodes             global 1-based ids of the local nodes (ascending)
+      conn              local 1-based connectivity, (len(elems), nnpe)
+      dofnums           local dof numbers (len(nodes), 6), 1-based; order-preserving renumbering of the global ones
+      nfree, nall       local counts
+      loc2glob          (nall,) global 1-based dof of local dof k+1  (the row map of fsgpu_result_block)
+      lcol_lo, lcol_hi  the owned columns in local numbering, 0-based
+    """
+
+    def __init__(self, conn, dofnums, nfree, kind, rank, world):
+        conn = np.asarray(conn, dtype=np.int64)
+        dofnums = np.asarray(dofnums, dtype=np.int64)
+        nn = dofnums.shape[0]
+        nallg = dofnums.size
+        self.rank, self.world, self.kind = int(rank), int(world), kind
+        self.nfree_global, self.nall_global = int(nfree), int(nallg)
+        self.ncols_global = int(nfree) if kind in _FF_KINDS else int(nallg)
+        node_of_dof = np.empty(nallg, dtype=np.int64)
+        node_of_dof[dofnums.ravel() - 1] = np.repeat(np.arange(nn), dofnums.shape[1])
+        self._bounds = self._column_bounds(dofnums, node_of_dof, int(nfree), self.ncols_global, world)
+        self.col_lo, self.col_hi = int(self._bounds[rank]), int(self._bounds[rank + 1])
+        owned = np.unique(node_of_dof[self.col_lo : self.col_hi])  # 0-based nodes holding an owned column
+        mark = np.zeros(nn + 1, dtype=bool)
+        mark[owned + 1] = True
+        self.elems = np.flatnonzero(mark[conn].any(axis=1)) if conn.size else np.zeros(0, dtype=np.int64)
+        # nodes without elements still own (empty) columns
+        self.nodes = np.unique(np.concatenate([conn[self.elems].ravel(), owned + 1]))
+        lut = np.zeros(nn + 1, dtype=np.int64)
+        lut[self.nodes] = np.arange(1, self.nodes.size + 1)
+        self.conn = lut[conn[self.elems]]
+        g = dofnums[self.nodes - 1]
+        self.loc2glob = np.sort(g.ravel())
+        self.dofnums = np.asfortranarray(np.searchsorted(self.loc2glob, g) + 1)
+        self.nall = int(self.loc2glob.size)
+        self.nfree = int(np.searchsorted(self.loc2glob, nfree, side="right"))
+        self.lcol_lo = int(np.searchsorted(self.loc2glob, self.col_lo + 1))
+        self.lcol_hi = int(np.searchsorted(self.loc2glob, self.col_hi + 1))
+        assert self.lcol_hi - self.lcol_lo == self.col_hi - self.col_lo
+
+    @staticmethod
+    def _column_bounds(dofnums, node_of_dof, nfree, ncols, world):
+        """Equal column counts, each interior boundary moved down to the first column of the run (free or
+        prescribed dofs of one node, consecutive by `numberdofs!`) it falls into."""
+        b = np.linspace(0, ncols, world + 1).astype(np.int64)
+        for k in range(1, world):
+            c = int(b[k])
+            if c <= 0 or c >= ncols:
+                continue
+            d = dofnums[node_of_dof[c]]
+            same = d[(d <= nfree) == (c + 1 <= nfree)]  # the node's dofs of the same class as column c
+            lo = c + 1
+            while lo - 1 in same:  # walk down the consecutive run
+                lo -= 1
+            b[k] = lo - 1
+        return np.maximum.accumulate(b)
+
+    def restrict_elements(self, a):
+        """Per-element data (first axis = elements) of the elements assembled here."""
+        return np.asarray(a)[self.elems]
+
+    def restrict_nodes(self, a):
+        """Nodal data (first axis = nodes) of the local nodes, e.g. geom0.values, nodal normals, u1, Rfield1."""
+        return np.asarray(a)[self.nodes - 1]
+
+    def local_ncols(self):
+        return self.nfree if self.kind in _FF_KINDS else self.nall
+
+
+def gather_blocks(fill, ncols_b, nnz_b, device, group=None):
+    """Concatenate per-rank column blocks into the global CSC on every rank.
+
+    `fill(colcount, rowval, nzval)` writes this rank's block (Int64 counts per column, Int64 1-based global rows,
+    Float64 values) into the three tensors it is given -- slices of the global arrays, so nothing is copied
+    before the collective.  Returns device tensors (colptr [ncols+1] Int64 1-based, rowval, nzval)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = torch.tensor([int(ncols_b), int(nnz_b)], dtype=torch.int64, device=device)
+    allsz = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(allsz, sizes, group=group)
+    allsz = torch.stack(allsz).cpu().numpy()
+    coff = np.concatenate([[0], np.cumsum(allsz[:, 0])])
+    zoff = np.concatenate([[0], np.cumsum(allsz[:, 1])])
+    colptr = torch.empty(int(coff[-1]) + 1, dtype=torch.int64, device=device)
+    rowval = torch.empty(int(zoff[-1]), dtype=torch.int64, device=device)
+    nzval = torch.empty(int(zoff[-1]), dtype=torch.float64, device=device)
+    counts = colptr[1:]
+    fill(counts[coff[rank] : coff[rank + 1]], rowval[zoff[rank] : zoff[rank + 1]], nzval[zoff[rank] : zoff[rank + 1]])
+    for r in range(world):
+        for buf, off in ((counts, coff), (rowval, zoff), (nzval, zoff)):
+            if off[r + 1] > off[r]:
+                dist.broadcast(buf[off[r] : off[r + 1]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    colptr[0] = 1
+    counts.cumsum_(0)
+    counts += 1
+    return colptr, rowval, nzval
+
+
+def gather_matrix(ctx, plan, device, group=None, to_host=True):
+    """`makematrix!` of an element-partitioned assembly: the GLOBAL SparseMatrixCSC from the per-rank results
+    of contexts that assembled `plan`'s local meshes (every rank gets the whole matrix: the solver hand-off)."""
+    import torch
+
+    from .context import SparseMatrixCSC
+
+    if plan.kind not in ("sparse", "diag") + _FF_KINDS:
+        raise ValueError("gather_matrix: targets sparse / ffblock / diag (symmetrise a gathered 'sparse' matrix on the host instead)")
+    row_map = torch.as_tensor(plan.loc2glob, device=device)
+    if row_map.is_cuda:
+        torch.cuda.current_stream(row_map.device).synchronize()  # the library works on its own stream
+    nnz_b = ctx.result_block(plan.lcol_lo, plan.lcol_hi)
+
+    def fill(cnt, rv, nz):
+        ctx.result_block(plan.lcol_lo, plan.lcol_hi, row_map, cnt if cnt.numel() else None, rv if rv.numel() else None, nz if nz.numel() else None)
+
+    colptr, rowval, nzval = gather_blocks(fill, plan.col_hi - plan.col_lo, nnz_b, device, group)
+    n = plan.ncols_global
+    if not to_host:
+        return n, colptr, rowval, nzval
+    return SparseMatrixCSC(n, n, colptr.cpu().numpy(), rowval.cpu().numpy(), nzval.cpu().numpy())
+
+
+def gather_vector(local_vec, plan, device, group=None):
+    """Global vector (SysvecAssembler: nalldofs, or FBlock: nfree -- as `plan.kind` says) from per-rank vectors
+    over the local dofs: every rank contributes the entries of the dofs it owns."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    b = plan._bounds
+    out = torch.empty(plan.ncols_global, dtype=torch.float64, device=device)
+    out[b[rank] : b[rank + 1]] = local_vec[plan.lcol_lo : plan.lcol_hi]
+    for r in range(world):
+        if b[r + 1] > b[r]:
+            dist.broadcast(out[b[r] : b[r + 1]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+    return out

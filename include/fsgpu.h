@@ -204,6 +204,20 @@ int fsgpu_fetch_vector(fsgpu_ctx* ctx, double* out, int64_t n);
 /* device-resident handles (int32 0-based pattern, float64 values) for chaining on the GPU */
 int fsgpu_result_device(fsgpu_ctx* ctx, const int32_t** colptr0, const int32_t** rowval0, const double** nzval);
 int fsgpu_vector_device(fsgpu_ctx* ctx, const double** v, int64_t* n);
+/* multi-GPU gathering of assembled blocks (option A: each rank assembles every element
+ * that touches the nodes whose columns it owns, so its owned columns are complete and no partial sums are
+ * exchanged).  Writes columns [col_lo, col_hi) (0-based, half open, this context's numbering) of the result as
+ * pieces of the GLOBAL SparseMatrixCSC into caller-owned DEVICE buffers -- normally this rank's slice of the
+ * gathered arrays, so the host's collective (NCCL broadcast / all-gather) runs in place:
+ *   colcount_dev [col_hi-col_lo] Int64 stored entries per column (global colptr = 1 + running sum),
+ *   rowval_dev   [*nnz_block]    Int64 1-based global rows = row_map_dev[local 0-based row]
+ *                                (row_map_dev: device Int64 [nrows]; NULL = identity + 1),
+ *   nzval_dev    [*nnz_block]    Float64.
+ * Any output pointer may be NULL; with all three NULL the call only reports *nnz_block.
+ * Targets SPARSE, FFBLOCK and their DIAG forms (a column of SPARSE_SYMM needs mirror entries of columns
+ * other ranks own; gather SPARSE and symmetrise on the host side instead). */
+int fsgpu_result_block(fsgpu_ctx* ctx, int64_t col_lo, int64_t col_hi, const int64_t* row_map_dev, int64_t* nnz_block,
+                       int64_t* colcount_dev, int64_t* rowval_dev, double* nzval_dev);
 
 /* ---- standalone COO -> CSC (Julia `sparse(I,J,V,m,n)`; makematrix! of any assembler) --- */
 /* two calls: (1) colptr/rowval/nzval NULL -> *nnz; (2) fill caller-owned arrays. */

@@ -416,6 +416,78 @@ def test_rcm_like_permuted_numbering(fs):
 
 
 # ---------------------------------------------------------------------------------------
+# column blocks for multi-GPU gathering; the collective itself: tests/test_gpu_multi.py
+# ---------------------------------------------------------------------------------------
+def _local_femm(fs, kind, plan, xyz, normals, valid):
+    f = fs.femm
+    femm = _make_femm(fs, kind, plan.conn)
+    geom = f.NodalField(plan.restrict_nodes(xyz))
+    # the nodal normals come from the GLOBAL mesh (halo nodes see elements this rank does not assemble)
+    femm._normals, femm._normal_valid = np.asfortranarray(plan.restrict_nodes(normals)), plan.restrict_nodes(valid)
+    femm._associatedgeometry = True
+    dchi = f.NodalField.__new__(f.NodalField)
+    dchi.values, dchi.dofnums, dchi._nfree = None, plan.dofnums, plan.nfree
+    return femm, geom, dchi
+
+
+@pytest.mark.parametrize("kind,asm,world,permute", [("t3", "ffblock", 3, False), ("q4", "sparse", 2, True), ("t3", "diag", 2, False)])
+def test_column_blocks_concatenate_to_global_matrix(fs, kind, asm, world, permute):
+    """Every 'rank' (here: one after the other on one GPU) assembles its plan's local mesh; the blocks that
+    fsgpu_result_block writes, concatenated, are the single-context global matrix: pattern bit-exact."""
+    import torch
+
+    f, pt = fs.femm, fs.partition
+    xyz, conn = meshes.shell_mesh(kind, n=9)
+    od = meshes.clamp_edge_dofs(xyz)
+    perm = np.random.default_rng(11).permutation(xyz.shape[0]) if permute else None
+    od.numberdofs(perm)
+    femm = _make_femm(fs, kind, conn)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs(perm)
+    f.associategeometry(femm, geom0)
+    Kg = f.stiffness(femm, _assembler(fs, asm), geom0, None, None, dchi)
+    dev = torch.device("cuda", 0)
+    cnts, rows, vals = [], [], []
+    for r in range(world):
+        plan = pt.ColumnBlockPlan(conn, dchi.dofnums, od.nfreedofs, asm, r, world)
+        lf, lg, ld = _local_femm(fs, kind, plan, xyz, femm._normals, femm._normal_valid)
+        f.stiffness(lf, _assembler(fs, asm), lg, None, None, ld)
+        nb = lf.ctx.result_block(plan.lcol_lo, plan.lcol_hi)
+        cnt = torch.empty(plan.col_hi - plan.col_lo, dtype=torch.int64, device=dev)
+        rv = torch.empty(nb, dtype=torch.int64, device=dev)
+        nz = torch.empty(nb, dtype=torch.float64, device=dev)
+        rm = torch.as_tensor(plan.loc2glob, device=dev)
+        torch.cuda.synchronize()
+        assert lf.ctx.result_block(plan.lcol_lo, plan.lcol_hi, rm, cnt, rv, nz) == nb
+        cnts.append(cnt.cpu().numpy()), rows.append(rv.cpu().numpy()), vals.append(nz.cpu().numpy())
+        if world > 1 and not permute:
+            assert len(plan.elems) < conn.shape[0]
+    colptr = np.concatenate([[1], 1 + np.cumsum(np.concatenate(cnts))])
+    assert np.array_equal(colptr, Kg.colptr)
+    assert np.array_equal(np.concatenate(rows), Kg.rowval)
+    assert relfro(np.concatenate(vals), Kg.nzval) < TOL
+
+
+def test_result_block_argument_checks(fs):
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh("t3", n=4)
+    femm = _make_femm(fs, "t3", conn)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6))).numberdofs()
+    f.associategeometry(femm, geom0)
+    K = f.stiffness(femm, f.SysmatAssemblerSparse(), geom0, None, None, dchi)
+    assert femm.ctx.result_block(0, K.n) == K.nzval.size
+    assert femm.ctx.result_block(5, 5) == 0
+    with pytest.raises(fs.FsgpuError):
+        femm.ctx.result_block(3, K.n + 1)
+    f.stiffness(femm, f.SysmatAssemblerSparseSymm(), geom0, None, None, dchi)
+    with pytest.raises(fs.FsgpuError):
+        femm.ctx.result_block(0, 6)
+
+
+# ---------------------------------------------------------------------------------------
 # corotational beam
 # ---------------------------------------------------------------------------------------
 EB, NUB, RHOB = 71240.0, 0.31, 5e-9
