@@ -94,8 +94,9 @@ def strip_links(rank, world, lo_dofs, hi_dofs):
 # assembles every element that touches a node holding one of those columns, on a local mesh whose
 # dofs are renumbered by an order-preserving map.  Its owned columns are then complete -- interface
 # elements are computed by both neighbours instead of exchanging partial sums -- rows stay ascending
-# after mapping back, and the global CSC is the concatenation of the blocks: one in-place broadcast
-# (NCCL over NVLink on GPUs, gloo in the CPU tests) of each rank's slice of the global arrays.
+# after mapping back, and the global CSC is the concatenation of the blocks: every rank writes its block
+# into its slice of the global arrays and the slices are exchanged in place in one batch of point-to-point
+# transfers (NCCL over NVLink on GPUs, gloo in the CPU tests).
 
 _FF_KINDS = ("ffblock", "ffblock_diag")
 
@@ -195,10 +196,22 @@ def gather_blocks(fill, ncols_b, nnz_b, device, group=None):
     nzval = torch.empty(int(zoff[-1]), dtype=torch.float64, device=device)
     counts = colptr[1:]
     fill(counts[coff[rank] : coff[rank + 1]], rowval[zoff[rank] : zoff[rank + 1]], nzval[zoff[rank] : zoff[rank + 1]])
-    for r in range(world):
-        for buf, off in ((counts, coff), (rowval, zoff), (nzval, zoff)):
+    # every rank sends its slices to all peers and receives theirs in place, as ONE batch: all transfers are in
+    # flight together (both directions of every NVLink; NVSwitch gives each pair full bandwidth)
+    grank = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    ops = []
+    for buf, off in ((counts, coff), (rowval, zoff), (nzval, zoff)):
+        mine = buf[off[rank] : off[rank + 1]]
+        for r in range(world):
+            if r == rank:
+                continue
+            if mine.numel():
+                ops.append(dist.P2POp(dist.isend, mine, grank(r), group))
             if off[r + 1] > off[r]:
-                dist.broadcast(buf[off[r] : off[r + 1]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+                ops.append(dist.P2POp(dist.irecv, buf[off[r] : off[r + 1]], grank(r), group))
+    if ops:
+        for wk in dist.batch_isend_irecv(ops):
+            wk.wait()
     colptr[0] = 1
     counts.cumsum_(0)
     counts += 1
@@ -240,7 +253,17 @@ def gather_vector(local_vec, plan, device, group=None):
     b = plan._bounds
     out = torch.empty(plan.ncols_global, dtype=torch.float64, device=device)
     out[b[rank] : b[rank + 1]] = local_vec[plan.lcol_lo : plan.lcol_hi]
+    grank = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    mine = out[b[rank] : b[rank + 1]]
+    ops = []
     for r in range(world):
+        if r == rank:
+            continue
+        if mine.numel():
+            ops.append(dist.P2POp(dist.isend, mine, grank(r), group))
         if b[r + 1] > b[r]:
-            dist.broadcast(out[b[r] : b[r + 1]], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+            ops.append(dist.P2POp(dist.irecv, out[b[r] : b[r + 1]], grank(r), group))
+    if ops:
+        for wk in dist.batch_isend_irecv(ops):
+            wk.wait()
     return out
