@@ -1029,6 +1029,41 @@ __device__ __forceinline__ void resultant_out(const ShellArgs& P, int quant, con
   out[2] = a00 * n + a01 * m;
 }
 
+// Laminated shells (src/FEMMShellT3FFCompModule.jl:892-937, src/FEMMShellQ4RSCompModule.jl:1164-1203):
+// mom = sB eps + sD kappa, frc = sA eps + sB kappa, shear = stab_fun sH gamma with the layup group's A, B, D, H
+// rotated into the element frame; the default output csys is the layup's.  lcs / ocs: row-major 3x3.
+__device__ __forceinline__ void resultant_out_laminate(int quant, const double (&st)[8], double stab, const Triad& E,
+                                                       const double* gd, const double* lcs, const double* ocs, double* out) {
+  double lm, ln, m, n;
+  layup_angle(E, lcs, lm, ln);
+  layup_angle(E, ocs ? ocs : lcs, m, n);
+  if (quant == 2) {
+    double sH[2][2];
+    rotate_ts(gd + 27, lm, ln, sH);
+    const double f0 = stab * (sH[0][0] * st[6] + sH[0][1] * st[7]);
+    const double f1 = stab * (sH[1][0] * st[6] + sH[1][1] * st[7]);
+    out[0] = m * f0 - n * f1;
+    out[1] = n * f0 + m * f1;
+    out[2] = 0.0;
+    return;
+  }
+  double sX[3][3], sB[3][3];
+  rotate_ps(gd + 9, lm, ln, sB);
+  rotate_ps(quant == 1 ? gd + 18 : gd, lm, ln, sX);  // D pairs with the curvatures, A with the membrane strains
+  const int ox = quant == 1 ? 3 : 0, ob = quant == 1 ? 0 : 3;
+  double v[3];
+  for (int i = 0; i < 3; ++i)
+    v[i] = sX[i][0] * st[ox] + sX[i][1] * st[ox + 1] + sX[i][2] * st[ox + 2] + sB[i][0] * st[ob] + sB[i][1] * st[ob + 1] +
+           sB[i][2] * st[ob + 2];
+  const double M00 = v[0], M11 = v[1], M01 = v[2];
+  const double a00 = m * M00 - n * M01, a01 = m * M01 - n * M11;
+  const double a10 = n * M00 + m * M01, a11 = n * M01 + m * M11;
+  out[0] = a00 * m - a01 * n;
+  out[1] = a10 * n + a11 * m;
+  out[2] = a00 * n + a01 * m;
+}
+
+template <bool COMP>
 __global__ void k_t3_resultants(ShellArgs P, const double* __restrict__ u, int quant, const double* __restrict__ ocs, int64_t nocs,
                                 double* __restrict__ out) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1063,12 +1098,21 @@ __global__ void k_t3_resultants(ShellArgs P, const double* __restrict__ u, int q
       }
     }
   }
-  const double t = P.nthick == 1 ? P.thick[0] : P.thick[e];
   const double h = sqrt(2 * g.Ae);
-  const double stab = P.nstab ? P.stabf[e] : t * t / (t * t + P.alpha * h * h);
-  resultant_out(P, quant, st, t, stab, g.E, nocs == 0 ? nullptr : ocs + (nocs == 1 ? 0 : e * 9), out + e * 3);
+  const double* oc = nocs == 0 ? nullptr : ocs + (nocs == 1 ? 0 : e * 9);
+  if (COMP) {
+    const double* gd = P.gdata + (size_t)P.gof[e] * 34;
+    const double t = gd[31];
+    const double stab = P.nstab ? P.stabf[e] : t * t / (t * t + P.alpha * h * h);
+    resultant_out_laminate(quant, st, stab, g.E, gd, P.cs + (P.ncs == 1 ? 0 : e * 9), oc, out + e * 3);
+  } else {
+    const double t = P.nthick == 1 ? P.thick[0] : P.thick[e];
+    const double stab = P.nstab ? P.stabf[e] : t * t / (t * t + P.alpha * h * h);
+    resultant_out(P, quant, st, t, stab, g.E, oc, out + e * 3);
+  }
 }
 
+template <bool COMP>
 __global__ void k_q4_resultants(ShellArgs P, const double* __restrict__ u, int quant, const double* __restrict__ ocs, int64_t nocs,
                                 double* __restrict__ out) {
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1092,6 +1136,37 @@ __global__ void k_q4_resultants(ShellArgs P, const double* __restrict__ u, int q
   double P1[5][3], P2[5][3];
   for (int r = 0; r < 5; ++r)
     for (int k = 0; k < 3; ++k) P1[r][k] = P2[r][k] = 0.0;
+  // FEMMShellQ4RSComp as written applies T = T_ae T_ga twice: `edisp_e = T edisp` (src/FEMMShellQ4RSCompModule.jl:1163)
+  // is then multiplied by B matrices that already carry T (:1181-1184, :1198) -- SURVEY App. B.9, replicated.
+  // ut[l] = (T u)[6l .. 6l+5] from the definitions of T_ga (src/FEMMShellT3FFModule.jl:398-419) and T_ae (:421-463).
+  double ut[4][6];
+  if (COMP) {
+    M3 Ak[4];
+    double un[4][6];
+    for (int l = 0; l < 4; ++l) {
+      const double4 nv = ldg4(P.nrm + nn[l]);
+      Ak[l] = nodal_triad(g.E, v3(nv.x, nv.y, nv.z), nv.w != 0.0);
+      const M3 G = global_to_nodal(Ak[l], g.E);
+      const double* ul = u + (int64_t)nn[l] * 6;
+      for (int i = 0; i < 3; ++i) {
+        un[l][i] = G.a[i][0] * ul[0] + G.a[i][1] * ul[1] + G.a[i][2] * ul[2];
+        un[l][3 + i] = G.a[i][0] * ul[3] + G.a[i][1] * ul[4] + G.a[i][2] * ul[5];
+      }
+    }
+    for (int l = 0; l < 4; ++l) {
+      const M3& A = Ak[l];
+      for (int i = 0; i < 3; ++i) ut[l][i] = A.a[i][0] * un[l][0] + A.a[i][1] * un[l][1] + A.a[i][2] * un[l][2];
+      double R[2][2];
+      node_R(A, R);
+      double cpl = 0.0;  // sum_j sum_k 1/2 (A[1][k] gx_j - A[0][k] gy_j) un_j[k]
+      for (int j = 0; j < 4; ++j)
+        for (int k = 0; k < 3; ++k) cpl += 0.5 * (A.a[1][k] * g.gN[j][0] - A.a[0][k] * g.gN[j][1]) * un[j][k];
+      const double ia = 1.0 / A.a[2][2];
+      ut[l][3] = R[0][0] * un[l][3] + R[0][1] * un[l][4] + ia * A.a[0][2] * cpl;
+      ut[l][4] = R[1][0] * un[l][3] + R[1][1] * un[l][4] + ia * A.a[1][2] * cpl;
+      ut[l][5] = 0.0;
+    }
+  }
   for (int pass = 0; pass < 2; ++pass) {
     for (int l = 0; l < 4; ++l) {
       const double4 nv = ldg4(P.nrm + nn[l]);
@@ -1109,16 +1184,24 @@ __global__ void k_q4_resultants(ShellArgs P, const double* __restrict__ u, int q
       } else {
         double bg[8][6];
         node_strip(g.E, A, g.gN[l][0], g.gN[l][1], bs, P1, P2, bg);
-        const double* ul = u + (int64_t)nn[l] * 6;
+        const double* ul = COMP ? ut[l] : u + (int64_t)nn[l] * 6;
         for (int s = 0; s < 8; ++s)
           for (int c = 0; c < 6; ++c) st[s] += bg[s][c] * ul[c];
       }
     }
   }
-  const double t = P.nthick == 1 ? P.thick[0] : (P.nthick == P.nelem ? P.thick[e] : P.thick[e * npts + gp]);
-  const double stab = P.nstab ? P.stabf[e] : t * t / (t * t + P.alpha * hq * hq);
   const double* oc = nocs == 0 ? nullptr : ocs + (nocs == 1 ? 0 : (nocs == P.nelem ? e : tid) * 9);
-  resultant_out(P, quant, st, t, stab, g.E, oc, out + tid * 3);
+  if (COMP) {
+    const double* gd = P.gdata + (size_t)P.gof[e] * 34;
+    const double t = gd[31];
+    const double stab = P.nstab ? P.stabf[e] : t * t / (t * t + P.alpha * hq * hq);
+    const int64_t ci = P.ncs == 1 ? 0 : (P.ncs == P.nelem ? e : tid);
+    resultant_out_laminate(quant, st, stab, g.E, gd, P.cs + ci * 9, oc, out + tid * 3);
+  } else {
+    const double t = P.nthick == 1 ? P.thick[0] : (P.nthick == P.nelem ? P.thick[e] : P.thick[e * npts + gp]);
+    const double stab = P.nstab ? P.stabf[e] : t * t / (t * t + P.alpha * hq * hq);
+    resultant_out(P, quant, st, t, stab, g.E, oc, out + tid * 3);
+  }
 }
 
 __global__ void k_element_sizes(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe, int64_t nelem,
@@ -1894,10 +1977,13 @@ extern "C" int fsgpu_element_matrices(fsgpu_ctx* c, int32_t kind, int32_t op, co
 extern "C" int fsgpu_shell_resultants(fsgpu_ctx* c, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
                                       const double* outputcsys, int64_t ncs, double* out) {
   FS_TRY(check_ctx(c));
-  FS_REQUIRE(kind == 3 || kind == 4, FSGPU_ERR_ARG, "resultants are implemented for the homogeneous T3FF (3) and Q4RS (4) shells");
+  FS_REQUIRE(kind == 3 || kind == 4 || kind == 13 || kind == 14, FSGPU_ERR_ARG,
+             "kind must be 3 (T3FF), 4 (Q4RS), 13 (T3FFComp) or 14 (Q4RSComp)");
   FS_REQUIRE(quantity >= 1 && quantity <= 3 && u && out, FSGPU_ERR_ARG, "quantity must be 1 (bending), 2 (shear) or 3 (membrane)");
+  const bool comp = kind > 10;
+  kind = comp ? kind - 10 : kind;
   ShellArgs A;
-  FS_TRY(shell_args(c, p, kind, false, true, A));
+  FS_TRY(shell_args(c, p, kind, comp, true, A));
   const int npts = kind == 3 ? 1 : c->rule.npts;
   FS_REQUIRE(ncs == 0 || ncs == 1 || ncs == c->nelem || ncs == c->nelem * npts, FSGPU_ERR_ARG, "bad output csys count");
   const int64_t n = c->nnodes, nout = c->nelem * npts * 3;
@@ -1918,10 +2004,14 @@ extern "C" int fsgpu_shell_resultants(fsgpu_ctx* c, const fsgpu_shell_params* p,
   }
   FS_TRY(dout.ensure((size_t)nout + 1));
   if (c->nelem > 0) {
-    if (kind == 3)
-      k_t3_resultants<<<grid_for(c->nelem, 128), 128, 0, c->stream>>>(A, du.p, quantity, dcs.p, ncs, dout.p);
+    if (kind == 3 && !comp)
+      k_t3_resultants<false><<<grid_for(c->nelem, 128), 128, 0, c->stream>>>(A, du.p, quantity, dcs.p, ncs, dout.p);
+    else if (kind == 3)
+      k_t3_resultants<true><<<grid_for(c->nelem, 128), 128, 0, c->stream>>>(A, du.p, quantity, dcs.p, ncs, dout.p);
+    else if (!comp)
+      k_q4_resultants<false><<<grid_for(c->nelem * npts, 128), 128, 0, c->stream>>>(A, du.p, quantity, dcs.p, ncs, dout.p);
     else
-      k_q4_resultants<<<grid_for(c->nelem * npts, 128), 128, 0, c->stream>>>(A, du.p, quantity, dcs.p, ncs, dout.p);
+      k_q4_resultants<true><<<grid_for(c->nelem * npts, 128), 128, 0, c->stream>>>(A, du.p, quantity, dcs.p, ncs, dout.p);
     c->launches++;
   }
   FS_CUDA(cudaGetLastError());

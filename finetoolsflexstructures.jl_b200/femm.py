@@ -469,14 +469,13 @@ _QUANTITY = {"bending": 1, "moment": 1, "bending_moment": 1, "transverse_shear":
 def inspectintegpoints(femm, geom0, u, felist=None, quantity="moment", outputcsys=None):
     """Batched `inspectintegpoints` (src/FEMMShellT3FFModule.jl:850-962): instead of calling a host
     `inspector` closure per point, returns the array of resultants, shape (len(felist), npts, 3),
-    in the output csys (default: the material csys = element triad).  Homogeneous T3FF / Q4RS."""
+    in the output csys.  Default output csys: the element triad for the homogeneous shells, the layup csys for
+    the laminated ones (src/FEMMShellT3FFCompModule.jl:846, src/FEMMShellQ4RSCompModule.jl:1119)."""
     _require_associated(femm)
-    if femm._comp:
-        raise FsgpuError(L.ERR_ARG, "batched resultants are implemented for the homogeneous shells only")
     femm._sync_mesh(geom0)
     femm._sync_stab()
     npts = 1 if femm._nnpe == 3 else femm.ctx.npts
-    out = femm.ctx.shell_resultants(femm._params(), femm._nnpe, _QUANTITY[quantity], u.values, outputcsys, npts)
+    out = femm.ctx.shell_resultants(femm._params(), femm._kind(), _QUANTITY[quantity], u.values, outputcsys, npts)
     return out if felist is None else out[np.asarray(felist) - 1]
 
 

@@ -178,12 +178,15 @@ int fsgpu_corotbeam_restoringforce(fsgpu_ctx* ctx, const fsgpu_beam_params* p, i
 /* lumped shell mass as a diagonal VECTOR over all dofs (the diag(M) the explicit loop uses,
  * examples/.../plate_expl_examples.jl:69-71); kind 3 = T3FF, 4 = Q4RS, 13 = T3FFComp, 14 = Q4RSComp */
 int fsgpu_shell_mass_diag(fsgpu_ctx* ctx, const fsgpu_shell_params* p, int32_t kind, int32_t nfree_only);
-/* inspectintegpoints, batched (no per-point host callback): stress resultants of the homogeneous
- * T3FF (kind 3, one point per element) / Q4RS (kind 4, one per integration point) shells
- * (src/FEMMShellT3FFModule.jl:850-962, src/FEMMShellQ4RSModule.jl:1061-1170).
+/* inspectintegpoints, batched (no per-point host callback): stress resultants of the T3FF (kind 3, one point
+ * per element) / Q4RS (kind 4, one per integration point) shells and their laminated variants (kind 13 / 14:
+ * A, B, D, H of fsgpu_set_layup rotated into the element frame, B-coupling included)
+ * (src/FEMMShellT3FFModule.jl:850-962, src/FEMMShellQ4RSModule.jl:1061-1170,
+ *  src/FEMMShellT3FFCompModule.jl:809-943, src/FEMMShellQ4RSCompModule.jl:1061-1210 -- the latter applies the
+ *  global->element transformation twice as written; replicated).
  * quantity: 1 = bending moments (m11, m22, m12), 2 = transverse shear forces (q1, q2, 0),
- * 3 = membrane forces (n11, n22, n12), in the output csys: ncs = 0 -> the default material csys
- * (element triad), else ncs = 1 | nelem | nelem*npts column-major 3x3 matrices.
+ * 3 = membrane forces (n11, n22, n12), in the output csys: ncs = 0 -> the default (homogeneous: the element
+ * triad; laminated: the layup csys), else ncs = 1 | nelem | nelem*npts column-major 3x3 matrices.
  * u: nnodes x 6 column-major (the displacement/rotation field); out: 3 x npts x nelem. */
 int fsgpu_shell_resultants(fsgpu_ctx* ctx, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
                            const double* outputcsys, int64_t ncs, double* out);

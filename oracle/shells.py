@@ -808,3 +808,76 @@ def q4rs_resultants(xyz, conn, normals, normal_valid, Dps, Dt, thickness, u, qua
             vec = (t * stab_fun(t, h))[:, None] * np.einsum("ij,ej->ei", Dt * (5 / 6), np.einsum("eij,ej->ei", B, edisp))
         out[:, j, :] = _rotate_out(quant, vec, E_G, ocs)
     return out
+
+
+def _laminate_resultant(quant, sA, sB, sD, sH, memstr, kurv, shrstr, stab):
+    """mom = sB eps + sD kappa; frc = sA eps + sB kappa; shear = stab_fun sH gamma
+    (src/FEMMShellT3FFCompModule.jl:916-937)."""
+    if quant == BENDING_MOMENT:
+        return np.einsum("eij,ej->ei", sB, memstr) + np.einsum("eij,ej->ei", sD, kurv)
+    if quant == MEMBRANE_FORCE:
+        return np.einsum("eij,ej->ei", sA, memstr) + np.einsum("eij,ej->ei", sB, kurv)
+    return stab[:, None] * np.einsum("eij,ej->ei", sH, shrstr)
+
+
+def t3ffcomp_resultants(xyz, conn, normals, normal_valid, A, B, D, H, layup_thickness, lcsmat, u, quant, ocs=None, stab_fun=None):
+    """(ne,3) resultants of FEMMShellT3FFComp (one layup group); the default output csys is the layup's
+    (`outputcsys = self.layup_groups[1][1].csys`).  src/FEMMShellT3FFCompModule.jl:809-943."""
+    stab_fun = stab_fun or stab_lyly(T3_DEFAULT_ALPHA)
+    c = np.asarray(conn) - 1
+    ne = c.shape[0]
+    X = xyz[c]
+    J0, E_G, ec, g, Ae = t3_geometry(X)
+    edisp = u[c].reshape(ne, 18)
+    A_Es, nvalid = nodal_triads_e(E_G, normals, normal_valid, conn)
+    edisp_n = np.einsum("eij,ej->ei", transfmat_g_to_a(A_Es, E_G), edisp)
+    edisp_e = np.einsum("eij,ej->ei", transfmat_a_to_e(A_Es, g), edisp_n)
+    lcs = np.broadcast_to(np.asarray(lcsmat, dtype=np.float64), (ne, 3, 3))
+    m, n = layup2element_angle(E_G, lcs)
+    Tps, Tts = plane_stress_Tbar(m, n), transverse_shear_T(m, n)
+    bc = lambda M: np.broadcast_to(M, (ne,) + M.shape).copy()
+    sA, sB, sD, sH = qteq(bc(A), Tps), qteq(bc(B), Tps), qteq(bc(D), Tps), qteq(bc(H), Tts)
+    kurv = np.einsum("eij,ej->ei", _bb(g), edisp_e)
+    memstr = np.einsum("eij,ej->ei", _bm(g), edisp_e)
+    shr = np.einsum("eij,ej->ei", _t3_bs(ec, Ae), edisp_e)
+    t = np.full(ne, float(layup_thickness))
+    vec = _laminate_resultant(quant, sA, sB, sD, sH, memstr, kurv, shr, stab_fun(t, np.sqrt(2 * Ae)))
+    return _rotate_out(quant, vec, E_G, lcs if ocs is None else ocs)
+
+
+def q4rscomp_resultants(xyz, conn, normals, normal_valid, A, B, D, H, layup_thickness, lcsmat, u, quant, ocs=None, rule=None, stab_fun=None):
+    """(ne,npts,3) resultants of FEMMShellQ4RSComp (one layup group).  As written in the reference the strains
+    are B T (T u): `edisp_e = T edisp` (:1163) and the B matrices already carry T (:1181-1184, :1198) -- SURVEY
+    App. B.9; restated as is.  src/FEMMShellQ4RSCompModule.jl:1061-1210."""
+    stab_fun = stab_fun or stab_lyly(Q4_DEFAULT_ALPHA)
+    pc, w = rule if rule is not None else fx.gauss_rule_2x2()
+    c = np.asarray(conn) - 1
+    ne = c.shape[0]
+    X = xyz[c]
+    h = q4_diameter(X)
+    t = np.full(ne, float(layup_thickness))
+    edisp = u[c].reshape(ne, 24)
+    lcs = np.asarray(lcsmat, dtype=np.float64)
+    bc = lambda M: np.broadcast_to(M, (ne,) + M.shape).copy()
+    out = np.zeros((ne, len(w), 3))
+    for j in range(len(w)):
+        _, _, Jac, E_G, ec, g, T = _q4_gp_setup(X, normals, normal_valid, conn, *pc[j])
+        l = lcs[:, j] if lcs.ndim == 4 else np.broadcast_to(lcs, (ne, 3, 3))
+        m, n = layup2element_angle(E_G, l)
+        Tps, Tts = plane_stress_Tbar(m, n), transverse_shear_T(m, n)
+        sA, sB, sD, sH = qteq(bc(A), Tps), qteq(bc(B), Tps), qteq(bc(D), Tps), qteq(bc(H), Tts)
+        edisp_e = np.einsum("eij,ej->ei", T, edisp)
+        Bm = np.einsum("eij,ejk->eik", _bm(g), T)
+        Bb = np.einsum("eij,ejk->eik", _bb(g), T)
+        Bs = np.einsum("eij,ejk->eik", _q4_mitc_bs(ec, *pc[j]), T)
+        kurv = np.einsum("eij,ej->ei", Bb, edisp_e)
+        memstr = np.einsum("eij,ej->ei", Bm, edisp_e)
+        shr = np.einsum("eij,ej->ei", Bs, edisp_e)
+        vec = _laminate_resultant(quant, sA, sB, sD, sH, memstr, kurv, shr, stab_fun(t, h))
+        if ocs is None:
+            o = l
+        else:
+            o = np.asarray(ocs, dtype=np.float64)
+            o = o[:, j] if o.ndim == 4 else o
+        out[:, j, :] = _rotate_out(quant, vec, E_G, o)
+    return out

@@ -209,6 +209,36 @@ def test_resultants(fs, kind):
         assert relfro(got, ref) < 1e-6
 
 
+@pytest.mark.parametrize("kind", ["t3", "q4"])
+def test_resultants_laminated(fs, kind):
+    """inspectintegpoints of FEMMShellT3FFComp / FEMMShellQ4RSComp (the latter with the reference's double
+    application of T): default output csys = layup csys, and an explicit one."""
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh(kind, n=7)
+    lay, cs = _layup()
+    femm = _make_femm(fs, kind, conn, comp=True, cs=cs)
+    geom0 = f.NodalField(xyz)
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals(kind, xyz, conn, fixed=cs[:, 2])
+    A, B, D = lay.laminate_stiffnesses()
+    H = lay.laminate_transverse_stiffness()
+    rng = np.random.default_rng(17)
+    u = rng.standard_normal((xyz.shape[0], 6)) * 1e-3
+    th = np.deg2rad(-35.0)
+    ocs = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    ofun = osh.t3ffcomp_resultants if kind == "t3" else osh.q4rscomp_resultants
+    for q, name in ((1, "moment"), (2, "shear"), (3, "membrane")):
+        for o in (None, ocs):
+            got = f.inspectintegpoints(femm, geom0, f.NodalField(u), None, name, outputcsys=o)
+            ref = ofun(xyz, conn, normals, valid, A, B, D, H, lay.thickness, cs, u, q, ocs=o).reshape(got.shape)
+            assert relfro(got, ref) < 1e-11, (name, o is None, relfro(got, ref))
+    # felist selects elements
+    sel = np.array([3, 1, 7])
+    got = f.inspectintegpoints(femm, geom0, f.NodalField(u), sel, "moment")
+    ref = ofun(xyz, conn, normals, valid, A, B, D, H, lay.thickness, cs, u, 1)
+    assert relfro(got, ref.reshape(conn.shape[0], -1, 3)[sel - 1]) < 1e-11
+
+
 # ---------------------------------------------------------------------------------------
 # assembled matrices, every assembler target: pattern bit-exact, values 1e-12
 # ---------------------------------------------------------------------------------------

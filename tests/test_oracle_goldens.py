@@ -285,3 +285,24 @@ def test_beam_fast_top_newmark():
     assert np.linalg.norm(np.array(reftipx) - tipx) / np.linalg.norm(reftipx) < 1e-5
     assert np.linalg.norm(np.array(reftipy) - tipy) / np.linalg.norm(reftipy) < 1e-5
 
+
+
+def test_laminated_resultants_reduce_to_homogeneous_for_one_isotropic_ply():
+    """The restated FEMMShellT3FFComp.inspectintegpoints (no reference golden exists for it) against the restated
+    homogeneous one (pinned through the shared kinematics): one isotropic ply gives A = t Dps, B = 0,
+    D = t^3/12 Dps, H = 5/6 t Dt, so all three resultants must coincide in a common output csys."""
+    from tests import meshes
+
+    xyz, conn = meshes.shell_mesh("t3", n=5)
+    nrm, val = osh.t3ff_associategeometry(xyz, conn)
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(200e9, 0.3))
+    t = 0.01
+    A, B, D, H = t * Dps, np.zeros((3, 3)), t**3 / 12 * Dps, 5 / 6 * t * Dt
+    u = np.random.default_rng(2).standard_normal((xyz.shape[0], 6)) * 1e-3
+    th = np.deg2rad(15.0)
+    ocs = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    lcs = np.eye(3)
+    for q in (1, 2, 3):
+        a = osh.t3ffcomp_resultants(xyz, conn, nrm, val, A, B, D, H, t, lcs, u, q, ocs=ocs)
+        b = osh.t3ff_resultants(xyz, conn, nrm, val, Dps, Dt, t, u, q, ocs=ocs)
+        assert np.linalg.norm(a - b) <= 1e-12 * np.linalg.norm(b), q
