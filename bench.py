@@ -680,6 +680,8 @@ def main():
     barrier()
     refresh_ms = (time.perf_counter() - t0) / args.e2e_steps * 1e3
 
+    # checksum of the single-GPU values: the gathered multi-GPU assembly of the same matrix must reproduce it
+    nz_checksum_single = float(np.sum(nz_p)) if world > 1 else None
     # free the C2 buffers before the 4M-element workload
     del K, cp_p, rv_p, nz_p, k4, k5, k6
     femm.ctx.close()
@@ -693,6 +695,8 @@ def main():
         gathered = gathered_c2(args, rank, local_rank, world, stream, w, nrm_host, val_host)
         if extras is None:
             extras = {}
+        gathered["nzval_checksum_single_gpu"] = nz_checksum_single
+        gathered["checksum_rel_diff"] = abs(gathered["nzval_checksum"] - nz_checksum_single) / abs(nz_checksum_single)
         extras["gathered_assembly_C2"] = gathered
 
     if rank != 0:

@@ -337,10 +337,41 @@ function state(e::ExplicitGPU)
     return U, V, A
 end
 
+# ---- batched inspectintegpoints (src/FEMMShellT3FFModule.jl:850-962 and the three sibling methods) ----
+# The reference calls `inspector(idat, i, conn, ecoords, out, loc)` per point; a Julia closure cannot cross the C
+# boundary, so the GPU method returns the 3 x npts x nelem array and the caller folds its inspector over it.
+const _QUANTITY = Dict(:bending => 1, :moment => 1, :bending_moment => 1, :transverse_shear => 2, :transverse => 2,
+                       :shear => 2, :membrane_force => 3, :membrane => 3)
+"kind: 3 T3FF, 4 Q4RS, 13 T3FFComp, 14 Q4RSComp; outputcsys: nothing (element triad / layup csys) or 3x3xN matrices"
+function shell_resultants(c::Context, params::ShellParams, kind::Integer, quantity::Symbol, u::NodalField{Float64}, npts::Integer,
+        nelem::Integer; outputcsys::Union{Nothing,Array{Float64,3}} = nothing)
+    out = Array{Float64,3}(undef, 3, npts, nelem)
+    cs, ncs = outputcsys === nothing ? (C_NULL, 0) : (pointer(outputcsys), size(outputcsys, 3))
+    uv = u.values
+    GC.@preserve uv outputcsys out _check(ccall((:fsgpu_shell_resultants, libfsgpu), Cint,
+        (Ptr{Cvoid}, Ref{ShellParams}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+        c.h, Ref(params), kind, _QUANTITY[quantity], pointer(uv), cs, ncs, pointer(out)))
+    return out
+end
+
+# ---- multi-GPU: this rank's column block of the global matrix (SURVEY section 8(e)) --------------------
+# One Julia process per GPU (MPI.jl / NCCL.jl for the exchange).  `row_map`, `colcount`, `rowval`, `nzval` are DEVICE
+# pointers (CuPtr of CUDA.jl arrays): the block is written in Julia's CSC layout straight into this rank's slice of
+# the gathered arrays; see finetoolsflexstructures.jl_b200/partition.py for the plan (owned columns, local mesh).
+function result_block!(c::Context, col_lo::Integer, col_hi::Integer, row_map, colcount, rowval, nzval)
+    nb = Ref{Int64}(0)
+    _check(ccall((:fsgpu_result_block, libfsgpu), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ref{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+        c.h, col_lo, col_hi, row_map, nb, colcount, rowval, nzval))
+    return nb[]
+end
+result_block_size(c::Context, col_lo::Integer, col_hi::Integer) = result_block!(c, col_lo, col_hi, C_NULL, C_NULL, C_NULL, C_NULL)
+
 "bitwise reproducible T3FF/T3FFComp stiffness (atomics-free owner-computes kernel); takes effect at the next symbolic phase"
 set_deterministic!(c::Context, on::Bool = true) = _check(ccall((:fsgpu_set_deterministic, libfsgpu), Cint, (Ptr{Cvoid}, Cint), c.h, on ? 1 : 0))
 
 export SysmatAssemblerGPU, SysvecAssemblerGPU, Context, ExplicitGPU, sparse_gpu, set_load!, start!, step!, state, set_deterministic!
+export shell_resultants, result_block!, result_block_size
 export SPARSE, SPARSE_SYMM, SPARSE_DIAG, FFBLOCK, FFBLOCK_DIAG, CSR_SYMM
 
 end # module
