@@ -813,7 +813,16 @@ __device__ __forceinline__ void q4_product_pass(const double* sb_, int bi, int b
   }
 }
 
-constexpr int Q4_WARP_DBL = 2 * 32 * 24 + (32 * 8 + 32 * 4) / 2;  // strips + addressing area (doubles)
+__device__ __forceinline__ void q4_async_normal(const ShellArgs& P, double* slot, bool on, int node) {
+  if (on) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(slot);
+    const double4* src = P.nrm + node;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(reinterpret_cast<const char*>(src) + 16) : "memory");
+  }
+}
+
+constexpr int Q4_WARP_DBL = 2 * 32 * 24 + (32 * 8 + 32 * 4) / 2 + 8 * 4;  // strips + addressing area + 8 nodal normals (doubles)
 
 // CHUNKED = false: rules with <= 4 points (GaussRule(2,2)), one setup + one product pass.  CHUNKED = true: any
 // rule, chunks of 4 points with the accumulators carried through the setup passes.  Two kernels rather than
@@ -830,6 +839,8 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   double* wbase = smem + (size_t)wib * WARP_DBL;
   double* sb_ = wbase + half * HW_DBL;
   int* addr = reinterpret_cast<int*>(wbase + 2 * HW_DBL);
+  // the nodal normal the drilling step of a diagonal-block lane needs arrives here (cp.async) during the product loop
+  double* nslot = wbase + 2 * HW_DBL + (32 * 8 + 32 * 4) / 2 + (half * 4 + ((lane & 15) >> 2)) * 4;
   const int64_t e = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wib) * 2 + half;
   const bool active = e < P.nelem;
   const int g4 = l16 >> 2, jn = l16 & 3;  // setup role
@@ -874,6 +885,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
       ecols = emit.cols(nbj);
       erows = emit.rows(e, bi, bj, nbi);
     }
+    q4_async_normal(P, nslot, active && bi == bj, nbi);
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -890,6 +902,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
       ecols = emit.cols(nbj);
       erows = emit.rows(e, bi, bj, nbi);
     }
+    q4_async_normal(P, nslot, active && bi == bj, nbi);
     for (int chunk = 0; chunk * 4 < npts; ++chunk) {
       const int gp = chunk * 4 + g4;
       q4_setup_pass<COMP>(P, active && gp < npts, e, gp, g4, jn, X, nvown, hq, gd, sb_);
@@ -904,8 +917,9 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   double tang = 0.0;
   int ok = 0;
   double nvec[3] = {0, 0, 0};
+  asm volatile("cp.async.wait_all;" ::: "memory");
   if (active && bi == bj) {
-    const double4 n4 = ldg4(P.nrm + nbi);
+    const double4 n4 = *reinterpret_cast<const double4*>(nslot);
     const double nl = sqrt(n4.x * n4.x + n4.y * n4.y + n4.z * n4.z);
     if (n4.w != 0.0 && nl != 0.0) {
       ok = 1;
