@@ -360,14 +360,17 @@ def extras_c3_c5(args, rank, local_rank, world, stream):
     mat = f.lamina_material(*w["lamina"])
     t = w["thickness"]
     plies = [f.Ply(f"p{k}", mat, t / 4, a) for k, a in enumerate(w["angles"])]
-    layup = f.CompositeLayup("C3", plies, w["csmat"])
+    layup = f.CompositeLayup("C3", plies, wl.cylindrical_csys)  # a csys CALLBACK, as in the reference example
     femm = f.FEMMShellT3FFComp(f.IntegDomain(w["conn"], None, t), layup, device=local_rank)
     femm.ctx.set_stream(stream.cuda_stream)
     geom0, dchi = field(w["xyz"]), field(None, w["dofnums"], w["nfree"])
-    femm._sync_mesh(geom0)
-    femm._normals, femm._normal_valid = w["normals"], np.ones(w["xyz"].shape[0], bool)  # radial = layup csys normal
-    femm.ctx.set_normals(femm._normals, femm._normal_valid)
-    femm._associatedgeometry = True
+    # associategeometry!: the host evaluates the callback at every node of every element, the device accumulates,
+    # normalises and validates (fsgpu_associategeometry_dirs)
+    t0 = time.perf_counter()
+    f.associategeometry(femm, geom0)
+    torch.cuda.synchronize()
+    assoc_s = time.perf_counter() - t0
+    assert np.abs(femm._normals - w["normals"]).max() < 1e-12 and femm._normal_valid.all()  # radial, all valid
     femm._startassembly(f.SysmatAssemblerFFBlock(), dchi)
     femm._sync_stab()
     p = femm._params()
@@ -377,7 +380,8 @@ def extras_c3_c5(args, rank, local_rank, world, stream):
     ms_m = timed(lambda: femm.ctx.shell_op("t3ffcomp_mass", p))
     out["t3ffcomp_C3"] = {"workload": f"T3FFComp 4-ply [0/90/90/0] cylinder, {ne} triangles per rank, per-element layup csys: stiffness and lumped mass -> CSC (FFBlock)",
                           "stiffness_elements_per_s": ne * world / (ms_k * 1e-3), "stiffness_ms": ms_k, "stiffness_kernel_ms": kms,
-                          "mass_elements_per_s": ne * world / (ms_m * 1e-3), "mass_ms": ms_m, "nnz": int(femm.ctx.result_size()[2])}
+                          "mass_elements_per_s": ne * world / (ms_m * 1e-3), "mass_ms": ms_m, "nnz": int(femm.ctx.result_size()[2]),
+                          "associategeometry_s_incl_host_csys_callback": assoc_s}
     femm.ctx.close()
 
     # ---- C5 ----

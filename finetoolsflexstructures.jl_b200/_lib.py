@@ -75,6 +75,7 @@ _SIGNATURES = {
     "fsgpu_set_dofnums": [_vp, _vp, _i64, _i64],
     "fsgpu_set_normals": [_vp, _vp, _vp],
     "fsgpu_associategeometry": [_vp, _dbl, _vp, _i32],
+    "fsgpu_associategeometry_dirs": [_vp, _dbl, _vp, _i32],
     "fsgpu_normals_accumulate": [_vp, _vp, _i32, _P(_vp)],
     "fsgpu_normals_finish": [_vp, _dbl, _vp, _P(_vp)],
     "fsgpu_get_normals": [_vp, _vp, _vp],

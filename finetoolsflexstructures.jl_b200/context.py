@@ -70,6 +70,11 @@ class Context:
         fd = None if fixed_dir is None else f64(fixed_dir)
         check(lib.fsgpu_associategeometry(self._h, float(threshold_angle), ptr(fd), 1 if accumulate else 0))
 
+    def associategeometry_dirs(self, dirs, threshold_angle=30.0, accumulate=False):
+        """dirs: (nelem, nnpe, 3) csys normal direction per element and node."""
+        d = np.ascontiguousarray(np.asarray(dirs, dtype=np.float64).reshape(self.nelem, self.nnpe, 3))
+        check(lib.fsgpu_associategeometry_dirs(self._h, float(threshold_angle), ptr(d), 1 if accumulate else 0))
+
     def normals_accumulate(self, fixed_dir=None, accumulate=False):
         fd = None if fixed_dir is None else f64(fixed_dir)
         p = C.c_void_p()

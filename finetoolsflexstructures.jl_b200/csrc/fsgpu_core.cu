@@ -352,7 +352,7 @@ __device__ inline fsm::V3 elem_normal_at(const double4* xyz, const int32_t* cn, 
 }
 __global__ void k_normals_accumulate(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe,
                                      int64_t nelem, double* __restrict__ acc /*[nnodes][3]*/, int use_fixed, double fx,
-                                     double fy, double fz) {
+                                     double fy, double fz, const double* __restrict__ dirs /*[nelem][nnpe][3] or null*/) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nelem * nnpe) return;
   int64_t e = i / nnpe;
@@ -361,6 +361,7 @@ __global__ void k_normals_accumulate(const int32_t* __restrict__ conn, const dou
   double w;
   fsm::V3 n = elem_normal_at(xyz, cn, nnpe, k, w);
   if (use_fixed) n = fsm::v3(fx, fy, fz);
+  if (dirs) n = fsm::v3(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2]);
   double* a = acc + (int64_t)cn[k] * 3;
   atomicAdd(a + 0, w * n.x);
   atomicAdd(a + 1, w * n.y);
@@ -381,7 +382,7 @@ __global__ void k_normals_normalize(const double* __restrict__ acc, double4* __r
 }
 __global__ void k_normals_validate(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe,
                                    int64_t nelem, double4* __restrict__ nrm, double limit, int use_fixed, double fx,
-                                   double fy, double fz, int fixed_in_check) {
+                                   double fy, double fz, int fixed_in_check, const double* __restrict__ dirs) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nelem * nnpe) return;
   int64_t e = i / nnpe;
@@ -390,6 +391,7 @@ __global__ void k_normals_validate(const int32_t* __restrict__ conn, const doubl
   double w;
   fsm::V3 n = elem_normal_at(xyz, cn, nnpe, k, w);
   if (use_fixed && fixed_in_check) n = fsm::v3(fx, fy, fz);
+  if (dirs && fixed_in_check) n = fsm::v3(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2]);
   double4 nn = nrm[cn[k]];
   double nd = nn.x * n.x + nn.y * n.y + nn.z * n.z;
   if (nd < limit) nrm[cn[k]].w = 0.0;  // benign race: every writer stores 0
@@ -423,7 +425,7 @@ extern "C" int fsgpu_normals_accumulate(fsgpu_ctx* c, const double* fixed_dir, i
   }
   const int uf = fixed_dir ? 1 : 0;
   const double fx = uf ? fixed_dir[0] : 0, fy = uf ? fixed_dir[1] : 0, fz = uf ? fixed_dir[2] : 0;
-  LAUNCH(c, k_normals_accumulate, c->nelem * c->nnpe, c->conn.p, c->xyz.p, c->nnpe, c->nelem, acc, uf, fx, fy, fz);
+  LAUNCH(c, k_normals_accumulate, c->nelem * c->nnpe, c->conn.p, c->xyz.p, c->nnpe, c->nelem, acc, uf, fx, fy, fz, c->ndirs);
   FS_CUDA(cudaStreamSynchronize(c->stream));
   if (dev_sums) *dev_sums = acc;
   return FSGPU_OK;
@@ -441,7 +443,7 @@ extern "C" int fsgpu_normals_finish(fsgpu_ctx* c, double threshold_angle_deg, co
   // ...CompModule.jl:528-538); Q4 checks against the csys normal (src/FEMMShellQ4RSModule.jl:508-519).
   const int fixed_in_check = (c->nnpe == 4) ? 1 : 0;
   LAUNCH(c, k_normals_validate, c->nelem * c->nnpe, c->conn.p, c->xyz.p, c->nnpe, c->nelem, c->nrm.p, 1 - ntol, uf, fx,
-         fy, fz, fixed_in_check);
+         fy, fz, fixed_in_check, c->ndirs);
   FS_CUDA(cudaStreamSynchronize(c->stream));
   c->associated = true;
   if (dev_normals4) *dev_normals4 = reinterpret_cast<double*>(c->nrm.p);
@@ -451,6 +453,23 @@ extern "C" int fsgpu_associategeometry(fsgpu_ctx* c, double threshold_angle_deg,
                                        int32_t accumulate) {
   FS_TRY(fsgpu_normals_accumulate(c, fixed_dir, accumulate, nullptr));
   return fsgpu_normals_finish(c, threshold_angle_deg, fixed_dir, nullptr);
+}
+
+// General csys: the direction csmat(csys)[:, 3] evaluated by the host glue per element and node
+// (`_compute_nodal_normal!`, src/FEMMShellT3FFCompModule.jl:203-207,509; src/FEMMShellQ4RSModule.jl:489-494).
+extern "C" int fsgpu_associategeometry_dirs(fsgpu_ctx* c, double threshold_angle_deg, const double* dirs, int32_t accumulate) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(dirs != nullptr, FSGPU_ERR_ARG, "null direction array");
+  FS_REQUIRE(c->nnpe == 3 || c->nnpe == 4, FSGPU_ERR_STATE, "associategeometry needs a T3 or Q4 mesh");
+  const size_t bytes = (size_t)c->nelem * c->nnpe * 3 * sizeof(double);
+  DBuf<double> d;
+  FS_TRY(d.ensure((size_t)c->nelem * c->nnpe * 3 + 1));
+  FS_TRY(upload(c, d.p, dirs, bytes));
+  c->ndirs = d.p;
+  int rc = fsgpu_normals_accumulate(c, nullptr, accumulate, nullptr);
+  if (rc == FSGPU_OK) rc = fsgpu_normals_finish(c, threshold_angle_deg, nullptr, nullptr);
+  c->ndirs = nullptr;
+  return rc;
 }
 
 extern "C" int fsgpu_set_thickness(fsgpu_ctx* c, const double* t, int64_t n) {

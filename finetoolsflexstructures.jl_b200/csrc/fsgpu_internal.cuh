@@ -109,6 +109,7 @@ struct fsgpu_ctx {
   fs::DBuf<double4> nrm;      // (nx, ny, nz, valid ? 1 : 0)
   fs::DBuf<double> nacc;      // [nnodes][3] unnormalised normal sums (associategeometry, split form)
   bool nacc_keep = false;
+  const double* ndirs = nullptr;  // per (element, node) csys normal directions during fsgpu_associategeometry_dirs
   // thickness / stab factor
   int64_t nthick = 0;
   fs::DBuf<double> thick;

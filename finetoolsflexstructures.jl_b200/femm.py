@@ -288,6 +288,7 @@ class _FEMMBase:
             conn = np.asarray(self.integdomain.conn)
             if conn.shape[1] != self._nnpe:
                 raise FsgpuError(L.ERR_ARG, f"element set has {conn.shape[1]} nodes per element, expected {self._nnpe}")
+            self._xyz = np.asarray(geom0.values)
             self.ctx.set_mesh(conn, geom0.values)
             self._mesh_key = key
             self._dof_key = self._sym_key = None
@@ -351,6 +352,13 @@ class _FEMMShell(_FEMMBase):
                 for gi, (_, eset) in enumerate(self.layup_groups):
                     gof[np.asarray(eset) - 1] = gi + 1
             cs = self.layup_groups[0][0].csys
+            if callable(cs):
+                # `updatecsmat!(layup.csys, centroid, J0, i, 0)` (src/FEMMShellT3FFCompModule.jl:617): the closure stays
+                # on the host, the library gets one matrix per element
+                if self._nnpe != 3:
+                    raise FsgpuError(L.ERR_ARG, "a csys callback is evaluated at the T3 centroids; pass per-point matrices for Q4RSComp (SURVEY App. B.9)")
+                conn = np.asarray(idom.conn)
+                cs = cs(self._xyz[conn - 1].mean(axis=1))
             ctx.set_layup(recs, gof, np.asarray(cs, dtype=np.float64))
         else:
             t = idom.otherdimension
@@ -391,7 +399,24 @@ def associategeometry(femm, geom0, interface=None):
     femm._sync_mesh(geom0)
     fixed = None
     if femm._comp:
-        fixed = np.asarray(femm.layup_groups[0][0].csys, dtype=np.float64)[:, 2].copy()
+        cs = femm.layup_groups[0][0].csys
+        dirs = None
+        conn = np.asarray(femm.integdomain.conn)
+        if callable(cs):
+            # `_compute_nodal_normal!(nnormal, layup.csys, geom.values[n, :], J0, el, 0)`: the csys evaluated AT THE NODE
+            # (src/FEMMShellT3FFCompModule.jl:203-207,509)
+            xyz = np.asarray(geom0.values)
+            dirs = np.asarray(cs(xyz[conn - 1].reshape(-1, 3)))[:, :, 2].reshape(conn.shape[0], conn.shape[1], 3)
+        elif np.ndim(cs) == 3 and interface is None:
+            dirs = np.repeat(np.asarray(cs, dtype=np.float64)[:, None, :, 2], conn.shape[1], axis=1)
+        if dirs is not None:
+            if interface is not None:
+                raise FsgpuError(L.ERR_ARG, "partitioned associategeometry supports the default and the cartesian csys")
+            femm.ctx.associategeometry_dirs(dirs, femm.threshold_angle, False)
+            femm._normals, femm._normal_valid = femm.ctx.get_normals()
+            femm._associatedgeometry = True
+            return femm
+        fixed = np.asarray(cs, dtype=np.float64)[:, 2].copy()
     # homogeneous T3FF never resets its arrays
     accumulate = (femm._nnpe == 3) and (not femm._comp)
     if interface is None:

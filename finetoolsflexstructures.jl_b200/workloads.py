@@ -129,6 +129,16 @@ def c1_small_t3(n=64):
     return w
 
 
+def cylindrical_csys(locs):
+    """Layup csys of the cylinder examples (`cylindrical!`, examples/shells/dynamics/homogeneous/explicit/
+    clamp_cyl_expl_examples.jl:62-68): e1 = axial (z), e3 = radial (outward), e2 = e3 x e1; (n, 3) -> (n, 3, 3)."""
+    locs = np.asarray(locs, dtype=np.float64)
+    er = np.column_stack([locs[:, 0], locs[:, 1], np.zeros(len(locs))])
+    er /= np.linalg.norm(er, axis=1)[:, None]
+    ez = np.tile([0.0, 0.0, 1.0], (len(locs), 1))
+    return np.stack([ez, np.cross(er, ez), er], axis=2)
+
+
 def c3_t3ffcomp_cylinder(ncirc=1000, nlen=1000):
     """C3: laminated cylinder R = 0.1, L = 0.8 (examples/shells/dynamics/homogeneous/explicit/
     clamp_cyl_expl_examples.jl:59-84), T3block(360 deg, L, ncirc, nlen) wrapped with the seam merged

@@ -119,6 +119,11 @@ int fsgpu_set_normals(fsgpu_ctx* ctx, const double* normals, const uint8_t* vali
  * src/FEMMShellT3FFCompModule.jl:489-543).  accumulate != 0 reproduces the homogeneous T3FF
  * quirk of not resetting the arrays. */
 int fsgpu_associategeometry(fsgpu_ctx* ctx, double threshold_angle_deg, const double* fixed_dir, int32_t accumulate);
+/* general csys (cylindrical, spherical, any CSys callback): dirs = 3 x nnpe x nelem column-major, the third column of
+ * the csys matrix the host glue evaluated at every node of every element (`_compute_nodal_normal!`,
+ * src/FEMMShellT3FFCompModule.jl:203-207,509); it replaces the element normal in the accumulation (and, for the Q4
+ * elements, in the validity check, src/FEMMShellQ4RSModule.jl:508-519) */
+int fsgpu_associategeometry_dirs(fsgpu_ctx* ctx, double threshold_angle_deg, const double* dirs, int32_t accumulate);
 /* the same in two halves for element-partitioned runs: after _accumulate the host sums the
  * interface-node entries of *dev_sums ([nnodes][3] doubles, device) across ranks; after _finish it
  * min-combines the validity flags, 4th component of *dev_normals4 ([nnodes][4] doubles, device) */

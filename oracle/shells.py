@@ -394,9 +394,11 @@ def t3ff_associategeometry(xyz, conn, threshold_angle=30.0, normal_dir=None, nor
     X = xyz[c]
     J0 = np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]], axis=-1)
     E3 = e_g(J0)[:, :, 2]
-    contrib = E3 if normal_dir is None else np.broadcast_to(np.asarray(normal_dir, float), E3.shape)
+    nd_ = None if normal_dir is None else np.asarray(normal_dir, float)
     normals = np.zeros((nn, 3)) if normals0 is None else normals0.copy()
     for k in range(3):
+        # per (element, node) directions: a general csys evaluated at the node (`_compute_nodal_normal!`, Comp :203-207,509)
+        contrib = E3 if nd_ is None else (nd_[:, k] if nd_.ndim == 3 else np.broadcast_to(nd_, E3.shape))
         np.add.at(normals, c[:, k], contrib)
     nrm = np.sqrt(np.sum(normals**2, axis=1))
     normals = np.where((nrm > 0)[:, None], normals / np.where(nrm > 0, nrm, 1.0)[:, None], normals)
@@ -652,7 +654,11 @@ def q4rs_associategeometry(xyz, conn, threshold_angle=30.0, normal_dir=None):
         _, dNp = fx.q4_shape(*pcn[j])
         J = np.einsum("eai,ak->eik", X, dNp)
         Jac = np.sqrt(np.sum(np.cross(J[:, :, 0], J[:, :, 1]) ** 2, axis=1))
-        n = e_g(J)[:, :, 2] if normal_dir is None else np.broadcast_to(np.asarray(normal_dir, float), (len(c), 3))
+        if normal_dir is None:
+            n = e_g(J)[:, :, 2]
+        else:
+            nd_ = np.asarray(normal_dir, float)
+            n = nd_[:, j] if nd_.ndim == 3 else np.broadcast_to(nd_, (len(c), 3))
         enormals.append(n)
         np.add.at(normals, c[:, j], Jac[:, None] * n)
     nrm = np.sqrt(np.sum(normals**2, axis=1))

@@ -111,6 +111,55 @@ def test_associategeometry(fs, kind):
 # ---------------------------------------------------------------------------------------
 # raw element matrices
 # ---------------------------------------------------------------------------------------
+def test_t3ffcomp_with_csys_callback(fs):
+    """FEMMShellT3FFComp with a cylindrical layup csys CALLBACK: nodal normals from the csys evaluated at the nodes,
+    laminate rotation from the csys evaluated at the centroids (src/FEMMShellT3FFCompModule.jl:509,617)."""
+    from fsb200 import workloads as wl
+
+    f = fs.femm
+    w = wl.c3_t3ffcomp_cylinder(24, 6)
+    xyz, conn = np.asarray(w["xyz"]), w["conn"]
+    lay, _ = _layup()
+    femm = f.FEMMShellT3FFComp(f.IntegDomain(conn, None, T_), _fs_layup(fs, wl.cylindrical_csys))
+    geom0 = f.NodalField(xyz)
+    f.associategeometry(femm, geom0)
+    dirs = wl.cylindrical_csys(xyz[conn - 1].reshape(-1, 3))[:, :, 2].reshape(conn.shape[0], 3, 3)
+    no, vo = osh.t3ff_associategeometry(xyz, conn, normal_dir=dirs)
+    assert np.abs(femm._normals - no).max() < 1e-14 and np.array_equal(femm._normal_valid, vo)
+    lcs = wl.cylindrical_csys(xyz[conn - 1].mean(axis=1))
+    A, B, D = lay.laminate_stiffnesses()
+    H = lay.laminate_transverse_stiffness()
+    Ko = osh.t3ffcomp_stiffness_elmats(xyz, conn, no, vo, A, B, D, H, lay.thickness, lcs)
+    femm._sync_mesh(geom0)
+    femm._sync_stab()
+    Kg = femm.ctx.element_matrices(13, 0, femm._params())
+    assert relfro(Kg, Ko) < TOL
+
+
+@pytest.mark.parametrize("kind", ["t3", "q4"])
+def test_associategeometry_general_csys(fs, kind):
+    """Nodal normals from a csys evaluated per element and node (cylindrical layup csys of a laminated cylinder,
+    examples/shells/dynamics/homogeneous/explicit/clamp_cyl_expl_examples.jl:62-68): fsgpu_associategeometry_dirs."""
+    rng = np.random.default_rng(4)
+    gen = fx.t3block if kind == "t3" else fx.q4block
+    xy, conn = gen(2 * np.pi * 0.9, 1.0, 14, 5)
+    R = 0.5
+    xyz = np.column_stack([R * np.cos(xy[:, 0]), R * np.sin(xy[:, 0]), xy[:, 1]])
+    xyz += rng.uniform(-1, 1, xyz.shape) * 0.01
+    X = xyz[conn - 1]  # (angle, z) parametrisation: the element normals point outward
+    dirs = X.copy()
+    dirs[:, :, 2] = 0.0
+    dirs /= np.linalg.norm(dirs, axis=2, keepdims=True)  # radial direction at every node of every element
+    ctx = fs.Context()
+    ctx.set_mesh(conn, xyz)
+    ctx.associategeometry_dirs(dirs, 30.0)
+    n, v = ctx.get_normals()
+    no, vo = _oracle_normals(kind, xyz, conn, fixed=dirs)
+    assert np.abs(n - no).max() < 1e-14
+    assert np.array_equal(v, vo)
+    assert v.sum() > v.size // 2
+
+
 @pytest.mark.parametrize("kind,comp,sheark", [("t3", False, 0), ("t3", False, 1), ("t3", True, 0), ("t3", True, 1), ("q4", False, 0), ("q4", True, 0)])
 def test_element_stiffness(fs, kind, comp, sheark):
     xyz, conn = meshes.shell_mesh(kind, n=7)
