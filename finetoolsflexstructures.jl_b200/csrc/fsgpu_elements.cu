@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
       // weights (membrane, bending, shear) depend on the element
       const double t = P.nthick == 1 ? __ldg(P.thick) : __ldg(P.thick + e);
       const double h2 = 2 * g.Ae;  // h^2, h = sqrt(2 Ae)
-      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h2);
+      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * h2);
       wm = t * g.Ae;
       wb = (t * t * t) / 12 * g.Ae;
       ws = t * stab * g.Ae * (SHEARK ? (1.0 / 3) : 1.0);
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
       } else {
         kpart += node_kavg_part_h(P.hf, wb, ws, brn, set > 0);
         fold_homogeneous(P.hf, bg);
-        const double qm = sqrt(wm), qb = sqrt(wb), qs = sqrt(ws);
+        const double qm = fs_sqrt(wm), qb = fs_sqrt(wb), qs = fs_sqrt(ws);
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           q[s] = qm * P.hf.sdps[s];
@@ -732,9 +732,9 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
       }
     } else {
       const double t = P.nthick == 1 ? __ldg(P.thick) : (P.nthick == P.nelem ? __ldg(P.thick + e) : __ldg(P.thick + e * npts + gp));
-      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * hq * hq);
+      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * hq * hq);
       // rows are pre-scaled by sqrt(d_s): sqrt(c) * sqrt(dps) with sqrt(dps), sqrt(dts) from the host
-      const double qm = sqrt(t * jw), qb = sqrt((t * t * t / 12.0) * jw), qs = sqrt(t * stab * jw);
+      const double qm = fs_sqrt(t * jw), qb = fs_sqrt((t * t * t / 12.0) * jw), qs = fs_sqrt(t * stab * jw);
       double* dst = sb_ + (g4 * 8) * 24 + jn * 6;
       {
         double m[3][6];
@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
       const V3 d = X[a] - X[0];
       md = fmax(md, dot(d, d));
     }
-    hq = sqrt(md);
+    hq = fs_sqrt(md);
     if (COMP) gd = P.gdata + (size_t)__ldg(P.gof + e) * 34;
   }
   const int nbi = bi == 0 ? nn[0] : (bi == 1 ? nn[1] : (bi == 2 ? nn[2] : nn[3]));

@@ -30,7 +30,40 @@ FS_HD V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 FS_HD V3 operator*(double s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
 FS_HD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 FS_HD V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-FS_HD double norm(V3 a) { return sqrt(dot(a, a)); }
+// Reciprocal, reciprocal square root and square root without the library routines' special-case paths (denormals,
+// infinities; the operands here are element sizes and moduli): one MUFU seed + two Newton steps, <= 1-2 ulp.  The
+// division/sqrt sequences were ~10 % of the warp-instructions of the shell stiffness kernels.  Host build (the CPU
+// check of these formulas, tests/hostmath) and -DFS_PRECISE_DIV use the IEEE operations.
+#if defined(__CUDA_ARCH__) && !defined(FS_PRECISE_DIV)
+__device__ __forceinline__ double fs_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double fs_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double fs_sqrt(double x) {
+  const double y = fs_rsqrt(x);
+  double s = x * y;
+  s = fma(fma(-s, s, x), 0.5 * y, s);
+  return x > 0.0 ? s : 0.0;
+}
+#else
+FS_HD double fs_rcp(double x) { return 1.0 / x; }
+FS_HD double fs_rsqrt(double x) { return 1.0 / sqrt(x); }
+FS_HD double fs_sqrt(double x) { return sqrt(x); }
+#endif
+FS_HD double norm(V3 a) { return fs_sqrt(dot(a, a)); }
 
 // Element triad: e1 along the first tangent, e3 = e1 x t2 normalised, e2 = e3 x e1.
 // (src/FEMMShellT3FFModule.jl:283-305, src/FEMMShellQ4RSModule.jl:248-263)
@@ -39,9 +72,9 @@ struct Triad {
 };
 FS_HD Triad element_triad(V3 t1, V3 t2) {
   Triad E;
-  E.e1 = (1.0 / norm(t1)) * t1;
+  E.e1 = fs_rsqrt(dot(t1, t1)) * t1;
   V3 n = cross(E.e1, t2);
-  E.e3 = (1.0 / norm(n)) * n;
+  E.e3 = fs_rsqrt(dot(n, n)) * n;
   E.e2 = cross(E.e3, E.e1);
   return E;
 }
@@ -60,10 +93,11 @@ FS_HD M3 nodal_triad(const Triad& E, V3 nk, bool valid) {
   }
   // r = (0,0,1) x (nx,ny,nz) = (-ny, nx, 0)
   double rx = -ny, ry = nx;
-  double nr = sqrt(rx * rx + ry * ry);
+  const double r2 = rx * rx + ry * ry;
   M3 A;
-  if (nr > 1.0e-12) {
-    double ux = rx / nr, uy = ry / nr;
+  if (r2 > 1.0e-24) {  // |r| > 1e-12
+    const double inr = fs_rsqrt(r2), nr = r2 * inr;
+    double ux = rx * inr, uy = ry * inr;
     double s, c;
 #if defined(__CUDA_ARCH__)
     sincos(nr, &s, &c);
@@ -153,16 +187,16 @@ FS_HD void rotate_ts(const double H[4], double m, double n, double (&out)[2][2])
 FS_HD void layup_angle(const Triad& E, const double cs[9], double& m, double& n) {
   const V3 c1 = v3(cs[0], cs[3], cs[6]), c2 = v3(cs[1], cs[4], cs[7]);
   double M11 = dot(E.e1, c1), M21 = dot(E.e2, c1), M12 = dot(E.e1, c2), M22 = dot(E.e2, c2);
-  double n1 = sqrt(M11 * M11 + M21 * M21), n2 = sqrt(M12 * M12 + M22 * M22);
-  M11 /= n1;
-  M21 /= n1;
-  M12 /= n2;
-  M22 /= n2;
+  const double n1 = fs_rsqrt(M11 * M11 + M21 * M21), n2 = fs_rsqrt(M12 * M12 + M22 * M22);
+  M11 *= n1;
+  M21 *= n1;
+  M12 *= n2;
+  M22 *= n2;
   m = (M11 + M22) / 2;
   double nn = (M12 - M21) / 2;
   double q = 1.0 - m * m;
   q = q > 0.0 ? q : 0.0;
-  n = (nn >= 0.0 ? 1.0 : -1.0) * sqrt(q);
+  n = (nn >= 0.0 ? 1.0 : -1.0) * fs_sqrt(q);
 }
 
 // Build the factored constitutive data.
@@ -254,7 +288,7 @@ FS_HD void node_brot(double gx, double gy, const double (&bs)[2][3], double (&c3
 // this node's contribution to P1, P2 (5 x 3 each)
 FS_HD void node_coupling_contrib(const M3& A, double gx, double gy, const double (&bs)[2][3], double (&p1)[5][3],
                                  double (&p2)[5][3]) {
-  const double ia = 1.0 / A.a[2][2];
+  const double ia = fs_rcp(A.a[2][2]);
   const double m1 = ia * A.a[0][2], m2 = ia * A.a[1][2];
   double c3[5], c4[5];
   node_brot(gx, gy, bs, c3, c4);
@@ -268,7 +302,7 @@ FS_HD void node_coupling_contrib(const M3& A, double gx, double gy, const double
 }
 // 2x2 reduced rotation block
 FS_HD void node_R(const M3& A, double (&R)[2][2]) {
-  const double ia = 1.0 / A.a[2][2];
+  const double ia = fs_rcp(A.a[2][2]);
   for (int rw = 0; rw < 2; ++rw)
     for (int cl = 0; cl < 2; ++cl) R[rw][cl] = A.a[rw][cl] - ia * A.a[rw][2] * A.a[cl][2];
 }
@@ -409,12 +443,13 @@ FS_HD T3Geom t3_geometry(V3 X0, V3 X1, V3 X2) {
   g.y2 = dot(t2, g.E.e2);
   const double a = g.x1, b = g.y1, c = g.x2, d = g.y2;
   const double J = a * d - b * c;
-  g.gN[0][0] = (b - d) / J;
-  g.gN[1][0] = d / J;
-  g.gN[2][0] = -b / J;
-  g.gN[0][1] = (c - a) / J;
-  g.gN[1][1] = -c / J;
-  g.gN[2][1] = a / J;
+  const double iJ = fs_rcp(J);
+  g.gN[0][0] = (b - d) * iJ;
+  g.gN[1][0] = d * iJ;
+  g.gN[2][0] = -b * iJ;
+  g.gN[0][1] = (c - a) * iJ;
+  g.gN[1][1] = -c * iJ;
+  g.gN[2][1] = a * iJ;
   g.Ae = J / 2;
   return g;
 }
@@ -422,7 +457,7 @@ FS_HD T3Geom t3_geometry(V3 X0, V3 X1, V3 X2) {
 FS_HD void t3_add_bs(const T3Geom& g, int s, int p, int q, double (&bs)[2][3][3]) {
   const double ex[3] = {0.0, g.x1, g.x2}, ey[3] = {0.0, g.y1, g.y2};
   const double a = ex[p] - ex[s], b = ey[p] - ey[s], c = ex[q] - ex[s], d = ey[q] - ey[s];
-  const double Ae = g.Ae, m = 1.0 / 2 / Ae;
+  const double Ae = g.Ae, m = fs_rcp(2 * Ae);
   bs[0][s][0] += m * (b - d);
   bs[0][s][2] += m * Ae;
   bs[1][s][0] += m * (c - a);
@@ -506,7 +541,8 @@ FS_HD Q4Geom q4_geometry(const V3 (&X)[4], double xi, double eta) {
   const double det = G11 * G22 - G12 * G12;
   // Julia `detG ≈ 0.0` is isapprox with atol 0: true only for an exact zero
   g.singular = (det == 0.0) || !(det == det);
-  const double i11 = G22 / det, i12 = -G12 / det, i22 = G11 / det;
+  const double idet = fs_rcp(det);
+  const double i11 = G22 * idet, i12 = -G12 * idet, i22 = G11 * idet;
   const double j1e1 = dot(t1, g.E.e1), j1e2 = dot(t1, g.E.e2), j2e1 = dot(t2, g.E.e1), j2e2 = dot(t2, g.E.e2);
   for (int a = 0; a < 4; ++a) {
     const double p = i11 * dN[a][0] + i12 * dN[a][1];
@@ -574,14 +610,14 @@ FS_HD void q4_mitc_bs_node(const Q4Geom& g, double r, double s, int a, double (&
   const double J21 = (Y[0] * (s - 1) - Y[1] * (s - 1) + Y[2] * (s + 1) - Y[3] * (s + 1)) / 4;
   const double J12 = (X[0] * (r - 1) - X[1] * (r + 1) + X[2] * (r + 1) - X[3] * (r - 1)) / 4;
   const double J22 = (Y[0] * (r - 1) - Y[1] * (r + 1) + Y[2] * (r + 1) - Y[3] * (r - 1)) / 4;
-  const double iA = 1.0 / sqrt(J11 * J11 + J21 * J21), iB = 1.0 / sqrt(J12 * J12 + J22 * J22);
+  const double iA = fs_rsqrt(J11 * J11 + J21 * J21), iB = fs_rsqrt(J12 * J12 + J22 * J22);
   const double ca = J11 * iA, sa = J21 * iA, cb = J12 * iB, sb = J22 * iB;
-  const double i8d = 1.0 / (8 * (J11 * J22 - J12 * J21));
+  const double i8d = fs_rcp(8 * (J11 * J22 - J12 * J21));
   const double Ax = X[0] - X[1] - X[2] + X[3], Ay = Y[0] - Y[1] - Y[2] + Y[3];
   const double Bx = X[0] - X[1] + X[2] - X[3], By = Y[0] - Y[1] + Y[2] - Y[3];
   const double Cx = X[0] + X[1] - X[2] - X[3], Cy = Y[0] + Y[1] - Y[2] - Y[3];
-  const double SC = sqrt((Cx + r * Bx) * (Cx + r * Bx) + (Cy + r * By) * (Cy + r * By)) * i8d;
-  const double SA = sqrt((Ax + s * Bx) * (Ax + s * Bx) + (Ay + s * By) * (Ay + s * By)) * i8d;
+  const double SC = fs_sqrt((Cx + r * Bx) * (Cx + r * Bx) + (Cy + r * By) * (Cy + r * By)) * i8d;
+  const double SA = fs_sqrt((Ax + s * Bx) * (Ax + s * Bx) + (Ay + s * By) * (Ay + s * By)) * i8d;
   // own coordinates and the partners across the r-edge / s-edge
   const bool lo = a < 2, out03 = (a == 0) || (a == 3);
   const double xa = a == 0 ? X[0] : (a == 1 ? X[1] : (a == 2 ? X[2] : X[3]));
