@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
         for (int s = 0; s < 8; ++s) {
           const double d = constit_d(C, s);
           if (d < 0.0) atomicExch(P.flag + 2, 1);
-          q[s] = sqrt(d);
+          q[s] = fs_sqrt(d);
         }
       } else {
         kpart += node_kavg_part_h(P.hf, wb, ws, brn, set > 0);
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
   double ksum = 0.0;
 #pragma unroll
   for (int l = 0; l < 3; ++l) ksum += __shfl_sync(full, kpart, (base + l) & 31);
-  const double kavg = ksum / 6 * P.drill;
+  const double kavg = ksum * (1.0 / 6) * P.drill;
   __syncwarp();
   const int nj = j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]);
   if constexpr (Emit::kCoop) {
@@ -726,7 +726,7 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
       for (int s = 0; s < 8; ++s) {
         const double d = constit_d(C, s);
         if (d < 0.0) atomicExch(P.flag + 2, 1);
-        const double q = sqrt(d);
+        const double q = fs_sqrt(d);
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = q * bg[s][cc];
       }
@@ -920,13 +920,14 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   asm volatile("cp.async.wait_all;" ::: "memory");
   if (active && bi == bj) {
     const double4 n4 = *reinterpret_cast<const double4*>(nslot);
-    const double nl = sqrt(n4.x * n4.x + n4.y * n4.y + n4.z * n4.z);
-    if (n4.w != 0.0 && nl != 0.0) {
+    const double nl2 = n4.x * n4.x + n4.y * n4.y + n4.z * n4.z;
+    if (n4.w != 0.0 && nl2 != 0.0) {
       ok = 1;
       nvec[0] = n4.x;
       nvec[1] = n4.y;
       nvec[2] = n4.z;
-      const double nh[3] = {n4.x / nl, n4.y / nl, n4.z / nl};
+      const double inl = fs_rsqrt(nl2);
+      const double nh[3] = {n4.x * inl, n4.y * inl, n4.z * inl};
       double Pm[3][3], KP[3][3];
       for (int r = 0; r < 3; ++r)
         for (int cc = 0; cc < 3; ++cc) Pm[r][cc] = (r == cc ? 1.0 : 0.0) - nh[r] * nh[cc];
@@ -947,7 +948,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   }
   if (!Emit::kCoop && !active) return;
   if (P.drill != 0.0 && cnt > 0) {
-    const double kavg = tsum / cnt * P.drill;
+    const double kavg = tsum * (cnt == 4 ? 0.25 : fs_rcp((double)cnt)) * P.drill;
     if (kavg != 0.0 && ok) {
       for (int r = 0; r < 3; ++r)
         for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * (nvec[r] * nvec[cc]);

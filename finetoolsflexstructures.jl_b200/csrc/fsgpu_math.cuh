@@ -140,10 +140,11 @@ FS_HD void ldlt(double (&a)[N][N], double (&d)[N]) {
     double dj = a[j][j];
     for (int k = 0; k < j; ++k) dj -= a[j][k] * a[j][k] * d[k];
     d[j] = dj;
+    const double idj = (dj != 0.0) ? fs_rcp(dj) : 0.0;
     for (int i = j + 1; i < N; ++i) {
       double v = a[i][j];
       for (int k = 0; k < j; ++k) v -= a[i][k] * a[j][k] * d[k];
-      a[i][j] = (dj != 0.0) ? v / dj : 0.0;
+      a[i][j] = v * idj;
     }
   }
 }

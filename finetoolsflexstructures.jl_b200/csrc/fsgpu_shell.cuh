@@ -41,17 +41,17 @@ __device__ __forceinline__ V3 ld3(const double4* p, int i) {
 
 __device__ __forceinline__ void build_constit_t3(const ShellArgs& P, int64_t e, const Triad& E, double Ae, double shear_scale,
                                                  bool comp, Constit& C) {
-  const double h = sqrt(2 * Ae);
+  const double h2 = 2 * Ae;  // h^2, h = sqrt(2 Ae)
   if (comp) {
     const double* gd = P.gdata + (size_t)__ldg(P.gof + e) * 34;
     const double t = gd[31];
-    const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h * h);
+    const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * h2);
     double m, n;
     layup_angle(E, P.cs + (P.ncs == 1 ? 0 : e * 9), m, n);
     constit_laminate(gd, gd + 9, gd + 18, gd + 27, m, n, Ae, stab * Ae * shear_scale, C);
   } else {
     const double t = P.nthick == 1 ? __ldg(P.thick) : __ldg(P.thick + e);
-    const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * h * h);
+    const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * h2);
     constit_homogeneous(P.Dps, P.Dt, t * Ae, (t * t * t) / 12 * Ae, t * stab * Ae * shear_scale, C);
   }
 }
