@@ -337,6 +337,26 @@ function state(e::ExplicitGPU)
     return U, V, A
 end
 
+# ---- associategeometry! with a non-default csys (cylindrical, spherical, any CSys callback) ---------------------------
+# The reference evaluates the csys AT EVERY NODE OF EVERY ELEMENT (`_compute_nodal_normal!`,
+# src/FEMMShellT3FFCompModule.jl:203-207,509); the closure stays in Julia, the device accumulates, normalises, validates.
+function associategeometry_dirs!(c::Context, fes, geom0::NodalField{Float64}, csys::CSys, threshold_angle::Float64; accumulate::Bool = false)
+    nnpe = nodesperelem(fes)
+    dirs = Array{Float64,3}(undef, 3, nnpe, count(fes))
+    J0 = zeros(3, 2)
+    for (el, conn) in enumerate(fes.conn)
+        J0[:, 1] .= geom0.values[conn[2], :] .- geom0.values[conn[1], :]
+        J0[:, 2] .= geom0.values[conn[end], :] .- geom0.values[conn[1], :]
+        for (k, n) in enumerate(conn)
+            updatecsmat!(csys, reshape(geom0.values[n, :], 1, 3), J0, el, 0)
+            dirs[:, k, el] .= view(csmat(csys), :, 3)
+        end
+    end
+    GC.@preserve dirs _check(ccall((:fsgpu_associategeometry_dirs, libfsgpu), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}, Int32),
+        c.h, threshold_angle, pointer(dirs), accumulate ? 1 : 0))
+    return c
+end
+
 # ---- batched inspectintegpoints (src/FEMMShellT3FFModule.jl:850-962 and the three sibling methods) ----
 # The reference calls `inspector(idat, i, conn, ecoords, out, loc)` per point; a Julia closure cannot cross the C
 # boundary, so the GPU method returns the 3 x npts x nelem array and the caller folds its inspector over it.
@@ -371,7 +391,7 @@ result_block_size(c::Context, col_lo::Integer, col_hi::Integer) = result_block!(
 set_deterministic!(c::Context, on::Bool = true) = _check(ccall((:fsgpu_set_deterministic, libfsgpu), Cint, (Ptr{Cvoid}, Cint), c.h, on ? 1 : 0))
 
 export SysmatAssemblerGPU, SysvecAssemblerGPU, Context, ExplicitGPU, sparse_gpu, set_load!, start!, step!, state, set_deterministic!
-export shell_resultants, result_block!, result_block_size
+export shell_resultants, result_block!, result_block_size, associategeometry_dirs!
 export SPARSE, SPARSE_SYMM, SPARSE_DIAG, FFBLOCK, FFBLOCK_DIAG, CSR_SYMM
 
 end # module
