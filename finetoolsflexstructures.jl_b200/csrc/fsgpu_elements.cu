@@ -315,8 +315,9 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   }
   // diagonal pass: `d` = upper triangle of the symmetric K_e[j, j] (row-major, r <= c); lanes with the same own node
   // are merged.  `stage`: 32 x kStageLd doubles (the dead strips).
+  template <bool MERGE>
   __device__ __forceinline__ void t3_emit_diag(double* stage, int* addr, int lane, bool on, int nj, const double (&d)[21]) const {
-    const int nlead = t3_groups(addr, lane, on, (unsigned long long)(unsigned)nj);
+    const int nlead = MERGE ? t3_groups(addr, lane, on, (unsigned long long)(unsigned)nj) : 30;
     const int* raw = addr + 32 * 8;
     {
       double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
@@ -331,22 +332,24 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     for (int g = 0; g * 5 < nlead; ++g) {
       const int k = g * 5 + sub;
       if (lane >= 30 || k >= nlead) continue;
-      const int o = addr[k * 8 + 7];
+      const int o = MERGE ? addr[k * 8 + 7] : k;
       const int4 c0 = *reinterpret_cast<const int4*>(addr + o * 8);
       const int4 c1 = *reinterpret_cast<const int4*>(addr + o * 8 + 4);
       const int4 r0 = *reinterpret_cast<const int4*>(raw + o * 8);
       const int rp = row_pos(c1.z, r0.x, r0.y, r);
       if (rp < 0) continue;
       const int cb[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
-      unsigned mm = (unsigned)raw[o * 8 + 6];
       const double* sp = stage + o * kStageLd + r;
       double v[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) v[c] = sp[c * 6];
-      for (mm &= mm - 1; mm; mm &= mm - 1) {
-        const double* sq = stage + (__ffs(mm) - 1) * kStageLd + r;
+      if (MERGE) {
+        unsigned mm = (unsigned)raw[o * 8 + 6];
+        for (mm &= mm - 1; mm; mm &= mm - 1) {
+          const double* sq = stage + (__ffs(mm) - 1) * kStageLd + r;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) v[c] += sq[c * 6];
+          for (int c = 0; c < 6; ++c) v[c] += sq[c * 6];
+        }
       }
 #pragma unroll
       for (int c = 0; c < 6; ++c)
@@ -359,13 +362,17 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   }
   // edge pass: `a` = K_e[next(j), j] (rows: node nnext, columns: own node nj).  Lanes on the same edge are merged,
   // the sum S goes to block (row, col) and S' to block (col, row).  `stage`: 32 x kStageLd doubles (the dead strips).
+  template <bool MERGE>
   __device__ __forceinline__ void t3_emit_edge(double* stage, int* addr, int lane, bool on, int nj, int nnext,
                                                const double (&a)[6][6]) const {
     const unsigned lo = (unsigned)min(nj, nnext), hi = (unsigned)max(nj, nnext);
     __syncwarp();  // every lane is done with the strips and with the diagonal pass
     int* raw = addr + 32 * 8;
-    raw[lane * 8 + 7] = nnext;
-    const int nlead = t3_groups(addr, lane, on, ((unsigned long long)lo << 32) | hi);
+    int nlead = 30;
+    if (MERGE) {
+      raw[lane * 8 + 7] = nnext;
+      nlead = t3_groups(addr, lane, on, ((unsigned long long)lo << 32) | hi);
+    }
     double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
 #pragma unroll
     for (int c = 0; c < 6; ++c)
@@ -377,7 +384,7 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     for (int g = 0; g * 5 < nlead; ++g) {
       const int k = g * 5 + sub;
       if (lane >= 30 || k >= nlead) continue;
-      const int o = addr[k * 8 + 7];
+      const int o = MERGE ? addr[k * 8 + 7] : k;
       const int eo = o / 3, jo = o - 3 * eo;
       const int ln = 3 * eo + (jo == 2 ? 0 : jo + 1);  // lane whose own node is this block's row node
       const int4 co0 = *reinterpret_cast<const int4*>(addr + o * 8);
@@ -389,7 +396,6 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
       // direct target (row node, own node) and transposed target (own node, row node)
       const int rpd = row_pos(cl1.z, r0.z, r0.w, r);
       const int rpt = row_pos(co1.z, r1.x, r1.y, r);
-      const int rowO = r1.w;
       const double* so = stage + o * kStageLd;
       double vd[6], vt[6];  // S[r][c] and S[c][r]
 #pragma unroll
@@ -397,16 +403,19 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
         vd[c] = so[c * 6 + r];
         vt[c] = so[r * 6 + c];
       }
-      unsigned mm = (unsigned)r1.z;
-      for (mm &= mm - 1; mm; mm &= mm - 1) {
-        const int p = __ffs(mm) - 1;
-        const bool same = raw[p * 8 + 7] == rowO;
-        const double* sp = stage + p * kStageLd;
+      if (MERGE) {
+        const int rowO = r1.w;
+        unsigned mm = (unsigned)r1.z;
+        for (mm &= mm - 1; mm; mm &= mm - 1) {
+          const int p = __ffs(mm) - 1;
+          const bool same = raw[p * 8 + 7] == rowO;
+          const double* sp = stage + p * kStageLd;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          const double x = sp[c * 6 + r], y = sp[r * 6 + c];
-          vd[c] += same ? x : y;
-          vt[c] += same ? y : x;
+          for (int c = 0; c < 6; ++c) {
+            const double x = sp[c * 6 + r], y = sp[r * 6 + c];
+            vd[c] += same ? x : y;
+            vt[c] += same ? y : x;
+          }
         }
       }
       const int cbd[6] = {co0.x, co0.y, co0.z, co0.w, co1.x, co1.y};
@@ -631,8 +640,13 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();  // every lane is done with the strips; the addressing data has landed
-    emit.t3_emit_diag(sw, addr, lane, active, nj, dd);
-    emit.t3_emit_edge(sw, addr, lane, active, nj, nnext, acc);
+#ifdef FS_T3_MERGE
+    constexpr bool kMerge = true;
+#else
+    constexpr bool kMerge = false;
+#endif
+    emit.template t3_emit_diag<kMerge>(sw, addr, lane, active, nj, dd);
+    emit.template t3_emit_edge<kMerge>(sw, addr, lane, active, nj, nnext, acc);
   } else {
     if (!active) return;
     typename Emit::Cols ecols = emit.cols(nj);
