@@ -515,34 +515,47 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
 #pragma unroll
   for (int set = 0; set < NSETS; ++set) {
     double bs[2][3];
-    double p1[5][3], p2[5][3];
+    double qf[5], af[6];  // this node's coupling contribution in factored form: p1 = qf (x) A[0,:], p2 = qf (x) A[1,:]
     double gx = 0.0, gy = 0.0;
     if (active) {
       gx = j == 0 ? g.gN[0][0] : (j == 1 ? g.gN[1][0] : g.gN[2][0]);
       gy = j == 0 ? g.gN[0][1] : (j == 1 ? g.gN[1][1] : g.gN[2][1]);
       t3_bs_node(g, j, SHEARK ? set : -1, bs);
-      node_coupling_contrib(A, gx, gy, bs, p1, p2);
+      node_coupling_factors(A, gx, gy, bs, qf);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        af[k] = A.a[0][k];
+        af[3 + k] = A.a[1][k];
+      }
     } else {
-      for (int r = 0; r < 5; ++r)
-        for (int k = 0; k < 3; ++k) p1[r][k] = p2[r][k] = 0.0;
+      for (int r = 0; r < 5; ++r) qf[r] = 0.0;
+      for (int k = 0; k < 6; ++k) af[k] = 0.0;
       for (int r = 0; r < 2; ++r)
         for (int k = 0; k < 3; ++k) bs[r][k] = 0.0;
     }
-    // sum the coupling matrices over the element's three lanes, in node order on every lane
+    // sum the coupling matrices over the element's three lanes, in node order on every lane (all three lanes get
+    // bitwise the same P1, P2); the factors travel (11 numbers per node) instead of the 30 products
     double P1[5][3], P2[5][3];
 #pragma unroll
     for (int r = 0; r < 5; ++r)
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        double s1 = 0.0, s2 = 0.0;
+      for (int k = 0; k < 3; ++k) P1[r][k] = P2[r][k] = 0.0;
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-          s1 += __shfl_sync(full, p1[r][k], (base + l) & 31);
-          s2 += __shfl_sync(full, p2[r][k], (base + l) & 31);
+    for (int l = 0; l < 3; ++l) {
+      const int srcl = (base + l) & 31;
+      double ql[5], al[6];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) ql[r] = __shfl_sync(full, qf[r], srcl);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) al[k] = __shfl_sync(full, af[k], srcl);
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          P1[r][k] = fma(ql[r], al[k], P1[r][k]);
+          P2[r][k] = fma(ql[r], al[3 + k], P2[r][k]);
         }
-        P1[r][k] = s1;
-        P2[r][k] = s2;
-      }
+    }
     if (active) {
       double R[2][2], brn[5][2];
       node_R(A, R);

@@ -301,6 +301,15 @@ FS_HD void node_coupling_contrib(const M3& A, double gx, double gy, const double
     }
   }
 }
+// the same in factored form: p1[r][k] = q[r] A[0][k], p2[r][k] = q[r] A[1][k] -- 5 + 6 numbers instead of 30, for
+// kernels that exchange the contributions between lanes
+FS_HD void node_coupling_factors(const M3& A, double gx, double gy, const double (&bs)[2][3], double (&q)[5]) {
+  const double ia = fs_rcp(A.a[2][2]);
+  const double m1 = ia * A.a[0][2], m2 = ia * A.a[1][2];
+  double c3[5], c4[5];
+  node_brot(gx, gy, bs, c3, c4);
+  for (int r = 0; r < 5; ++r) q[r] = c3[r] * m1 + c4[r] * m2;
+}
 // 2x2 reduced rotation block
 FS_HD void node_R(const M3& A, double (&R)[2][2]) {
   const double ia = fs_rcp(A.a[2][2]);
