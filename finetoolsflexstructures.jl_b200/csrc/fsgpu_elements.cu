@@ -955,14 +955,11 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
       nvec[2] = n4.z;
       const double inl = fs_rsqrt(nl2);
       const double nh[3] = {n4.x * inl, n4.y * inl, n4.z * inl};
-      double Pm[3][3], KP[3][3];
+      // tr(P Krr P) with P = I - n n' (idempotent): tr(Krr P) = tr(Krr) - n' Krr n
+      double tr = acc[3][3] + acc[4][4] + acc[5][5];
+#pragma unroll
       for (int r = 0; r < 3; ++r)
-        for (int cc = 0; cc < 3; ++cc) Pm[r][cc] = (r == cc ? 1.0 : 0.0) - nh[r] * nh[cc];
-      for (int r = 0; r < 3; ++r)
-        for (int cc = 0; cc < 3; ++cc)
-          KP[r][cc] = acc[3 + r][3] * Pm[0][cc] + acc[3 + r][4] * Pm[1][cc] + acc[3 + r][5] * Pm[2][cc];
-      double tr = 0.0;
-      for (int r = 0; r < 3; ++r) tr += Pm[r][0] * KP[0][r] + Pm[r][1] * KP[1][r] + Pm[r][2] * KP[2][r];
+        tr -= nh[r] * (acc[3 + r][3] * nh[0] + acc[3 + r][4] * nh[1] + acc[3 + r][5] * nh[2]);
       tang = fmax(0.0, tr / 2.0);
     }
   }
