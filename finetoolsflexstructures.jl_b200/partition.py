@@ -144,6 +144,7 @@ class ColumnBlockPlan:
         self.lcol_lo = int(np.searchsorted(self.loc2glob, self.col_lo + 1))
         self.lcol_hi = int(np.searchsorted(self.loc2glob, self.col_hi + 1))
         assert self.lcol_hi - self.lcol_lo == self.col_hi - self.col_lo
+        self.empty = self.col_hi == self.col_lo  # more ranks than node runs: nothing to assemble, nothing to contribute
 
     @staticmethod
     def _column_bounds(dofnums, node_of_dof, nfree, ncols, world):
@@ -230,9 +231,11 @@ def gather_matrix(ctx, plan, device, group=None, to_host=True):
     row_map = torch.as_tensor(plan.loc2glob, device=device)
     if row_map.is_cuda:
         torch.cuda.current_stream(row_map.device).synchronize()  # the library works on its own stream
-    nnz_b = ctx.result_block(plan.lcol_lo, plan.lcol_hi)
+    nnz_b = 0 if plan.empty else ctx.result_block(plan.lcol_lo, plan.lcol_hi)
 
     def fill(cnt, rv, nz):
+        if plan.empty:
+            return
         ctx.result_block(plan.lcol_lo, plan.lcol_hi, row_map, cnt if cnt.numel() else None, rv if rv.numel() else None, nz if nz.numel() else None)
 
     colptr, rowval, nzval = gather_blocks(fill, plan.col_hi - plan.col_lo, nnz_b, device, group)

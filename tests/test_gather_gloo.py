@@ -116,3 +116,25 @@ def test_plan_bounds_fall_on_node_boundaries():
         for p in plans:
             assert np.all(np.diff(p.loc2glob) > 0)
             assert p.dofnums.min() == 1 and p.dofnums.max() == p.nall
+
+
+def test_plan_with_more_ranks_than_node_runs():
+    """Degenerate split: 2 triangles (4 nodes, some dofs fixed) over 7 ranks -- some ranks own nothing; the owned ranges
+    still tile the columns and every element is assembled by the ranks that need it."""
+    from fsb200 import partition as pt
+
+    conn = np.array([[1, 2, 3], [2, 4, 3]])
+    d = fx.DofField(4)
+    d.setebc([0], 1)
+    d.setebc([0], 2)
+    d.numberdofs()
+    nfree = int((~d.is_fixed).sum())
+    plans = [pt.ColumnBlockPlan(conn, d.dofnums, nfree, "ffblock", r, 7) for r in range(7)]
+    assert plans[0].col_lo == 0 and plans[-1].col_hi == nfree
+    assert all(a.col_hi == b.col_lo for a, b in zip(plans[:-1], plans[1:]))
+    assert any(p.empty for p in plans)
+    for p in plans:
+        if p.empty:
+            assert len(p.elems) == 0
+        else:
+            assert len(p.elems) >= 1 and p.lcol_hi - p.lcol_lo == p.col_hi - p.col_lo
