@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
       const double h2 = 2 * g.Ae;  // h^2, h = sqrt(2 Ae)
       const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * h2);
       wm = t * g.Ae;
-      wb = (t * t * t) / 12 * g.Ae;
+      wb = (t * t * t) * (1.0 / 12.0) * g.Ae;
       ws = t * stab * g.Ae * (SHEARK ? (1.0 / 3) : 1.0);
     }
   }
@@ -761,7 +761,7 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
       const double t = P.nthick == 1 ? __ldg(P.thick) : (P.nthick == P.nelem ? __ldg(P.thick + e) : __ldg(P.thick + e * npts + gp));
       const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * hq * hq);
       // rows are pre-scaled by sqrt(d_s): sqrt(c) * sqrt(dps) with sqrt(dps), sqrt(dts) from the host
-      const double qm = fs_sqrt(t * jw), qb = fs_sqrt((t * t * t / 12.0) * jw), qs = fs_sqrt(t * stab * jw);
+      const double qm = fs_sqrt(t * jw), qb = fs_sqrt((t * t * t * (1.0 / 12.0)) * jw), qs = fs_sqrt(t * stab * jw);
       double* dst = sb_ + (g4 * 8) * 24 + jn * 6;
       {
         double m[3][6];
@@ -1146,7 +1146,7 @@ __device__ __forceinline__ void resultant_out(const ShellArgs& P, int quant, con
     return;
   }
   const int o = quant == 1 ? 3 : 0;
-  const double c = quant == 1 ? (t * t * t) / 12 : t;
+  const double c = quant == 1 ? (t * t * t) * (1.0 / 12.0) : t;
   double v[3];
   for (int i = 0; i < 3; ++i) v[i] = c * (P.Dps[i * 3] * st[o] + P.Dps[i * 3 + 1] * st[o + 1] + P.Dps[i * 3 + 2] * st[o + 2]);
   // mo = o2' [v0 v2; v2 v1] o2

@@ -52,7 +52,7 @@ __device__ __forceinline__ void build_constit_t3(const ShellArgs& P, int64_t e, 
   } else {
     const double t = P.nthick == 1 ? __ldg(P.thick) : __ldg(P.thick + e);
     const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * h2);
-    constit_homogeneous(P.Dps, P.Dt, t * Ae, (t * t * t) / 12 * Ae, t * stab * Ae * shear_scale, C);
+    constit_homogeneous(P.Dps, P.Dt, t * Ae, (t * t * t) * (1.0 / 12.0) * Ae, t * stab * Ae * shear_scale, C);
   }
 }
 
