@@ -1003,3 +1003,33 @@ def test_full_size_c2_properties(fs):
     femm.ctx.shell_op("q4rs_stiffness", femm._params())
     vals2 = torch.as_tensor(DevicePointer(nz.value, nnz), device="cuda")
     assert abs(float(vals2.sum()) - s1) <= 1e-9 * abs(s1) + 1e-6 * scale
+
+
+# ---------------------------------------------------------------------------------------
+# committed fixtures (tests/golden/oracle_fixtures.npz): the GPU path against frozen numbers
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["t3", "q4"])
+def test_against_committed_fixtures(fs, kind):
+    fxt = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_fixtures.npz"))
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh(kind, n=3)
+    femm = _make_femm(fs, kind, conn)
+    geom0 = f.NodalField(xyz)
+    f.associategeometry(femm, geom0)
+    assert np.abs(femm._normals - fxt[f"{kind}_normals"]).max() < 1e-14
+    assert np.array_equal(femm._normal_valid, fxt[f"{kind}_valid"])
+    femm._sync_stab()
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    assert relfro(Kg, fxt[f"{kind}_K"]) < TOL
+    od = meshes.clamp_edge_dofs(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs()
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, None, None, dchi)
+    assert np.array_equal(K.colptr, fxt[f"{kind}_colptr"]) and np.array_equal(K.rowval, fxt[f"{kind}_rowval"])
+    assert relfro(K.nzval, fxt[f"{kind}_nzval"]) < TOL
+    u = np.random.default_rng(5).standard_normal((xyz.shape[0], 6)) * 1e-3
+    th = np.deg2rad(20.0)
+    cs = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    got = f.inspectintegpoints(femm, geom0, f.NodalField(u), None, "moment", outputcsys=cs)
+    assert relfro(got, fxt[f"{kind}_moment"].reshape(got.shape)) < 1e-11

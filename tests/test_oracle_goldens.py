@@ -306,3 +306,25 @@ def test_laminated_resultants_reduce_to_homogeneous_for_one_isotropic_ply():
         a = osh.t3ffcomp_resultants(xyz, conn, nrm, val, A, B, D, H, t, lcs, u, q, ocs=ocs)
         b = osh.t3ff_resultants(xyz, conn, nrm, val, Dps, Dt, t, u, q, ocs=ocs)
         assert np.linalg.norm(a - b) <= 1e-12 * np.linalg.norm(b), q
+
+
+def test_oracle_fixtures():
+    """The oracle reproduces its own frozen outputs (tests/golden/oracle_fixtures.npz, tests/golden/make_fixtures.py):
+    guards the checker of the GPU parity tests against accidental changes.  Integer arrays bit-exact, floats 1e-13."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_fixtures", os.path.join(here, "make_fixtures.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.compute()
+    ref = np.load(os.path.join(here, "oracle_fixtures.npz"))
+    assert set(ref.files) == set(now)
+    for k in ref.files:
+        a, b = np.asarray(now[k]), ref[k]
+        assert a.shape == b.shape, k
+        if a.dtype.kind in "biu":
+            assert np.array_equal(a, b), k
+        else:
+            assert np.linalg.norm((a - b).ravel()) <= 1e-13 * max(np.linalg.norm(b.ravel()), 1e-300), k
