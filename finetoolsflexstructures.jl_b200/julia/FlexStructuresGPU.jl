@@ -357,6 +357,15 @@ function associategeometry_dirs!(c::Context, fes, geom0::NodalField{Float64}, cs
     return c
 end
 
+# ---- update_rotation_field! (src/RotUtilModule.jl:29-42): R <- exp(dtheta) R per node, on the device ---------------
+# updates the context's copy of Rfield1 (uploaded by the last beam operator, fsgpu_set_state) and writes it back
+function update_rotation_field_gpu!(c::Context, Rfield::NodalField{Float64}, dchi::NodalField{Float64})
+    dv, Rv = dchi.values, Rfield.values          # nnodes x 6, nnodes x 9 column-major
+    GC.@preserve dv Rv _check(ccall((:fsgpu_update_rotation_field, libfsgpu), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        c.h, pointer(dv), pointer(Rv)))
+    return Rfield
+end
+
 # ---- batched inspectintegpoints (src/FEMMShellT3FFModule.jl:850-962 and the three sibling methods) ----
 # The reference calls `inspector(idat, i, conn, ecoords, out, loc)` per point; a Julia closure cannot cross the C
 # boundary, so the GPU method returns the 3 x npts x nelem array and the caller folds its inspector over it.
@@ -391,7 +400,7 @@ result_block_size(c::Context, col_lo::Integer, col_hi::Integer) = result_block!(
 set_deterministic!(c::Context, on::Bool = true) = _check(ccall((:fsgpu_set_deterministic, libfsgpu), Cint, (Ptr{Cvoid}, Cint), c.h, on ? 1 : 0))
 
 export SysmatAssemblerGPU, SysvecAssemblerGPU, Context, ExplicitGPU, sparse_gpu, set_load!, start!, step!, state, set_deterministic!
-export shell_resultants, result_block!, result_block_size, associategeometry_dirs!
+export shell_resultants, result_block!, result_block_size, associategeometry_dirs!, update_rotation_field_gpu!
 export SPARSE, SPARSE_SYMM, SPARSE_DIAG, FFBLOCK, FFBLOCK_DIAG, CSR_SYMM
 
 end # module
