@@ -81,6 +81,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def load_workloads():
+    """The pure-numpy workload generators of the package, imported by file: the CPU reference arm must not load
+    libfsgpu.so (importing the package does)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("fsb200_workloads", os.path.join(ROOT, "finetoolsflexstructures.jl_b200", "workloads.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def dist_env():
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), ws
@@ -117,9 +128,14 @@ def load_refport():
     return lib
 
 
+_CPU_BUF = {}
+
+
 def cpu_q4rs_assembly(w, nelem_sample, nthreads, normals, valid):
-    """Times the reference algorithm (element loop + COO append + sparse()) on the first
-    `nelem_sample` elements of the workload.  Returns elements/s."""
+    """Times the reference algorithm on the first `nelem_sample` elements of the workload: the element loop with
+    its COO append (OpenMP element-parallel; the reference's loop is serial) and ONE pass of the COO->CSC
+    conversion (serial, like Julia's `sparse`).  All buffers are allocated and touched before the timers start.
+    Returns elements/s for the whole and for the element loop alone."""
     from oracle import fe_external as fx
     from oracle import shells as osh
 
@@ -133,21 +149,27 @@ def cpu_q4rs_assembly(w, nelem_sample, nthreads, normals, valid):
     pc, wt = fx.gauss_rule_2x2()
     pc = np.ascontiguousarray(pc)
     nt = nelem_sample * n * n
-    I, J, V = np.empty(nt, np.int64), np.empty(nt, np.int64), np.empty(nt)
+    nall, nfree = w["dofnums"].size, w["nfree"]
+    key = (nt, nfree)
+    if key not in _CPU_BUF:
+        _CPU_BUF.clear()
+        _CPU_BUF[key] = (np.zeros(nt, np.int64), np.zeros(nt, np.int64), np.zeros(nt), np.zeros(nfree + 1, np.int64),
+                         np.zeros(nt, np.int64), np.zeros(nt))  # zeros: the pages are touched outside the timers
+    I, J, V, cp, rv, nz = _CPU_BUF[key]
     v8 = np.ascontiguousarray(valid.astype(np.uint8))
     nF = np.asfortranarray(normals)
     nnodes = w["xyz"].shape[0]
-    nall, nfree = w["dofnums"].size, w["nfree"]
     alpha = 0.1 if nn == 4 else 5 / 12 / 1.5
     t0 = time.perf_counter()
     lib.ref_shell_stiffness_coo(nn, C.c_int64(nelem_sample), P(conn), C.c_int64(nnodes), P(w["xyz"]), P(nF), P(v8),
                                 P(w["dofnums"]), P(Dps), P(Dt), C.c_double(w["thickness"]), C.c_double(alpha), C.c_double(1.0), 4,
                                 P(pc), P(wt), nthreads, P(I), P(J), P(V))
-    nnz = lib.ref_coo_to_csc(C.c_int64(nt), P(I), P(J), P(V), C.c_int64(nall), C.c_int64(nall), C.c_int64(nfree), C.c_int64(nfree), None, None, None)
-    cp, rv, nz = np.empty(nfree + 1, np.int64), np.empty(nnz, np.int64), np.empty(nnz)
+    t1 = time.perf_counter()
+    # one pass: the outputs are sized for the worst case (every triple its own entry), so no counting pre-pass
     lib.ref_coo_to_csc(C.c_int64(nt), P(I), P(J), P(V), C.c_int64(nall), C.c_int64(nall), C.c_int64(nfree), C.c_int64(nfree), P(cp), P(rv), P(nz))
-    dt = time.perf_counter() - t0
-    return nelem_sample / dt, dt
+    t2 = time.perf_counter()
+    return {"value": nelem_sample / (t2 - t0), "seconds": t2 - t0, "loop_s": t1 - t0, "sparse_s": t2 - t1,
+            "loop_value": nelem_sample / (t1 - t0)}
 
 
 def oracle_normals(w):
@@ -167,6 +189,10 @@ EXPL_FLOPS_PER_NNZ = 2.0
 
 
 def explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
+    """BASELINE configs[3]: ONE T3FF panel (4M elements at the default size), RCM-numbered as the reference example
+    does (plate_expl_examples.jl:119-121,147), row-partitioned over the ranks (STRONG scaling): rank r owns a
+    contiguous block of global rows and assembles every element that touches one of its nodes; the explicit loop
+    exchanges halo displacements inside the step kernel (peer-mapped windows, no NCCL call on the step path)."""
     import torch
     import torch.distributed as dist
 
@@ -176,25 +202,18 @@ def explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
 
     f = fsb200.femm
     nx, ny = args.c4_nx, args.c4_nx // 2
-    w = wl.c4_strip(rank, world, nx, ny)
-    nelem = w["conn"].shape[0]
-    femm = f.FEMMShellT3FF(f.IntegDomain(w["conn"], None, w["thickness"]), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]), device=local_rank)
-    femm.ctx.set_stream(stream.cuda_stream)
-    geom0 = f.NodalField.__new__(f.NodalField)
-    geom0.values = w["xyz"]
-    dchi = f.NodalField.__new__(f.NodalField)
-    dchi.values, dchi.dofnums, dchi._nfree = None, w["dofnums"], w["nfree"]
-    if world > 1:  # nodal normals of interface nodes see the elements of both partitions
-        with torch.cuda.stream(stream):
-            f.associategeometry(femm, geom0, interface=(pt.strip_links(rank, world, w["lo_nodes"], w["hi_nodes"]), torch.device("cuda", local_rank)))
-    else:
-        f.associategeometry(femm, geom0)
     t0 = time.perf_counter()
-    femm._startassembly(f.SysmatAssemblerFFBlock(), dchi)
-    femm.ctx.sync()
-    sym_ms = (time.perf_counter() - t0) * 1e3
-    femm._sync_stab()
-    p = femm._params()
+    w = wl.c4_t3ff_panel(nx, ny)
+    perm = pt.rcm_permutation(w["conn"], w["xyz"].shape[0])
+    w["dofnums"], w["nfree"] = wl.number_dofs(w["dofnums"] > w["nfree"], perm)
+    mesh_s = time.perf_counter() - t0
+    nelem_g = w["conn"].shape[0]
+    mat = f.MatDeforElastIso(w["E"], w["nu"], w["rho"])
+
+    def field(values=None, dofnums=None, nfree=0):
+        x = f.NodalField.__new__(f.NodalField)
+        x.values, x.dofnums, x._nfree = values, dofnums, nfree
+        return x
 
     def barrier():
         torch.cuda.synchronize()
@@ -202,7 +221,44 @@ def explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # --- T3FF stiffness assembly (numeric phase, device resident) ---
+    # nodal normals of the GLOBAL mesh on the device (halo nodes see elements this rank does not assemble)
+    fg = f.FEMMShellT3FF(f.IntegDomain(w["conn"], None, w["thickness"]), mat, device=local_rank)
+    fg.ctx.set_stream(stream.cuda_stream)
+    geom_g = field(w["xyz"])
+    f.associategeometry(fg, geom_g)
+    ag_ms = None
+    if world == 1:
+        fg.ctx.associategeometry(fg.threshold_angle, None, True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            fg.ctx.associategeometry(fg.threshold_angle, None, True)
+        barrier()
+        ag_ms = (time.perf_counter() - t0) / 5 * 1e3
+        plan = None
+        femm, dchi = fg, field(None, w["dofnums"], w["nfree"])
+        nelem = nelem_g
+    else:
+        t0 = time.perf_counter()
+        plan = pt.ColumnBlockPlan(w["conn"], w["dofnums"], w["nfree"], "ffblock", rank, world)
+        plan_s = time.perf_counter() - t0
+        femm = f.FEMMShellT3FF(f.IntegDomain(plan.conn, None, w["thickness"]), mat, device=local_rank)
+        femm.ctx.set_stream(stream.cuda_stream)
+        femm._normals, femm._normal_valid = np.asfortranarray(plan.restrict_nodes(fg._normals)), plan.restrict_nodes(fg._normal_valid)
+        femm._associatedgeometry = True
+        fg.ctx.close()
+        geom_l = field(np.asfortranarray(plan.restrict_nodes(w["xyz"])))
+        dchi = field(None, plan.dofnums, plan.nfree)
+        femm._sync_mesh(geom_l)
+        nelem = int(len(plan.elems))
+    t0 = time.perf_counter()
+    femm._startassembly(f.SysmatAssemblerFFBlock(), dchi)
+    femm.ctx.sync()
+    sym_ms = (time.perf_counter() - t0) * 1e3
+    femm._sync_stab()
+    p = femm._params()
+
+    # --- T3FF stiffness assembly (numeric phase, device resident; N > 1: the rank's share of the ONE mesh) ---
     for _ in range(3):
         femm.ctx.shell_op("t3ff_stiffness", p)
     barrier()
@@ -215,100 +271,88 @@ def explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
         kms.append(femm.ctx.last_kernel_ms)
     e1.record(stream)
     barrier()
-    tm = torch.tensor([e0.elapsed_time(e1) / nrep], device="cuda", dtype=torch.float64)
+    tm = torch.tensor([e0.elapsed_time(e1) / nrep, float(np.mean(kms))], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    asm_ms = float(tm.item())
+    asm_ms, kernel_ms = float(tm[0].item()), float(tm[1].item())
     nnz = femm.ctx.result_size()[2]
-    kernel_ms = float(np.mean(kms))
+    t_fp64 = T3_FLOPS * nelem / (fp64_peak * 1e12) * 1e3
     alg = T3_IN_BYTES + 8.0 * nnz / nelem
-    # associategeometry! on the device: nodal normals + crease detection, single rank only
-    ag_ms = None
-    if world == 1:
-        femm.ctx.associategeometry(femm.threshold_angle, None, True)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(5):
-            femm.ctx.associategeometry(femm.threshold_angle, None, True)
-        barrier()
-        ag_ms = (time.perf_counter() - t0) / 5 * 1e3
-    asm = {"workload": f"T3FF stiffness -> CSC (FFBlock), {nelem} elements per rank", "value": nelem * world / (asm_ms * 1e-3),
-           "unit": "elements/s", "ms_per_step": asm_ms, "kernel_ms": kernel_ms, "symbolic_ms": sym_ms, "nnz": int(nnz),
-           "associategeometry_ms": ag_ms,
-           "roofline": {"bound": "hbm", "achieved": alg * nelem / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": alg * nelem / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_element": alg,
-                        "kernel": "k_t3_stiffness<false,false,EmitRuns>"},
-           "fp64": {"achieved_tflops": T3_FLOPS * nelem / (kernel_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
-                    "frac": T3_FLOPS * nelem / (kernel_ms * 1e-3) / 1e12 / fp64_peak, "flops_per_element": T3_FLOPS}}
+    t_hbm = alg * nelem / (hbm_peak * 1e9) * 1e3
+    asm = {"workload": f"T3FF stiffness -> CSC (FFBlock), ONE {nelem_g}-element panel over {world} rank(s) ({nelem} elements on this rank incl. interface elements)",
+           "value": nelem_g / (asm_ms * 1e-3), "unit": "elements/s", "scaling": "strong", "ms_per_step": asm_ms, "kernel_ms": kernel_ms,
+           "symbolic_ms": sym_ms, "nnz_this_rank": int(nnz), "associategeometry_ms": ag_ms,
+           "roofline": {"bound": "fp64" if t_fp64 >= t_hbm else "hbm", "t_roof_ms": max(t_fp64, t_hbm), "frac": max(t_fp64, t_hbm) / asm_ms,
+                        "frac_kernel_only": max(t_fp64, t_hbm) / kernel_ms, "basis": "this rank's elements, step = value-array clear + kernel",
+                        "flops_per_element": T3_FLOPS, "peak_tflops": fp64_peak, "achieved_tflops": T3_FLOPS * nelem / (asm_ms * 1e-3) / 1e12,
+                        "hbm": {"algorithmic_bytes_per_element": alg, "achieved_gbs": alg * nelem / (asm_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                "frac": t_hbm / asm_ms},
+                        "kernel": "k_t3_stiffness<false,false,EmitRuns>"}}
 
     # --- explicit central differences: K = FF block (device resident), lumped M ---
     femm.ctx.shell_mass_diag(p, 3, nfree_only=True)
-    nf = w["nfree"]
-    links = pt.strip_links(rank, world, w["lo_dofs"], w["hi_dofs"])
-    ex_if = pt.InterfaceExchange(links, torch.device("cuda", local_rank)) if world > 1 else None
-    with torch.cuda.stream(stream):
-        if world > 1:  # lumped mass of interface nodes: sum of both partitions' contributions
-            import ctypes as C
-
-            vp, vn = C.c_void_p(), C.c_int64()
-            fsb200._lib.check(fsb200._lib.lib.fsgpu_vector_device(femm.ctx._h, C.byref(vp), C.byref(vn)))
-            Mt = torch.as_tensor(pt.DevicePointer(vp.value, vn.value), device="cuda")
-            ex_if.exchange_sum(Mt)
-            torch.cuda.synchronize()
-        ex = fsb200.Explicit(femm.ctx, c_scale=100.0, dt=0.0)
-        lam = ex.omega_max_sq(args.power_its)
-        if world > 1:
-            lt = torch.tensor([lam], device="cuda", dtype=torch.float64)
-            dist.all_reduce(lt, op=dist.ReduceOp.MAX)
-            lam = float(lt.item())
-        ex.close()
-        dt = 0.9 * 2 / np.sqrt(lam)
-        ex = fsb200.Explicit(femm.ctx, c_scale=100.0, dt=dt)
-        F0 = np.zeros(nf)
-        F0[2::6][: nf // 600] = 1.0  # a small pressure patch
-        ex.set_load(F0)
-        ex.start(1.0)
-        U, V, A, E = ex.device_state()
-        Et = torch.as_tensor(pt.DevicePointer(E, nf), device="cuda")
-        nsteps = args.expl_steps
-
-        def run(n):
-            if world == 1:
-                ex.step(n)
-            else:
-                for _ in range(n):
-                    ex.step_begin()
-                    ex_if.exchange_sum(Et)
-                    ex.step_end(1.0)
-
-        run(20)
-        barrier()
-        l0 = femm.ctx.launch_count
-        e0.record(stream)
-        run(nsteps)
-        e1.record(stream)
-        barrier()
-        launches = femm.ctx.launch_count - l0
-        tm = torch.tensor([e0.elapsed_time(e1) / nsteps], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        step_ms = float(tm.item())
-        Uh = ex.get_state()[0]
-        ke = ex.kinetic_energy()
-    knnz = nnz
-    _, _, nruns, idx_entries = ex.layout()
+    cs = 100.0
+    if world == 1:
+        ex = fsb200.Explicit(femm.ctx, c_scale=cs, dt=0.0)
+        b = np.array([0, w["nfree"]])
+    else:
+        ex = fsb200.Explicit.create_dist(femm.ctx, rank, world, plan.lcol_lo, plan.lcol_hi, plan.loc2glob[: plan.nfree], plan._bounds,
+                                         c_scale=cs, dt=0.0)
+        with torch.cuda.stream(stream):
+            pt.connect_ranks(ex)
+        b = plan._bounds
+    lam = ex.omega_max_sq(args.power_its)  # row-partitioned: a global value, identical on every rank
+    dt = 0.9 * 2 / np.sqrt(lam)
+    ex.set_timestep(cs, dt)
+    # load: a pressure patch on the nodes nearest the panel centre (w dofs), the same global vector on every rank
+    F0g = np.zeros(w["nfree"])
+    c = np.array([w["xyz"][:, 0].mean(), w["xyz"][:, 1].mean()])
+    near = np.argsort((w["xyz"][:, 0] - c[0]) ** 2 + (w["xyz"][:, 1] - c[1]) ** 2)[: max(1, w["xyz"].shape[0] // 100)]
+    wd = w["dofnums"][near, 2]
+    F0g[wd[wd <= w["nfree"]] - 1] = 1.0
+    ex.set_load(F0g[b[rank] : b[rank + 1]] if world > 1 else F0g)
+    ex.start(1.0)
+    nsteps = args.expl_steps
+    ex.step(50)
+    barrier()
+    l0 = femm.ctx.launch_count
+    e0.record(stream)
+    ex.step(nsteps)
+    e1.record(stream)
+    barrier()
+    launches = femm.ctx.launch_count - l0
+    tm = torch.tensor([e0.elapsed_time(e1) / nsteps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    step_ms = float(tm.item())
+    Uh = ex.get_state()[0]
+    umax = torch.tensor([float(np.abs(Uh).max())], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(umax, op=dist.ReduceOp.MAX)
+    ke = ex.kinetic_energy()
+    nrows, knnz, nruns, idx_entries = ex.layout()
+    info = ex.dist_info() if world > 1 else None
     # f64 value per entry + one i32 column index per entry of every distinct row pattern (runs of <= 6 rows share
     # one), ~10 vector passes.  SURVEY 8(d)'s figure for the plain Int32 CSR form is 12 B per entry.
-    alg_step = (8.0 * knnz + 4.0 * idx_entries + 10 * 8.0 * nf) / nelem
-    alg_step_csr = (12.0 * knnz + 10 * 8.0 * nf) / nelem
-    expl = {"workload": f"explicit central differences, T3FF, {nelem} elements per rank x {world} rank(s), SpMV form (K_ff CSR, lumped M)",
-            "steps_per_s": 1e3 / step_ms, "element_steps_per_s": nelem * world * 1e3 / step_ms, "ms_per_step": step_ms, "dt": dt,
-            "omega_max": float(np.sqrt(lam)), "nsteps_timed": nsteps, "gpu_launches": int(launches), "max_abs_U": float(np.abs(Uh).max()),
-            "kinetic_energy": ke, "interface_exchange": "pairwise NCCL isend/irecv of packed interface E entries" if world > 1 else "none",
-            "roofline": {"bound": "hbm", "achieved": alg_step * nelem / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": alg_step * nelem / (step_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_element_step": alg_step,
-                         "plain_csr_bytes_per_element_step": alg_step_csr, "row_runs": int(nruns), "index_entries_read": int(idx_entries),
-                         "kernel": "k_spmv_step + k_update_u"}}
+    tot = torch.tensor([8.0 * knnz + 4.0 * idx_entries + 10 * 8.0 * nrows, 12.0 * knnz + 10 * 8.0 * nrows, float(knnz)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    bytes_step, bytes_step_csr, knnz_g = float(tot[0].item()), float(tot[1].item()), float(tot[2].item())
+    expl = {"workload": f"explicit central differences, T3FF, ONE {nelem_g}-element RCM-numbered panel row-partitioned over {world} rank(s), SpMV form (K_ff CSR, lumped M)",
+            "scaling": "strong", "steps_per_s": 1e3 / step_ms, "element_steps_per_s": nelem_g * 1e3 / step_ms, "ms_per_step": step_ms, "dt": dt,
+            "omega_max": float(np.sqrt(lam)), "nsteps_timed": nsteps, "gpu_launches": int(launches), "max_abs_U": float(umax.item()),
+            "kinetic_energy": ke, "nnz_global": int(knnz_g),
+            "interface_exchange": ("halo displacements written by the fused step kernel into the neighbours' peer-mapped windows "
+                                   "(cudaIpc over NVLink) + flag; boundary rows first, interior rows overlap the exchange; no NCCL on the step path")
+            if world > 1 else "none",
+            "partition": None if info is None else {"own_rows": info[0], "halo_entries": info[1], "pushed_entries_per_step": info[2],
+                                                    "boundary_runs": info[3], "neighbours": info[4], "plan_host_s": plan_s},
+            "roofline": {"bound": "hbm", "achieved": bytes_step / world / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": bytes_step / world / (step_ms * 1e-3) / 1e9 / hbm_peak, "basis": "per GPU: the job's algorithmic bytes / ranks / step time",
+                         "algorithmic_bytes_per_element_step": bytes_step / nelem_g,
+                         "plain_csr_bytes_per_element_step": bytes_step_csr / nelem_g, "row_runs_this_rank": int(nruns),
+                         "kernel": "k_spmv_step<dist>" if world > 1 else "k_spmv_step"},
+            "mesh_and_rcm_host_s": mesh_s}
     # CPU arm for the explicit loop (rank 0, bounded sample: a 1/100-size strip, all host threads)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -316,11 +360,13 @@ def explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
             cpu = cpu_explicit(local_rank)
         except Exception as ex_:  # never let the side measurement kill the bench line
             cpu = {"error": repr(ex_)}
+    barrier()
     ex.close()
+    femm.ctx.close()
     return {"t3ff_assembly_C4": asm, "explicit_C4": expl, "explicit_cpu_baseline": cpu}
 
 
-def extras_c3_c5(args, rank, local_rank, world, stream):
+def extras_c3_c5(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
     """BASELINE configs[2] (T3FFComp laminated cylinder, 2M triangles: stiffness + mass) and configs[4]
     (corotational beam lattice, 1.01M elements: restoringforce + stiffness + geostiffness = one Newton
     iteration's assembly).  Numeric phase, device-resident, max over ranks."""
@@ -378,7 +424,14 @@ def extras_c3_c5(args, rank, local_rank, world, stream):
     ms_k = timed(lambda: femm.ctx.shell_op("t3ffcomp_stiffness", p))
     kms = femm.ctx.last_kernel_ms
     ms_m = timed(lambda: femm.ctx.shell_op("t3ffcomp_mass", p))
-    out["t3ffcomp_C3"] = {"workload": f"T3FFComp 4-ply [0/90/90/0] cylinder, {ne} triangles per rank, per-element layup csys: stiffness and lumped mass -> CSC (FFBlock)",
+
+    def roof(flops, in_bytes, nnz_, ne_, ms):
+        t_f = flops * ne_ / (fp64_peak * 1e12) * 1e3
+        t_h = (in_bytes * ne_ + 8.0 * nnz_) / (hbm_peak * 1e9) * 1e3
+        return {"bound": "fp64" if t_f >= t_h else "hbm", "t_roof_ms": max(t_f, t_h), "frac": max(t_f, t_h) / ms, "t_fp64_ms": t_f, "t_hbm_ms": t_h,
+                "flops_per_element": flops, "algorithmic_bytes_per_element": in_bytes + 8.0 * nnz_ / ne_, "basis": "step = value-array clear + kernel"}
+
+    out["t3ffcomp_C3"] = {"roofline": roof(10.5e3, 73.0 + 72.0 + 8.0, femm.ctx.result_size()[2], ne, ms_k),"workload": f"T3FFComp 4-ply [0/90/90/0] cylinder, {ne} triangles per rank, per-element layup csys: stiffness and lumped mass -> CSC (FFBlock)",
                           "stiffness_elements_per_s": ne * world / (ms_k * 1e-3), "stiffness_ms": ms_k, "stiffness_kernel_ms": kms,
                           "mass_elements_per_s": ne * world / (ms_m * 1e-3), "mass_ms": ms_m, "nnz": int(femm.ctx.result_size()[2]),
                           "associategeometry_s_incl_host_csys_callback": assoc_s}
@@ -400,7 +453,9 @@ def extras_c3_c5(args, rank, local_rank, world, stream):
     ms_s = timed(lambda: bf.ctx.beam_op("stiffness", bp))
     ms_g = timed(lambda: bf.ctx.beam_op("geostiffness", bp))
     tot = ms_r + ms_s + ms_g
-    out["corotbeam_C5"] = {"workload": f"corotational beam lattice, {ne} elements per rank: restoringforce + stiffness + geostiffness (one Newton iteration's assembly, FFBlock)",
+    nnz5 = bf.ctx.result_size()[2]
+    out["corotbeam_C5"] = {"roofline": {"stiffness": roof(1.5e3, 152.0, nnz5, ne, ms_s), "geostiffness": roof(1.5e3, 152.0, nnz5, ne, ms_g),
+                                        "restoringforce": roof(450.0, 170.0, 0, ne, ms_r)},"workload": f"corotational beam lattice, {ne} elements per rank: restoringforce + stiffness + geostiffness (one Newton iteration's assembly, FFBlock)",
                            "newton_assemblies_per_s": 1e3 / tot, "elements_per_s": ne * world / (tot * 1e-3), "restoringforce_ms": ms_r,
                            "stiffness_ms": ms_s, "geostiffness_ms": ms_g, "nnz": int(bf.ctx.result_size()[2])}
     bf.ctx.close()
@@ -516,17 +571,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1000, help="quads per side (1000 -> 1M elements, the BASELINE config)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-sample", type=int, default=256000, help="elements per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (T3FF assembly / explicit loop on C4)")
+    ap.add_argument("--all-extras", action="store_true", help="N > 1: also run the C3 / C5 workloads (replicas) on every rank")
     ap.add_argument("--c4-nx", type=int, default=2000, help="C4 strip: nx x nx/2 cells x 2 triangles (2000 -> 4M elements per rank)")
-    ap.add_argument("--expl-steps", type=int, default=200)
+    ap.add_argument("--expl-steps", type=int, default=1000)
     ap.add_argument("--power-its", type=int, default=30)
     ap.add_argument("--c3-n", type=int, default=1000, help="C3 cylinder: n x n x 2 triangles (1000 -> 2M)")
     ap.add_argument("--c5-n", type=int, default=69, help="C5 lattice cells per side (69 -> 1,014,300 beams)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     metric, unit = "element matrices assembled/sec (Q4RS stiffness -> CSC)", "elements/s"
-    from fsb200 import workloads as wl  # noqa: E402  (pure numpy part of the package)
+    wl = load_workloads()
 
     w = wl.c2_q4rs_plate(args.n)
     nelem = w["conn"].shape[0]
@@ -542,19 +599,22 @@ def main():
             return
         ncores = os.cpu_count() or 1
         normals, valid = oracle_normals(w)
-        sample = min(nelem, max(20000, 4000 * ncores))
+        sample = min(nelem, args.ref_sample)
         vals = []
         for s in range(args.warmup + args.steps):
-            v, dt = cpu_q4rs_assembly(w, sample, ncores, normals, valid)
+            r = cpu_q4rs_assembly(w, sample, ncores, normals, valid)
             if s >= args.warmup:
-                vals.append((v, dt))
-        v = float(np.mean([x[0] for x in vals]))
-        ms = float(np.mean([x[1] for x in vals])) * 1e3
+                vals.append(r)
+        v = float(np.mean([x["value"] for x in vals]))
+        ms = float(np.mean([x["seconds"] for x in vals])) * 1e3
+        loop_s, sparse_s = float(np.mean([x["loop_s"] for x in vals])), float(np.mean([x["sparse_s"] for x in vals]))
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": config,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": unit, "cores": ncores, "kind": "port",
-                                 "sample": f"first {sample} elements of the workload per step: element loop + COO append + COO->CSC, OpenMP element-parallel"},
+                                 "sample": f"first {sample} elements of the workload per step: element loop + COO append (OpenMP element-parallel, "
+                                           f"{loop_s:.2f} s) + ONE serial COO->CSC pass as Julia's sparse() does ({sparse_s:.2f} s); buffers preallocated",
+                                 "element_loop_only_value": float(np.mean([x["loop_value"] for x in vals]))},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -575,14 +635,34 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_kind = peaks()
+    mat = f.MatDeforElastIso(w["E"], w["nu"], w["rho"])
+    stream = torch.cuda.Stream()
+    wg = w  # the global workload
+    plan = None
+    if world > 1:
+        # STRONG scaling: the ONE mesh of the configuration is split over the ranks.  Rank r owns a contiguous block
+        # of columns of the global matrix and assembles every element touching a node of that block
+        # (partition.ColumnBlockPlan; interface elements are computed by both neighbours, no partial sums travel).
+        # Nodal normals come from the global mesh (one device pass per rank, untimed setup).
+        from fsb200 import partition as pt
+
+        fg = f.FEMMShellQ4RS(f.IntegDomain(wg["conn"], f.GaussRule2x2(), wg["thickness"]), mat, device=local_rank)
+        gg = f.NodalField.__new__(f.NodalField)
+        gg.values = wg["xyz"]
+        f.associategeometry(fg, gg)
+        nrm_g, val_g = fg._normals, fg._normal_valid
+        fg.ctx.close()
+        plan = pt.ColumnBlockPlan(wg["conn"], wg["dofnums"], wg["nfree"], "ffblock", rank, world)
+        w = dict(wg, conn=plan.conn, xyz=np.asfortranarray(plan.restrict_nodes(wg["xyz"])), dofnums=plan.dofnums, nfree=plan.nfree)
+        config["parallelism"] = (f"STRONG scaling: the one {nelem}-element mesh split over {world} ranks by owned column blocks "
+                                 f"(this rank: {len(plan.elems)} elements incl. interface elements); no data-path collective, "
+                                 "the matrix stays distributed (column block per rank)")
 
     # host (pinned) inputs, as a Julia host would hold them
     xyz_p, k1 = pin_copy(w["xyz"])
     conn_p, k2 = pin_copy(np.ascontiguousarray(w["conn"]))
     dof_p, k3 = pin_copy(w["dofnums"])
-    mat = f.MatDeforElastIso(w["E"], w["nu"], w["rho"])
     femm = f.FEMMShellQ4RS(f.IntegDomain(conn_p, f.GaussRule2x2(), w["thickness"]), mat, device=local_rank)
-    stream = torch.cuda.Stream()
     femm.ctx.set_stream(stream.cuda_stream)
     geom0 = f.NodalField.__new__(f.NodalField)
     geom0.values = xyz_p
@@ -591,7 +671,12 @@ def main():
     u0 = R0 = None
 
     # --- setup (untimed): nodal normals, first symbolic phase -------------------------------
-    f.associategeometry(femm, geom0)
+    if plan is None:
+        f.associategeometry(femm, geom0)
+    else:
+        femm._normals, femm._normal_valid = np.asfortranarray(plan.restrict_nodes(nrm_g)), plan.restrict_nodes(val_g)
+        femm._associatedgeometry = True
+        femm._sync_mesh(geom0)
     t0 = time.perf_counter()
     femm._startassembly(f.SysmatAssemblerFFBlock(), dchi)
     femm.ctx.sync()
@@ -633,8 +718,9 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_per_step = float(tmax.item()) / args.steps
-    value = nelem * world / (ms_per_step * 1e-3)
+    value = nelem / (ms_per_step * 1e-3)  # N > 1: the same global mesh, split (strong scaling)
     kernel_ms = float(np.mean(kms))
+    nelem_rank = int(w["conn"].shape[0])
 
     # --- end to end through the reference-facing operator API: `e2e` -------------------------
     cp_p, k4 = pinned((nc + 1,), np.int64)
@@ -652,6 +738,11 @@ def main():
         femm.reset_uploads()
         return f.stiffness(femm, f.SysmatAssemblerFFBlock(), g, u0, R0, d, out=(cp_p, rv_p, nz_p))
 
+    e2e_includes = ("H2D mesh+dofs+normals, symbolic phase, numeric phase, D2H of the CSC result into host colptr+rowval+nzval (Int64/f64; "
+                    "the row indices cross PCIe run-length coded and are expanded by host threads inside the call)")
+    if world > 1:
+        e2e_includes += (f"; N > 1: every rank does this for its share of the ONE mesh (its elements, its local matrix in local numbering "
+                         "with the local->global row map; the owned column block is a contiguous slice of it), all ranks concurrently")
     e2e_step()
     # PCIe probe (pinned, this box): explains the end-to-end number, which is dominated by the CSC D2H
     probe = torch.empty(1 << 27, dtype=torch.float64, device="cuda")
@@ -673,7 +764,7 @@ def main():
     te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = nelem * world / float(te.item())
+    e2e_value = nelem / float(te.item())
     # secondary figure (not the headline): a re-assembly on the SAME mesh and numbering -- only the values
     # change (a Newton / time-stepping loop), so only nzval crosses PCIe
     barrier()
@@ -684,23 +775,27 @@ def main():
     barrier()
     refresh_ms = (time.perf_counter() - t0) / args.e2e_steps * 1e3
 
-    # checksum of the single-GPU values: the gathered multi-GPU assembly of the same matrix must reproduce it
-    nz_checksum_single = float(np.sum(nz_p)) if world > 1 else None
+    # checksum of the values of the owned column blocks: the gathered multi-GPU assembly of the same matrix must reproduce it
+    nz_checksum_blocks = None
+    if world > 1:
+        c0, c1 = int(cp_p[plan.lcol_lo]) - 1, int(cp_p[plan.lcol_hi]) - 1
+        t = torch.tensor([float(np.sum(nz_p[c0:c1]))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        nz_checksum_blocks = float(t.item())
     # free the C2 buffers before the 4M-element workload
     del K, cp_p, rv_p, nz_p, k4, k5, k6
     femm.ctx.close()
     extras = None
     if not args.no_extras:
         extras = explicit_c4(args, rank, local_rank, world, stream, hbm_peak, fp64_peak)
-        with torch.cuda.stream(stream):
-            extras.update(extras_c3_c5(args, rank, local_rank, world, stream))
+        if world == 1 or args.all_extras:
+            with torch.cuda.stream(stream):
+                extras.update(extras_c3_c5(args, rank, local_rank, world, stream, hbm_peak, fp64_peak))
 
     if world > 1 and not args.no_extras:
-        gathered = gathered_c2(args, rank, local_rank, world, stream, w, nrm_host, val_host)
-        if extras is None:
-            extras = {}
-        gathered["nzval_checksum_single_gpu"] = nz_checksum_single
-        gathered["checksum_rel_diff"] = abs(gathered["nzval_checksum"] - nz_checksum_single) / abs(nz_checksum_single)
+        gathered = gathered_c2(args, rank, local_rank, world, stream, wg, nrm_g, val_g)
+        gathered["nzval_checksum_of_the_distributed_blocks"] = nz_checksum_blocks
+        gathered["checksum_rel_diff"] = abs(gathered["nzval_checksum"] - nz_checksum_blocks) / abs(nz_checksum_blocks)
         extras["gathered_assembly_C2"] = gathered
 
     if rank != 0:
@@ -708,56 +803,63 @@ def main():
             dist.destroy_process_group()
         return
 
-    # --- roofline of the dominant kernel ------------------------------------------------------
-    out_bytes = 8.0 * nnz / nelem  # values written once (pattern reused)
+    # --- roofline of the dominant kernel: north star = "the slower of FP64 peak and HBM bytes at peak bandwidth",
+    # taken on the STEP (value-array clear + element kernel), for the elements this rank processes ----------------
+    out_bytes = 8.0 * nnz / nelem_rank  # values written once (pattern reused)
     alg_bytes = Q4_IN_BYTES + out_bytes
-    achieved = alg_bytes * nelem / (kernel_ms * 1e-3) / 1e9
+    t_hbm = alg_bytes * nelem_rank / (hbm_peak * 1e9) * 1e3
+    t_fp64 = Q4_FLOPS * nelem_rank / (fp64_peak * 1e12) * 1e3
     # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture (same workload size)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_q4_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            if int(tj.get("nelem", -1)) == int(nelem):
-                traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source")
-        except (OSError, ValueError, KeyError):
-            pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "kernel": "k_q4_stiffness<false,false,EmitRuns>",
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_element": alg_bytes,
-                "kernel_share_of_step": kernel_ms / ms_per_step}
-    # north_star: "the slower of FP64 peak and HBM bytes at peak bandwidth"
-    t_hbm = alg_bytes * nelem / (hbm_peak * 1e9)
-    t_fp64 = Q4_FLOPS * nelem / (fp64_peak * 1e12)
-    roofline["north_star"] = {"binding": "fp64" if t_fp64 >= t_hbm else "hbm", "t_roof_ms": max(t_hbm, t_fp64) * 1e3,
-                              "frac": max(t_hbm, t_fp64) * 1e3 / kernel_ms}
-    fl = Q4_FLOPS * nelem / (kernel_ms * 1e-3) / 1e12
-    fp64 = {"achieved_tflops": fl, "peak_tflops": fp64_peak, "frac": fl / fp64_peak, "flops_per_element": Q4_FLOPS,
-            "peak_source": "fsgpu_measure_peaks DFMA micro-kernel on this device", "copy_gbs_this_device": copy_bw}
+    for name in ("r02_q4_traffic.json", "r01_q4_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                if int(tj.get("nelem", -1)) == int(nelem_rank):
+                    traffic, traffic_src = float(tj["dram_bytes_per_launch"]), tj.get("source")
+                    break
+            except (OSError, ValueError, KeyError):
+                pass
+    fp64_bound = t_fp64 >= t_hbm
+    fl_step = Q4_FLOPS * nelem_rank / (ms_per_step * 1e-3) / 1e12
+    gb_step = alg_bytes * nelem_rank / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "fp64" if fp64_bound else "hbm",
+                "achieved": fl_step if fp64_bound else gb_step, "peak": fp64_peak if fp64_bound else hbm_peak,
+                "unit": "TFLOP/s" if fp64_bound else "GB/s", "frac": max(t_fp64, t_hbm) / ms_per_step,
+                "basis": "step = value-array clear + element kernel + status read-back, this rank's elements",
+                "t_roof_ms": max(t_fp64, t_hbm), "frac_kernel_only": max(t_fp64, t_hbm) / kernel_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_q4_stiffness<false,false,EmitRuns>",
+                "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step, "flops_per_element": Q4_FLOPS,
+                "peak_source": "FP64: fsgpu_measure_peaks DFMA micro-kernel on this device in this run (record with clocks: "
+                               "profiles/r02_fp64_peak.json); HBM: MEASURED_PEAKS.json (" + peak_kind + ")",
+                "hbm": {"achieved": gb_step, "peak": hbm_peak, "unit": "GB/s", "frac": t_hbm / ms_per_step,
+                        "algorithmic_bytes_per_element": alg_bytes},
+                "copy_gbs_this_device": copy_bw}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         ncores = os.cpu_count() or 1
-        normals, valid = nrm_host, val_host
-        s1 = min(nelem, 20000)
-        v1, t1 = cpu_q4rs_assembly(w, s1, 1, normals, valid)
-        sN = min(nelem, max(40000, 8000 * ncores))
-        vN, tN = cpu_q4rs_assembly(w, sN, ncores, normals, valid)
-        cpu = {"value": vN, "unit": unit, "cores": ncores, "kind": "port",
-               "sample": f"first {sN} elements (all {ncores} threads, {tN:.1f} s); single-thread = reference behaviour: "
-                         f"{v1:.0f} elements/s on the first {s1} elements ({t1:.1f} s)",
-               "single_thread_value": v1}
+        s1 = min(nelem, 32000)
+        r1 = cpu_q4rs_assembly(wg, s1, 1, nrm_host, val_host)
+        sN = min(nelem, max(64000, 16000 * ncores))
+        rN = cpu_q4rs_assembly(wg, sN, ncores, nrm_host, val_host)
+        cpu = {"value": rN["value"], "unit": unit, "cores": ncores, "kind": "port",
+               "sample": f"first {sN} elements of the workload (all {ncores} threads): element loop {rN['loop_s']:.2f} s + COO->CSC "
+                         f"{rN['sparse_s']:.2f} s; single thread (= the reference's serial loop) on the first {s1} elements: "
+                         f"{r1['value']:.0f} elements/s (loop {r1['loop_s']:.2f} s + COO->CSC {r1['sparse_s']:.2f} s)",
+               "single_thread_value": r1["value"], "element_loop_only_value": rN["loop_value"],
+               "single_thread_element_loop_only_value": r1["loop_value"]}
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config, "clocks": clocks,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_link),
                     "host_result_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3, "includes": "H2D mesh+dofs+normals, symbolic phase, numeric phase, D2H of the CSC result into host colptr+rowval+nzval (Int64/f64; the row indices cross PCIe run-length coded and are expanded by 8 host threads inside the call)",
+                    "ms_per_step": e2e_s * 1e3, "includes": e2e_includes,
                     "pinned_d2h_gbs_this_box": d2h_gbs,
                     "values_refresh_ms_same_pattern": refresh_ms},
-            "gpu_launches": int(launches), "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "symbolic_ms": {"first": symbolic_ms, "warm": symbolic_warm_ms}, "nnz": int(nnz), "other_workloads": extras}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

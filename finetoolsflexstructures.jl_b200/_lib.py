@@ -119,6 +119,7 @@ _SIGNATURES = {
     "fsgpu_explicit_destroy": [_vp],
     "fsgpu_explicit_set_state": [_vp, _vp, _vp],
     "fsgpu_explicit_set_load": [_vp, _vp],
+    "fsgpu_explicit_set_timestep": [_vp, _dbl, _dbl],
     "fsgpu_explicit_start": [_vp, _dbl],
     "fsgpu_explicit_step": [_vp, _i64, _vp],
     "fsgpu_explicit_get_state": [_vp, _vp, _vp, _vp],
@@ -130,7 +131,12 @@ _SIGNATURES = {
     "fsgpu_explicit_step_end": [_vp, _dbl],
     "fsgpu_d2h_bytes": [_vp, _P(_i64)],
     "fsgpu_explicit_layout": [_vp, _P(_i64), _P(_i64), _P(_i64), _P(_i64)],
+    "fsgpu_explicit_create_dist": [_P(_vp), _vp, _i32, _i32, _i64, _i64, _vp, _vp, _dbl, _dbl],
+    "fsgpu_explicit_export": [_vp, _vp],
+    "fsgpu_explicit_connect": [_vp, _vp],
+    "fsgpu_explicit_dist_info": [_vp, _P(_i64), _P(_i64), _P(_i64), _P(_i64), _P(_i32)],
 }
+EXPLICIT_BLOB_BYTES = 1024
 _RESTYPE = {"fsgpu_last_error": C.c_char_p, "fsgpu_launch_count": _i64}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -294,6 +294,41 @@ class Explicit:
             check(lib.fsgpu_explicit_create(C.byref(h), ctx._h, self.n, ptr(rowptr), ptr(colval), ptr(nzval), ptr(md), float(c_scale), float(dt)))
         self._h = h
 
+    @classmethod
+    def create_dist(cls, ctx: Context, rank, world, row_lo, row_hi, loc2glob, bounds, c_scale=0.0, dt=0.0):
+        """Row-partitioned run (fsgpu_explicit_create_dist): this rank owns local rows [row_lo, row_hi) of the
+        FFBLOCK result of `ctx` = global rows [bounds[rank], bounds[rank+1]).  Follow with `export()` on every
+        rank, an all-gather of the blobs by the host, and `connect(blobs)`; after that every call is collective."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        l2g = None if loc2glob is None else i64(loc2glob, "C")
+        b = i64(bounds, "C")
+        h = C.c_void_p()
+        check(lib.fsgpu_explicit_create_dist(C.byref(h), ctx._h, int(rank), int(world), int(row_lo), int(row_hi), ptr(l2g), ptr(b),
+                                             float(c_scale), float(dt)))
+        self._h = h
+        self.n = int(row_hi) - int(row_lo)
+        self.rank, self.world = int(rank), int(world)
+        return self
+
+    def export(self):
+        buf = np.zeros(L.EXPLICIT_BLOB_BYTES, dtype=np.uint8)
+        check(lib.fsgpu_explicit_export(self._h, ptr(buf)))
+        return buf
+
+    def connect(self, blobs):
+        """blobs: the exports of all ranks, in rank order (sequence of uint8 arrays, or one (world, BLOB) array)."""
+        b = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint8).ravel() for x in blobs]))
+        assert b.size == self.world * L.EXPLICIT_BLOB_BYTES
+        check(lib.fsgpu_explicit_connect(self._h, ptr(b)))
+
+    def dist_info(self):
+        """(own rows, halo entries, entries pushed per step, boundary runs, neighbouring ranks)."""
+        v = [C.c_int64() for _ in range(4)]
+        k = C.c_int32()
+        check(lib.fsgpu_explicit_dist_info(self._h, *[C.byref(x) for x in v], C.byref(k)))
+        return tuple(x.value for x in v) + (k.value,)
+
     def close(self):
         if self._h:
             lib.fsgpu_explicit_destroy(self._h)
@@ -309,6 +344,9 @@ class Explicit:
         U0 = None if U0 is None else f64(U0, "C")
         V0 = None if V0 is None else f64(V0, "C")
         check(lib.fsgpu_explicit_set_state(self._h, ptr(U0), ptr(V0)))
+
+    def set_timestep(self, c_scale, dt):
+        check(lib.fsgpu_explicit_set_timestep(self._h, float(c_scale), float(dt)))
 
     def set_load(self, F0):
         F0 = None if F0 is None else f64(F0, "C")

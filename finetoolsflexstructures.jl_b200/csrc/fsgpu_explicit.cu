@@ -9,8 +9,11 @@
 // node -- found from the CSR arrays alone, no mesh knowledge) read one shared copy of the indices, which
 // cuts the index traffic ~6x (12 -> ~8.7 B per entry).
 #include <cub/cub.cuh>
+#include <unistd.h>
 
+#include <algorithm>
 #include <utility>
+#include <vector>
 
 #include "fsgpu_internal.cuh"
 
@@ -19,6 +22,7 @@ using namespace fs;
 struct fsgpu_explicit {
   fsgpu_ctx* ctx = nullptr;
   int64_t n = 0, nnz = 0;
+  int64_t row0 = 0;  // global index of the first row (row-partitioned runs)
   DBuf<int32_t> rowptr, colval;
   DBuf<int32_t> runs;   // [nruns + 1] first rows of the runs of <= 6 consecutive rows with one column pattern
   int64_t nruns = 0;
@@ -26,14 +30,125 @@ struct fsgpu_explicit {
   DBuf<double> val;
   DBuf<double> M, C, invMC, U, V, A, F0, E, X, Y;
   DBuf<double> Un;       // displacements of the NEXT step, written by the fused step's epilogue
-  bool u_ahead = false;  // Un holds U + dt V + dt^2/2 A of the current (V, A): the next step swaps instead of updating
+  // current / next displacement buffers: U.p / Un.p, or -- row-partitioned runs -- two vectors of the peer-visible window
+  double* Uc = nullptr;
+  double* Unx = nullptr;
+  bool u_ahead = false;  // Unx holds U + dt V + dt^2/2 A of the current (V, A): the next step swaps instead of updating
+  struct Dist* dist = nullptr;  // row-partitioned run (fsgpu_explicit_create_dist): peers, window, halo lists
   double dt = 0, c_scale = 0;
   bool have_load = false;
 };
 
+// ---- row-partitioned runs (one rank per GPU) -------------------------------------------
+// Every rank owns a contiguous block of rows of the global K_ff and holds, besides its own entries of the
+// displacement vector, HALO entries (the columns its rows reference in other ranks' blocks).  All peer-visible
+// state lives in one device allocation per rank, the WINDOW, which the other ranks map (cudaIpc across
+// processes, the plain pointer inside one process) and write directly over NVLink:
+//   [0, kCtrlBytes)   control words (uint64): step flags [sender rank], barrier flags, reduction flags,
+//                     reduction values double[2][kMaxWorld][kRedN] at byte kRedOff
+//   then kNVec vectors of `ext` doubles: displacement buffers 0 / 1 and the power-iteration vector, each
+//                     [own rows | padding to a 128 B line | halo entries grouped by owner rank, ascending]
+constexpr int kMaxWorld = 32;
+constexpr int kMaxPeers = 16;
+constexpr size_t kCtrlBytes = 16384;
+constexpr int kFlagStep = 0, kFlagBar = 64, kFlagRed = 128;  // uint64 word offsets
+constexpr size_t kRedOff = 4096;
+constexpr int kRedN = 8;
+constexpr int kNVec = 3;
+constexpr uint64_t kBlobMagic = 0x46534750555f5631ull;  // "FSGPU_V1"
+
+struct DistDev {  // by-value kernel argument
+  int me, world, npeers;
+  int nb_ctas;  // CTAs [0, nb_ctas) of the fused step hold the boundary runs (rows that read halo entries)
+  int n_push;
+  unsigned long long wait_epoch;  // step flags of all halo peers must have reached this value before halo reads
+  unsigned long long timeout_ns;
+  unsigned char* ctrl[kMaxWorld];  // window base of every rank (ctrl[me] = own)
+  int peer_rank[kMaxPeers];        // halo peers
+  double* peer_vec[kMaxPeers];     // the vector of the peer's window this launch pushes into
+  const int32_t* push_src;         // [n_push] own row
+  const int32_t* push_dst;         // [n_push] entry of the peer's vector
+  const int32_t* push_peer;        // [n_push] index into peer_rank / peer_vec
+  const int32_t* order;            // [nruns] run handled by slot s: boundary runs first
+  unsigned int* done;              // boundary CTAs finished (fused step)
+  int* err;                        // set when a wait timed out
+};
+
+struct Dist {
+  int rank = 0, world = 1;
+  unsigned char* win = nullptr;
+  size_t win_bytes = 0;
+  int64_t n_own = 0, n_halo = 0, halo0 = 0, ext = 0;
+  int64_t halo_base[kMaxWorld] = {}, halo_cnt[kMaxWorld] = {};  // my halo entries of rank p's rows
+  int64_t peer_ext[kMaxWorld] = {};
+  int64_t send_cnt[kMaxWorld] = {};
+  std::vector<int32_t> push_src, push_peer, push_rank;  // host copies (push_dst is known at connect)
+  int npeers = 0;
+  int peer_rank[kMaxPeers] = {};
+  unsigned char* ctrl[kMaxWorld] = {};
+  bool ipc_opened[kMaxWorld] = {};
+  bool connected = false;
+  fs::DBuf<int32_t> d_push_src, d_push_dst, d_push_peer, order;
+  fs::DBuf<unsigned int> done;
+  fs::DBuf<int> err;
+  fs::DBuf<double> red;  // [2 * kRedN] allreduce in / out
+  int n_push = 0, nb_ctas = 0;
+  int64_t n_bruns = 0;
+  unsigned long long epoch = 0, bar_epoch = 0, red_epoch = 0;
+  int cur = 0;  // window vector that holds the current displacements
+  unsigned long long timeout_ns = 20000000000ull;
+  cudaStream_t own_stream = nullptr;
+  double* vec(int p, int b) const { return (double*)(ctrl[p] + kCtrlBytes) + (size_t)b * (size_t)peer_ext[p]; }
+};
+
+struct DistBlob {  // what fsgpu_explicit_export writes; FSGPU_EXPLICIT_BLOB_BYTES in fsgpu.h
+  uint64_t magic;
+  int32_t rank, world;
+  int64_t pid;
+  uint64_t proc_token;
+  int32_t device, pad;
+  uint64_t devptr, win_bytes;
+  int64_t n_own, ext;
+  cudaIpcMemHandle_t ipc;
+  int64_t halo_base[kMaxWorld], halo_cnt[kMaxWorld];
+};
+static_assert(sizeof(DistBlob) <= 1024, "blob size");
+
 namespace {
 
 constexpr int LPR = 8;  // lanes per row
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until *p >= target (a peer's release store); gives up after timeout_ns and raises *err
+__device__ __noinline__ bool spin_until(const unsigned long long* p, unsigned long long target, unsigned long long timeout_ns,
+                                        int* err) {
+  if (ld_acquire_sys(p) >= target) return true;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(p) < target) {
+    if (*(volatile int*)err) return false;
+    if (global_ns() - t0 > timeout_ns) {
+      atomicExch(err, 1);
+      return false;
+    }
+    __nanosleep(64);
+  }
+  return true;
+}
+__device__ __forceinline__ unsigned long long* ctrl_word(const DistDev& d, int rank, int word) {
+  return reinterpret_cast<unsigned long long*>(d.ctrl[rank]) + word;
+}
 
 __global__ void k_setup_damping(const double* __restrict__ M, double c_scale, double dt, double* __restrict__ C,
                                 double* __restrict__ invMC, int64_t n) {
@@ -140,18 +255,32 @@ __global__ void k_spmv(const int32_t* __restrict__ runs, int64_t nruns, const in
     if (ok && sub == r && r < nr) y[r0 + r] = sums[r];
 }
 // E = K U, then :88-91 for the row: F = fs*F0 - (E + C (V + dt/2 A)); V += dt/2 A; A = invMC F; V += dt/2 A
+// DIST (row-partitioned run): the first d.nb_ctas CTAs hold the boundary runs -- they wait for the peers' halo
+// entries of U (step flags), and when the last of them is done that CTA writes the boundary entries of the NEXT
+// displacements straight into the peers' windows and raises this rank's step flag there, while the interior CTAs
+// are still working: the exchange rides under the interior rows.
+template <bool DIST>
 __global__ void k_spmv_step(const int32_t* __restrict__ runs, int64_t nruns, const int32_t* __restrict__ rowptr,
                             const int32_t* __restrict__ colval, const double* __restrict__ val,
                             const double* __restrict__ U, const double* __restrict__ F0, double fs,
                             const double* __restrict__ C, const double* __restrict__ invMC, double* __restrict__ V,
                             double* __restrict__ A, double* __restrict__ E, double dt_2, double dt, double dt2_2,
-                            double* __restrict__ Unext) {
+                            double* __restrict__ Unext, const DistDev d) {
   const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t run = g / LPR;
+  const int64_t slot = g / LPR;
   const int sub = (int)(g % LPR);
-  const bool ok = run < nruns;
-  const int64_t r0 = runs[ok ? run : nruns - 1];
-  const int nr = (int)(runs[(ok ? run : nruns - 1) + 1] - r0);
+  const bool ok = slot < nruns;
+  int64_t run = ok ? slot : nruns - 1;
+  if (DIST) {
+    if ((int)blockIdx.x < d.nb_ctas) {
+      if ((int)threadIdx.x < d.npeers)
+        spin_until(ctrl_word(d, d.me, kFlagStep + d.peer_rank[threadIdx.x]), d.wait_epoch, d.timeout_ns, d.err);
+      __syncthreads();
+    }
+    run = d.order[run];
+  }
+  const int64_t r0 = runs[run];
+  const int nr = (int)(runs[run + 1] - r0);
   double sums[SNR];
   run_dot(rowptr, colval, val, U, r0, nr, sub, sums);
   double e = 0.0;
@@ -172,6 +301,70 @@ __global__ void k_spmv_step(const int32_t* __restrict__ runs, int64_t nruns, con
     // the next step's first statement (:85, U += dt V + dt^2/2 A) for this row, into the other buffer: this
     // kernel still reads U of other rows
     Unext[row] = U[row] + dt * v + dt2_2 * a1;
+  }
+  if (DIST) {
+    if ((int)blockIdx.x < d.nb_ctas) {
+      __shared__ int s_last;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = atomicAdd(d.done, 1u) == (unsigned)(d.nb_ctas - 1);
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        for (int i = threadIdx.x; i < d.n_push; i += blockDim.x)
+          d.peer_vec[d.push_peer[i]][d.push_dst[i]] = __ldcg(Unext + d.push_src[i]);
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < d.npeers)
+          st_release_sys(ctrl_word(d, d.peer_rank[threadIdx.x], kFlagStep + d.me), d.wait_epoch + 1);
+        if (threadIdx.x == 0) *d.done = 0u;
+      }
+    }
+  }
+}
+// all ranks: every rank's stream has reached this point (previous kernels of the stream are complete)
+__global__ void k_dist_barrier(const DistDev d, unsigned long long value) {
+  const int t = threadIdx.x;
+  if (t < d.world && t != d.me) {
+    __threadfence_system();
+    st_release_sys(ctrl_word(d, t, kFlagBar + d.me), value);
+    spin_until(ctrl_word(d, d.me, kFlagBar + t), value, d.timeout_ns, d.err);
+  }
+}
+// boundary entries of `vec` (own rows) into the halo entries of the peers' vectors, then the step flag
+__global__ void k_dist_push(const DistDev d, const double* __restrict__ vec, unsigned long long value) {
+  for (int i = threadIdx.x; i < d.n_push; i += blockDim.x) d.peer_vec[d.push_peer[i]][d.push_dst[i]] = vec[d.push_src[i]];
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < d.npeers) st_release_sys(ctrl_word(d, d.peer_rank[threadIdx.x], kFlagStep + d.me), value);
+}
+// the halo entries announced by step flag d.wait_epoch have arrived
+__global__ void k_dist_wait(const DistDev d) {
+  if ((int)threadIdx.x < d.npeers)
+    spin_until(ctrl_word(d, d.me, kFlagStep + d.peer_rank[threadIdx.x]), d.wait_epoch, d.timeout_ns, d.err);
+}
+// io[0..nv) <- sum (op 0) or max (op 1) over all ranks, summed in rank order: identical bits on every rank
+__global__ void k_dist_allreduce(const DistDev d, double* __restrict__ io, int nv, unsigned long long r, int op) {
+  const int t = threadIdx.x;
+  const int slot = (int)(r & 1ull);
+  if (t < d.world) {
+    double* dst = reinterpret_cast<double*>(d.ctrl[t] + kRedOff) + ((size_t)slot * kMaxWorld + d.me) * kRedN;
+    for (int k = 0; k < nv; ++k) dst[k] = io[k];
+    __threadfence_system();
+    if (t != d.me) {
+      st_release_sys(ctrl_word(d, t, kFlagRed + d.me), r);
+      spin_until(ctrl_word(d, d.me, kFlagRed + t), r, d.timeout_ns, d.err);
+    }
+  }
+  __syncthreads();
+  if (t < nv) {
+    const volatile double* src = reinterpret_cast<const volatile double*>(d.ctrl[d.me] + kRedOff) + (size_t)slot * kMaxWorld * kRedN;
+    double s = src[t];
+    for (int p = 1; p < d.world; ++p) {
+      const double x = src[(size_t)p * kRedN + t];
+      s = op == 0 ? s + x : (x > s ? x : s);
+    }
+    io[t] = s;
   }
 }
 // second half alone (element-partitioned runs: E already summed across ranks)
@@ -203,11 +396,11 @@ __global__ void k_scale(double* __restrict__ x, const double* __restrict__ y, do
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) x[i] = s * y[i];
 }
-__global__ void k_fill_start(double* __restrict__ x, int64_t n) {
+__global__ void k_fill_start(double* __restrict__ x, int64_t n, int64_t row0) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   // deterministic pseudo-random start vector in (-1, 1)
-  uint64_t z = (uint64_t)i * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+  uint64_t z = (uint64_t)(i + row0) * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
   z ^= z >> 31;
   z *= 0xBF58476D1CE4E5B9ull;
   z ^= z >> 29;
@@ -238,6 +431,82 @@ __global__ void k_wdot(const double* __restrict__ a, const double* __restrict__ 
     }                                                                          \
   } while (0)
 
+DistDev dist_dev(const fsgpu_explicit* h, int push_vec) {
+  const Dist* D = h->dist;
+  DistDev d;
+  memset(&d, 0, sizeof d);
+  d.me = D->rank;
+  d.world = D->world;
+  d.npeers = D->npeers;
+  d.nb_ctas = D->nb_ctas;
+  d.n_push = D->n_push;
+  d.wait_epoch = D->epoch;
+  d.timeout_ns = D->timeout_ns;
+  for (int p = 0; p < D->world; ++p) d.ctrl[p] = D->ctrl[p];
+  for (int k = 0; k < D->npeers; ++k) {
+    d.peer_rank[k] = D->peer_rank[k];
+    d.peer_vec[k] = push_vec >= 0 ? D->vec(D->peer_rank[k], push_vec) : nullptr;
+  }
+  d.push_src = D->d_push_src.p;
+  d.push_dst = D->d_push_dst.p;
+  d.push_peer = D->d_push_peer.p;
+  d.order = D->order.p;
+  d.done = D->done.p;
+  d.err = D->err.p;
+  return d;
+}
+int dist_check(fsgpu_explicit* h) {  // after a stream synchronisation
+  Dist* D = h->dist;
+  int e = 0;
+  FS_CUDA(cudaMemcpy(&e, D->err.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) {
+    cudaMemsetAsync(D->err.p, 0, sizeof(int), h->ctx->stream);
+    cudaStreamSynchronize(h->ctx->stream);
+    set_error("rank %d: waiting for a peer rank timed out (%.1f s): ranks out of step, or a peer has gone", D->rank,
+              (double)D->timeout_ns * 1e-9);
+    return FSGPU_ERR_STATE;
+  }
+  return FSGPU_OK;
+}
+int dist_require(fsgpu_explicit* h) {
+  FS_REQUIRE(!h->dist || h->dist->connected, FSGPU_ERR_STATE,
+             "row-partitioned run: call fsgpu_explicit_export / fsgpu_explicit_connect on every rank first");
+  return FSGPU_OK;
+}
+// all ranks: barrier of the streams (asynchronous on this rank's stream)
+int dist_barrier(fsgpu_explicit* h) {
+  Dist* D = h->dist;
+  if (D->world == 1) return FSGPU_OK;
+  k_dist_barrier<<<1, kMaxWorld, 0, h->ctx->stream>>>(dist_dev(h, -1), ++D->bar_epoch);
+  h->ctx->launches++;
+  FS_CUDA(cudaGetLastError());
+  return FSGPU_OK;
+}
+// halo entries of window vector b on all ranks <- the owners' current values; complete for kernels launched after
+int dist_sync_halo(fsgpu_explicit* h, int b) {
+  Dist* D = h->dist;
+  if (D->world == 1) return FSGPU_OK;
+  FS_TRY(dist_barrier(h));  // nobody still reads the halo entries this overwrites
+  k_dist_push<<<1, 1024, 0, h->ctx->stream>>>(dist_dev(h, b), D->vec(D->rank, b), D->epoch + 1);
+  D->epoch++;
+  k_dist_wait<<<1, 32, 0, h->ctx->stream>>>(dist_dev(h, -1));
+  h->ctx->launches += 2;
+  FS_CUDA(cudaGetLastError());
+  return FSGPU_OK;
+}
+// vals[0..nv) <- sum / max over all ranks (host values; synchronous)
+int dist_allreduce(fsgpu_explicit* h, double* vals, int nv, int op) {
+  Dist* D = h->dist;
+  if (D->world == 1) return FSGPU_OK;
+  cudaStream_t st = h->ctx->stream;
+  FS_CUDA(cudaMemcpyAsync(D->red.p, vals, nv * sizeof(double), cudaMemcpyHostToDevice, st));
+  k_dist_allreduce<<<1, kMaxWorld, 0, st>>>(dist_dev(h, -1), D->red.p, nv, ++D->red_epoch, op);
+  h->ctx->launches++;
+  FS_CUDA(cudaMemcpyAsync(vals, D->red.p, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+  FS_CUDA(cudaStreamSynchronize(st));
+  return dist_check(h);
+}
+
 int wdot(fsgpu_explicit* h, const double* a, const double* b, const double* w, double* result) {
   fsgpu_ctx* c = h->ctx;
   FS_TRY(c->flag.ensure(8));
@@ -249,6 +518,7 @@ int wdot(fsgpu_explicit* h, const double* a, const double* b, const double* w, d
   }
   FS_CUDA(cudaMemcpyAsync(result, acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   FS_CUDA(cudaStreamSynchronize(c->stream));
+  if (h->dist) FS_TRY(dist_allreduce(h, result, 1, 0));  // partial sums of the row blocks
   return FSGPU_OK;
 }
 
@@ -256,13 +526,19 @@ int alloc_vectors(fsgpu_explicit* h) {
   const size_t n = (size_t)h->n + 1;
   FS_TRY(h->C.ensure(n));
   FS_TRY(h->invMC.ensure(n));
-  FS_TRY(h->U.ensure(n));
+  if (h->dist) {  // the displacement buffers are vectors 0 / 1 of the peer-visible window (zeroed at creation)
+    h->Uc = h->dist->vec(h->dist->rank, 0);
+    h->Unx = h->dist->vec(h->dist->rank, 1);
+  } else {
+    FS_TRY(h->U.ensure(n));
+    h->Uc = h->U.p;
+  }
   FS_TRY(h->V.ensure(n));
   FS_TRY(h->A.ensure(n));
   FS_TRY(h->F0.ensure(n));
   FS_TRY(h->E.ensure(n));
   cudaStream_t st = h->ctx->stream;
-  FS_CUDA(cudaMemsetAsync(h->U.p, 0, n * sizeof(double), st));
+  if (!h->dist) FS_CUDA(cudaMemsetAsync(h->U.p, 0, n * sizeof(double), st));
   FS_CUDA(cudaMemsetAsync(h->V.p, 0, n * sizeof(double), st));
   FS_CUDA(cudaMemsetAsync(h->A.p, 0, n * sizeof(double), st));
   FS_CUDA(cudaMemsetAsync(h->E.p, 0, n * sizeof(double), st));
@@ -383,11 +659,366 @@ extern "C" int fsgpu_explicit_layout(fsgpu_explicit* h, int64_t* nrows, int64_t*
   return FSGPU_OK;
 }
 
+namespace {
+void dist_release(fsgpu_explicit* h) {
+  Dist* D = h->dist;
+  if (!D) return;
+  for (int p = 0; p < D->world; ++p)
+    if (D->ipc_opened[p] && D->ctrl[p]) cudaIpcCloseMemHandle(D->ctrl[p]);
+  if (D->win) cudaFree(D->win);
+  if (D->own_stream) {
+    if (h->ctx->stream == D->own_stream) h->ctx->stream = 0;
+    cudaStreamDestroy(D->own_stream);
+  }
+  delete D;
+  h->dist = nullptr;
+}
+}  // namespace
+
 extern "C" int fsgpu_explicit_destroy(fsgpu_explicit* h) {
   if (!h) return FSGPU_OK;
   cudaSetDevice(h->ctx->device);
+  if (h->dist && h->dist->connected && h->dist->world > 1) {
+    // peers may still be writing their last halo entries into this rank's window: leave together
+    h->dist->timeout_ns = std::min<unsigned long long>(h->dist->timeout_ns, 5000000000ull);
+    dist_barrier(h);
+  }
   cudaStreamSynchronize(h->ctx->stream);
+  dist_release(h);
   delete h;
+  return FSGPU_OK;
+}
+
+// ---- row-partitioned run ----------------------------------------------------------------------------
+namespace {
+// per own row: bit p set when the row has an entry in a column owned by rank p; used[col] = 1 for every such column
+__global__ void k_dist_scan(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+                            const signed char* __restrict__ owner, int64_t n, unsigned char* __restrict__ used,
+                            uint32_t* __restrict__ rowmask) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = g / LPR;
+  const int sub = (int)(g % LPR);
+  uint32_t m = 0;
+  if (row < n) {
+    for (int p = rowptr[row] + sub; p < rowptr[row + 1]; p += LPR) {
+      const int c = colval[p];
+      const int o = owner[c];
+      if (o >= 0) {
+        used[c] = 1;
+        m |= 1u << o;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+  if (row < n && sub == 0) rowmask[row] = m;
+}
+__global__ void k_remap(int32_t* __restrict__ colval, const int32_t* __restrict__ colmap, int64_t nnz) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < nnz) colval[i] = colmap[colval[i]];
+}
+__global__ void k_shift_i32(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t base, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] - base;
+}
+uint64_t process_token() {
+  static uint64_t tok = 0;
+  if (!tok) {
+    tok = ((uint64_t)getpid() << 32) ^ (uint64_t)(uintptr_t)&tok ^ 0x9E3779B97F4A7C15ull;
+    if (!tok) tok = 1;
+  }
+  return tok;
+}
+}  // namespace
+
+extern "C" int fsgpu_explicit_create_dist(fsgpu_explicit** out, fsgpu_ctx* c, int32_t rank, int32_t world, int64_t row_lo,
+                                          int64_t row_hi, const int64_t* loc2glob, const int64_t* bounds, double c_scale,
+                                          double dt) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(out && bounds, FSGPU_ERR_ARG, "null argument");
+  FS_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, FSGPU_ERR_ARG, "rank %d / world %d (at most %d ranks)",
+             rank, world, kMaxWorld);
+  FS_REQUIRE(c->have_matrix && c->target == FSGPU_FFBLOCK, FSGPU_ERR_STATE,
+             "the context must hold an FFBLOCK stiffness result (SysmatAssemblerFFBlock)");
+  FS_REQUIRE(c->have_vector && c->vlen == c->rrows, FSGPU_ERR_STATE,
+             "the context must hold the lumped mass vector of the free dofs (fsgpu_shell_mass_diag, nfree_only)");
+  const int64_t nfl = c->rrows;
+  FS_REQUIRE(0 <= row_lo && row_lo < row_hi && row_hi <= nfl, FSGPU_ERR_ARG, "own rows [%lld, %lld) of %lld", (long long)row_lo,
+             (long long)row_hi, (long long)nfl);
+  for (int p = 0; p < world; ++p) FS_REQUIRE(bounds[p] <= bounds[p + 1], FSGPU_ERR_ARG, "bounds must ascend");
+  FS_REQUIRE(bounds[rank + 1] - bounds[rank] == row_hi - row_lo, FSGPU_ERR_ARG,
+             "bounds[rank+1] - bounds[rank] = %lld but %lld own rows", (long long)(bounds[rank + 1] - bounds[rank]),
+             (long long)(row_hi - row_lo));
+  const int64_t g_lo = loc2glob ? loc2glob[row_lo] - 1 : row_lo;
+  FS_REQUIRE(g_lo == bounds[rank], FSGPU_ERR_ARG, "first own row is global row %lld, bounds[rank] = %lld", (long long)g_lo,
+             (long long)bounds[rank]);
+  const int64_t n_own = row_hi - row_lo;
+  fsgpu_explicit* h = new fsgpu_explicit();
+  h->ctx = c;
+  Dist* D = h->dist = new Dist();
+  D->rank = rank;
+  D->world = world;
+  if (const char* ev = getenv("FSGPU_PEER_TIMEOUT_MS")) D->timeout_ns = (unsigned long long)atoll(ev) * 1000000ull;
+  int rc = FSGPU_OK;
+  auto body = [&]() -> int {
+    if (c->stream == 0) {  // kernels that wait for peers must not sit on the legacy default stream
+      FS_CUDA(cudaStreamCreateWithFlags(&D->own_stream, cudaStreamNonBlocking));
+      FS_CUDA(cudaStreamSynchronize(0));
+      c->stream = D->own_stream;
+    }
+    cudaStream_t st = c->stream;
+    // owner rank of every local column (-1: own)
+    std::vector<signed char> owner((size_t)nfl);
+    for (int64_t k = 0; k < nfl; ++k) {
+      if (k >= row_lo && k < row_hi) {
+        owner[k] = -1;
+        continue;
+      }
+      const int64_t g = loc2glob ? loc2glob[k] - 1 : k;
+      const int p = (int)(std::upper_bound(bounds, bounds + world + 1, g) - bounds) - 1;
+      FS_REQUIRE(p >= 0 && p < world && p != rank, FSGPU_ERR_ARG, "local row %lld (global %lld) has no owner rank", (long long)k,
+                 (long long)g);
+      owner[k] = (signed char)p;
+    }
+    // CSR of the local matrix, own rows sliced out
+    DBuf<int32_t> rp, cv;
+    DBuf<double> vv;
+    FS_TRY(csc_to_csr(c, c->colptr.p, c->rowval.p, c->nzval.p, c->rrows, c->rcols, c->rnnz, rp, cv, vv));
+    int32_t ends[2];
+    FS_CUDA(cudaMemcpy(&ends[0], rp.p + row_lo, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    FS_CUDA(cudaMemcpy(&ends[1], rp.p + row_hi, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const int64_t nnz = (int64_t)ends[1] - ends[0];
+    h->n = n_own;
+    h->row0 = bounds[rank];
+    h->nnz = nnz;
+    h->dt = dt;
+    h->c_scale = c_scale;
+    FS_TRY(h->rowptr.ensure((size_t)n_own + 1));
+    FS_TRY(h->colval.ensure((size_t)nnz + 1));
+    FS_TRY(h->val.ensure((size_t)nnz + 1));
+    FS_TRY(h->M.ensure((size_t)n_own + 1));
+    XL(h, k_shift_i32, n_own + 1, rp.p + row_lo, h->rowptr.p, ends[0], n_own + 1);
+    FS_CUDA(cudaMemcpyAsync(h->colval.p, cv.p + ends[0], (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    FS_CUDA(cudaMemcpyAsync(h->val.p, vv.p + ends[0], (size_t)nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    FS_CUDA(cudaMemcpyAsync(h->M.p, c->vec.p + row_lo, (size_t)n_own * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // which foreign columns the own rows reference, and which ranks every own row couples to
+    DBuf<signed char> d_owner;
+    DBuf<unsigned char> d_used;
+    DBuf<uint32_t> d_mask;
+    FS_TRY(d_owner.ensure((size_t)nfl));
+    FS_TRY(d_used.ensure((size_t)nfl));
+    FS_TRY(d_mask.ensure((size_t)n_own));
+    FS_TRY(upload(c, d_owner.p, owner.data(), (size_t)nfl));
+    FS_CUDA(cudaMemsetAsync(d_used.p, 0, (size_t)nfl, st));
+    XL(h, k_dist_scan, n_own * LPR, h->rowptr.p, h->colval.p, d_owner.p, n_own, d_used.p, d_mask.p);
+    std::vector<unsigned char> used((size_t)nfl);
+    std::vector<uint32_t> mask((size_t)n_own);
+    FS_CUDA(cudaMemcpyAsync(used.data(), d_used.p, (size_t)nfl, cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaMemcpyAsync(mask.data(), d_mask.p, (size_t)n_own * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaStreamSynchronize(st));
+    // halo layout: [own | pad to 16 doubles | entries of rank 0's rows, ascending | rank 1's | ...]
+    D->n_own = n_own;
+    D->halo0 = (n_own + 15) / 16 * 16;
+    for (int64_t k = 0; k < nfl; ++k)
+      if (used[k]) D->halo_cnt[(int)owner[k]]++;
+    int64_t run = D->halo0;
+    for (int p = 0; p < world; ++p) {
+      D->halo_base[p] = run;
+      run += D->halo_cnt[p];
+    }
+    D->n_halo = run - D->halo0;
+    D->ext = (run + 31) / 32 * 32;
+    {
+      std::vector<int32_t> colmap((size_t)nfl, -1);
+      int64_t next[kMaxWorld];
+      for (int p = 0; p < world; ++p) next[p] = D->halo_base[p];
+      for (int64_t k = 0; k < nfl; ++k) {
+        if (owner[k] < 0)
+          colmap[k] = (int32_t)(k - row_lo);
+        else if (used[k])
+          colmap[k] = (int32_t)next[(int)owner[k]]++;
+      }
+      DBuf<int32_t> d_map;
+      FS_TRY(d_map.ensure((size_t)nfl));
+      FS_TRY(upload(c, d_map.p, colmap.data(), (size_t)nfl * sizeof(int32_t)));
+      XL(h, k_remap, nnz, h->colval.p, d_map.p, nnz);
+      FS_CUDA(cudaStreamSynchronize(st));
+    }
+    // send lists: own rows a peer's rows reference (= the peer's halo entries of this rank, by the symmetry of the
+    // pattern; the counts are cross-checked at connect), ascending
+    for (int p = 0; p < world; ++p) {
+      if (p == rank) continue;
+      for (int64_t r = 0; r < n_own; ++r)
+        if (mask[r] >> p & 1u) {
+          D->push_src.push_back((int32_t)r);
+          D->push_rank.push_back(p);
+          D->send_cnt[p]++;
+        }
+      if (D->send_cnt[p] > 0 || D->halo_cnt[p] > 0) {
+        FS_REQUIRE(D->npeers < kMaxPeers, FSGPU_ERR_ARG, "more than %d neighbouring ranks", kMaxPeers);
+        D->peer_rank[D->npeers++] = p;
+      }
+    }
+    D->n_push = (int)D->push_src.size();
+    D->push_peer.resize(D->push_src.size());
+    for (size_t i = 0; i < D->push_src.size(); ++i)
+      for (int k = 0; k < D->npeers; ++k)
+        if (D->peer_rank[k] == D->push_rank[i]) D->push_peer[i] = k;
+    // the window
+    D->win_bytes = kCtrlBytes + (size_t)kNVec * (size_t)D->ext * sizeof(double);
+    FS_CUDA(cudaMalloc((void**)&D->win, D->win_bytes));
+    FS_CUDA(cudaMemsetAsync(D->win, 0, D->win_bytes, st));
+    D->ctrl[rank] = D->win;
+    D->peer_ext[rank] = D->ext;
+    FS_TRY(D->done.ensure(1));
+    FS_TRY(D->err.ensure(1));
+    FS_TRY(D->red.ensure(2 * kRedN));
+    FS_CUDA(cudaMemsetAsync(D->done.p, 0, sizeof(unsigned int), st));
+    FS_CUDA(cudaMemsetAsync(D->err.p, 0, sizeof(int), st));
+    FS_TRY(D->d_push_src.ensure((size_t)D->n_push + 1));
+    FS_TRY(D->d_push_dst.ensure((size_t)D->n_push + 1));
+    FS_TRY(D->d_push_peer.ensure((size_t)D->n_push + 1));
+    FS_TRY(upload(c, D->d_push_src.p, D->push_src.data(), (size_t)D->n_push * sizeof(int32_t)));
+    FS_TRY(upload(c, D->d_push_peer.p, D->push_peer.data(), (size_t)D->n_push * sizeof(int32_t)));
+    FS_CUDA(cudaStreamSynchronize(st));
+    FS_TRY(alloc_vectors(h));
+    // runs that read halo entries go first (CTAs [0, nb_ctas) of the fused step)
+    {
+      std::vector<int32_t> runs((size_t)h->nruns + 1), order;
+      FS_CUDA(cudaMemcpy(runs.data(), h->runs.p, ((size_t)h->nruns + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      order.reserve((size_t)h->nruns);
+      std::vector<int32_t> inner;
+      inner.reserve((size_t)h->nruns);
+      for (int64_t k = 0; k < h->nruns; ++k) {
+        uint32_t m = 0;
+        for (int32_t r = runs[k]; r < runs[k + 1]; ++r) m |= mask[r];
+        (m ? order : inner).push_back((int32_t)k);
+      }
+      D->n_bruns = (int64_t)order.size();
+      D->nb_ctas = (int)((D->n_bruns * LPR + 255) / 256);
+      order.insert(order.end(), inner.begin(), inner.end());
+      FS_TRY(D->order.ensure((size_t)h->nruns + 1));
+      FS_TRY(upload(c, D->order.p, order.data(), (size_t)h->nruns * sizeof(int32_t)));
+      FS_CUDA(cudaStreamSynchronize(st));
+    }
+    // CUDA loads kernels lazily, and loading may need the device idle: a first launch issued while a peer rank of
+    // the same process spins on this device would never return.  Load everything the collective calls launch now.
+    {
+      cudaFuncAttributes fa;
+      const void* fns[] = {(const void*)k_dist_barrier, (const void*)k_dist_push, (const void*)k_dist_wait,
+                           (const void*)k_dist_allreduce, (const void*)k_spmv_step<true>, (const void*)k_spmv_step<false>,
+                           (const void*)k_spmv, (const void*)k_update_u, (const void*)k_start, (const void*)k_div,
+                           (const void*)k_scale, (const void*)k_fill_start, (const void*)k_wdot, (const void*)k_setup_damping,
+                           (const void*)k_finish_step};
+      for (const void* fn : fns) FS_CUDA(cudaFuncGetAttributes(&fa, fn));
+    }
+    FS_TRY(h->Y.ensure((size_t)n_own + 1));  // no allocation inside the collective calls either
+    FS_TRY(c->flag.ensure(8));
+    if (world == 1) D->connected = true;
+    return FSGPU_OK;
+  };
+  rc = body();
+  if (rc != FSGPU_OK) {
+    dist_release(h);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_explicit_export(fsgpu_explicit* h, void* blob) {
+  FS_REQUIRE(h && blob, FSGPU_ERR_ARG, "null argument");
+  FS_REQUIRE(h->dist, FSGPU_ERR_STATE, "not a row-partitioned run (fsgpu_explicit_create_dist)");
+  FS_TRY(check_ctx(h->ctx));
+  Dist* D = h->dist;
+  FS_CUDA(cudaStreamSynchronize(h->ctx->stream));  // the window is zeroed before anybody can map it
+  DistBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = kBlobMagic;
+  b.rank = D->rank;
+  b.world = D->world;
+  b.pid = (int64_t)getpid();
+  b.proc_token = process_token();
+  b.device = h->ctx->device;
+  b.devptr = (uint64_t)(uintptr_t)D->win;
+  b.win_bytes = D->win_bytes;
+  b.n_own = D->n_own;
+  b.ext = D->ext;
+  // the handle is only opened by OTHER processes; inside one process the pointer is used as it is
+  cudaError_t e = cudaIpcGetMemHandle(&b.ipc, D->win);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    memset(&b.ipc, 0, sizeof b.ipc);
+  }
+  for (int p = 0; p < D->world; ++p) {
+    b.halo_base[p] = D->halo_base[p];
+    b.halo_cnt[p] = D->halo_cnt[p];
+  }
+  memset(blob, 0, FSGPU_EXPLICIT_BLOB_BYTES);
+  memcpy(blob, &b, sizeof b);
+  return FSGPU_OK;
+}
+
+extern "C" int fsgpu_explicit_connect(fsgpu_explicit* h, const void* blobs) {
+  FS_REQUIRE(h && blobs, FSGPU_ERR_ARG, "null argument");
+  FS_REQUIRE(h->dist, FSGPU_ERR_STATE, "not a row-partitioned run (fsgpu_explicit_create_dist)");
+  FS_TRY(check_ctx(h->ctx));
+  Dist* D = h->dist;
+  FS_REQUIRE(!D->connected || D->world == 1, FSGPU_ERR_STATE, "already connected");
+  std::vector<int32_t> dst((size_t)D->n_push);
+  for (int p = 0; p < D->world; ++p) {
+    DistBlob b;
+    memcpy(&b, (const unsigned char*)blobs + (size_t)p * FSGPU_EXPLICIT_BLOB_BYTES, sizeof b);
+    FS_REQUIRE(b.magic == kBlobMagic && b.rank == p && b.world == D->world, FSGPU_ERR_ARG,
+               "blob %d is not the export of rank %d of %d", p, p, D->world);
+    D->peer_ext[p] = b.ext;
+    if (p == D->rank) continue;
+    FS_REQUIRE(b.halo_cnt[D->rank] == D->send_cnt[p], FSGPU_ERR_ARG,
+               "rank %d expects %lld halo entries of rank %d, which would send %lld: the matrix pattern is not symmetric "
+               "or the ranks disagree about the row bounds",
+               p, (long long)b.halo_cnt[D->rank], D->rank, (long long)D->send_cnt[p]);
+    if (b.proc_token == process_token() && b.pid == (int64_t)getpid()) {
+      D->ctrl[p] = (unsigned char*)(uintptr_t)b.devptr;
+      if (b.device != h->ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FS_CUDA(e);
+        cudaGetLastError();
+      }
+    } else {
+      void* q = nullptr;
+      FS_CUDA(cudaIpcOpenMemHandle(&q, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+      D->ctrl[p] = (unsigned char*)q;
+      D->ipc_opened[p] = true;
+    }
+  }
+  // destination of every pushed entry: the peer's halo segment of this rank's rows, same (ascending) order
+  {
+    int64_t pos[kMaxWorld] = {};
+    for (int i = 0; i < D->n_push; ++i) {
+      const int p = D->push_rank[i];
+      DistBlob b;
+      memcpy(&b, (const unsigned char*)blobs + (size_t)p * FSGPU_EXPLICIT_BLOB_BYTES, sizeof b);
+      dst[i] = (int32_t)(b.halo_base[D->rank] + pos[p]++);
+    }
+    FS_TRY(upload(h->ctx, D->d_push_dst.p, dst.data(), (size_t)D->n_push * sizeof(int32_t)));
+    FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  }
+  D->connected = true;
+  // every rank has mapped every window before anybody pushes
+  FS_TRY(dist_barrier(h));
+  FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return dist_check(h);
+}
+
+extern "C" int fsgpu_explicit_dist_info(fsgpu_explicit* h, int64_t* n_own, int64_t* n_halo, int64_t* n_push,
+                                        int64_t* boundary_runs, int32_t* npeers) {
+  FS_REQUIRE(h && h->dist, FSGPU_ERR_STATE, "not a row-partitioned run");
+  if (n_own) *n_own = h->dist->n_own;
+  if (n_halo) *n_halo = h->dist->n_halo;
+  if (n_push) *n_push = h->dist->n_push;
+  if (boundary_runs) *boundary_runs = h->dist->n_bruns;
+  if (npeers) *npeers = h->dist->npeers;
   return FSGPU_OK;
 }
 
@@ -396,8 +1027,19 @@ extern "C" int fsgpu_explicit_set_state(fsgpu_explicit* h, const double* U0, con
   FS_TRY(check_ctx(h->ctx));
   const size_t b = (size_t)h->n * sizeof(double);
   h->u_ahead = false;
-  if (U0) FS_TRY(upload(h->ctx, h->U.p, U0, b));
+  if (U0) FS_TRY(upload(h->ctx, h->Uc, U0, b));
   if (V0) FS_TRY(upload(h->ctx, h->V.p, V0, b));
+  FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_explicit_set_timestep(fsgpu_explicit* h, double c_scale, double dt) {
+  FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
+  FS_TRY(check_ctx(h->ctx));
+  FS_REQUIRE(dt >= 0.0, FSGPU_ERR_ARG, "negative time step");
+  h->dt = dt;
+  h->c_scale = c_scale;
+  h->u_ahead = false;  // the displacements written ahead were formed with the old step
+  XL(h, k_setup_damping, h->n, h->M.p, h->c_scale, h->dt, h->C.p, h->invMC.p, h->n);
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
   return FSGPU_OK;
 }
@@ -419,45 +1061,71 @@ extern "C" int fsgpu_explicit_start(fsgpu_explicit* h, double fscale0) {
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
   return FSGPU_OK;
 }
+namespace {
+void swap_u(fsgpu_explicit* h) {
+  std::swap(h->Uc, h->Unx);
+  if (h->dist) h->dist->cur ^= 1;
+}
+}  // namespace
 extern "C" int fsgpu_explicit_step(fsgpu_explicit* h, int64_t nsteps, const double* fscale) {
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
+  FS_TRY(dist_require(h));
   const double dt = h->dt;
-  FS_TRY(h->Un.ensure((size_t)h->n + 1));
+  Dist* D = h->dist;
+  if (!D) {
+    FS_TRY(h->Un.ensure((size_t)h->n + 1));
+    if (!h->Unx) h->Unx = h->Un.p;
+  }
   for (int64_t s = 0; s < nsteps; ++s) {
     if (h->u_ahead) {
-      std::swap(h->U.p, h->Un.p);
-      std::swap(h->U.n, h->Un.n);
+      swap_u(h);
     } else {
-      XL(h, k_update_u, h->n, h->U.p, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
+      XL(h, k_update_u, h->n, h->Uc, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
+      if (D) FS_TRY(dist_sync_halo(h, D->cur));
     }
-    XL(h, k_spmv_step, h->nruns * LPR, h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, h->U.p,
-       h->have_load ? h->F0.p : nullptr, fscale ? fscale[s] : 1.0, h->C.p, h->invMC.p, h->V.p, h->A.p, h->E.p, dt / 2, dt,
-       (dt * dt) / 2, h->Un.p);
+    const double fs_ = fscale ? fscale[s] : 1.0;
+    if (D) {
+      // waits for the halo entries announced by step flag `epoch`, pushes the next displacements with flag epoch + 1
+      const DistDev dd = dist_dev(h, D->cur ^ 1);
+      k_spmv_step<true><<<grid_for(h->nruns * LPR, 256), 256, 0, h->ctx->stream>>>(
+          h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, h->Uc, h->have_load ? h->F0.p : nullptr, fs_, h->C.p,
+          h->invMC.p, h->V.p, h->A.p, h->E.p, dt / 2, dt, (dt * dt) / 2, h->Unx, dd);
+      h->ctx->launches++;
+      if (D->world > 1) D->epoch++;
+    } else {
+      DistDev dd;
+      memset(&dd, 0, sizeof dd);
+      XL(h, k_spmv_step<false>, h->nruns * LPR, h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, h->Uc,
+         h->have_load ? h->F0.p : nullptr, fs_, h->C.p, h->invMC.p, h->V.p, h->A.p, h->E.p, dt / 2, dt, (dt * dt) / 2, h->Unx,
+         dd);
+    }
     h->u_ahead = true;
   }
   FS_CUDA(cudaGetLastError());
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  if (D) FS_TRY(dist_check(h));
   return FSGPU_OK;
 }
 extern "C" int fsgpu_explicit_step_begin(fsgpu_explicit* h) {
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
+  FS_REQUIRE(!h->dist, FSGPU_ERR_STATE, "row-partitioned runs exchange inside fsgpu_explicit_step");
   const double dt = h->dt;
   if (h->u_ahead) {
-    std::swap(h->U.p, h->Un.p);
-    std::swap(h->U.n, h->Un.n);
+    swap_u(h);
     h->u_ahead = false;
   } else {
-    XL(h, k_update_u, h->n, h->U.p, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
+    XL(h, k_update_u, h->n, h->Uc, h->V.p, h->A.p, dt, (dt * dt) / 2, h->n);
   }
-  XL(h, k_spmv, h->nruns * LPR, h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, h->U.p, h->E.p);
+  XL(h, k_spmv, h->nruns * LPR, h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, h->Uc, h->E.p);
   FS_CUDA(cudaGetLastError());
   return FSGPU_OK;  // asynchronous: the host's exchange is enqueued on the same stream
 }
 extern "C" int fsgpu_explicit_step_end(fsgpu_explicit* h, double fscale) {
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
+  FS_REQUIRE(!h->dist, FSGPU_ERR_STATE, "row-partitioned runs exchange inside fsgpu_explicit_step");
   XL(h, k_finish_step, h->n, h->E.p, h->have_load ? h->F0.p : nullptr, fscale, h->C.p, h->invMC.p, h->V.p, h->A.p,
      h->dt / 2, h->n);
   FS_CUDA(cudaGetLastError());
@@ -467,7 +1135,7 @@ extern "C" int fsgpu_explicit_get_state(fsgpu_explicit* h, double* U, double* V,
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
   const size_t b = (size_t)h->n * sizeof(double);
-  if (U) FS_TRY(download(h->ctx, U, h->U.p, b));
+  if (U) FS_TRY(download(h->ctx, U, h->Uc, b));
   if (V) FS_TRY(download(h->ctx, V, h->V.p, b));
   if (A) FS_TRY(download(h->ctx, A, h->A.p, b));
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
@@ -475,40 +1143,66 @@ extern "C" int fsgpu_explicit_get_state(fsgpu_explicit* h, double* U, double* V,
 }
 extern "C" int fsgpu_explicit_device_state(fsgpu_explicit* h, double** U, double** V, double** A, double** E) {
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
-  if (U) *U = h->U.p;
+  // U is the CURRENT displacement buffer: fsgpu_explicit_step / _step_begin alternate between two buffers, so the
+  // pointer must be asked for again after every call that advances the state
+  if (U) *U = h->Uc;
   if (V) *V = h->V.p;
   if (A) *A = h->A.p;
   if (E) *E = h->E.p;
   return FSGPU_OK;
 }
+namespace {
+// y = K x with x in the device vector xv (own entries); row-partitioned: xv is window vector 2, halo entries fetched first
+int spmv_any(fsgpu_explicit* h, double* xv, double* y) {
+  if (h->dist) FS_TRY(dist_sync_halo(h, 2));
+  XL(h, k_spmv, h->nruns * LPR, h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, xv, y);
+  return FSGPU_OK;
+}
+}  // namespace
 extern "C" int fsgpu_explicit_spmv(fsgpu_explicit* h, const double* x, double* y) {
   FS_REQUIRE(h && x && y, FSGPU_ERR_ARG, "null argument");
   FS_TRY(check_ctx(h->ctx));
-  FS_TRY(h->X.ensure((size_t)h->n + 1));
+  FS_TRY(dist_require(h));
+  double* xv;
+  if (h->dist) {
+    xv = h->dist->vec(h->dist->rank, 2);
+  } else {
+    FS_TRY(h->X.ensure((size_t)h->n + 1));
+    xv = h->X.p;
+  }
   FS_TRY(h->Y.ensure((size_t)h->n + 1));
-  FS_TRY(upload(h->ctx, h->X.p, x, (size_t)h->n * sizeof(double)));
-  XL(h, k_spmv, h->nruns * LPR, h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, h->X.p, h->Y.p);
+  FS_TRY(upload(h->ctx, xv, x, (size_t)h->n * sizeof(double)));
+  FS_TRY(spmv_any(h, xv, h->Y.p));
   FS_TRY(download(h->ctx, y, h->Y.p, (size_t)h->n * sizeof(double)));
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  if (h->dist) FS_TRY(dist_check(h));
   return FSGPU_OK;
 }
 extern "C" int fsgpu_explicit_omega_max(fsgpu_explicit* h, int32_t maxit, double* lambda_max) {
   FS_REQUIRE(h && lambda_max, FSGPU_ERR_ARG, "null argument");
   FS_TRY(check_ctx(h->ctx));
-  FS_TRY(h->X.ensure((size_t)h->n + 1));
+  FS_TRY(dist_require(h));
+  double* xv;
+  if (h->dist) {
+    xv = h->dist->vec(h->dist->rank, 2);
+  } else {
+    FS_TRY(h->X.ensure((size_t)h->n + 1));
+    xv = h->X.p;
+  }
   FS_TRY(h->Y.ensure((size_t)h->n + 1));
-  XL(h, k_fill_start, h->n, h->X.p, h->n);
+  // start vector: a function of the GLOBAL row, so a partitioned run iterates on the same vector
+  XL(h, k_fill_start, h->n, xv, h->n, h->dist ? h->row0 : 0);
   double lam = 0.0;
   for (int it = 0; it < maxit; ++it) {
     // y = M^-1 K x ; lambda = (x' M y) / (x' M x) ; x = y / |y|
-    XL(h, k_spmv, h->nruns * LPR, h->runs.p, h->nruns, h->rowptr.p, h->colval.p, h->val.p, h->X.p, h->Y.p);
+    FS_TRY(spmv_any(h, xv, h->Y.p));
     XL(h, k_div, h->n, h->Y.p, h->M.p, h->Y.p, h->n);
     double xmy, xmx, yy;
-    FS_TRY(wdot(h, h->X.p, h->Y.p, h->M.p, &xmy));
-    FS_TRY(wdot(h, h->X.p, h->X.p, h->M.p, &xmx));
+    FS_TRY(wdot(h, xv, h->Y.p, h->M.p, &xmy));
+    FS_TRY(wdot(h, xv, xv, h->M.p, &xmx));
     FS_TRY(wdot(h, h->Y.p, h->Y.p, nullptr, &yy));
     lam = xmy / xmx;
-    XL(h, k_scale, h->n, h->X.p, h->Y.p, 1.0 / sqrt(yy), h->n);
+    XL(h, k_scale, h->n, xv, h->Y.p, 1.0 / sqrt(yy), h->n);
   }
   *lambda_max = lam;
   return FSGPU_OK;
@@ -516,6 +1210,7 @@ extern "C" int fsgpu_explicit_omega_max(fsgpu_explicit* h, int32_t maxit, double
 extern "C" int fsgpu_explicit_kinetic_energy(fsgpu_explicit* h, double* ke) {
   FS_REQUIRE(h && ke, FSGPU_ERR_ARG, "null argument");
   FS_TRY(check_ctx(h->ctx));
+  FS_TRY(dist_require(h));
   double s;
   FS_TRY(wdot(h, h->V.p, h->V.p, h->M.p, &s));
   *ke = 0.5 * s;

@@ -37,9 +37,15 @@ class NodalField:
         self.is_fixed = np.zeros(self.values.shape, dtype=bool)
         self.dofnums = np.zeros(self.values.shape, dtype=np.int64, order="F")
         self._nfree = 0
+        self._version = 0  # bumped by every call that edits the field in place: the FEMMs' upload caches key on it
+
+    def touch(self):
+        """Call after editing `values` / `dofnums` in place by hand: operators then re-upload this field."""
+        self._version = getattr(self, "_version", 0) + 1
 
     def setebc(self, nodes, comp):
         self.is_fixed[np.asarray(nodes, dtype=np.int64), comp - 1] = True
+        self.touch()
 
     def numberdofs(self, perm=None):
         nn, nd = self.is_fixed.shape
@@ -50,6 +56,7 @@ class NodalField:
         nums[free] = np.arange(1, self._nfree + 1)
         nums[~free] = np.arange(self._nfree + 1, nn * nd + 1)
         self.dofnums[order] = nums.reshape(nn, nd)
+        self.touch()
         return self
 
 
@@ -278,13 +285,26 @@ class _FEMMBase:
         self.ctx = Context(device)
         self._associatedgeometry = False
         self._mesh_key = None
+        self._conn_key = None
         self._dof_key = None
         self._sym_key = None
 
     # upload mesh / dofs once per distinct array (the Julia glue keys on objectid)
+    @staticmethod
+    def _field_key(f, arr):
+        # identity of the object (held strongly, so the id cannot be recycled), its edit counter, and the buffer the
+        # device copy was made from: numberdofs!/setebc! on the same field, or a swapped array, invalidate the copy
+        return (f, getattr(f, "_version", 0), None if arr is None else (arr.__array_interface__["data"][0], arr.shape))
+
+    @staticmethod
+    def _same_key(a, b):
+        return a is not None and b is not None and a[0] is b[0] and a[1:] == b[1:]
+
     def _sync_mesh(self, geom0):
-        key = (id(geom0), id(self.integdomain.conn))
-        if self._mesh_key != key:
+        conn_obj = self.integdomain.conn
+        key = self._field_key(geom0, np.asarray(geom0.values))
+        if not (self._same_key(self._mesh_key, key) and self._conn_key is conn_obj):
+            self._conn_key = conn_obj
             conn = np.asarray(self.integdomain.conn)
             if conn.shape[1] != self._nnpe:
                 raise FsgpuError(L.ERR_ARG, f"element set has {conn.shape[1]} nodes per element, expected {self._nnpe}")
@@ -302,18 +322,17 @@ class _FEMMBase:
         self._mesh_key = self._dof_key = self._sym_key = None
 
     def _sync_dofs(self, dchi):
-        key = id(dchi)
-        if self._dof_key != key:
+        key = self._field_key(dchi, np.asarray(dchi.dofnums)) + (nfreedofs(dchi),)
+        if not self._same_key(self._dof_key, key):
             self.ctx.set_dofnums(dchi.dofnums, nfreedofs(dchi), nalldofs(dchi))
             self._dof_key = key
             self._sym_key = None
 
     def _startassembly(self, assembler, dchi):
         self._sync_dofs(dchi)
-        key = (self._dof_key, assembler.target)
-        if self._sym_key != key:
+        if self._sym_key != assembler.target:  # reset to None whenever the mesh or the dofs are re-uploaded
             self.ctx.symbolic(assembler.target)
-            self._sym_key = key
+            self._sym_key = assembler.target
 
 
 class _FEMMShell(_FEMMBase):

@@ -270,3 +270,57 @@ def gather_vector(local_vec, plan, device, group=None):
         for wk in dist.batch_isend_irecv(ops):
             wk.wait()
     return out
+
+
+# ---- row-partitioned explicit loop (fsgpu_explicit_create_dist) -----------------------------------
+#
+# The exchange itself lives in the library (peer-mapped windows written by the step kernel); the host only
+# carries the opaque address blobs between the ranks once.
+
+
+def connect_ranks(ex, group=None):
+    """All-gather the export blobs of a row-partitioned `Explicit` over torch.distributed (any backend) and
+    connect: one process per GPU."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.from_numpy(ex.export()).to(dev)
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine, group=group)
+    ex.connect([b.cpu().numpy() for b in allb])
+
+
+def connect_local(exs):
+    """Contexts of ONE process (several GPUs, or several partitions on one GPU in the tests): every collective call
+    -- connect included -- must be issued concurrently, one host thread per rank."""
+    blobs = [e.export() for e in exs]
+    run_collective([lambda e=e: e.connect(blobs) for e in exs])
+
+
+def run_collective(calls):
+    """Run one callable per rank concurrently (ctypes releases the GIL during library calls); returns their results."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=len(calls)) as pool:
+        futs = [pool.submit(c) for c in calls]
+        errs = [(r, f.exception()) for r, f in enumerate(futs)]
+        errs = [(r, e) for r, e in errs if e is not None]
+        if errs:  # a rank that fails makes its peers time out: report every rank's own error
+            raise RuntimeError("; ".join(f"rank {r}: {e!r}" for r, e in errs)) from errs[0][1]
+        return [f.result() for f in futs]
+
+
+def rcm_permutation(conn, nnodes):
+    """Reverse Cuthill-McKee node order of the mesh graph (`symrcm` of plate_expl_examples.jl:119-121): the
+    permutation handed to `numberdofs!` so that contiguous dof ranges are compact strips of the mesh."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+
+    c = np.asarray(conn, dtype=np.int64) - 1
+    nn = c.shape[1]
+    i = np.repeat(c, nn, axis=1).ravel()
+    j = np.tile(c, (1, nn)).ravel()
+    g = sp.csr_matrix((np.ones(i.size, dtype=np.int8), (i, j)), shape=(nnodes, nnodes))
+    return np.asarray(reverse_cuthill_mckee(g, symmetric_mode=True), dtype=np.int64)

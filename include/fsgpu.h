@@ -247,6 +247,9 @@ int fsgpu_explicit_create_from_ctx(fsgpu_explicit** h, fsgpu_ctx* ctx, double c_
 int fsgpu_explicit_layout(fsgpu_explicit* h, int64_t* nrows, int64_t* nnz, int64_t* nruns, int64_t* index_entries);
 int fsgpu_explicit_destroy(fsgpu_explicit* h);
 int fsgpu_explicit_set_state(fsgpu_explicit* h, const double* U0, const double* V0);
+/* new time step / damping factor after the handle was created (dt = 0.9 * 2/omega_max * ... is only known after
+ * fsgpu_explicit_omega_max, examples/.../spherical_cap_expl_examples.jl:166-173): C and invMC are rebuilt */
+int fsgpu_explicit_set_timestep(fsgpu_explicit* h, double c_scale, double dt);
 /* constant load vector F0 scaled by a per-step factor table (force!(F,t) closures of the
  * examples are constant or windowed sines): F(t_k) = fscale[k] * F0; fscale NULL -> 1 */
 int fsgpu_explicit_set_load(fsgpu_explicit* h, const double* F0);
@@ -262,12 +265,47 @@ int fsgpu_explicit_spmv(fsgpu_explicit* h, const double* x, double* y);
 int fsgpu_explicit_omega_max(fsgpu_explicit* h, int32_t maxit, double* lambda_max);
 /* kinetic energy 1/2 V' M V (peek closures) */
 int fsgpu_explicit_kinetic_energy(fsgpu_explicit* h, double* ke);
-/* multi-GPU: device pointers of U, V, A, F-scratch for halo exchange by the host's NCCL plumbing */
+/* multi-GPU: device pointers of U, V, A, F-scratch for halo exchange by the host's NCCL plumbing.  U is the CURRENT
+ * displacement buffer: _step / _step_begin alternate between two buffers, ask again after every advancing call. */
 int fsgpu_explicit_device_state(fsgpu_explicit* h, double** U, double** V, double** A, double** E);
 /* split step for element-partitioned runs: (1) U update + E = K_local U, (2) after the host has
  * summed interface entries of E across ranks: finish the step */
 int fsgpu_explicit_step_begin(fsgpu_explicit* h);
 int fsgpu_explicit_step_end(fsgpu_explicit* h, double fscale);
+
+
+/* ---- row-partitioned explicit loop: ONE global mesh, one rank (process or context) per GPU ------------
+ * SURVEY section 8(e); loop: examples/shells/dynamics/homogeneous/explicit/plate_expl_examples.jl:61-94 with the
+ * node numbering of :119-121,147 (any numbering works; a banded one keeps the interfaces short).
+ * Rank r owns the contiguous global rows [bounds[r], bounds[r+1]) (0-based) of K_ff, M and of all state vectors.
+ * Its context has assembled, on a LOCAL mesh that contains every element touching a node with an owned row
+ * (interface elements are assembled by both neighbours, no partial sums are exchanged), the FFBLOCK stiffness and
+ * the nfree_only lumped-mass vector; local rows are numbered by an order-preserving map, loc2glob[k] = global 1-based
+ * row of local row k (NULL: identity), and the own rows are the local rows [row_lo, row_hi).
+ * Columns of other ranks become HALO entries of the displacement vector.  All peer-visible state of a rank lives in
+ * one device allocation (the window) that the other ranks map -- cudaIpc across processes, the plain pointer for
+ * contexts of one process -- and the fused step kernel writes the boundary entries of the next displacements
+ * straight into the neighbours' windows over NVLink and raises a flag there; the neighbours' boundary rows wait
+ * for that flag, their interior rows do not.  No host round trip, no NCCL call, no separate exchange launch per step.
+ *
+ * Bootstrap (like an NCCL unique id, but all-to-all): every rank calls _export, the host all-gathers the blobs
+ * (MPI.Allgather, torch.distributed.all_gather, a shared file ...) in rank order and hands them to _connect.
+ * After that the fsgpu_explicit_* calls below (set_state, set_load, start, step, get_state, spmv, omega_max,
+ * kinetic_energy, destroy) are COLLECTIVE: every rank calls them in the same order; vectors are the rank's own
+ * rows.  omega_max and kinetic_energy return the global value on every rank (partial sums are combined in rank
+ * order: identical bits everywhere).  A wait for a peer gives up after FSGPU_PEER_TIMEOUT_MS (default 20 000)
+ * and the call returns FSGPU_ERR_STATE instead of hanging.  If the context still uses the legacy default
+ * stream the handle gives it a private non-blocking one (kernels that wait for peers must not serialise with
+ * other work of the process). */
+#define FSGPU_EXPLICIT_BLOB_BYTES 1024
+int fsgpu_explicit_create_dist(fsgpu_explicit** h, fsgpu_ctx* ctx, int32_t rank, int32_t world, int64_t row_lo,
+                               int64_t row_hi, const int64_t* loc2glob, const int64_t* bounds, double c_scale, double dt);
+int fsgpu_explicit_export(fsgpu_explicit* h, void* blob /* FSGPU_EXPLICIT_BLOB_BYTES */);
+int fsgpu_explicit_connect(fsgpu_explicit* h, const void* blobs /* world x FSGPU_EXPLICIT_BLOB_BYTES, rank order */);
+/* partition facts (measurement support): own rows, halo entries, entries pushed per step, row runs that read halo
+ * entries (they are scheduled first), neighbouring ranks */
+int fsgpu_explicit_dist_info(fsgpu_explicit* h, int64_t* n_own, int64_t* n_halo, int64_t* n_push, int64_t* boundary_runs,
+                             int32_t* npeers);
 
 #ifdef __cplusplus
 }

@@ -31,3 +31,16 @@ def test_two_gpu_gathered_assembly_matches_single_gpu():
            "--master-port", "29537", os.path.join(root, "tests", "mgpu_gather_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_two_gpu_row_partitioned_explicit_matches_single_gpu():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (the single-GPU form of this check is tests/test_gpu_dist_explicit.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tests", "mgpu_dist_explicit_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
