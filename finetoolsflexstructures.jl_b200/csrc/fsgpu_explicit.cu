@@ -44,15 +44,18 @@ struct fsgpu_explicit {
 // displacement vector, HALO entries (the columns its rows reference in other ranks' blocks).  All peer-visible
 // state lives in one device allocation per rank, the WINDOW, which the other ranks map (cudaIpc across
 // processes, the plain pointer inside one process) and write directly over NVLink:
-//   [0, kCtrlBytes)   control words (uint64): step flags [sender rank], barrier flags, reduction flags,
-//                     reduction values double[2][kMaxWorld][kRedN] at byte kRedOff
+//   [0, kCtrlBytes)   control words (uint64): step flags [sender rank], barrier flags, reduction flags (one 128 B
+//                     line each), reduction values double[2][kMaxWorld][kRedN] at byte kRedOff
 //   then kNVec vectors of `ext` doubles: displacement buffers 0 / 1 and the power-iteration vector, each
 //                     [own rows | padding to a 128 B line | halo entries grouped by owner rank, ascending]
 constexpr int kMaxWorld = 32;
 constexpr int kMaxPeers = 16;
-constexpr size_t kCtrlBytes = 16384;
-constexpr int kFlagStep = 0, kFlagBar = 64, kFlagRed = 128;  // uint64 word offsets
-constexpr size_t kRedOff = 4096;
+constexpr size_t kCtrlBytes = 32768;
+// uint64 word offsets of the three flag arrays; the flag of sender rank p is word base + p * kFlagStride: every
+// flag has its own 128 B line (one writer -- the sender --, one polling reader)
+constexpr int kFlagStride = 16;
+constexpr int kFlagStep = 0, kFlagBar = kMaxWorld * kFlagStride, kFlagRed = 2 * kMaxWorld * kFlagStride;
+constexpr size_t kRedOff = 16384;
 constexpr int kRedN = 8;
 constexpr int kNVec = 3;
 constexpr uint64_t kBlobMagic = 0x46534750555f5631ull;  // "FSGPU_V1"
@@ -92,6 +95,10 @@ struct Dist {
   fs::DBuf<unsigned int> done;
   fs::DBuf<int> err;
   fs::DBuf<double> red;  // [2 * kRedN] allreduce in / out
+  // pinned host scratch for the few bytes the collective calls read back (reduction results, error flag): a copy
+  // to PAGEABLE memory queued behind a kernel that waits for a peer holds driver-internal staging resources, and a
+  // pageable copy of another rank of the same process then blocks behind it -- the peer never launches, deadlock
+  double* hpin = nullptr;
   int n_push = 0, nb_ctas = 0;
   int64_t n_bruns = 0;
   unsigned long long epoch = 0, bar_epoch = 0, red_epoch = 0;
@@ -146,8 +153,18 @@ __device__ __noinline__ bool spin_until(const unsigned long long* p, unsigned lo
   }
   return true;
 }
-__device__ __forceinline__ unsigned long long* ctrl_word(const DistDev& d, int rank, int word) {
-  return reinterpret_cast<unsigned long long*>(d.ctrl[rank]) + word;
+// flag `base` (kFlagStep / kFlagBar / kFlagRed) of sender `from` in the window of rank `rank`
+__device__ __forceinline__ unsigned long long* ctrl_flag(const DistDev& d, int rank, int base, int from) {
+  return reinterpret_cast<unsigned long long*>(d.ctrl[rank]) + base + from * kFlagStride;
+}
+// one thread waits for the flags of a list of senders, one after the other (no divergent spinning inside a warp)
+__device__ __forceinline__ void wait_flags(const DistDev& d, int base, const int* senders, int n, bool all_ranks,
+                                           unsigned long long target) {
+  for (int k = 0; k < n; ++k) {
+    const int from = all_ranks ? k : senders[k];
+    if (from == d.me) continue;
+    if (!spin_until(ctrl_flag(d, d.me, base, from), target, d.timeout_ns, d.err)) return;
+  }
 }
 
 __global__ void k_setup_damping(const double* __restrict__ M, double c_scale, double dt, double* __restrict__ C,
@@ -273,8 +290,7 @@ __global__ void k_spmv_step(const int32_t* __restrict__ runs, int64_t nruns, con
   int64_t run = ok ? slot : nruns - 1;
   if (DIST) {
     if ((int)blockIdx.x < d.nb_ctas) {
-      if ((int)threadIdx.x < d.npeers)
-        spin_until(ctrl_word(d, d.me, kFlagStep + d.peer_rank[threadIdx.x]), d.wait_epoch, d.timeout_ns, d.err);
+      if (threadIdx.x == 0) wait_flags(d, kFlagStep, d.peer_rank, d.npeers, false, d.wait_epoch);
       __syncthreads();
     }
     run = d.order[run];
@@ -316,7 +332,7 @@ __global__ void k_spmv_step(const int32_t* __restrict__ runs, int64_t nruns, con
         __threadfence_system();
         __syncthreads();
         if ((int)threadIdx.x < d.npeers)
-          st_release_sys(ctrl_word(d, d.peer_rank[threadIdx.x], kFlagStep + d.me), d.wait_epoch + 1);
+          st_release_sys(ctrl_flag(d, d.peer_rank[threadIdx.x], kFlagStep, d.me), d.wait_epoch + 1);
         if (threadIdx.x == 0) *d.done = 0u;
       }
     }
@@ -327,21 +343,21 @@ __global__ void k_dist_barrier(const DistDev d, unsigned long long value) {
   const int t = threadIdx.x;
   if (t < d.world && t != d.me) {
     __threadfence_system();
-    st_release_sys(ctrl_word(d, t, kFlagBar + d.me), value);
-    spin_until(ctrl_word(d, d.me, kFlagBar + t), value, d.timeout_ns, d.err);
+    st_release_sys(ctrl_flag(d, t, kFlagBar, d.me), value);
   }
+  __syncthreads();
+  if (t == 0) wait_flags(d, kFlagBar, nullptr, d.world, true, value);
 }
 // boundary entries of `vec` (own rows) into the halo entries of the peers' vectors, then the step flag
 __global__ void k_dist_push(const DistDev d, const double* __restrict__ vec, unsigned long long value) {
   for (int i = threadIdx.x; i < d.n_push; i += blockDim.x) d.peer_vec[d.push_peer[i]][d.push_dst[i]] = vec[d.push_src[i]];
   __threadfence_system();
   __syncthreads();
-  if ((int)threadIdx.x < d.npeers) st_release_sys(ctrl_word(d, d.peer_rank[threadIdx.x], kFlagStep + d.me), value);
+  if ((int)threadIdx.x < d.npeers) st_release_sys(ctrl_flag(d, d.peer_rank[threadIdx.x], kFlagStep, d.me), value);
 }
 // the halo entries announced by step flag d.wait_epoch have arrived
 __global__ void k_dist_wait(const DistDev d) {
-  if ((int)threadIdx.x < d.npeers)
-    spin_until(ctrl_word(d, d.me, kFlagStep + d.peer_rank[threadIdx.x]), d.wait_epoch, d.timeout_ns, d.err);
+  if (threadIdx.x == 0) wait_flags(d, kFlagStep, d.peer_rank, d.npeers, false, d.wait_epoch);
 }
 // io[0..nv) <- sum (op 0) or max (op 1) over all ranks, summed in rank order: identical bits on every rank
 __global__ void k_dist_allreduce(const DistDev d, double* __restrict__ io, int nv, unsigned long long r, int op) {
@@ -351,11 +367,10 @@ __global__ void k_dist_allreduce(const DistDev d, double* __restrict__ io, int n
     double* dst = reinterpret_cast<double*>(d.ctrl[t] + kRedOff) + ((size_t)slot * kMaxWorld + d.me) * kRedN;
     for (int k = 0; k < nv; ++k) dst[k] = io[k];
     __threadfence_system();
-    if (t != d.me) {
-      st_release_sys(ctrl_word(d, t, kFlagRed + d.me), r);
-      spin_until(ctrl_word(d, d.me, kFlagRed + t), r, d.timeout_ns, d.err);
-    }
+    if (t != d.me) st_release_sys(ctrl_flag(d, t, kFlagRed, d.me), r);
   }
+  __syncthreads();
+  if (t == 0) wait_flags(d, kFlagRed, nullptr, d.world, true, r);
   __syncthreads();
   if (t < nv) {
     const volatile double* src = reinterpret_cast<const volatile double*>(d.ctrl[d.me] + kRedOff) + (size_t)slot * kMaxWorld * kRedN;
@@ -455,11 +470,21 @@ DistDev dist_dev(const fsgpu_explicit* h, int push_vec) {
   d.err = D->err.p;
   return d;
 }
-int dist_check(fsgpu_explicit* h) {  // after a stream synchronisation
+int dist_check(fsgpu_explicit* h) {  // synchronises the stream
   Dist* D = h->dist;
-  int e = 0;
-  FS_CUDA(cudaMemcpy(&e, D->err.p, sizeof(int), cudaMemcpyDeviceToHost));
-  if (e) {
+  int* eh = reinterpret_cast<int*>(D->hpin + 16);
+  FS_CUDA(cudaMemcpyAsync(eh, D->err.p, sizeof(int), cudaMemcpyDeviceToHost, h->ctx->stream));
+  FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  if (*eh) {
+    if (getenv("FSGPU_DIST_TRACE")) {
+      static unsigned long long w[3 * kMaxWorld * kFlagStride];
+      cudaMemcpy(w, D->win, sizeof w, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[fsgpu rank %d] timeout: epoch %llu bar %llu red %llu |", D->rank, D->epoch, D->bar_epoch, D->red_epoch);
+      for (int p = 0; p < D->world; ++p)
+        fprintf(stderr, " from %d: step %llu bar %llu red %llu;", p, w[kFlagStep + p * kFlagStride], w[kFlagBar + p * kFlagStride],
+                w[kFlagRed + p * kFlagStride]);
+      fprintf(stderr, "\n");
+    }
     cudaMemsetAsync(D->err.p, 0, sizeof(int), h->ctx->stream);
     cudaStreamSynchronize(h->ctx->stream);
     set_error("rank %d: waiting for a peer rank timed out (%.1f s): ranks out of step, or a peer has gone", D->rank,
@@ -494,17 +519,14 @@ int dist_sync_halo(fsgpu_explicit* h, int b) {
   FS_CUDA(cudaGetLastError());
   return FSGPU_OK;
 }
-// vals[0..nv) <- sum / max over all ranks (host values; synchronous)
-int dist_allreduce(fsgpu_explicit* h, double* vals, int nv, int op) {
+// dev[0..nv) <- sum / max over all ranks, in place on device memory (asynchronous on this rank's stream)
+int dist_allreduce_dev(fsgpu_explicit* h, double* dev, int nv, int op) {
   Dist* D = h->dist;
   if (D->world == 1) return FSGPU_OK;
-  cudaStream_t st = h->ctx->stream;
-  FS_CUDA(cudaMemcpyAsync(D->red.p, vals, nv * sizeof(double), cudaMemcpyHostToDevice, st));
-  k_dist_allreduce<<<1, kMaxWorld, 0, st>>>(dist_dev(h, -1), D->red.p, nv, ++D->red_epoch, op);
+  k_dist_allreduce<<<1, kMaxWorld, 0, h->ctx->stream>>>(dist_dev(h, -1), dev, nv, ++D->red_epoch, op);
   h->ctx->launches++;
-  FS_CUDA(cudaMemcpyAsync(vals, D->red.p, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
-  FS_CUDA(cudaStreamSynchronize(st));
-  return dist_check(h);
+  FS_CUDA(cudaGetLastError());
+  return FSGPU_OK;
 }
 
 int wdot(fsgpu_explicit* h, const double* a, const double* b, const double* w, double* result) {
@@ -516,9 +538,15 @@ int wdot(fsgpu_explicit* h, const double* a, const double* b, const double* w, d
     k_wdot<<<592, 256, 0, c->stream>>>(a, b, w, h->n, acc);
     c->launches++;
   }
+  if (h->dist) {
+    FS_TRY(dist_allreduce_dev(h, acc, 1, 0));  // partial sums of the row blocks, combined in rank order
+    FS_CUDA(cudaMemcpyAsync(h->dist->hpin, acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FS_TRY(dist_check(h));
+    *result = h->dist->hpin[0];
+    return FSGPU_OK;
+  }
   FS_CUDA(cudaMemcpyAsync(result, acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   FS_CUDA(cudaStreamSynchronize(c->stream));
-  if (h->dist) FS_TRY(dist_allreduce(h, result, 1, 0));  // partial sums of the row blocks
   return FSGPU_OK;
 }
 
@@ -666,6 +694,7 @@ void dist_release(fsgpu_explicit* h) {
   for (int p = 0; p < D->world; ++p)
     if (D->ipc_opened[p] && D->ctrl[p]) cudaIpcCloseMemHandle(D->ctrl[p]);
   if (D->win) cudaFree(D->win);
+  if (D->hpin) cudaFreeHost(D->hpin);
   if (D->own_stream) {
     if (h->ctx->stream == D->own_stream) h->ctx->stream = 0;
     cudaStreamDestroy(D->own_stream);
@@ -873,6 +902,7 @@ extern "C" int fsgpu_explicit_create_dist(fsgpu_explicit** out, fsgpu_ctx* c, in
     FS_TRY(D->done.ensure(1));
     FS_TRY(D->err.ensure(1));
     FS_TRY(D->red.ensure(2 * kRedN));
+    FS_CUDA(cudaHostAlloc((void**)&D->hpin, 32 * sizeof(double), cudaHostAllocDefault));
     FS_CUDA(cudaMemsetAsync(D->done.p, 0, sizeof(unsigned int), st));
     FS_CUDA(cudaMemsetAsync(D->err.p, 0, sizeof(int), st));
     FS_TRY(D->d_push_src.ensure((size_t)D->n_push + 1));
@@ -1027,6 +1057,7 @@ extern "C" int fsgpu_explicit_set_state(fsgpu_explicit* h, const double* U0, con
   FS_TRY(check_ctx(h->ctx));
   const size_t b = (size_t)h->n * sizeof(double);
   h->u_ahead = false;
+  if (h->dist) FS_CUDA(cudaStreamSynchronize(h->ctx->stream));  // pageable copies only on an idle stream (see Dist::hpin)
   if (U0) FS_TRY(upload(h->ctx, h->Uc, U0, b));
   if (V0) FS_TRY(upload(h->ctx, h->V.p, V0, b));
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
@@ -1047,6 +1078,7 @@ extern "C" int fsgpu_explicit_set_load(fsgpu_explicit* h, const double* F0) {
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
   if (F0) {
+    if (h->dist) FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
     FS_TRY(upload(h->ctx, h->F0.p, F0, (size_t)h->n * sizeof(double)));
     FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
   }
@@ -1135,6 +1167,7 @@ extern "C" int fsgpu_explicit_get_state(fsgpu_explicit* h, double* U, double* V,
   FS_REQUIRE(h, FSGPU_ERR_ARG, "null handle");
   FS_TRY(check_ctx(h->ctx));
   const size_t b = (size_t)h->n * sizeof(double);
+  if (h->dist) FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
   if (U) FS_TRY(download(h->ctx, U, h->Uc, b));
   if (V) FS_TRY(download(h->ctx, V, h->V.p, b));
   if (A) FS_TRY(download(h->ctx, A, h->A.p, b));
@@ -1171,11 +1204,13 @@ extern "C" int fsgpu_explicit_spmv(fsgpu_explicit* h, const double* x, double* y
     xv = h->X.p;
   }
   FS_TRY(h->Y.ensure((size_t)h->n + 1));
+  if (h->dist) FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
   FS_TRY(upload(h->ctx, xv, x, (size_t)h->n * sizeof(double)));
+  if (h->dist) FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
   FS_TRY(spmv_any(h, xv, h->Y.p));
+  if (h->dist) FS_TRY(dist_check(h));  // the kernels that wait for peers are done before the pageable copy is queued
   FS_TRY(download(h->ctx, y, h->Y.p, (size_t)h->n * sizeof(double)));
   FS_CUDA(cudaStreamSynchronize(h->ctx->stream));
-  if (h->dist) FS_TRY(dist_check(h));
   return FSGPU_OK;
 }
 extern "C" int fsgpu_explicit_omega_max(fsgpu_explicit* h, int32_t maxit, double* lambda_max) {
