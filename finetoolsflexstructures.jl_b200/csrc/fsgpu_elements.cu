@@ -243,6 +243,58 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
         if (cb[c] >= 0 FS_RED_GUARD) atomicAdd(nz + cb[c] + rp, v[c]);
     }
   }
+  // ---- Q4 (DMMA kernel): the element matrix K_e (24 x 24, row stride kQ4KLd) is staged in shared memory by the
+  // product stage; the addressing data is kept per NODE (ncol[8][8]: the nodecol rows of the warp's 2 x 4 nodes) and per
+  // block (pr[32][2]: run offsets oA, oB of block (bi, bj)), fetched with cp.async while the setup / product stages run
+  static constexpr int kQ4KLd = 26;
+  __device__ __forceinline__ void q4_async_addr(int* ncol, int* pr, int lane, bool on, int nown, int64_t e, int bi, int bj) const {
+    const int l16 = lane & 15;
+    if (on) {
+      if (l16 < 4) {
+        const unsigned dc = (unsigned)__cvta_generic_to_shared(ncol + ((lane >> 4) * 4 + l16) * 8);
+        const int32_t* sc = nodecol + (int64_t)nown * 8;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dc), "l"(sc) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dc + 16), "l"(sc + 4) : "memory");
+      }
+      const unsigned dr = (unsigned)__cvta_generic_to_shared(pr + lane * 2);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr), "l"(pairoff + ((int64_t)(bi * 2 + 0) * nelem + e) * nnpe + bj)
+                   : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr + 4),
+                   "l"(pairoff + ((int64_t)(bi * 2 + 1) * nelem + e) * nnpe + bj)
+                   : "memory");
+    } else {
+      if (l16 < 4) {
+        int* c = ncol + ((lane >> 4) * 4 + l16) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = k < 6 ? -1 : 0;
+      }
+      pr[lane * 2] = pr[lane * 2 + 1] = -1;
+    }
+  }
+  // lane = (block sub-index, row): six consecutive lanes add six consecutive rows of one column; the six values of a
+  // row of a block are three 16-byte reads of the staged matrix
+  __device__ __forceinline__ void q4_emit_k(const double* k0, int kel, const int* ncol, const int* pr, int lane) const {
+    const int sub = lane / 6, r = lane - sub * 6;
+#pragma unroll 1
+    for (int g = 0; g < 7; ++g) {
+      const int o = g * 5 + sub;
+      if (lane >= 30 || o >= 32) continue;
+      const int h = o >> 4, bi = (o >> 2) & 3, bj = o & 3;
+      const int2 oab = *reinterpret_cast<const int2*>(pr + o * 2);
+      const int rp = row_pos(ncol[(h * 4 + bi) * 8 + 6], oab.x, oab.y, r);
+      if (rp < 0) continue;
+      const int4 c0 = *reinterpret_cast<const int4*>(ncol + (h * 4 + bj) * 8);
+      const int2 c1 = *reinterpret_cast<const int2*>(ncol + (h * 4 + bj) * 8 + 4);
+      const double2* kv = reinterpret_cast<const double2*>(k0 + h * kel + (6 * bi + r) * kQ4KLd + 6 * bj);
+      const double2 v0 = kv[0], v1 = kv[1], v2 = kv[2];
+      if (c0.x >= 0 FS_RED_GUARD) atomicAdd(nz + c0.x + rp, v0.x);
+      if (c0.y >= 0 FS_RED_GUARD) atomicAdd(nz + c0.y + rp, v0.y);
+      if (c0.z >= 0 FS_RED_GUARD) atomicAdd(nz + c0.z + rp, v1.x);
+      if (c0.w >= 0 FS_RED_GUARD) atomicAdd(nz + c0.w + rp, v1.y);
+      if (c1.x >= 0 FS_RED_GUARD) atomicAdd(nz + c1.x + rp, v2.x);
+      if (c1.y >= 0 FS_RED_GUARD) atomicAdd(nz + c1.y + rp, v2.y);
+    }
+  }
   __device__ __forceinline__ Cols cols(int nj) const {
     Cols c;
     const int32_t* dj = dof + (int64_t)nj * 6;
@@ -707,6 +759,28 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
 // =====================================================================================
 // Q4RS / Q4RSComp stiffness
 // =====================================================================================
+// Layout of the strips S (one row per generalised strain and integration point, 24 global dofs per row) in shared
+// memory, chosen for the DMMA product K_e = S' S:
+//   row base = 24 * row + 4 * (row >> 1)  (832 doubles per element and chunk of 4 points), so that
+//   * the m8n8k4 fragment loads (lane l reads S[4q + l%4][8I + l/4]) are conflict-free: the four rows of a k-step
+//     start at 0, 8, 4, 12 (mod 16 doubles);
+//   * the setup pass's 16-byte stores are conflict-free: lanes of odd integration points write their rows pairwise
+//     swapped (s ^ 1), which moves them by 8 doubles (mod 16) against the even points -- the product sums over all
+//     rows, their order is free.
+constexpr int Q4S_EL = 832;
+__host__ __device__ constexpr int q4s_rowoff(int s) { return 24 * s + 4 * (s >> 1); }  // rows of one point: 208 doubles
+struct Q4Row {
+  double* base;  // element strips + 208 * g4 + 6 * jn
+  int od;        // 24 for odd points
+  __device__ __forceinline__ double* operator()(int s) const { return base + q4s_rowoff(s) + ((s & 1) ? -od : od); }
+};
+__device__ __forceinline__ void q4_store_row(double* d, const double (&v)[6]) {
+  double2* d2 = reinterpret_cast<double2*>(d);
+  d2[0] = make_double2(v[0], v[1]);
+  d2[1] = make_double2(v[2], v[3]);
+  d2[2] = make_double2(v[4], v[5]);
+}
+
 // One setup pass: lane (g4, jn) builds the folded strip of node jn at integration point gp
 // (own triad / own shear entries only; the coupling matrices are summed over the four lanes of
 // the same point by a shuffle butterfly) and stores it in the half-warp's shared tile.
@@ -714,6 +788,7 @@ template <bool COMP>
 __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64_t e, int gp, int g4, int jn, const V3 (&X)[4],
                                               const double4& nvown, double hq, const double* gd, double* sb_) {
   const unsigned full = 0xffffffffu;
+  const Q4Row row{sb_ + 208 * g4 + 6 * jn, (g4 & 1) * 24};
   double p1[5][3], p2[5][3], bs[2][3];
   Q4Geom g;
   M3 A;
@@ -761,23 +836,27 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
         const double d = constit_d(C, s);
         if (d < 0.0) atomicExch(P.flag + 2, 1);
         const double q = fs_sqrt(d);
+        double v[6];
 #pragma unroll
-        for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = q * bg[s][cc];
+        for (int cc = 0; cc < 6; ++cc) v[cc] = q * bg[s][cc];
+        q4_store_row(row(s), v);
       }
     } else {
       const double t = P.nthick == 1 ? __ldg(P.thick) : (P.nthick == P.nelem ? __ldg(P.thick + e) : __ldg(P.thick + e * npts + gp));
       const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * hq * hq);
       // rows are pre-scaled by sqrt(d_s): sqrt(c) * sqrt(dps) with sqrt(dps), sqrt(dts) from the host
       const double qm = fs_sqrt(t * jw), qb = fs_sqrt((t * t * t * (1.0 / 12.0)) * jw), qs = fs_sqrt(t * stab * jw);
-      double* dst = sb_ + (g4 * 8) * 24 + jn * 6;
       {
         double m[3][6];
         strip_membrane(g.E, gx, gy, m);
         fold3(P.hf, m);
 #pragma unroll
-        for (int s = 0; s < 3; ++s)
+        for (int s = 0; s < 3; ++s) {
+          double v[6];
 #pragma unroll
-          for (int cc = 0; cc < 6; ++cc) dst[s * 24 + cc] = (qm * P.hf.sdps[s]) * m[s][cc];
+          for (int cc = 0; cc < 6; ++cc) v[cc] = (qm * P.hf.sdps[s]) * m[s][cc];
+          q4_store_row(row(s), v);
+        }
       }
       const M3 G = global_to_nodal(A, g.E);
       double R[2][2], brn[5][2];
@@ -789,61 +868,76 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
         for (int r = 0; r < 3; ++r) strip_row(g.E, G, brn, gx, gy, 0.0, p1, p2, r, m[r]);
         fold3(P.hf, m);
 #pragma unroll
-        for (int s = 0; s < 3; ++s)
+        for (int s = 0; s < 3; ++s) {
+          double v[6];
 #pragma unroll
-          for (int cc = 0; cc < 6; ++cc) dst[(3 + s) * 24 + cc] = (qb * P.hf.sdps[s]) * m[s][cc];
+          for (int cc = 0; cc < 6; ++cc) v[cc] = (qb * P.hf.sdps[s]) * m[s][cc];
+          q4_store_row(row(3 + s), v);
+        }
       }
       {
-        double r6[6], r7[6];
+        double r6[6], r7[6], v6[6], v7[6];
         strip_row(g.E, G, brn, gx, gy, bs[0][0], p1, p2, 3, r6);
         strip_row(g.E, G, brn, gx, gy, bs[1][0], p1, p2, 4, r7);
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) {
-          dst[6 * 24 + cc] = (qs * P.hf.sdts[0]) * (r6[cc] + P.hf.Lt * r7[cc]);
-          dst[7 * 24 + cc] = (qs * P.hf.sdts[1]) * r7[cc];
+          v6[cc] = (qs * P.hf.sdts[0]) * (r6[cc] + P.hf.Lt * r7[cc]);
+          v7[cc] = (qs * P.hf.sdts[1]) * r7[cc];
         }
+        q4_store_row(row(6), v6);
+        q4_store_row(row(7), v7);
       }
     }
   } else {
+    const double z[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int s = 0; s < 8; ++s)
-#pragma unroll
-      for (int cc = 0; cc < 6; ++cc) sb_[(g4 * 8 + s) * 24 + jn * 6 + cc] = 0.0;
+    for (int s = 0; s < 8; ++s) q4_store_row(row(s), z);
   }
 }
 
-// Product pass over the 32 strain rows of one chunk.  Homogeneous shells: the membrane rows
-// (0..2 of every point) have no rotation columns in global dofs, so they only touch the
-// translation 3x3 sub-block (9 instead of 36 FMAs per row); laminates with B-coupling are dense.
-template <bool COMP>
-__device__ __forceinline__ void q4_product_pass(const double* sb_, int bi, int bj, double (&acc)[6][6]) {
-#pragma unroll 2
-  for (int g = 0; g < 4; ++g) {
+// K_e += S' S on the FP64 tensor-core path (DMMA.8x8x4, the same peak as DFMA on B200 but one instruction per 256 FMA
+// and two fragment registers per operand: profiles/r02_dmma_microbench.txt).  The whole warp works on its two
+// elements: per k-step of 4 strain rows three fragment loads (column blocks 0..7, 8..15, 16..23; the A fragment of
+// block I is the B fragment of block I) and the six upper tiles (0,0) (0,1) (0,2) (1,1) (1,2) (2,2).
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void q4_mma_product(const double* wbase, int lane, double (&acc)[2][6][2]) {
+  const int t = lane & 3;
+  const double* p = wbase + 24 * t + 4 * (t >> 1) + (lane >> 2);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int s = g * 8 + q;
-      if (!COMP && q < 3) {
-        double vi[3], vj[3];
+  for (int q = 0; q < 8; ++q) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r) vi[r] = sb_[s * 24 + bi * 6 + r];
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) vj[cc] = sb_[s * 24 + bj * 6 + cc];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
-      } else {
-        double vi[6], vj[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) vi[r] = sb_[s * 24 + bi * 6 + r];
-#pragma unroll
-        for (int cc = 0; cc < 6; ++cc) vj[cc] = sb_[s * 24 + bj * 6 + cc];
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 6; ++cc) acc[r][cc] = fma(vi[r], vj[cc], acc[r][cc]);
-      }
+    for (int h = 0; h < 2; ++h) {
+      const double* ph = p + h * Q4S_EL + 104 * q;
+      const double f0 = ph[0], f1 = ph[8], f2 = ph[16];
+      dmma884(acc[h][0], f0, f0);
+      dmma884(acc[h][1], f0, f1);
+      dmma884(acc[h][2], f0, f2);
+      dmma884(acc[h][3], f1, f1);
+      dmma884(acc[h][4], f1, f2);
+      dmma884(acc[h][5], f2, f2);
     }
+  }
+}
+// accumulator fragments -> the full symmetric K_e (24 x 24, row stride kQ4KLd) over the element's dead strips.  Lane l
+// holds K[8I + l/4][8J + 2 (l%4) + {0, 1}] of tile (I, J); off-diagonal tiles are mirrored.
+__device__ __forceinline__ void q4_stage_k(double* wbase, int lane, const double (&acc)[2][6][2]) {
+  constexpr int LD = EmitRuns::kQ4KLd;
+  const int t = lane & 3, g = lane >> 2;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    double* K = wbase + h * Q4S_EL;
+#pragma unroll
+    for (int ti = 0, k = 0; ti < 3; ++ti)
+#pragma unroll
+      for (int tj = ti; tj < 3; ++tj, ++k) {
+        *reinterpret_cast<double2*>(K + (8 * ti + g) * LD + 8 * tj + 2 * t) = make_double2(acc[h][k][0], acc[h][k][1]);
+        if (ti != tj) {
+          K[(8 * tj + 2 * t) * LD + 8 * ti + g] = acc[h][k][0];
+          K[(8 * tj + 2 * t + 1) * LD + 8 * ti + g] = acc[h][k][1];
+        }
+      }
   }
 }
 
@@ -856,29 +950,30 @@ __device__ __forceinline__ void q4_async_normal(const ShellArgs& P, double* slot
   }
 }
 
-constexpr int Q4_WARP_DBL = 2 * 32 * 24 + (32 * 8 + 32 * 4) / 2 + 8 * 4;  // strips + addressing area + 8 nodal normals (doubles)
+// per warp: strips of its two elements (later their staged matrices) + node addressing ncol[8][8] + block run offsets
+// pr[32][2] (ints) + 8 nodal normals
+constexpr int Q4_WARP_DBL = 2 * Q4S_EL + 32 + 32 + 8 * 4;
 
-// CHUNKED = false: rules with <= 4 points (GaussRule(2,2)), one setup + one product pass.  CHUNKED = true: any
-// rule, chunks of 4 points with the accumulators carried through the setup passes.  Two kernels rather than
-// two branches of one: the second copy of setup + product doubled the code and the instruction-cache misses.
+// Stages: (1) setup, roles (integration point g4, node jn) per half-warp: strips into shared memory; (2) product on the
+// DMMA path, whole warp, both elements; rules with more than 4 points repeat (1)-(2) in chunks of 4 points with the
+// accumulators carried; (3) accumulators -> staged K_e; (4) drilling stiffness on the staged matrix (lanes 0..3 of each
+// half-warp = the element's nodes); (5) emission from the staged matrix.
 template <bool COMP, bool CHUNKED, class Emit>
 __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, Emit emit) {
-  // per warp: strips b[32][24] of its two elements (one per half-warp) + the addressing area of the
-  // cooperative emission (EmitRuns::kAddrInts ints)
   extern __shared__ double smem[];
-  constexpr int HW_DBL = 32 * 24;
   constexpr int WARP_DBL = Q4_WARP_DBL;
+  constexpr int LD = EmitRuns::kQ4KLd;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int half = lane >> 4, l16 = lane & 15;
   double* wbase = smem + (size_t)wib * WARP_DBL;
-  double* sb_ = wbase + half * HW_DBL;
-  int* addr = reinterpret_cast<int*>(wbase + 2 * HW_DBL);
-  // the nodal normal the drilling step of a diagonal-block lane needs arrives here (cp.async) during the product loop
-  double* nslot = wbase + 2 * HW_DBL + (32 * 8 + 32 * 4) / 2 + (half * 4 + ((lane & 15) >> 2)) * 4;
+  double* sb_ = wbase + half * Q4S_EL;
+  int* ncol = reinterpret_cast<int*>(wbase + 2 * Q4S_EL);
+  int* pr = ncol + 64;
+  double* nslot = wbase + 2 * Q4S_EL + 64 + (half * 4 + (l16 & 3)) * 4;  // normal of node (l16 & 3) of this half's element
   const int64_t e = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wib) * 2 + half;
   const bool active = e < P.nelem;
   const int g4 = l16 >> 2, jn = l16 & 3;  // setup role
-  const int bi = l16 >> 2, bj = l16 & 3;  // product role
+  const int bi = l16 >> 2, bj = l16 & 3;  // block role (addressing, non-cooperative emitters)
   const unsigned full = 0xffffffffu;
 
   V3 X[4];
@@ -907,54 +1002,47 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   const int nbj = bj == 0 ? nn[0] : (bj == 1 ? nn[1] : (bj == 2 ? nn[2] : nn[3]));
   typename Emit::Cols ecols;
   typename Emit::Rows erows;
-  double acc[6][6];
+  // addressing data and the nodal normals of the drilling stage: requested first (cp.async into their own areas), the
+  // loads overlap every stage up to the emission
+  if constexpr (Emit::kCoop) {
+    emit.q4_async_addr(ncol, pr, lane, active, nbj, e, bi, bj);  // lanes l16 < 4: bj = l16, nbj = node l16
+  } else if (active) {
+    ecols = emit.cols(nbj);
+    erows = emit.rows(e, bi, bj, nbi);
+  }
+  q4_async_normal(P, nslot, active && l16 < 4, nbj);
+  double acc[2][6][2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[h][k][0] = acc[h][k][1] = 0.0;
   const int npts = P.rule.npts;
   if constexpr (!CHUNKED) {
-    // addressing data: requested first (cp.async into its own shared-memory area), so the element index is dead
-    // before the register-heavy passes and the loads overlap all of them (2.92 -> 2.84 ms on C2)
-    if constexpr (Emit::kCoop) emit.async_addr(addr, lane, active, nbj, nbi, e, bi, bj);
     q4_setup_pass<COMP>(P, active && g4 < npts, e, g4, g4, jn, X, nvown, hq, gd, sb_);
     __syncwarp();
-    if constexpr (!Emit::kCoop) {
-      if (active) {
-        ecols = emit.cols(nbj);
-        erows = emit.rows(e, bi, bj, nbi);
-      }
-    }
-    q4_async_normal(P, nslot, active && bi == bj, nbi);
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-    q4_product_pass<COMP>(sb_, bi, bj, acc);
+    q4_mma_product(wbase, lane, acc);
   } else {
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-    if constexpr (Emit::kCoop) {
-      emit.async_addr(addr, lane, active, nbj, nbi, e, bi, bj);
-    } else if (active) {
-      ecols = emit.cols(nbj);
-      erows = emit.rows(e, bi, bj, nbi);
-    }
-    q4_async_normal(P, nslot, active && bi == bj, nbi);
     for (int chunk = 0; chunk * 4 < npts; ++chunk) {
       const int gp = chunk * 4 + g4;
       q4_setup_pass<COMP>(P, active && gp < npts, e, gp, g4, jn, X, nvown, hq, gd, sb_);
       __syncwarp();
-      q4_product_pass<COMP>(sb_, bi, bj, acc);
+      q4_mma_product(wbase, lane, acc);
       __syncwarp();
     }
   }
+  __syncwarp();  // every lane is done with the strips
+  q4_stage_k(wbase, lane, acc);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
 
-  // drilling stiffness (src/FEMMShellQ4RSModule.jl:807-859): lanes (k,k) hold the rotational blocks;
-  // for those lanes the setup-role node jn equals the block node, so `nvown` is its normal
+  // drilling stiffness (src/FEMMShellQ4RSModule.jl:807-859) on the rotational diagonal blocks of the staged matrix:
+  // lane l16 = k < 4 of each half-warp handles node k
+  double* Ke = wbase + half * Q4S_EL;
   double tang = 0.0;
   int ok = 0;
   double nvec[3] = {0, 0, 0};
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  if (active && bi == bj) {
+  double* krr = Ke + (6 * (l16 & 3) + 3) * LD + 6 * (l16 & 3) + 3;
+  if (active && l16 < 4) {
     const double4 n4 = *reinterpret_cast<const double4*>(nslot);
     const double nl2 = n4.x * n4.x + n4.y * n4.y + n4.z * n4.z;
     if (n4.w != 0.0 && nl2 != 0.0) {
@@ -965,38 +1053,39 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
       const double inl = fs_rsqrt(nl2);
       const double nh[3] = {n4.x * inl, n4.y * inl, n4.z * inl};
       // tr(P Krr P) with P = I - n n' (idempotent): tr(Krr P) = tr(Krr) - n' Krr n
-      double tr = acc[3][3] + acc[4][4] + acc[5][5];
+      double tr = krr[0] + krr[LD + 1] + krr[2 * LD + 2];
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
-        tr -= nh[r] * (acc[3 + r][3] * nh[0] + acc[3 + r][4] * nh[1] + acc[3 + r][5] * nh[2]);
+      for (int r = 0; r < 3; ++r) tr -= nh[r] * (krr[r * LD] * nh[0] + krr[r * LD + 1] * nh[1] + krr[r * LD + 2] * nh[2]);
       tang = fmax(0.0, tr / 2.0);
     }
   }
-  double tsum = 0.0;
-  int cnt = 0;
-  const int hb = lane & 16;
-  for (int k = 0; k < 4; ++k) {
-    tsum += __shfl_sync(full, tang, hb + 5 * k);
-    cnt += __shfl_sync(full, ok, hb + 5 * k);
-  }
-  if (!Emit::kCoop && !active) return;
-  if (P.drill != 0.0 && cnt > 0) {
+  double tsum = tang;
+  int cnt = ok;
+  tsum += __shfl_xor_sync(full, tsum, 1);
+  cnt += __shfl_xor_sync(full, cnt, 1);
+  tsum += __shfl_xor_sync(full, tsum, 2);
+  cnt += __shfl_xor_sync(full, cnt, 2);
+  if (P.drill != 0.0 && cnt > 0 && ok) {
     const double kavg = tsum * (cnt == 4 ? 0.25 : fs_rcp((double)cnt)) * P.drill;
-    if (kavg != 0.0 && ok) {
+    if (kavg != 0.0) {
+#pragma unroll
       for (int r = 0; r < 3; ++r)
-        for (int cc = 0; cc < 3; ++cc) acc[3 + r][3 + cc] += kavg * (nvec[r] * nvec[cc]);
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) krr[r * LD + cc] += kavg * (nvec[r] * nvec[cc]);
     }
   }
+  __syncwarp();
   if constexpr (Emit::kCoop) {
-    // the strips are dead: the warp's tile becomes the staging area of the cooperative emission
-#ifdef FS_Q4_MERGE  // measured on C2: 3.33 ms against 3.20 ms without merging (12.5 % fewer RED, but the match /
-                    // leader bookkeeping and the extra staged reads cost more): off by default
-    emit.coop_emit_merged(wbase, addr, lane, active, ((unsigned long long)(unsigned)nbi << 32) | (unsigned)nbj, acc);
-#else
-    emit.coop_emit_full(wbase, addr, lane, acc);
-#endif
+    emit.q4_emit_k(wbase, Q4S_EL, ncol, pr, lane);
   } else {
-    emit.block(BlockRef{e, bi, bj}, ecols, erows, acc);
+    if (!active) return;
+    double a[6][6];
+    const double* kb = Ke + (6 * bi) * LD + 6 * bj;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) a[r][cc] = kb[r * LD + cc];
+    emit.block(BlockRef{e, bi, bj}, ecols, erows, a);
   }
 }
 
