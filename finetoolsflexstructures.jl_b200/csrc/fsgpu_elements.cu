@@ -247,41 +247,55 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   // product stage; the addressing data is kept per NODE (ncol[8][8]: the nodecol rows of the warp's 2 x 4 nodes) and per
   // block (pr[32][2]: run offsets oA, oB of block (bi, bj)), fetched with cp.async while the setup / product stages run
   static constexpr int kQ4KLd = 26;
-  __device__ __forceinline__ void q4_async_addr(int* ncol, int* pr, int lane, bool on, int nown, int64_t e, int bi, int bj) const {
+  __device__ __forceinline__ void q4_async_addr(int* ncol, int* pr, int lane, bool on, int nown, int64_t e) const {
+    // ncol: lanes l16 < 4 of each half-warp fetch the nodecol row (32 B) of their node.  pr[i*2+w][half][j]: the run
+    // offsets of the warp's two elements are 8 consecutive ints of pairoff[i][w][nelem][4] per (i, w): 16 lanes x 16 B
+    // (scattered 4-byte cp.async cost one shared-memory wavefront per lane)
     const int l16 = lane & 15;
-    if (on) {
-      if (l16 < 4) {
-        const unsigned dc = (unsigned)__cvta_generic_to_shared(ncol + ((lane >> 4) * 4 + l16) * 8);
+    if (l16 < 4) {
+      int* c = ncol + ((lane >> 4) * 4 + l16) * 8;
+      if (on) {
+        const unsigned dc = (unsigned)__cvta_generic_to_shared(c);
         const int32_t* sc = nodecol + (int64_t)nown * 8;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dc), "l"(sc) : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dc + 16), "l"(sc + 4) : "memory");
-      }
-      const unsigned dr = (unsigned)__cvta_generic_to_shared(pr + lane * 2);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr), "l"(pairoff + ((int64_t)(bi * 2 + 0) * nelem + e) * nnpe + bj)
-                   : "memory");
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr + 4),
-                   "l"(pairoff + ((int64_t)(bi * 2 + 1) * nelem + e) * nnpe + bj)
-                   : "memory");
-    } else {
-      if (l16 < 4) {
-        int* c = ncol + ((lane >> 4) * 4 + l16) * 8;
+      } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) c[k] = k < 6 ? -1 : 0;
       }
-      pr[lane * 2] = pr[lane * 2 + 1] = -1;
+    }
+    // lane -> (iw = l16 >> 1 .. , element of the pair): lanes 0..15 cover iw = 0..7 x 2 elements
+    if (lane < 16) {
+      const int iw = lane >> 1, hh = lane & 1;
+      const int64_t e0 = e - (lane >> 4);  // (lane < 16: this lane's own element is the warp's first)
+      int* d = pr + iw * 8 + hh * 4;
+      if (e0 + hh < nelem) {
+        const unsigned dr = (unsigned)__cvta_generic_to_shared(d);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dr), "l"(pairoff + ((int64_t)iw * nelem + e0 + hh) * 4) : "memory");
+      } else {
+        d[0] = d[1] = d[2] = d[3] = -1;
+      }
     }
   }
-  // lane = (block sub-index, row): six consecutive lanes add six consecutive rows of one column; the six values of a
-  // row of a block are three 16-byte reads of the staged matrix
+  // lane = (block sub-index 0..4, row 0..5): six consecutive lanes add six consecutive rows of one column; the six
+  // values of a row of a block are three 16-byte reads of the staged matrix
   __device__ __forceinline__ void q4_emit_k(const double* k0, int kel, const int* ncol, const int* pr, int lane) const {
+#ifndef FS_Q4_EMIT4  // (build flag: 4 blocks x 8 lanes per round, conflict-free reads but 48 instead of 42 RED instructions: 2.35 against 2.30 ms)
     const int sub = lane / 6, r = lane - sub * 6;
+    if (lane >= 30) return;
 #pragma unroll 1
     for (int g = 0; g < 7; ++g) {
       const int o = g * 5 + sub;
-      if (lane >= 30 || o >= 32) continue;
+      if (o >= 32) continue;
+#else
+    const int sub = lane >> 3, r = lane & 7;
+    if (r >= 6) return;
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+      const int o = g * 4 + sub;
+#endif
       const int h = o >> 4, bi = (o >> 2) & 3, bj = o & 3;
-      const int2 oab = *reinterpret_cast<const int2*>(pr + o * 2);
-      const int rp = row_pos(ncol[(h * 4 + bi) * 8 + 6], oab.x, oab.y, r);
+      const int rp = row_pos(ncol[(h * 4 + bi) * 8 + 6], pr[(bi * 2) * 8 + h * 4 + bj], pr[(bi * 2 + 1) * 8 + h * 4 + bj], r);
       if (rp < 0) continue;
       const int4 c0 = *reinterpret_cast<const int4*>(ncol + (h * 4 + bj) * 8);
       const int2 c1 = *reinterpret_cast<const int2*>(ncol + (h * 4 + bj) * 8 + 4);
@@ -314,37 +328,39 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     r.oB = __ldg(pairoff + ((int64_t)(i * 2 + 1) * nelem + e) * nnpe + j);
     return r;
   }
-  // ---- T3 path: cooperative emission with IN-WARP MERGING.  A lane (element, own node j) forms only two
-  // products: D = K_e[j, j] and X = K_e[next(j), j]; K_e[j, next(j)] = X' by symmetry.  Blocks of different elements
-  // of the warp that land on the same matrix block (same node on the diagonal; same edge, either orientation) are
-  // summed in shared memory and added once: the RED unit (266 G RED/s on B200, the scatter's bound) sees 194 instead
-  // of 324 requests per element for a strip of 5 quads.
-  //   addr area per warp: colb[32][8] = nodecol row of the own node ([6] = nodeinfo, [7] = list of group leaders);
-  //   raw[32][8] = (oA, oB) of the three targets (j,j), (next,j), (j,next); [6] = merge group mask; [7] = row node
+  // ---- T3 path: cooperative emission (optionally with IN-WARP MERGING, build flag FS_T3_MERGE).  A lane (element,
+  // own node j) forms only two products: D = K_e[j, j] and X = K_e[next(j), j]; K_e[j, next(j)] = X' by symmetry.
+  // With merging, blocks of different elements of the warp that land on the same matrix block (same node on the
+  // diagonal; same edge, either orientation) are summed in shared memory and added once (194 instead of 324 RED per
+  // element for a strip of 5 quads).
+  //   Lanes: elements 0..4 on lanes 0..14, elements 5..9 on lanes 16..30 (lanes 15, 31 idle), so that no element
+  //   straddles a half-warp: the product stage's reads of the neighbour lane's strip stay conflict-free.
+  //   addr area per warp, structure of arrays (a cp.async / read of one plane by consecutive lanes is conflict-free):
+  //   C0[32] int4 = column starts of dofs 0..3 of the own node; C1[32] int4 = (dof 4, dof 5, nodeinfo, leader list);
+  //   P[6][32] = run offsets (oA, oB) of the three targets (j,j), (next,j), (j,next); M[2][32] = merge group mask, row node
+  static constexpr int kT3C1 = 128, kT3P = 256, kT3M = 448;  // int offsets of the planes (512 ints = COOP_DBL doubles)
+  static __device__ __forceinline__ int t3_lane_j(int lane) { return (lane & 15) % 3; }
   __device__ __forceinline__ void t3_async_addr(int* addr, int lane, bool on, int nj, int64_t e, int j, int jn) const {
-    int* colb = addr + lane * 8;
-    int* raw = addr + 32 * 8 + lane * 8;
     if (on) {
-      const unsigned dc = (unsigned)__cvta_generic_to_shared(colb);
-      const unsigned dr = (unsigned)__cvta_generic_to_shared(raw);
+      const unsigned d0 = (unsigned)__cvta_generic_to_shared(addr + lane * 4);
+      const unsigned d1 = (unsigned)__cvta_generic_to_shared(addr + kT3C1 + lane * 4);
       const int32_t* sc = nodecol + (int64_t)nj * 8;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dc), "l"(sc) : "memory");
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dc + 16), "l"(sc + 4) : "memory");
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dc + 24), "l"(sc + 6) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(sc) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(sc + 4) : "memory");
+      const unsigned dp = (unsigned)__cvta_generic_to_shared(addr + kT3P + lane);
       const int ii[3] = {j, jn, j}, jj[3] = {j, j, jn};
 #pragma unroll
       for (int t = 0; t < 3; ++t)
 #pragma unroll
         for (int w = 0; w < 2; ++w)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dr + (t * 2 + w) * 4),
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dp + (t * 2 + w) * 128),
                        "l"(pairoff + ((int64_t)(ii[t] * 2 + w) * nelem + e) * 3 + jj[t])
                        : "memory");
     } else {
+      *reinterpret_cast<int4*>(addr + lane * 4) = make_int4(-1, -1, -1, -1);
+      *reinterpret_cast<int4*>(addr + kT3C1 + lane * 4) = make_int4(-1, -1, 0, 0);
 #pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        colb[k] = k < 6 ? -1 : 0;
-        raw[k] = -1;
-      }
+      for (int k = 0; k < 6; ++k) addr[kT3P + k * 32 + lane] = -1;
     }
   }
   // position (relative to the column start) of dof r of a node with run masks `inf` and run offsets oA / oB
@@ -355,14 +371,14 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     return -1;
   }
   // merge groups of the warp: lanes with equal keys; the lowest lane of a group is its leader.  Writes the group
-  // mask to raw[lane][6] and the compact leader list to colb[k][7]; returns the number of leaders.
+  // mask to M[0][lane] and the compact leader list to C1[k].w; returns the number of leaders.
   __device__ __forceinline__ int t3_groups(int* addr, int lane, bool on, unsigned long long key) const {
     const unsigned full = 0xffffffffu;
     const unsigned grp = __match_any_sync(full, on ? key : (0xffffffff00000000ull | (unsigned)lane));
     const bool leader = on && (__ffs(grp) - 1 == lane);
     const unsigned leaders = __ballot_sync(full, leader);
-    addr[32 * 8 + lane * 8 + 6] = (int)grp;
-    if (leader) addr[__popc(leaders & ((1u << lane) - 1)) * 8 + 7] = lane;
+    addr[kT3M + lane] = (int)grp;
+    if (leader) addr[kT3C1 + __popc(leaders & ((1u << lane) - 1)) * 4 + 3] = lane;
     return __popc(leaders);
   }
   // diagonal pass: `d` = upper triangle of the symmetric K_e[j, j] (row-major, r <= c); lanes with the same own node
@@ -370,7 +386,6 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   template <bool MERGE>
   __device__ __forceinline__ void t3_emit_diag(double* stage, int* addr, int lane, bool on, int nj, const double (&d)[21]) const {
     const int nlead = MERGE ? t3_groups(addr, lane, on, (unsigned long long)(unsigned)nj) : 30;
-    const int* raw = addr + 32 * 8;
     {
       double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
 #pragma unroll
@@ -384,11 +399,10 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     for (int g = 0; g * 5 < nlead; ++g) {
       const int k = g * 5 + sub;
       if (lane >= 30 || k >= nlead) continue;
-      const int o = MERGE ? addr[k * 8 + 7] : k;
-      const int4 c0 = *reinterpret_cast<const int4*>(addr + o * 8);
-      const int4 c1 = *reinterpret_cast<const int4*>(addr + o * 8 + 4);
-      const int4 r0 = *reinterpret_cast<const int4*>(raw + o * 8);
-      const int rp = row_pos(c1.z, r0.x, r0.y, r);
+      const int o = MERGE ? addr[kT3C1 + k * 4 + 3] : k + (k >= 15);  // lane that staged the block
+      const int4 c0 = *reinterpret_cast<const int4*>(addr + o * 4);
+      const int4 c1 = *reinterpret_cast<const int4*>(addr + kT3C1 + o * 4);
+      const int rp = row_pos(c1.z, addr[kT3P + o], addr[kT3P + 32 + o], r);
       if (rp < 0) continue;
       const int cb[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
       const double* sp = stage + o * kStageLd + r;
@@ -396,7 +410,7 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
 #pragma unroll
       for (int c = 0; c < 6; ++c) v[c] = sp[c * 6];
       if (MERGE) {
-        unsigned mm = (unsigned)raw[o * 8 + 6];
+        unsigned mm = (unsigned)addr[kT3M + o];
         for (mm &= mm - 1; mm; mm &= mm - 1) {
           const double* sq = stage + (__ffs(mm) - 1) * kStageLd + r;
 #pragma unroll
@@ -419,10 +433,9 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
                                                const double (&a)[6][6]) const {
     const unsigned lo = (unsigned)min(nj, nnext), hi = (unsigned)max(nj, nnext);
     __syncwarp();  // every lane is done with the strips and with the diagonal pass
-    int* raw = addr + 32 * 8;
     int nlead = 30;
     if (MERGE) {
-      raw[lane * 8 + 7] = nnext;
+      addr[kT3M + 32 + lane] = nnext;
       nlead = t3_groups(addr, lane, on, ((unsigned long long)lo << 32) | hi);
     }
     double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
@@ -436,18 +449,16 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     for (int g = 0; g * 5 < nlead; ++g) {
       const int k = g * 5 + sub;
       if (lane >= 30 || k >= nlead) continue;
-      const int o = MERGE ? addr[k * 8 + 7] : k;
-      const int eo = o / 3, jo = o - 3 * eo;
-      const int ln = 3 * eo + (jo == 2 ? 0 : jo + 1);  // lane whose own node is this block's row node
-      const int4 co0 = *reinterpret_cast<const int4*>(addr + o * 8);
-      const int4 co1 = *reinterpret_cast<const int4*>(addr + o * 8 + 4);
-      const int4 cl0 = *reinterpret_cast<const int4*>(addr + ln * 8);
-      const int4 cl1 = *reinterpret_cast<const int4*>(addr + ln * 8 + 4);
-      const int4 r0 = *reinterpret_cast<const int4*>(raw + o * 8);
-      const int4 r1 = *reinterpret_cast<const int4*>(raw + o * 8 + 4);
+      const int o = MERGE ? addr[kT3C1 + k * 4 + 3] : k + (k >= 15);
+      const int jo = t3_lane_j(o);
+      const int ln = o - jo + (jo == 2 ? 0 : jo + 1);  // lane whose own node is this block's row node
+      const int4 co0 = *reinterpret_cast<const int4*>(addr + o * 4);
+      const int4 co1 = *reinterpret_cast<const int4*>(addr + kT3C1 + o * 4);
+      const int4 cl0 = *reinterpret_cast<const int4*>(addr + ln * 4);
+      const int4 cl1 = *reinterpret_cast<const int4*>(addr + kT3C1 + ln * 4);
       // direct target (row node, own node) and transposed target (own node, row node)
-      const int rpd = row_pos(cl1.z, r0.z, r0.w, r);
-      const int rpt = row_pos(co1.z, r1.x, r1.y, r);
+      const int rpd = row_pos(cl1.z, addr[kT3P + 64 + o], addr[kT3P + 96 + o], r);
+      const int rpt = row_pos(co1.z, addr[kT3P + 128 + o], addr[kT3P + 160 + o], r);
       const double* so = stage + o * kStageLd;
       double vd[6], vt[6];  // S[r][c] and S[c][r]
 #pragma unroll
@@ -456,11 +467,11 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
         vt[c] = so[r * 6 + c];
       }
       if (MERGE) {
-        const int rowO = r1.w;
-        unsigned mm = (unsigned)r1.z;
+        const int rowO = addr[kT3M + 32 + o];
+        unsigned mm = (unsigned)addr[kT3M + o];
         for (mm &= mm - 1; mm; mm &= mm - 1) {
           const int p = __ffs(mm) - 1;
-          const bool same = raw[p * 8 + 7] == rowO;
+          const bool same = addr[kT3M + 32 + p] == rowO;
           const double* sp = stage + p * kStageLd;
 #pragma unroll
           for (int c = 0; c < 6; ++c) {
@@ -527,9 +538,10 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sw = smem + (size_t)wib * WARP_DBL;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  const int el = lane / 3, j = lane - 3 * el;
+  // elements 0..4 on lanes 0..14, elements 5..9 on lanes 16..30 (no element straddles a half-warp)
+  const int l15 = lane & 15, el = (lane >> 4) * 5 + l15 / 3, j = l15 % 3;
   const int64_t e = warp * T3_EPW + el;
-  const bool active = (lane < 3 * T3_EPW) && (e < P.nelem);
+  const bool active = (l15 < 15) && (e < P.nelem);
   const unsigned full = 0xffffffffu;
   const int base = lane - j;
 
@@ -1005,7 +1017,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   // addressing data and the nodal normals of the drilling stage: requested first (cp.async into their own areas), the
   // loads overlap every stage up to the emission
   if constexpr (Emit::kCoop) {
-    emit.q4_async_addr(ncol, pr, lane, active, nbj, e, bi, bj);  // lanes l16 < 4: bj = l16, nbj = node l16
+    emit.q4_async_addr(ncol, pr, lane, active, nbj, e);  // lanes l16 < 4: bj = l16, nbj = node l16
   } else if (active) {
     ecols = emit.cols(nbj);
     erows = emit.rows(e, bi, bj, nbi);
