@@ -26,6 +26,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_DOF_RANGE, ERR_SINGULAR = range(6)
 
 # enum fsgpu_target
 SPARSE, SPARSE_SYMM, SPARSE_DIAG, FFBLOCK, FFBLOCK_DIAG, CSR_SYMM = range(6)
+CSYS_CYLINDRICAL, CSYS_SPHERICAL, CSYS_NORMAL_AXIS = 1, 2, 3
 
 
 class ShellParams(C.Structure):
@@ -76,6 +77,8 @@ _SIGNATURES = {
     "fsgpu_set_normals": [_vp, _vp, _vp],
     "fsgpu_associategeometry": [_vp, _dbl, _vp, _i32],
     "fsgpu_associategeometry_dirs": [_vp, _dbl, _vp, _i32],
+    "fsgpu_associategeometry_csys": [_vp, _dbl, _i32, _vp, _vp, _i32],
+    "fsgpu_set_layup_csys": [_vp, _i32, _vp, _vp],
     "fsgpu_normals_accumulate": [_vp, _vp, _i32, _P(_vp)],
     "fsgpu_normals_finish": [_vp, _dbl, _vp, _P(_vp)],
     "fsgpu_get_normals": [_vp, _vp, _vp],
@@ -109,6 +112,8 @@ _SIGNATURES = {
     "fsgpu_element_vectors": [_vp, _P(BeamParams), _vp],
     "fsgpu_result_size": [_vp, _P(_i64), _P(_i64), _P(_i64)],
     "fsgpu_fetch_matrix": [_vp, _vp, _vp, _vp],
+    "fsgpu_result_size_uplo": [_vp, _i32, _P(_i64)],
+    "fsgpu_fetch_matrix_uplo": [_vp, _i32, _vp, _vp, _vp],
     "fsgpu_fetch_vector": [_vp, _vp, _i64],
     "fsgpu_result_device": [_vp, _P(_vp), _P(_vp), _P(_vp)],
     "fsgpu_vector_device": [_vp, _P(_vp), _P(_i64)],

@@ -75,6 +75,16 @@ class Context:
         d = np.ascontiguousarray(np.asarray(dirs, dtype=np.float64).reshape(self.nelem, self.nnpe, 3))
         check(lib.fsgpu_associategeometry_dirs(self._h, float(threshold_angle), ptr(d), 1 if accumulate else 0))
 
+    def associategeometry_csys(self, kind, origin, axis, threshold_angle=30.0, accumulate=False):
+        """Nodal normals from a built-in csys kind (L.CSYS_*), evaluated on the device."""
+        o = None if origin is None else f64(origin)
+        check(lib.fsgpu_associategeometry_csys(self._h, float(threshold_angle), int(kind), ptr(o), ptr(f64(axis)), 1 if accumulate else 0))
+
+    def set_layup_csys(self, kind, origin, axis):
+        """Layup csys matrices from a built-in csys kind, evaluated on the device (after set_layup)."""
+        o = None if origin is None else f64(origin)
+        check(lib.fsgpu_set_layup_csys(self._h, int(kind), ptr(o), ptr(f64(axis))))
+
     def normals_accumulate(self, fixed_dir=None, accumulate=False):
         fd = None if fixed_dir is None else f64(fixed_dir)
         p = C.c_void_p()
@@ -214,6 +224,27 @@ class Context:
             colptr, rowval, nzval = out
         check(lib.fsgpu_fetch_matrix(self._h, ptr(colptr), ptr(rowval), ptr(nzval)))
         return SparseMatrixCSC(m, n, colptr, rowval, nzval, csr=(self.target == L.CSR_SYMM))
+
+    def result_size_uplo(self, uplo):
+        nnz = C.c_int64()
+        check(lib.fsgpu_result_size_uplo(self._h, ord(uplo), C.byref(nnz)))
+        return nnz.value
+
+    def fetch_matrix_uplo(self, uplo="L", out=None):
+        """One triangle (diagonal included) of a square result, e.g. for `cholesky(Symmetric(K, :L))`:
+        half the bytes of fetch_matrix cross PCIe.  `out`: optional (colptr, rowval, nzval) arrays,
+        rowval / nzval at least result_size_uplo(uplo) long."""
+        m, n, _ = self.result_size()
+        if out is None:
+            nnz = self.result_size_uplo(uplo)
+            colptr = np.empty(n + 1, dtype=np.int64)
+            rowval = np.empty(nnz, dtype=np.int64)
+            nzval = np.empty(nnz, dtype=np.float64)
+        else:
+            colptr, rowval, nzval = out
+        check(lib.fsgpu_fetch_matrix_uplo(self._h, ord(uplo), ptr(colptr), ptr(rowval), ptr(nzval)))
+        nnz = int(colptr[n]) - 1
+        return SparseMatrixCSC(m, n, colptr, rowval[:nnz], nzval[:nnz])
 
     def result_block(self, col_lo, col_hi, row_map=None, colcount=None, rowval=None, nzval=None):
         """Columns [col_lo, col_hi) of the device-resident result as pieces of the global CSC, written into

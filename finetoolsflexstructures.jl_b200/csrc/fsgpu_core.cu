@@ -5,6 +5,7 @@
 #include <emmintrin.h>
 #endif
 
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -337,6 +338,31 @@ __device__ inline fsm::V3 ldxyz(const double4* p, int i) {
   double4 v = p[i];
   return fsm::v3(v.x, v.y, v.z);
 }
+// Built-in coordinate-system kinds (include/fsgpu.h FSGPU_CSYS_*): the reference's CSys callbacks of its examples,
+// evaluated on the device.  Columns e1, e2, e3 of the csys matrix at location X with surface normal nsurf.
+__device__ inline void csys_eval(const CsysK& k, fsm::V3 X, fsm::V3 nsurf, fsm::V3& e1, fsm::V3& e2, fsm::V3& e3) {
+  using namespace fsm;
+  const V3 a = v3(k.a[0], k.a[1], k.a[2]);
+  const V3 r = X - v3(k.o[0], k.o[1], k.o[2]);
+  if (k.kind == FSGPU_CSYS_CYLINDRICAL) {
+    // clamp_cyl_expl_examples.jl:62-68: r with its axial component removed, e2 = axis, e1 = e2 x e3
+    const V3 q = r - dot(r, a) * a;
+    e3 = (1.0 / sqrt(dot(q, q))) * q;
+    e2 = a;
+    e1 = cross(e2, e3);
+  } else if (k.kind == FSGPU_CSYS_SPHERICAL) {
+    // hemisphere_examples.jl:31-39: e3 radial, e1 = normalize(axis x e3), e2 = e3 x e1
+    e3 = (1.0 / sqrt(dot(r, r))) * r;
+    const V3 c = cross(a, e3);
+    e1 = (1.0 / sqrt(dot(c, c))) * c;
+    e2 = cross(e3, e1);
+  } else {
+    // FSGPU_CSYS_NORMAL_AXIS, pressurized_cylinder_free_examples.jl:16-23: e3 = surface normal, e2 = axis, e1 = e2 x e3
+    e3 = nsurf;
+    e2 = a;
+    e1 = cross(e2, e3);
+  }
+}
 __device__ inline fsm::V3 elem_normal_at(const double4* xyz, const int32_t* cn, int nnpe, int k, double& wgt) {
   using namespace fsm;
   if (nnpe == 3) {
@@ -352,7 +378,7 @@ __device__ inline fsm::V3 elem_normal_at(const double4* xyz, const int32_t* cn, 
 }
 __global__ void k_normals_accumulate(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe,
                                      int64_t nelem, double* __restrict__ acc /*[nnodes][3]*/, int use_fixed, double fx,
-                                     double fy, double fz, const double* __restrict__ dirs /*[nelem][nnpe][3] or null*/) {
+                                     double fy, double fz, const double* __restrict__ dirs /*[nelem][nnpe][3] or null*/, CsysK ck) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nelem * nnpe) return;
   int64_t e = i / nnpe;
@@ -362,6 +388,11 @@ __global__ void k_normals_accumulate(const int32_t* __restrict__ conn, const dou
   fsm::V3 n = elem_normal_at(xyz, cn, nnpe, k, w);
   if (use_fixed) n = fsm::v3(fx, fy, fz);
   if (dirs) n = fsm::v3(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2]);
+  if (ck.kind) {
+    fsm::V3 e1, e2, e3;
+    csys_eval(ck, ldxyz(xyz, cn[k]), n, e1, e2, e3);  // the csys evaluated AT THE NODE (`_compute_nodal_normal!`)
+    n = e3;
+  }
   double* a = acc + (int64_t)cn[k] * 3;
   atomicAdd(a + 0, w * n.x);
   atomicAdd(a + 1, w * n.y);
@@ -382,7 +413,7 @@ __global__ void k_normals_normalize(const double* __restrict__ acc, double4* __r
 }
 __global__ void k_normals_validate(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe,
                                    int64_t nelem, double4* __restrict__ nrm, double limit, int use_fixed, double fx,
-                                   double fy, double fz, int fixed_in_check, const double* __restrict__ dirs) {
+                                   double fy, double fz, int fixed_in_check, const double* __restrict__ dirs, CsysK ck) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nelem * nnpe) return;
   int64_t e = i / nnpe;
@@ -392,6 +423,11 @@ __global__ void k_normals_validate(const int32_t* __restrict__ conn, const doubl
   fsm::V3 n = elem_normal_at(xyz, cn, nnpe, k, w);
   if (use_fixed && fixed_in_check) n = fsm::v3(fx, fy, fz);
   if (dirs && fixed_in_check) n = fsm::v3(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2]);
+  if (ck.kind && fixed_in_check) {
+    fsm::V3 e1, e2, e3;
+    csys_eval(ck, ldxyz(xyz, cn[k]), n, e1, e2, e3);
+    n = e3;
+  }
   double4 nn = nrm[cn[k]];
   double nd = nn.x * n.x + nn.y * n.y + nn.z * n.z;
   if (nd < limit) nrm[cn[k]].w = 0.0;  // benign race: every writer stores 0
@@ -425,7 +461,7 @@ extern "C" int fsgpu_normals_accumulate(fsgpu_ctx* c, const double* fixed_dir, i
   }
   const int uf = fixed_dir ? 1 : 0;
   const double fx = uf ? fixed_dir[0] : 0, fy = uf ? fixed_dir[1] : 0, fz = uf ? fixed_dir[2] : 0;
-  LAUNCH(c, k_normals_accumulate, c->nelem * c->nnpe, c->conn.p, c->xyz.p, c->nnpe, c->nelem, acc, uf, fx, fy, fz, c->ndirs);
+  LAUNCH(c, k_normals_accumulate, c->nelem * c->nnpe, c->conn.p, c->xyz.p, c->nnpe, c->nelem, acc, uf, fx, fy, fz, c->ndirs, c->ncsys);
   FS_CUDA(cudaStreamSynchronize(c->stream));
   if (dev_sums) *dev_sums = acc;
   return FSGPU_OK;
@@ -443,7 +479,7 @@ extern "C" int fsgpu_normals_finish(fsgpu_ctx* c, double threshold_angle_deg, co
   // ...CompModule.jl:528-538); Q4 checks against the csys normal (src/FEMMShellQ4RSModule.jl:508-519).
   const int fixed_in_check = (c->nnpe == 4) ? 1 : 0;
   LAUNCH(c, k_normals_validate, c->nelem * c->nnpe, c->conn.p, c->xyz.p, c->nnpe, c->nelem, c->nrm.p, 1 - ntol, uf, fx,
-         fy, fz, fixed_in_check, c->ndirs);
+         fy, fz, fixed_in_check, c->ndirs, c->ncsys);
   FS_CUDA(cudaStreamSynchronize(c->stream));
   c->associated = true;
   if (dev_normals4) *dev_normals4 = reinterpret_cast<double*>(c->nrm.p);
@@ -470,6 +506,76 @@ extern "C" int fsgpu_associategeometry_dirs(fsgpu_ctx* c, double threshold_angle
   if (rc == FSGPU_OK) rc = fsgpu_normals_finish(c, threshold_angle_deg, nullptr, nullptr);
   c->ndirs = nullptr;
   return rc;
+}
+
+// Built-in csys kinds: nothing but the kind and two vectors crosses the boundary (C3: the host evaluation of the
+// callback at 6 M element nodes took 1.2 s against 2 ms for the stiffness itself).
+static int make_csys(int32_t kind, const double* origin, const double* axis, CsysK& k) {
+  FS_REQUIRE(kind == FSGPU_CSYS_CYLINDRICAL || kind == FSGPU_CSYS_SPHERICAL || kind == FSGPU_CSYS_NORMAL_AXIS, FSGPU_ERR_ARG,
+             "unknown csys kind %d", (int)kind);
+  FS_REQUIRE(axis != nullptr, FSGPU_ERR_ARG, "the csys kinds need an axis");
+  const double al = sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+  FS_REQUIRE(al > 0.0, FSGPU_ERR_ARG, "zero csys axis");
+  k.kind = kind;
+  for (int i = 0; i < 3; ++i) {
+    k.o[i] = origin ? origin[i] : 0.0;
+    k.a[i] = axis[i] / al;
+  }
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_associategeometry_csys(fsgpu_ctx* c, double threshold_angle_deg, int32_t kind, const double* origin,
+                                            const double* axis, int32_t accumulate) {
+  FS_TRY(check_ctx(c));
+  CsysK k;
+  FS_TRY(make_csys(kind, origin, axis, k));
+  c->ncsys = k;
+  int rc = fsgpu_normals_accumulate(c, nullptr, accumulate, nullptr);
+  if (rc == FSGPU_OK) rc = fsgpu_normals_finish(c, threshold_angle_deg, nullptr, nullptr);
+  c->ncsys.kind = 0;
+  return rc;
+}
+// layup csys matrices (row-major 3x3) on the device: T3FFComp one per element at the centroid with J0
+// (src/FEMMShellT3FFCompModule.jl:617); Q4RSComp one per element and integration point with the SHAPE-FUNCTION VALUES
+// as the location (src/FEMMShellQ4RSCompModule.jl:929, SURVEY App. B.9 -- reproduced) and the point's Jacobian
+__global__ void k_layup_csys(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe, int64_t nelem, fs::Rule rule,
+                             CsysK ck, double* __restrict__ cs) {
+  using namespace fsm;
+  const int npts = nnpe == 3 ? 1 : rule.npts;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nelem * npts) return;
+  const int64_t e = i / npts;
+  const int j = (int)(i % npts);
+  const int32_t* cn = conn + e * nnpe;
+  V3 X, n;
+  if (nnpe == 3) {
+    const V3 a = ldxyz(xyz, cn[0]), b = ldxyz(xyz, cn[1]), cc = ldxyz(xyz, cn[2]);
+    X = (1.0 / 3) * (a + b + cc);
+    n = element_triad(b - a, cc - a).e3;
+  } else {
+    const V3 Xe[4] = {ldxyz(xyz, cn[0]), ldxyz(xyz, cn[1]), ldxyz(xyz, cn[2]), ldxyz(xyz, cn[3])};
+    const double xi = rule.xi[j], eta = rule.eta[j];
+    n = q4_geometry(Xe, xi, eta).E.e3;
+    X = v3(0.25 * (1 - xi) * (1 - eta), 0.25 * (1 + xi) * (1 - eta), 0.25 * (1 + xi) * (1 + eta));  // Ns[j][1:3]
+  }
+  V3 e1, e2, e3;
+  csys_eval(ck, X, n, e1, e2, e3);
+  double* o = cs + i * 9;
+  o[0] = e1.x; o[1] = e2.x; o[2] = e3.x;
+  o[3] = e1.y; o[4] = e2.y; o[5] = e3.y;
+  o[6] = e1.z; o[7] = e2.z; o[8] = e3.z;
+}
+extern "C" int fsgpu_set_layup_csys(fsgpu_ctx* c, int32_t kind, const double* origin, const double* axis) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->ngroups >= 1, FSGPU_ERR_STATE, "call fsgpu_set_layup first (group data; its csys argument is replaced)");
+  FS_REQUIRE(c->nnpe == 3 || (c->nnpe == 4 && c->rule.npts >= 1), FSGPU_ERR_STATE, "needs a T3 mesh, or a Q4 mesh with its integration rule");
+  CsysK k;
+  FS_TRY(make_csys(kind, origin, axis, k));
+  const int64_t ncs = c->nelem * (c->nnpe == 3 ? 1 : c->rule.npts);
+  FS_TRY(c->csmat.ensure((size_t)ncs * 9 + 1));
+  LAUNCH(c, k_layup_csys, ncs, c->conn.p, c->xyz.p, c->nnpe, c->nelem, c->rule, k, c->csmat.p);
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  c->ncs = ncs;
+  return FSGPU_OK;
 }
 
 extern "C" int fsgpu_set_thickness(fsgpu_ctx* c, const double* t, int64_t n) {
@@ -1160,20 +1266,37 @@ static int fetch_rows_narrow(fsgpu_ctx* c, const int32_t* rv, int64_t nnz, int64
     if (v >= 16 && v < per_chunk) per_chunk = v;
   }
   const char* src = use_rle ? reinterpret_cast<const char*>(c->rle_runs.p) : reinterpret_cast<const char*>(rv);
-  // values: second stream, after everything already queued on the context's stream
+  // Order on the link.  The device-to-host copies of both streams share one copy engine, which serves them in issue
+  // order: a single 2.6 GB copy of the values issued first made the (small) run-length pieces wait for all of it, and
+  // the host-side expansion (30 ms for C2) then ran after the transfer instead of under it.  So: the first row pieces
+  // are issued before any values, and the values follow in pieces of 64 MB with at most two in flight, which lets
+  // later row pieces slip in between them.
   cudaError_t nz_err = cudaSuccess;
   std::thread nz_thread;
   FS_CUDA(cudaEventRecord(c->ev_x, c->stream));
   FS_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_x, 0));
-  if (nzval) {
+  std::atomic<int> rows_issued{0};
+  auto start_values = [&] {
+    if (!nzval) return;
     c->d2h_bytes += nnz * (int64_t)sizeof(double);
     // from a helper thread: with a pageable destination the copy call blocks its caller
     nz_thread = std::thread([&] {
       cudaSetDevice(c->device);
-      nz_err = cudaMemcpyAsync(nzval, nz, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream2);
+      while (rows_issued.load(std::memory_order_acquire) == 0) std::this_thread::yield();
+      const int64_t piece = (int64_t)8 << 20;  // entries (64 MB)
+      cudaEvent_t ev[2];
+      for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      int64_t k = 0;
+      for (int64_t o = 0; o < nnz && nz_err == cudaSuccess; o += piece, ++k) {
+        if (k >= 2) nz_err = cudaEventSynchronize(ev[k & 1]);
+        const int64_t m = nnz - o < piece ? nnz - o : piece;
+        if (nz_err == cudaSuccess) nz_err = cudaMemcpyAsync(nzval + o, nz + o, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream2);
+        if (nz_err == cudaSuccess) nz_err = cudaEventRecord(ev[k & 1], c->stream2);
+      }
       if (nz_err == cudaSuccess) nz_err = cudaStreamSynchronize(c->stream2);
+      for (auto& e : ev) cudaEventDestroy(e);
     });
-  }
+  };
   // measured on a 16-core host: 8 threads keep up with the PCIe link; more only compete with the copy-issuing
   // threads for cores (occasional 4x outliers at 16)
   int nth = (int)std::thread::hardware_concurrency() - 2;
@@ -1195,8 +1318,11 @@ static int fetch_rows_narrow(fsgpu_ctx* c, const int32_t* rv, int64_t nnz, int64
     if (err == cudaSuccess) err = cudaEventRecord(c->ring_ev[k % kRing], c->stream);
   };
   if (nchunks > 0) issue(0);
+  if (nchunks > 1) issue(1);
+  rows_issued.store(1, std::memory_order_release);
+  start_values();
   for (int64_t k = 0; k < nchunks && err == cudaSuccess; ++k) {
-    if (k + 1 < nchunks) issue(k + 1);  // its buffer was released when piece k - 1 was joined
+    if (k >= 1 && k + 1 < nchunks) issue(k + 1);  // its buffer was released when piece k - 1 was joined
     if (err == cudaSuccess) err = cudaEventSynchronize(c->ring_ev[k % kRing]);
     if (err != cudaSuccess) break;
     const int64_t o = k * per_chunk, m = nunits - o < per_chunk ? nunits - o : per_chunk;
@@ -1225,22 +1351,10 @@ extern "C" int fsgpu_d2h_bytes(fsgpu_ctx* c, int64_t* bytes) {
   *bytes = c->d2h_bytes;
   return FSGPU_OK;
 }
-extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval, double* nzval) {
-  FS_TRY(check_ctx(c));
-  FS_REQUIRE(c->have_matrix, FSGPU_ERR_STATE, "no matrix result available");
-  const int32_t* cp = c->compacted ? c->c_colptr.p : c->colptr.p;
-  const int32_t* rv = c->compacted ? c->c_rowval.p : c->rowval.p;
-  const double* nz = c->compacted ? c->c_nzval.p : c->nzval.p;
-  const int64_t nnz = c->rnnz, nc = c->rcols;
-  DBuf<int32_t> rp2, cv2;
-  DBuf<double> v2;
-  if (c->target == FSGPU_CSR_SYMM) {
-    // src/AssemblyModule.jl:47-53: findnz -> sparsecsr
-    FS_TRY(csc_to_csr(c, cp, rv, nz, c->rrows, c->rcols, nnz, rp2, cv2, v2));
-    cp = rp2.p;
-    rv = cv2.p;
-    nz = v2.p;
-  }
+namespace fs {
+// device CSC (int32, 0-based) -> host arrays in the Julia layout (Int64, 1-based)
+static int fetch_csc(fsgpu_ctx* c, const int32_t* cp, const int32_t* rv, const double* nz, int64_t nc, int64_t nnz, int64_t* colptr,
+                     int64_t* rowval, double* nzval, bool transient_pattern) {
   DBuf<int64_t>& wide = c->scr_wide;
   const int64_t chunk = (int64_t)1 << 26;  // widen in chunks to bound the scratch
   {
@@ -1262,10 +1376,10 @@ extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval
     // FSGPU_FETCH_MODE=entries: int32 entries; default: run-length form when it is the smaller one
     const char* fm = getenv("FSGPU_FETCH_MODE");
     const int mode = (fm && fm[0] == 'e') ? 1 : 2;
-    // the compacted (SparseSymm) and CSR index arrays change from call to call: no caching of their run form
-    if (c->compacted || c->target == FSGPU_CSR_SYMM) c->rle_for = nullptr;
+    // index arrays that change from call to call (compacted SparseSymm, CSR, triangles): no caching of their run form
+    if (transient_pattern) c->rle_for = nullptr;
     FS_TRY(fetch_rows_narrow(c, rv, nnz, rowval, nzval ? nz : nullptr, nzval, mode));
-    if (c->compacted || c->target == FSGPU_CSR_SYMM) c->rle_for = nullptr;
+    if (transient_pattern) c->rle_for = nullptr;
   } else {
     if (rowval && nnz > 0) {
       for (int64_t o = 0; o < nnz; o += chunk) {
@@ -1281,6 +1395,99 @@ extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval
     }
   }
   return FSGPU_OK;
+}
+
+// one triangle of a square result.  Rows ascend within a column, so the triangle of column j is a suffix
+// (lower: rows >= j) or a prefix (upper: rows <= j) of its segment.
+__global__ void k_tri_count(const int32_t* __restrict__ cp, const int32_t* __restrict__ rv, int64_t nc, int lower,
+                            int32_t* __restrict__ cnt, int32_t* __restrict__ first) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= nc) return;
+  int lo = cp[j], hi = cp[j + 1];
+  const int b = lo, e = hi;
+  const int key = lower ? (int)j : (int)j + 1;  // first position with row >= key
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (rv[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  first[j] = lower ? lo : b;
+  cnt[j] = lower ? e - lo : lo - b;
+}
+__global__ void k_tri_gather(const int32_t* __restrict__ tcp, const int32_t* __restrict__ first, const int32_t* __restrict__ rv,
+                             const double* __restrict__ nz, int64_t nc, int32_t* __restrict__ trv, double* __restrict__ tnz) {
+  const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= nc) return;
+  const int o = tcp[j], n = tcp[j + 1] - o, s = first[j];
+  for (int k = lane; k < n; k += 32) {
+    trv[o + k] = rv[s + k];
+    tnz[o + k] = nz[s + k];
+  }
+}
+static int build_triangle(fsgpu_ctx* c, int uplo, int64_t* tnnz) {
+  FS_REQUIRE(c->have_matrix, FSGPU_ERR_STATE, "no matrix result available");
+  FS_REQUIRE(uplo == 'L' || uplo == 'U', FSGPU_ERR_ARG, "uplo must be 'L' or 'U'");
+  FS_REQUIRE(c->target != FSGPU_CSR_SYMM && c->rrows == c->rcols, FSGPU_ERR_STATE, "a triangle needs a square CSC result");
+  const int32_t* cp = c->compacted ? c->c_colptr.p : c->colptr.p;
+  const int32_t* rv = c->compacted ? c->c_rowval.p : c->rowval.p;
+  const int64_t nc = c->rcols;
+  FS_TRY(c->t_cnt.ensure((size_t)nc + 1));
+  FS_TRY(c->t_first.ensure((size_t)nc + 1));
+  FS_TRY(c->t_colptr.ensure((size_t)nc + 1));
+  FS_CUDA(cudaMemsetAsync(c->t_cnt.p + nc, 0, sizeof(int32_t), c->stream));
+  LAUNCH(c, k_tri_count, nc, cp, rv, nc, uplo == 'L' ? 1 : 0, c->t_cnt.p, c->t_first.p);
+  size_t tb = 0;
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, c->t_cnt.p, c->t_colptr.p, nc + 1, c->stream));
+  FS_TRY(c->tmp.ensure(tb));
+  FS_CUDA(cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, c->t_cnt.p, c->t_colptr.p, nc + 1, c->stream));
+  c->launches++;
+  int32_t n32 = 0;
+  FS_CUDA(cudaMemcpyAsync(&n32, c->t_colptr.p + nc, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  *tnnz = n32;
+  return FSGPU_OK;
+}
+}  // namespace fs
+
+extern "C" int fsgpu_fetch_matrix(fsgpu_ctx* c, int64_t* colptr, int64_t* rowval, double* nzval) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(c->have_matrix, FSGPU_ERR_STATE, "no matrix result available");
+  const int32_t* cp = c->compacted ? c->c_colptr.p : c->colptr.p;
+  const int32_t* rv = c->compacted ? c->c_rowval.p : c->rowval.p;
+  const double* nz = c->compacted ? c->c_nzval.p : c->nzval.p;
+  const int64_t nnz = c->rnnz, nc = c->rcols;
+  DBuf<int32_t> rp2, cv2;
+  DBuf<double> v2;
+  if (c->target == FSGPU_CSR_SYMM) {
+    // src/AssemblyModule.jl:47-53: findnz -> sparsecsr
+    FS_TRY(csc_to_csr(c, cp, rv, nz, c->rrows, c->rcols, nnz, rp2, cv2, v2));
+    cp = rp2.p;
+    rv = cv2.p;
+    nz = v2.p;
+  }
+  return fetch_csc(c, cp, rv, nz, nc, nnz, colptr, rowval, nzval, c->compacted || c->target == FSGPU_CSR_SYMM);
+}
+
+extern "C" int fsgpu_result_size_uplo(fsgpu_ctx* c, int32_t uplo, int64_t* nnz) {
+  FS_TRY(check_ctx(c));
+  FS_REQUIRE(nnz != nullptr, FSGPU_ERR_ARG, "null argument");
+  return build_triangle(c, uplo, nnz);
+}
+extern "C" int fsgpu_fetch_matrix_uplo(fsgpu_ctx* c, int32_t uplo, int64_t* colptr, int64_t* rowval, double* nzval) {
+  FS_TRY(check_ctx(c));
+  int64_t tnnz = 0;
+  FS_TRY(build_triangle(c, uplo, &tnnz));
+  const int32_t* rv = c->compacted ? c->c_rowval.p : c->rowval.p;
+  const double* nz = c->compacted ? c->c_nzval.p : c->nzval.p;
+  const int64_t nc = c->rcols;
+  FS_TRY(c->t_rowval.ensure((size_t)tnnz + 1));
+  FS_TRY(c->t_nzval.ensure((size_t)tnnz + 1));
+  if (nc > 0) {
+    k_tri_gather<<<grid_for(nc * 32, 256), 256, 0, c->stream>>>(c->t_colptr.p, c->t_first.p, rv, nz, nc, c->t_rowval.p, c->t_nzval.p);
+    c->launches++;
+    FS_CUDA(cudaGetLastError());
+  }
+  return fetch_csc(c, c->t_colptr.p, c->t_rowval.p, c->t_nzval.p, nc, tnnz, colptr, rowval, nzval, true);
 }
 
 extern "C" int fsgpu_fetch_vector(fsgpu_ctx* c, double* out, int64_t n) {

@@ -71,6 +71,11 @@ struct Rule {
   int npts = 0;
   double xi[kMaxGP], eta[kMaxGP], w[kMaxGP];
 };
+// built-in csys kind (FSGPU_CSYS_*; 0 = none) with its origin and unit axis
+struct CsysK {
+  int kind = 0;
+  double o[3] = {0, 0, 0}, a[3] = {0, 0, 1};
+};
 
 }  // namespace fs
 
@@ -110,6 +115,7 @@ struct fsgpu_ctx {
   fs::DBuf<double> nacc;      // [nnodes][3] unnormalised normal sums (associategeometry, split form)
   bool nacc_keep = false;
   const double* ndirs = nullptr;  // per (element, node) csys normal directions during fsgpu_associategeometry_dirs
+  fs::CsysK ncsys;                // built-in csys kind during fsgpu_associategeometry_csys
   // thickness / stab factor
   int64_t nthick = 0;
   fs::DBuf<double> thick;
@@ -170,6 +176,9 @@ struct fsgpu_ctx {
   bool compacted = false;     // SPARSE_SYMM after zero dropping: use c_* below
   fs::DBuf<int32_t> c_colptr, c_rowval;
   fs::DBuf<double> c_nzval;
+  // one triangle of the result (fsgpu_fetch_matrix_uplo)
+  fs::DBuf<int32_t> t_cnt, t_first, t_colptr, t_rowval;
+  fs::DBuf<double> t_nzval;
   // result vector
   bool have_vector = false;
   int64_t vlen = 0;

@@ -227,6 +227,7 @@ class SysmatAssemblerGPU:
     (SURVEY section 8(b)): kind in 'sparse' | 'symm' | 'diag' | 'ffblock' | 'ffblock_diag' | 'csrsymm'."""
 
     kind: str = "symm"
+    uplo: str = ""  # "L" / "U": makematrix! returns that triangle only (for Symmetric(K, :L) consumers; half the PCIe bytes)
     TARGETS = {
         "sparse": L.SPARSE,
         "symm": L.SPARSE_SYMM,
@@ -275,6 +276,76 @@ def SysvecAssemblerFBlock():
 
 
 # ---- FEMMs -------------------------------------------------------------------------------------
+
+
+class CSysKind:
+    """A built-in coordinate system the library evaluates ON THE DEVICE (`fsgpu_associategeometry_csys`,
+    `fsgpu_set_layup_csys`): the CSys callbacks of the reference's examples -- `cylindrical!`
+    (clamp_cyl_expl_examples.jl:62-68), `spherical!` (hemisphere_examples.jl:31-39), the surface-normal variant of
+    pressurized_cylinder_free_examples.jl:16-23.  Calling the object evaluates the same formulas with NumPy
+    (host-side consumers, tests)."""
+
+    def __init__(self, kind, axis, origin=None):
+        self.kind, self.axis = int(kind), np.asarray(axis, dtype=np.float64) / np.linalg.norm(axis)
+        self.origin = np.zeros(3) if origin is None else np.asarray(origin, dtype=np.float64)
+
+    @classmethod
+    def cylindrical(cls, axis=(0.0, 1.0, 0.0), origin=None):
+        return cls(L.CSYS_CYLINDRICAL, axis, origin)
+
+    @classmethod
+    def spherical(cls, axis=(0.0, 0.0, 1.0), origin=None):
+        return cls(L.CSYS_SPHERICAL, axis, origin)
+
+    @classmethod
+    def normal_axis(cls, axis=(0.0, 1.0, 0.0)):
+        return cls(L.CSYS_NORMAL_AXIS, axis, None)
+
+    def __call__(self, XYZ, tangents=None, feid=None, qpid=None):
+        X = np.asarray(XYZ, dtype=np.float64)[:, :3]
+        a = np.broadcast_to(self.axis, X.shape)
+        r = X - self.origin
+        unit = lambda v: v / np.linalg.norm(v, axis=1, keepdims=True)
+        if self.kind == L.CSYS_CYLINDRICAL:
+            e3 = unit(r - np.sum(r * a, axis=1, keepdims=True) * a)
+            e2 = a
+            e1 = np.cross(e2, e3)
+        elif self.kind == L.CSYS_SPHERICAL:
+            e3 = unit(r)
+            e1 = unit(np.cross(a, e3))
+            e2 = np.cross(e3, e1)
+        else:
+            e3 = unit(np.cross(tangents[:, :, 0], tangents[:, :, 1]))
+            e2 = a
+            e1 = np.cross(e2, e3)
+        return np.stack([e1, e2, e3], axis=-1)
+
+
+_Q4_NODE_PC = ((-1.0, -1.0), (1.0, -1.0), (1.0, 1.0), (-1.0, 1.0))  # NodalTensorProductRule(2): the nodes, in node order
+
+
+def _q4_shape(xi, eta):
+    """Q4 shape functions and parametric derivatives (FinEtools FESetQ4: nodes (-1,-1), (1,-1), (1,1), (-1,1))."""
+    N = 0.25 * np.array([(1 - xi) * (1 - eta), (1 + xi) * (1 - eta), (1 + xi) * (1 + eta), (1 - xi) * (1 + eta)])
+    dN = 0.25 * np.array([[-(1 - eta), -(1 - xi)], [(1 - eta), -(1 + xi)], [(1 + eta), (1 + xi)], [-(1 + eta), (1 - xi)]])
+    return N, dN
+
+
+def _eval_csys(cs, XYZ, tangents, feid, qpid, elems=None):
+    """FinEtools `updatecsmat!(csys, XYZ, tangents, feid, qpid)`, batched: a constant matrix is broadcast, a callable
+    gets the locations (n, k) and -- if it accepts them -- tangents (n, 3, 2), feid, qpid; returns (n, 3, 3)."""
+    n = XYZ.shape[0]
+    if not callable(cs):
+        c = np.asarray(cs, dtype=np.float64)
+        return np.broadcast_to(c, (n, 3, 3)) if c.ndim == 2 else c.reshape(-1, 3, 3)[elems]  # per-element matrices
+    import inspect
+
+    try:
+        npar = len(inspect.signature(cs).parameters)
+    except (TypeError, ValueError):
+        npar = 1
+    out = cs(XYZ) if npar < 2 else cs(XYZ, tangents, feid, qpid)
+    return np.asarray(out, dtype=np.float64).reshape(n, 3, 3)
 
 
 class _FEMMBase:
@@ -370,21 +441,54 @@ class _FEMMShell(_FEMMBase):
                 gof = np.zeros(ctx.nelem, dtype=np.int64)
                 for gi, (_, eset) in enumerate(self.layup_groups):
                     gof[np.asarray(eset) - 1] = gi + 1
-            cs = self.layup_groups[0][0].csys
-            if callable(cs):
-                # `updatecsmat!(layup.csys, centroid, J0, i, 0)` (src/FEMMShellT3FFCompModule.jl:617): the closure stays
-                # on the host, the library gets one matrix per element
-                if self._nnpe != 3:
-                    raise FsgpuError(L.ERR_ARG, "a csys callback is evaluated at the T3 centroids; pass per-point matrices for Q4RSComp (SURVEY App. B.9)")
-                conn = np.asarray(idom.conn)
-                cs = cs(self._xyz[conn - 1].mean(axis=1))
-            ctx.set_layup(recs, gof, np.asarray(cs, dtype=np.float64))
+            css = [lg[0].csys for lg in self.layup_groups]
+            if isinstance(css[0], CSysKind) and all(c is css[0] for c in css):
+                ctx.set_layup(recs, gof, np.eye(3))
+                ctx.set_layup_csys(css[0].kind, css[0].origin, css[0].axis)  # evaluated on the device
+            else:
+                ctx.set_layup(recs, gof, self._layup_csmats())
         else:
             t = idom.otherdimension
             ctx.set_thickness(t)
         # the nodal normals belong to the FEMM (femm._normals) and survive a re-upload
         if self._associatedgeometry and self._normals is not None:
             ctx.set_normals(self._normals, self._normal_valid)
+
+    def _group_elements(self, gi):
+        eset = self.layup_groups[gi][1]
+        return np.arange(self.ctx.nelem) if eset is None else np.asarray(eset) - 1
+
+    def _layup_csmats(self):
+        """Layup csys matrices for `fsgpu_set_layup`: one (3, 3) matrix when every group has the same constant csys,
+        else one per element (T3FFComp: `updatecsmat!(layup.csys, centroid, J0, i, 0)`,
+        src/FEMMShellT3FFCompModule.jl:617) or one per element and integration point (Q4RSComp:
+        `updatecsmat!(layup.csys, Ns[j], J, -1, 0)`, src/FEMMShellQ4RSCompModule.jl:929 -- the SHAPE-FUNCTION VALUES
+        are passed as the location; reproduced here).  Each group uses its own csys."""
+        css = [lg[0].csys for lg in self.layup_groups]
+        if not any(callable(c) for c in css) and all(np.ndim(c) == 2 for c in css) and all(np.array_equal(css[0], c) for c in css[1:]):
+            return np.asarray(css[0], dtype=np.float64)
+        conn = np.asarray(self.integdomain.conn)
+        ne = conn.shape[0]
+        X = self._xyz[conn - 1]  # (ne, nnpe, 3)
+        if self._nnpe == 3:
+            out = np.zeros((ne, 3, 3))
+            J0 = np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]], axis=-1)
+            for gi, c in enumerate(css):
+                el = self._group_elements(gi)
+                out[el] = _eval_csys(c, X[el].mean(axis=1), J0[el], el + 1, 0, el)
+            return out
+        pc, _ = self.integdomain.rule if self.integdomain.rule is not None else GaussRule2x2()
+        out = np.zeros((ne, len(pc), 3, 3))
+        for j, (xi, eta) in enumerate(pc):
+            N, dN = _q4_shape(xi, eta)
+            J = np.einsum("eai,ak->eik", X, dN)
+            for gi, c in enumerate(css):
+                el = self._group_elements(gi)
+                if not callable(c) and np.ndim(c) == 4:  # matrices given per element and integration point
+                    out[el, j] = np.asarray(c, dtype=np.float64)[el, j]
+                    continue
+                out[el, j] = _eval_csys(c, np.broadcast_to(N, (len(el), 4)), J[el], -1, 0, el)
+        return out
 
     def _params(self):
         p = ShellParams()
@@ -402,7 +506,9 @@ class _FEMMShell(_FEMMBase):
         if self.stab_fun is not None:
             h = self.ctx.element_sizes()
             if self._comp:
-                t = np.full(self.ctx.nelem, self.layup_groups[0][0].thickness())
+                t = np.zeros(self.ctx.nelem)
+                for gi, (lay, _) in enumerate(self.layup_groups):  # `thickness(layup)` of the element's group
+                    t[self._group_elements(gi)] = lay.thickness()
             else:
                 t = np.broadcast_to(np.asarray(self.integdomain.otherdimension, dtype=np.float64), (self.ctx.nelem,))
             self.ctx.set_stab_factor(self.stab_fun(t, h))
@@ -418,24 +524,36 @@ def associategeometry(femm, geom0, interface=None):
     femm._sync_mesh(geom0)
     fixed = None
     if femm._comp:
-        cs = femm.layup_groups[0][0].csys
-        dirs = None
-        conn = np.asarray(femm.integdomain.conn)
-        if callable(cs):
-            # `_compute_nodal_normal!(nnormal, layup.csys, geom.values[n, :], J0, el, 0)`: the csys evaluated AT THE NODE
-            # (src/FEMMShellT3FFCompModule.jl:203-207,509)
-            xyz = np.asarray(geom0.values)
-            dirs = np.asarray(cs(xyz[conn - 1].reshape(-1, 3)))[:, :, 2].reshape(conn.shape[0], conn.shape[1], 3)
-        elif np.ndim(cs) == 3 and interface is None:
-            dirs = np.repeat(np.asarray(cs, dtype=np.float64)[:, None, :, 2], conn.shape[1], axis=1)
-        if dirs is not None:
+        css = [lg[0].csys for lg in femm.layup_groups]
+        if isinstance(css[0], CSysKind) and all(c is css[0] for c in css) and interface is None:
+            femm.ctx.associategeometry_csys(css[0].kind, css[0].origin, css[0].axis, femm.threshold_angle, False)
+            femm._normals, femm._normal_valid = femm.ctx.get_normals()
+            femm._associatedgeometry = True
+            return femm
+        same_const = not any(callable(c) for c in css) and all(np.ndim(c) == 2 for c in css) and all(np.array_equal(css[0], c) for c in css[1:])
+        if not same_const:
+            # `_compute_nodal_normal!(nnormal, layup.csys, geom.values[n, :], J0, el, 0)`: each group's csys evaluated AT
+            # THE NODE (src/FEMMShellT3FFCompModule.jl:203-207,509; src/FEMMShellQ4RSCompModule.jl:228-232,471)
             if interface is not None:
                 raise FsgpuError(L.ERR_ARG, "partitioned associategeometry supports the default and the cartesian csys")
+            conn = np.asarray(femm.integdomain.conn)
+            xyz = np.asarray(geom0.values)
+            X = xyz[conn - 1]
+            nn = conn.shape[1]
+            dirs = np.zeros((conn.shape[0], nn, 3))
+            for gi, c in enumerate(css):
+                el = femm._group_elements(gi)
+                for k in range(nn):
+                    if nn == 3:
+                        J = np.stack([X[el, 1] - X[el, 0], X[el, 2] - X[el, 0]], axis=-1)
+                    else:
+                        J = np.einsum("eai,ak->eik", X[el], _q4_shape(*_Q4_NODE_PC[k])[1])
+                    dirs[el, k] = _eval_csys(c, X[el, k], J, el + 1, k + 1, el)[:, :, 2]
             femm.ctx.associategeometry_dirs(dirs, femm.threshold_angle, False)
             femm._normals, femm._normal_valid = femm.ctx.get_normals()
             femm._associatedgeometry = True
             return femm
-        fixed = np.asarray(cs, dtype=np.float64)[:, 2].copy()
+        fixed = np.asarray(css[0], dtype=np.float64)[:, 2].copy()
     # homogeneous T3FF never resets its arrays
     accumulate = (femm._nnpe == 3) and (not femm._comp)
     if interface is None:
@@ -481,6 +599,8 @@ def stiffness(femm, *args, out=None):
     femm._startassembly(assembler, dchi)
     femm._sync_stab()
     femm.ctx.shell_op(femm._opname + "_stiffness", femm._params())
+    if assembler.uplo:
+        return femm.ctx.fetch_matrix_uplo(assembler.uplo, out)
     return femm.ctx.fetch_matrix(out)
 
 
@@ -497,6 +617,8 @@ def mass(femm, *args, mass_type=1):
     femm._sync_mesh(geom0)
     femm._startassembly(assembler, dchi)
     femm.ctx.shell_op(femm._opname + "_mass", femm._params())
+    if assembler.uplo:
+        return femm.ctx.fetch_matrix_uplo(assembler.uplo)
     return femm.ctx.fetch_matrix()
 
 
@@ -614,6 +736,8 @@ class FEMMCorotBeam(_FEMMBase):
         self._startassembly(assembler, dchi)
         self.ctx.set_state(u1.values, Rfield1.values)
         self.ctx.beam_op(name, self._params(mass_type))
+        if assembler.uplo:
+            return self.ctx.fetch_matrix_uplo(assembler.uplo)
         return self.ctx.fetch_matrix()
 
 

@@ -124,6 +124,22 @@ int fsgpu_associategeometry(fsgpu_ctx* ctx, double threshold_angle_deg, const do
  * src/FEMMShellT3FFCompModule.jl:203-207,509); it replaces the element normal in the accumulation (and, for the Q4
  * elements, in the validity check, src/FEMMShellQ4RSModule.jl:508-519) */
 int fsgpu_associategeometry_dirs(fsgpu_ctx* ctx, double threshold_angle_deg, const double* dirs, int32_t accumulate);
+/* Built-in csys kinds evaluated ON THE DEVICE (the CSys callbacks of the reference's examples; only the kind, an
+ * origin and an axis cross the boundary; origin NULL = (0,0,0); the axis is normalised):
+ *   FSGPU_CSYS_CYLINDRICAL  e3 = radial from the axis, e2 = axis, e1 = e2 x e3
+ *                           (examples/shells/dynamics/homogeneous/explicit/clamp_cyl_expl_examples.jl:62-68, axis = y)
+ *   FSGPU_CSYS_SPHERICAL    e3 = radial from the origin, e1 = normalize(axis x e3), e2 = e3 x e1
+ *                           (examples/shells/statics/homogeneous/hemisphere/hemisphere_examples.jl:31-39, axis = z)
+ *   FSGPU_CSYS_NORMAL_AXIS  e3 = surface normal t1 x t2, e2 = axis, e1 = e2 x e3
+ *                           (examples/shells/statics/homogeneous/miscellaneous/pressurized_cylinder_free_examples.jl:16-23)
+ * fsgpu_associategeometry_csys: nodal normals from the csys evaluated at every node of every element.
+ * fsgpu_set_layup_csys (after fsgpu_set_layup, whose csmat argument it replaces): layup csys matrices per element
+ * (T3FFComp: at the centroid, src/FEMMShellT3FFCompModule.jl:617) or per element and integration point (Q4RSComp: with
+ * the shape-function values Ns[j] as the location, as the reference passes them, src/FEMMShellQ4RSCompModule.jl:929). */
+enum fsgpu_csys_kind { FSGPU_CSYS_CYLINDRICAL = 1, FSGPU_CSYS_SPHERICAL = 2, FSGPU_CSYS_NORMAL_AXIS = 3 };
+int fsgpu_associategeometry_csys(fsgpu_ctx* ctx, double threshold_angle_deg, int32_t kind, const double* origin,
+                                 const double* axis, int32_t accumulate);
+int fsgpu_set_layup_csys(fsgpu_ctx* ctx, int32_t kind, const double* origin, const double* axis);
 /* the same in two halves for element-partitioned runs: after _accumulate the host sums the
  * interface-node entries of *dev_sums ([nnodes][3] doubles, device) across ranks; after _finish it
  * min-combines the validity flags, 4th component of *dev_normals4 ([nnodes][4] doubles, device) */
@@ -208,6 +224,12 @@ int fsgpu_element_vectors(fsgpu_ctx* ctx, const fsgpu_beam_params* p, double* ou
 int fsgpu_result_size(fsgpu_ctx* ctx, int64_t* nrows, int64_t* ncols, int64_t* nnz);
 /* makematrix! equivalent; any pointer may be NULL to skip that array */
 int fsgpu_fetch_matrix(fsgpu_ctx* ctx, int64_t* colptr, int64_t* rowval, double* nzval);
+/* One triangle of a square CSC result, diagonal included: uplo = 'L' (rows >= column) or 'U' (rows <= column).
+ * For consumers that read one triangle of a symmetric operator (Julia: cholesky(Symmetric(K, :L)), the
+ * SysmatAssemblerSparseSymm convention of src/AssemblyModule.jl / FinEtools keeps i >= j only): half the bytes
+ * cross PCIe.  Same two-call convention: size query, then the caller's arrays are filled. */
+int fsgpu_result_size_uplo(fsgpu_ctx* ctx, int32_t uplo, int64_t* nnz);
+int fsgpu_fetch_matrix_uplo(fsgpu_ctx* ctx, int32_t uplo, int64_t* colptr, int64_t* rowval, double* nzval);
 int fsgpu_fetch_vector(fsgpu_ctx* ctx, double* out, int64_t n);
 /* device-resident handles (int32 0-based pattern, float64 values) for chaining on the GPU */
 int fsgpu_result_device(fsgpu_ctx* ctx, const int32_t** colptr0, const int32_t** rowval0, const double** nzval);

@@ -1,0 +1,544 @@
+"""GPU parity tests, part 2 (round 2): product paths the first suite did not reach -- per-element / per-point
+thickness, the sampled stabilisation factor, T3FF's accumulating associategeometry!, Q4RSComp's per-point layup csys
+with the shape-function "location" quirk, permuted numbering for Q4RS and the beam, load-factor tables of the
+explicit loop, one triangle of the result, and 100k-element slices of the actual bench meshes (C2, C3, C4, C5)
+against the C port / the NumPy oracle.  Tolerances as in test_gpu_parity.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import beam as obeam
+from oracle import explicit as oexp
+from oracle import fe_external as fx
+from oracle import layup as oly
+from oracle import shells as osh
+from tests import meshes
+from tests.test_gpu_parity import E_, NU_, RHO_, T_, TOL, _check_matrix, _fs_layup, _iso, _layup, _make_femm, _oracle_normals, relfro
+
+pytestmark = pytest.mark.gpu
+
+P = lambda a: a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def fs():
+    import fsb200
+
+    return fsb200
+
+
+@pytest.fixture(scope="module")
+def refport():
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "cport")
+    subprocess.run(["make", "-C", d, "-s", "-B"], check=True)
+    lib = C.CDLL(os.path.join(d, "librefport.so"))
+    lib.ref_coo_to_csc.restype = C.c_int64
+    return lib
+
+
+def _fields(f, xyz, od=None, perm=None):
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    if od is not None:
+        dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs(perm) if perm is not None else dchi.numberdofs()
+    u0, R0 = f.NodalField(np.zeros((xyz.shape[0], 3))), f.initial_Rfield(xyz.shape[0])
+    return geom0, dchi, u0, R0
+
+
+# ---------------------------------------------------------------------------------------
+# thickness arrays (src/FEMMShellT3FFModule.jl:676 `t = self.integdomain.otherdimension(centroid, fes.conn[i], ...)`;
+# src/FEMMShellQ4RSModule.jl:921 per integration point)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,per_point", [("t3", False), ("q4", False), ("q4", True)])
+def test_thickness_arrays(fs, kind, per_point):
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh(kind, n=7)
+    ne = conn.shape[0]
+    rng = np.random.default_rng(11)
+    t = T_ * rng.uniform(0.5, 2.0, (ne, 4) if per_point else ne)
+    normals, valid = _oracle_normals(kind, xyz, conn)
+    Dps, Dt = _iso()
+    idom = f.IntegDomain(conn, None if kind == "t3" else f.GaussRule2x2(), t)
+    femm = (f.FEMMShellT3FF if kind == "t3" else f.FEMMShellQ4RS)(idom, f.MatDeforElastIso(E_, NU_, RHO_))
+    geom0, dchi, u0, R0 = _fields(f, xyz, meshes.clamp_edge_dofs(xyz))
+    f.associategeometry(femm, geom0)
+    femm._sync_stab()
+    if kind == "t3":
+        Ko, Mo = osh.t3ff_stiffness_elmats(xyz, conn, normals, valid, Dps, Dt, t), osh.t3ff_mass_elmats(xyz, conn, RHO_, t)
+    else:
+        Ko, Mo = osh.q4rs_stiffness_elmats(xyz, conn, normals, valid, Dps, Dt, t), osh.q4rs_mass_elmats(xyz, conn, RHO_, t)
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    assert max(relfro(Kg[e], Ko[e]) for e in range(ne)) < TOL
+    Mg = femm.ctx.element_matrices(femm._kind(), 1, femm._params())
+    assert relfro(Mg, Mo) < TOL
+    od = meshes.clamp_edge_dofs(xyz)
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, u0, R0, dchi)
+    _check_matrix(K, fx.assemble_matrix("ffblock", Ko, od.gatherdofnums(conn), od.nalldofs, od.nfreedofs), od.nfreedofs)
+
+
+# ---------------------------------------------------------------------------------------
+# stab_fun outside the t^2/(t^2 + alpha h^2) family: sampled per element into fsgpu_set_stab_factor
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,comp", [("t3", False), ("q4", False), ("t3", True), ("q4", True)])
+def test_sampled_stab_factor(fs, kind, comp):
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh(kind, n=6)
+    lay, cs = _layup()
+    stab = lambda t, h: t**2 / (t**2 + 0.3 * h**2 + 0.05 * t * h)
+    femm = _make_femm(fs, kind, conn, comp, cs)
+    femm.stab_fun = stab
+    geom0, dchi, u0, R0 = _fields(f, xyz)
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals(kind, xyz, conn, fixed=cs[:, 2] if comp else None)
+    Dps, Dt = _iso()
+    if comp:
+        A, B, D = lay.laminate_stiffnesses()
+        H = lay.laminate_transverse_stiffness()
+        fn = osh.t3ffcomp_stiffness_elmats if kind == "t3" else osh.q4rscomp_stiffness_elmats
+        Ko = fn(xyz, conn, normals, valid, A, B, D, H, lay.thickness, cs, stab_fun=stab)
+    else:
+        fn = osh.t3ff_stiffness_elmats if kind == "t3" else osh.q4rs_stiffness_elmats
+        Ko = fn(xyz, conn, normals, valid, Dps, Dt, T_, stab_fun=stab)
+    K = f.stiffness(femm, f.SysmatAssemblerSparse(), geom0, u0, R0, dchi)
+    od = fx.DofField(xyz.shape[0]).numberdofs()
+    _check_matrix(K, fx.assemble_matrix("sparse", Ko, od.gatherdofnums(conn), od.nalldofs), od.nalldofs)
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    assert max(relfro(Kg[e], Ko[e]) for e in range(conn.shape[0])) < TOL
+
+
+# ---------------------------------------------------------------------------------------
+# T3FF associategeometry! never resets (src/FEMMShellT3FFModule.jl:575-587): a second call
+# accumulates onto the unit normals of the first and can only turn more nodes invalid
+# ---------------------------------------------------------------------------------------
+def test_t3ff_associategeometry_twice(fs):
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh("t3", n=9)
+    femm = _make_femm(fs, "t3", conn)
+    geom0 = f.NodalField(xyz)
+    f.associategeometry(femm, geom0)
+    n1, v1 = femm._normals.copy(), femm._normal_valid.copy()
+    o1, ov1 = osh.t3ff_associategeometry(xyz, conn)
+    assert np.abs(n1 - o1).max() < 1e-13 and np.array_equal(v1, ov1)
+    f.associategeometry(femm, geom0)
+    o2, ov2 = osh.t3ff_associategeometry(xyz, conn, normals0=o1)
+    assert np.abs(femm._normals - o2).max() < 1e-13
+    assert np.array_equal(femm._normal_valid, ov1 & ov2)
+    # (unit normal + the same element normals again: the direction cannot change, "harmless after normalisation")
+    assert np.abs(femm._normals - n1).max() < 1e-13 and not ov1.all()
+    # the Q4RS FEMM resets (src/FEMMShellQ4RSModule.jl:483-484): a second call reproduces the first
+    xyz4, conn4 = meshes.shell_mesh("q4", n=9)
+    fq = _make_femm(fs, "q4", conn4)
+    g4 = f.NodalField(xyz4)
+    f.associategeometry(fq, g4)
+    a = fq._normals.copy()
+    f.associategeometry(fq, g4)
+    assert np.abs(a - fq._normals).max() < 1e-14  # (the accumulation uses atomics: not bitwise)
+
+
+# ---------------------------------------------------------------------------------------
+# Q4RSComp: layup csys per element AND integration point, `updatecsmat!(layup.csys, Ns[j], J, -1, 0)`
+# (src/FEMMShellQ4RSCompModule.jl:929): the location handed to the csys is the vector of shape-function values
+# ---------------------------------------------------------------------------------------
+def _csys_from_tangents(XYZ, tangents, feid, qpid):
+    """A csys callback that uses BOTH arguments the reference passes: e1 along the first tangent rotated about the
+    surface normal by an angle that depends on the 'location' (for Q4RSComp: the shape-function values)."""
+    t1, t2 = tangents[:, :, 0], tangents[:, :, 1]
+    e3 = np.cross(t1, t2)
+    e3 /= np.linalg.norm(e3, axis=1, keepdims=True)
+    a = t1 / np.linalg.norm(t1, axis=1, keepdims=True)
+    b = np.cross(e3, a)
+    th = 0.3 + 1.1 * XYZ[:, 0] - 0.7 * XYZ[:, 1] + 0.4 * XYZ[:, 2]
+    e1 = np.cos(th)[:, None] * a + np.sin(th)[:, None] * b
+    e2 = np.cross(e3, e1)
+    return np.stack([e1, e2, e3], axis=-1)
+
+
+@pytest.mark.parametrize("rule", ["gauss2x2", "simpson13"])
+def test_q4rscomp_per_point_csys_callback(fs, rule):
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh("q4", n=6, crease=0.0)
+    lay, _ = _layup()
+    orule = fx.gauss_rule_2x2() if rule == "gauss2x2" else fx.simpson13_rule_2d()
+    grule = f.GaussRule2x2() if rule == "gauss2x2" else f.Simpson13Rule2()
+    femm = f.FEMMShellQ4RSComp(f.IntegDomain(conn, grule, T_), _fs_layup(fs, _csys_from_tangents))
+    geom0, dchi, u0, R0 = _fields(f, xyz)
+    f.associategeometry(femm, geom0)
+    # independent evaluation of what the reference does
+    X = xyz[conn - 1]
+    ne = conn.shape[0]
+    pcn, _ = fx.nodal_rule_q4()
+    dirs = np.zeros((ne, 4, 3))
+    for j in range(4):
+        _, dNp = fx.q4_shape(*pcn[j])
+        J = np.einsum("eai,ak->eik", X, dNp)
+        dirs[:, j] = _csys_from_tangents(X[:, j], J, None, None)[:, :, 2]  # evaluated AT THE NODE (:471)
+    no, vo = osh.q4rs_associategeometry(xyz, conn, normal_dir=dirs)
+    assert np.abs(femm._normals - no).max() < 1e-13 and np.array_equal(femm._normal_valid, vo)
+    pc, w = orule
+    lcs = np.zeros((ne, len(w), 3, 3))
+    for j in range(len(w)):
+        N, dNp = fx.q4_shape(*pc[j])
+        J = np.einsum("eai,ak->eik", X, dNp)
+        lcs[:, j] = _csys_from_tangents(np.broadcast_to(np.ravel(N), (ne, 4)), J, None, None)  # location = Ns[j]  (:929)
+    A, B, D = lay.laminate_stiffnesses()
+    H = lay.laminate_transverse_stiffness()
+    Ko = osh.q4rscomp_stiffness_elmats(xyz, conn, no, vo, A, B, D, H, lay.thickness, lcs, rule=orule)
+    femm._sync_stab()
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    assert max(relfro(Kg[e], Ko[e]) for e in range(ne)) < TOL
+    # the location quirk matters: the centroid as location gives a different matrix
+    lcs_c = np.repeat(_csys_from_tangents(X.mean(axis=1), np.einsum("eai,ak->eik", X, fx.q4_shape(0.0, 0.0)[1]), None, None)[:, None], len(w), axis=1)
+    Kc = osh.q4rscomp_stiffness_elmats(xyz, conn, no, vo, A, B, D, H, lay.thickness, lcs_c, rule=orule)
+    assert relfro(Kc, Ko) > 1e-3
+    K = f.stiffness(femm, f.SysmatAssemblerSparse(), geom0, u0, R0, dchi)
+    od = fx.DofField(xyz.shape[0]).numberdofs()
+    _check_matrix(K, fx.assemble_matrix("sparse", Ko, od.gatherdofnums(conn), od.nalldofs), od.nalldofs)
+
+
+def test_two_layup_groups_with_different_csys(fs):
+    """Each layup group uses its own csys and thickness (src/FEMMShellT3FFCompModule.jl:501-509,600-620)."""
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh("t3", n=6, crease=0.0)
+    ne = conn.shape[0]
+    lay, cs1 = _layup()
+    th = np.deg2rad(-55.0)
+    cs2 = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    g1, g2 = np.arange(1, ne // 2 + 1), np.arange(ne // 2 + 1, ne + 1)
+    femm = f.FEMMShellT3FFComp(f.IntegDomain(conn, None, T_), [(_fs_layup(fs, cs1), g1), (_fs_layup(fs, cs2), g2)])
+    geom0, dchi, u0, R0 = _fields(f, xyz)
+    f.associategeometry(femm, geom0)
+    lcs = np.zeros((ne, 3, 3))
+    lcs[g1 - 1], lcs[g2 - 1] = cs1, cs2
+    no, vo = osh.t3ff_associategeometry(xyz, conn, normal_dir=np.repeat(lcs[:, None, :, 2], 3, axis=1))
+    assert np.abs(femm._normals - no).max() < 1e-13 and np.array_equal(femm._normal_valid, vo)
+    A, B, D = lay.laminate_stiffnesses()
+    H = lay.laminate_transverse_stiffness()
+    Ko = osh.t3ffcomp_stiffness_elmats(xyz, conn, no, vo, A, B, D, H, lay.thickness, lcs)
+    femm._sync_stab()
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    assert max(relfro(Kg[e], Ko[e]) for e in range(ne)) < TOL
+
+
+# ---------------------------------------------------------------------------------------
+# numberdofs!(dchi, perm) for Q4RS and the beam (the first suite permutes only T3FF)
+# ---------------------------------------------------------------------------------------
+def test_permuted_numbering_q4(fs):
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh("q4", n=7)
+    perm = np.random.default_rng(6).permutation(xyz.shape[0])
+    od = meshes.clamp_edge_dofs(xyz)
+    od.numberdofs(perm)
+    femm = _make_femm(fs, "q4", conn)
+    geom0, dchi, u0, R0 = _fields(f, xyz, od, perm)
+    assert np.array_equal(dchi.dofnums, od.dofnums)
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals("q4", xyz, conn)
+    Dps, Dt = _iso()
+    Ko = osh.q4rs_stiffness_elmats(xyz, conn, normals, valid, Dps, Dt, T_)
+    for asm, a in (("ffblock", f.SysmatAssemblerFFBlock()), ("sparse", f.SysmatAssemblerSparse())):
+        K = f.stiffness(femm, a, geom0, u0, R0, dchi)
+        n = od.nfreedofs if asm == "ffblock" else od.nalldofs
+        _check_matrix(K, fx.assemble_matrix(asm, Ko, od.gatherdofnums(conn), od.nalldofs, od.nfreedofs), n)
+
+
+def test_permuted_numbering_beam(fs):
+    f = fs.femm
+    xyz, conn, u1, R1, sec = meshes.beam_lattice()
+    EB, NUB = 71240.0, 0.31
+    perm = np.random.default_rng(7).permutation(xyz.shape[0])
+    od = fx.DofField(xyz.shape[0])
+    for c in range(1, 7):
+        od.setebc([0], c)
+    od.setebc([17], 3)
+    od.numberdofs(perm)
+    secs = f.FESetL2Beam(sec["A"], sec["I1"], sec["I2"], sec["I3"], sec["J"], sec["A2s"], sec["A3s"], sec["x1x2"])
+    femm = f.FEMMCorotBeam(f.IntegDomain(conn), f.MatDeforElastIso(EB, NUB, 5e-9), secs)
+    geom0 = f.NodalField(xyz)
+    dchi = f.NodalField(np.zeros((xyz.shape[0], 6)))
+    dchi.is_fixed[:] = od.is_fixed
+    dchi.numberdofs(perm)
+    uf, Rf = f.NodalField(u1), f.NodalField(R1)
+    dn = od.gatherdofnums(conn)
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, uf, Rf, dchi)
+    _check_matrix(K, fx.assemble_matrix("ffblock", obeam.beam_stiffness_elmats(xyz, conn, u1, R1, sec, EB, NUB), dn, od.nalldofs, od.nfreedofs), od.nfreedofs)
+    Kg = f.geostiffness(femm, f.SysmatAssemblerSparse(), geom0, uf, Rf, dchi)
+    _check_matrix(Kg, fx.assemble_matrix("sparse", obeam.beam_geostiffness_elmats(xyz, conn, u1, R1, sec, EB, NUB), dn, od.nalldofs), od.nalldofs)
+    Fr = f.restoringforce(femm, f.SysvecAssemblerFBlock(), geom0, uf, Rf, dchi)
+    ev = obeam.beam_restoringforce_elvecs(xyz, conn, u1, R1, sec, EB, NUB)
+    assert relfro(Fr, fx.assemble_vector(ev, dn, od.nalldofs, od.nfreedofs)) < TOL
+
+
+# ---------------------------------------------------------------------------------------
+# one triangle of the result (fsgpu_fetch_matrix_uplo)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("asm", ["ffblock", "sparse", "symm"])
+@pytest.mark.parametrize("narrow", [False, True])
+def test_fetch_triangle(fs, asm, narrow, monkeypatch):
+    import scipy.sparse as sp
+
+    if narrow:  # force the pinned-ring / host-expansion path and many pieces on a small matrix
+        monkeypatch.setenv("FSGPU_FETCH_NARROW_MIN", "0")
+        monkeypatch.setenv("FSGPU_FETCH_CHUNK_UNITS", "64")
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh("q4", n=8)
+    od = meshes.clamp_edge_dofs(xyz)
+    femm = _make_femm(fs, "q4", conn)
+    geom0, dchi, u0, R0 = _fields(f, xyz, od)
+    f.associategeometry(femm, geom0)
+    mk = {"ffblock": f.SysmatAssemblerFFBlock, "sparse": f.SysmatAssemblerSparse, "symm": f.SysmatAssemblerSparseSymm}[asm]
+    f.stiffness(femm, mk(), geom0, u0, R0, dchi)
+    Kf = femm.ctx.fetch_matrix()  # full matrix and both triangles of the SAME device result: bitwise comparable
+    Kc = Kf.to_scipy().tocsc()
+    cp, rv, nz = Kf.colptr - 1, Kf.rowval - 1, Kf.nzval
+    col = np.repeat(np.arange(Kf.n), np.diff(cp))
+    for uplo in ("L", "U"):
+        keep = rv >= col if uplo == "L" else rv <= col
+        T = femm.ctx.fetch_matrix_uplo(uplo)
+        assert np.array_equal(T.rowval - 1, rv[keep]), "explicit zeros are kept by the triangle as by the full fetch"
+        assert np.array_equal(T.nzval, nz[keep])
+        assert np.array_equal(np.diff(T.colptr), np.bincount(col[keep], minlength=Kf.n))
+        assert femm.ctx.result_size_uplo(uplo) == int(keep.sum())
+    # through the operator API: the assembler carries the triangle request
+    a = mk()
+    a.uplo = "L"
+    T = f.stiffness(femm, a, geom0, u0, R0, dchi)
+    ref = sp.tril(Kc, format="csc")
+    assert abs(T.to_scipy() - ref).max() < 1e-12 * abs(ref).max()
+
+
+# ---------------------------------------------------------------------------------------
+# explicit loop: arbitrary load-factor table (force!(F, t) of plate_expl_examples.jl:86 sampled per step)
+# ---------------------------------------------------------------------------------------
+def test_explicit_load_factor_table(fs):
+    f = fs.femm
+    xy, conn = fx.t3block(1.0, 0.6, 10, 6)
+    xyz = fx.xyz3(xy)
+    xyz[:, 2] = 0.04 * np.cos(2 * xyz[:, 0]) * xyz[:, 1]
+    od = meshes.clamp_edge_dofs(xyz, n_extra_fixed=0)
+    femm = _make_femm(fs, "t3", conn)
+    geom0, dchi, u0, R0 = _fields(f, xyz, od)
+    f.associategeometry(femm, geom0)
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, u0, R0, dchi)
+    femm.ctx.shell_mass_diag(femm._params(), 3, nfree_only=True)
+    nf = od.nfreedofs
+    Mo = femm.ctx.fetch_vector(nf)
+    Ko = K.to_scipy().tocsr()
+    lam = oexp.pwr_largest(Ko, Mo, 200)
+    dt = 0.8 * 2 / np.sqrt(lam)
+    cs = 350.0
+    rng = np.random.default_rng(8)
+    F0 = rng.standard_normal(nf)
+    nsteps = 120
+    tab = np.where(np.arange(nsteps) < 40, np.linspace(0, 3, nsteps), 0.0) + 0.2 * rng.standard_normal(nsteps)  # ramp, drop, noise
+    ex = fs.Explicit(femm.ctx, c_scale=cs, dt=dt)
+    ex.set_load(F0)
+    ex.start(float(0.0))
+    ex.step(50, tab[:50])
+    ex.step(nsteps - 50, tab[50:])
+    U, V, A = ex.get_state()
+    k = {"i": -1}
+
+    def force(t):  # call 0: the initial acceleration (factor of ex.start); call s >= 1: step s
+        v = F0 * (0.0 if k["i"] < 0 else tab[k["i"]])
+        k["i"] += 1
+        return v
+
+    Uo, Vo, Ao = oexp.cd_loop(Mo, Ko, cs, np.zeros(nf), np.zeros(nf), nsteps, dt, force)
+    assert relfro(U, Uo) < 1e-9 and relfro(V, Vo) < 1e-9 and relfro(A, Ao) < 1e-9
+    ex.close()
+
+
+# ---------------------------------------------------------------------------------------
+# slices of the ACTUAL bench meshes (full-size node sets, first 100k elements) against the C port of the
+# reference algorithm (C2, C4) and the NumPy oracle (C3, C5): element matrices and the assembled CSC
+# ---------------------------------------------------------------------------------------
+NSLICE = 100_000
+
+
+def _ws_fields(f, w):
+    geom0 = f.NodalField.__new__(f.NodalField)
+    geom0.values = w["xyz"]
+    dchi = f.NodalField.__new__(f.NodalField)
+    dchi.values, dchi.dofnums, dchi._nfree = None, w["dofnums"], w["nfree"]
+    return geom0, dchi
+
+
+def _cport_elmats_and_csc(refport, nn, conn, xyz, normals, valid, dofnums, nfree, E, nu, t, alpha):
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(E, nu))
+    Dps, Dt = np.ascontiguousarray(Dps), np.ascontiguousarray(Dt)
+    pc, wt = fx.gauss_rule_2x2()
+    pc = np.ascontiguousarray(pc)
+    n, ne, nnodes = 6 * nn, conn.shape[0], xyz.shape[0]
+    connC = np.ascontiguousarray(conn)
+    xyzF, nF, v8, dF = np.asfortranarray(xyz), np.asfortranarray(normals), np.ascontiguousarray(valid.astype(np.uint8)), np.asfortranarray(dofnums)
+    out = np.zeros((ne, n, n))
+    refport.ref_shell_stiffness_elmats(nn, C.c_int64(ne), P(connC), C.c_int64(nnodes), P(xyzF), P(nF), P(v8), P(Dps), P(Dt), C.c_double(t),
+                                       C.c_double(alpha), C.c_double(1.0), 4, P(pc), P(wt), P(out))
+    nt = ne * n * n
+    I, J, V = np.zeros(nt, np.int64), np.zeros(nt, np.int64), np.zeros(nt)
+    refport.ref_shell_stiffness_coo(nn, C.c_int64(ne), P(connC), C.c_int64(nnodes), P(xyzF), P(nF), P(v8), P(dF), P(Dps), P(Dt), C.c_double(t),
+                                    C.c_double(alpha), C.c_double(1.0), 4, P(pc), P(wt), os.cpu_count() or 1, P(I), P(J), P(V))
+    nall = dofnums.size
+    cp, rv, nz = np.zeros(nfree + 1, np.int64), np.zeros(nt, np.int64), np.zeros(nt)
+    nnz = refport.ref_coo_to_csc(C.c_int64(nt), P(I), P(J), P(V), C.c_int64(nall), C.c_int64(nall), C.c_int64(nfree), C.c_int64(nfree), P(cp), P(rv), P(nz))
+    return out.transpose(0, 2, 1), cp, rv[:nnz], nz[:nnz]
+
+
+@pytest.mark.parametrize("cfg", ["C2", "C4"])
+def test_bench_mesh_slice_against_c_port(fs, refport, cfg):
+    from fsb200 import workloads as wl
+
+    f = fs.femm
+    if cfg == "C2":
+        w, nn, alpha = wl.c2_q4rs_plate(1000), 4, 0.1
+    else:
+        w, nn, alpha = wl.c4_t3ff_panel(2000, 1000), 3, osh.T3_DEFAULT_ALPHA
+    mat = f.MatDeforElastIso(w["E"], w["nu"], w["rho"])
+    geom0, dchi = _ws_fields(f, w)
+    # nodal normals of the FULL mesh (device), then operators on the first NSLICE elements of it
+    full = (f.FEMMShellQ4RS if nn == 4 else f.FEMMShellT3FF)(f.IntegDomain(w["conn"], f.GaussRule2x2() if nn == 4 else None, w["thickness"]), mat)
+    f.associategeometry(full, geom0)
+    normals, valid = full._normals, full._normal_valid
+    full.ctx.close()
+    conn = np.ascontiguousarray(w["conn"][:NSLICE])
+    femm = (f.FEMMShellQ4RS if nn == 4 else f.FEMMShellT3FF)(f.IntegDomain(conn, f.GaussRule2x2() if nn == 4 else None, w["thickness"]), mat)
+    femm._normals, femm._normal_valid, femm._associatedgeometry = normals, valid, True
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, None, None, dchi)
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    Ke, cp, rv, nz = _cport_elmats_and_csc(refport, nn, conn, np.asarray(w["xyz"]), np.asarray(normals), np.asarray(valid), w["dofnums"], w["nfree"],
+                                           w["E"], w["nu"], w["thickness"], alpha)
+    num = np.sqrt(np.einsum("eij,eij->e", Kg - Ke, Kg - Ke))
+    den = np.sqrt(np.einsum("eij,eij->e", Ke, Ke))
+    assert (num / den).max() < TOL, (num / den).max()
+    assert np.array_equal(K.colptr, cp) and np.array_equal(K.rowval, rv), "pattern of the bench-mesh slice"
+    assert relfro(K.nzval, nz) < TOL
+    femm.ctx.close()
+
+
+def test_bench_mesh_slice_c3(fs):
+    from fsb200 import workloads as wl
+
+    f = fs.femm
+    w = wl.c3_t3ffcomp_cylinder(1000, 1000)
+    lam = w["lamina"]
+    t = w["thickness"]
+    mat = f.lamina_material(*lam)
+    plies = [f.Ply(f"p{k}", mat, t / 4, a) for k, a in enumerate(w["angles"])]
+    conn = np.ascontiguousarray(w["conn"][:NSLICE])
+    femm = f.FEMMShellT3FFComp(f.IntegDomain(conn, None, t), f.CompositeLayup("C3", plies, wl.cylindrical_csys))
+    geom0, dchi = _ws_fields(f, w)
+    xyz = np.asarray(w["xyz"])
+    femm._sync_mesh(geom0)
+    femm._normals, femm._normal_valid, femm._associatedgeometry = np.asfortranarray(w["normals"]), np.ones(xyz.shape[0], bool), True
+    femm.ctx.set_normals(femm._normals, femm._normal_valid)
+    femm._sync_stab()
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    D6 = oly.lamina_moduli(*lam[1:])
+    lay = oly.CompositeLayup("c3", [oly.Ply(f"p{k}", D6, t / 4, a, lam[0]) for k, a in enumerate(w["angles"])])
+    A, B, D = lay.laminate_stiffnesses()
+    H = lay.laminate_transverse_stiffness()
+    lcs = wl.cylindrical_csys(xyz[conn - 1].mean(axis=1))
+    Ko = osh.t3ffcomp_stiffness_elmats(xyz, conn, np.asarray(w["normals"]), np.ones(xyz.shape[0], bool), A, B, D, H, lay.thickness, lcs)
+    num = np.sqrt(np.einsum("eij,eij->e", Kg - Ko, Kg - Ko))
+    den = np.sqrt(np.einsum("eij,eij->e", Ko, Ko))
+    assert (num / den).max() < TOL, (num / den).max()
+    md, mi = lay.laminate_inertia()
+    Mg = femm.ctx.element_matrices(femm._kind(), 1, femm._params())
+    assert relfro(Mg, osh.t3ffcomp_mass_elmats(xyz, conn, md, mi)) < TOL
+    femm.ctx.close()
+
+
+def test_bench_mesh_slice_c5(fs):
+    from fsb200 import workloads as wl
+
+    f = fs.femm
+    w = wl.c5_beam_lattice(69)
+    sl = slice(0, NSLICE)
+    sc = {k: (v[sl] if k != "x1x2" else v[sl]) for k, v in w["sections"].items()}
+    conn = np.ascontiguousarray(w["conn"][sl])
+    secs = f.FESetL2Beam(sc["A"], sc["I1"], sc["I2"], sc["I3"], sc["J"], sc["A2s"], sc["A3s"], sc["x1x2"])
+    femm = f.FEMMCorotBeam(f.IntegDomain(conn), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]), secs)
+    geom0, dchi = _ws_fields(f, w)
+    xyz, u1, R1 = np.asarray(w["xyz"]), np.asarray(w["u1"]), np.asarray(w["Rfield1"])
+    femm._sync_mesh(geom0)
+    femm.ctx.set_state(u1, R1)
+    for op, ref in ((0, obeam.beam_stiffness_elmats(xyz, conn, u1, R1, sc, w["E"], w["nu"])), (2, obeam.beam_geostiffness_elmats(xyz, conn, u1, R1, sc, w["E"], w["nu"]))):
+        got = femm.ctx.element_matrices(2, op, femm._params())
+        # 1e-12 on the relative Frobenius norm of the whole slice (the north star's measure); single elements whose
+        # natural deformations nearly cancel are conditioned worse than that in the reference arithmetic itself
+        assert relfro(got, ref) < TOL
+        num = np.sqrt(np.einsum("eij,eij->e", got - ref, got - ref))
+        den = np.sqrt(np.einsum("eij,eij->e", ref, ref))
+        rel = num / np.where(den > 0, den, 1.0)
+        assert np.median(rel) < 1e-14 and rel.max() < 1e-10, (np.median(rel), rel.max())
+    ev = femm.ctx.element_vectors(femm._params())
+    ref = obeam.beam_restoringforce_elvecs(xyz, conn, u1, R1, sc, w["E"], w["nu"])
+    assert relfro(ev, ref) < TOL
+    femm.ctx.close()
+
+
+# ---------------------------------------------------------------------------------------
+# built-in csys kinds evaluated on the device (fsgpu_associategeometry_csys, fsgpu_set_layup_csys)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,csname", [("t3", "cylindrical"), ("t3", "spherical"), ("t3", "normal_axis"), ("q4", "cylindrical"), ("q4", "normal_axis")])
+def test_device_csys_kinds(fs, kind, csname):
+    f = fs.femm
+    rng = np.random.default_rng(21)
+    gen = fx.t3block if kind == "t3" else fx.q4block
+    xy, conn = gen(1.2, 0.9, 9, 6)
+    if csname == "spherical":  # a spherical cap around the z axis, away from the pole
+        th, ph = 0.5 + xy[:, 0], 0.4 + xy[:, 1]
+        xyz = 0.7 * np.column_stack([np.sin(ph) * np.cos(th), np.sin(ph) * np.sin(th), np.cos(ph)]) + np.array([0.1, -0.2, 0.3])
+        cs = f.CSysKind.spherical(axis=(0.0, 0.0, 1.0), origin=(0.1, -0.2, 0.3))
+    else:  # a cylindrical panel around an inclined axis through a shifted origin
+        ax = np.array([0.2, 1.0, -0.1])
+        ax /= np.linalg.norm(ax)
+        p1 = np.cross(ax, [0.0, 0.0, 1.0])
+        p1 /= np.linalg.norm(p1)
+        p2 = np.cross(ax, p1)
+        org = np.array([0.3, -0.1, 0.2])
+        a = 0.3 + xy[:, 0]
+        xyz = org + 0.5 * (np.cos(a)[:, None] * p1 + np.sin(a)[:, None] * p2) + xy[:, 1][:, None] * ax
+        cs = f.CSysKind.cylindrical(axis=ax, origin=org) if csname == "cylindrical" else f.CSysKind.normal_axis(axis=ax)
+    xyz = xyz + rng.uniform(-1, 1, xyz.shape) * 2e-3
+    lay, _ = _layup()
+    idom = f.IntegDomain(conn, None if kind == "t3" else f.GaussRule2x2(), T_)
+    femm = (f.FEMMShellT3FFComp if kind == "t3" else f.FEMMShellQ4RSComp)(idom, _fs_layup(fs, cs))
+    geom0, dchi, u0, R0 = _fields(f, xyz)
+    f.associategeometry(femm, geom0)
+    X = xyz[conn - 1]
+    ne, nn = conn.shape
+    dirs = np.zeros((ne, nn, 3))
+    for k in range(nn):
+        if nn == 3:
+            J = np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]], axis=-1)
+        else:
+            J = np.einsum("eai,ak->eik", X, fx.q4_shape(*fx.nodal_rule_q4()[0][k])[1])
+        dirs[:, k] = cs(X[:, k], J)[:, :, 2]
+    no, vo = (osh.t3ff_associategeometry if kind == "t3" else osh.q4rs_associategeometry)(xyz, conn, normal_dir=dirs)
+    assert np.abs(femm._normals - no).max() < 1e-13 and np.array_equal(femm._normal_valid, vo)
+    A, B, D = lay.laminate_stiffnesses()
+    H = lay.laminate_transverse_stiffness()
+    if kind == "t3":
+        J0 = np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]], axis=-1)
+        lcs = cs(X.mean(axis=1), J0)
+        Ko = osh.t3ffcomp_stiffness_elmats(xyz, conn, no, vo, A, B, D, H, lay.thickness, lcs)
+    else:
+        if csname == "cylindrical":
+            # the reference hands Q4RSComp's layup csys the shape-function values as the location (App. B.9): a
+            # position-based csys is meaningless there (the normals above ARE position-based and are checked);
+            # normal_axis (tangent-based) is the usable kind for the stiffness and is tested
+            return
+        pc, w = fx.gauss_rule_2x2()
+        lcs = np.zeros((ne, len(w), 3, 3))
+        for j in range(len(w)):
+            N, dNp = fx.q4_shape(*pc[j])
+            lcs[:, j] = cs(np.broadcast_to(np.ravel(N), (ne, 4)), np.einsum("eai,ak->eik", X, dNp))
+        Ko = osh.q4rscomp_stiffness_elmats(xyz, conn, no, vo, A, B, D, H, lay.thickness, lcs)
+    femm._sync_stab()
+    Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
+    assert max(relfro(Kg[e], Ko[e]) for e in range(ne)) < TOL
