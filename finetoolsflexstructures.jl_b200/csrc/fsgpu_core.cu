@@ -1567,7 +1567,8 @@ extern "C" int fsgpu_vector_device(fsgpu_ctx* c, const double** v, int64_t* n) {
 // in input order, explicit zeros retained.
 // ------------------------------------------------------------------------------------
 namespace fs {
-__global__ void k_coo_keys(const int64_t* __restrict__ I, const int64_t* __restrict__ J, int64_t n, int64_t m, int64_t nc,
+// key = (column << rbits) | row with rbits = ceil(log2 m): only the significant ceil(log2 m) + ceil(log2 n) bits are sorted
+__global__ void k_coo_keys(const int64_t* __restrict__ I, const int64_t* __restrict__ J, int64_t n, int64_t m, int64_t nc, int rbits,
                            uint64_t* __restrict__ keys, int32_t* __restrict__ flag) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1576,15 +1577,27 @@ __global__ void k_coo_keys(const int64_t* __restrict__ I, const int64_t* __restr
     atomicExch(flag, 1);
     r = cc = 1;
   }
-  keys[i] = ((uint64_t)(cc - 1) << 32) | (uint64_t)(r - 1);
+  keys[i] = ((uint64_t)(cc - 1) << rbits) | (uint64_t)(r - 1);
 }
-__global__ void k_csc_from_unique(const uint64_t* __restrict__ ukeys, int64_t nu, int64_t* __restrict__ rowval,
-                                  int64_t* __restrict__ colcnt) {
+__global__ void k_coo_heads(const uint64_t* __restrict__ keys, int64_t n, unsigned char* __restrict__ head) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+// One thread per stored entry: the duplicates of an entry are adjacent and in INPUT ORDER after the stable sort; they
+// are added one after the other, left to right, exactly as Julia's `sparse` combines them (segments of a finite-element
+// COO list have <= a few entries)
+__global__ void k_coo_segments(const uint64_t* __restrict__ keys, const double* __restrict__ v, const int64_t* __restrict__ start,
+                               int64_t nu, int64_t nt, int rbits, int64_t* __restrict__ rowval, double* __restrict__ nz,
+                               int64_t* __restrict__ colcnt) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nu) return;
-  uint64_t k = ukeys[i];
-  rowval[i] = (int64_t)(k & 0xffffffffu) + 1;
-  atomicAdd((unsigned long long*)(colcnt + (k >> 32)), 1ull);
+  const int64_t b = start[i], e = (i + 1 < nu) ? start[i + 1] : nt;
+  double s = v[b];
+  for (int64_t k = b + 1; k < e; ++k) s += v[k];
+  nz[i] = s;
+  const uint64_t key = keys[b];
+  rowval[i] = (int64_t)(key & ((1ull << rbits) - 1)) + 1;
+  atomicAdd((unsigned long long*)(colcnt + (key >> rbits)), 1ull);
 }
 __global__ void k_add1_i64(int64_t* p, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1641,10 +1654,30 @@ extern "C" int fsgpu_coo_to_csc(fsgpu_ctx* c, int64_t m, int64_t n, int64_t nt, 
   FS_REQUIRE(nnz_out, FSGPU_ERR_ARG, "null nnz");
   cudaStream_t st = c->stream;
   FS_TRY(ensure_flag(c));
+  // two-call convention: the size query does the whole conversion and keeps the result on the device; the fill call
+  // with the same arguments only downloads it
+  DBuf<int64_t>&drow = c->coo_row, &dptr = c->coo_ptr;
+  DBuf<double>& dVr = c->coo_val;
+  const bool cached = c->coo_key[0] == (const void*)I && c->coo_key[1] == (const void*)J && c->coo_key[2] == (const void*)V &&
+                      c->coo_dims[0] == m && c->coo_dims[1] == n && c->coo_dims[2] == nt && (colptr || rowval || nzval);
+  if (cached) {
+    const int64_t nu = c->coo_dims[3];
+    *nnz_out = nu;
+    if (colptr) FS_TRY(download(c, colptr, dptr.p, ((size_t)n + 1) * sizeof(int64_t)));
+    if (rowval) FS_TRY(download(c, rowval, drow.p, (size_t)nu * sizeof(int64_t)));
+    if (nzval) FS_TRY(download(c, nzval, dVr.p, (size_t)nu * sizeof(double)));
+    FS_CUDA(cudaStreamSynchronize(st));
+    c->coo_key[0] = c->coo_key[1] = c->coo_key[2] = nullptr;
+    drow.release();
+    dptr.release();
+    dVr.release();
+    return FSGPU_OK;
+  }
+  c->coo_key[0] = c->coo_key[1] = c->coo_key[2] = nullptr;
   DBuf<int64_t> dI, dJ;
-  DBuf<double> dV, dV2, dVr;
-  DBuf<uint64_t> k1, k2, ku;
-  DBuf<int64_t> nu_d, drow, dcnt, dptr;
+  DBuf<double> dV, dV2;
+  DBuf<uint64_t> k1, k2;
+  DBuf<int64_t> nu_d, dcnt;
   FS_TRY(dI.ensure((size_t)nt + 1));
   FS_TRY(dJ.ensure((size_t)nt + 1));
   FS_TRY(dV.ensure((size_t)nt + 1));
@@ -1654,39 +1687,57 @@ extern "C" int fsgpu_coo_to_csc(fsgpu_ctx* c, int64_t m, int64_t n, int64_t nt, 
   FS_TRY(upload(c, dI.p, I, (size_t)nt * sizeof(int64_t)));
   FS_TRY(upload(c, dJ.p, J, (size_t)nt * sizeof(int64_t)));
   FS_TRY(upload(c, dV.p, V, (size_t)nt * sizeof(double)));
-  LAUNCH(c, k_coo_keys, nt, dI.p, dJ.p, nt, m, n, k1.p, c->flag.p);
+  int rbits = 1, cbits = 1;
+  while (((int64_t)1 << rbits) < m) ++rbits;
+  while (((int64_t)1 << cbits) < n) ++cbits;
+  LAUNCH(c, k_coo_keys, nt, dI.p, dJ.p, nt, m, n, rbits, k1.p, c->flag.p);
   int32_t f;
   FS_TRY(read_flag(c, 0, &f));
   FS_REQUIRE(f == 0, FSGPU_ERR_DOF_RANGE, "row or column index outside the matrix");
   size_t tb = 0, tb2 = 0;
   int64_t nu = 0;
-  FS_TRY(ku.ensure((size_t)nt + 1));
+  DBuf<unsigned char> head;
+  DBuf<int64_t> start;
+  FS_TRY(head.ensure((size_t)nt + 1));
+  FS_TRY(start.ensure((size_t)nt + 1));
   FS_TRY(dVr.ensure((size_t)nt + 1));
   FS_TRY(nu_d.ensure(1));
   if (nt > 0) {
-    // LSD radix sort is stable: equal (col,row) keys keep input order, so the segmented
-    // sum below adds duplicates in input order like `sparse` does.
-    FS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k1.p, k2.p, dV.p, dV2.p, nt, 0, 64, st));
-    FS_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tb2, k2.p, ku.p, dV2.p, dVr.p, nu_d.p, ::cuda::std::plus<>(), nt, st));
+    // LSD radix sort over the significant key bits only (C2-sized index spaces: 46 instead of 64 bits); it is stable:
+    // equal (column, row) keys keep their input order
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k1.p, k2.p, dV.p, dV2.p, nt, 0, rbits + cbits, st));
+    cub::CountingInputIterator<int64_t> iota(0);
+    FS_CUDA(cub::DeviceSelect::Flagged(nullptr, tb2, iota, head.p, start.p, nu_d.p, nt, st));
     FS_TRY(c->tmp.ensure(tb > tb2 ? tb : tb2));
-    FS_CUDA(cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k1.p, k2.p, dV.p, dV2.p, nt, 0, 64, st));
-    FS_CUDA(cub::DeviceReduce::ReduceByKey(c->tmp.p, tb2, k2.p, ku.p, dV2.p, dVr.p, nu_d.p, ::cuda::std::plus<>(), nt, st));
-    c->launches += 10;
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k1.p, k2.p, dV.p, dV2.p, nt, 0, rbits + cbits, st));
+    LAUNCH(c, k_coo_heads, nt, k2.p, nt, head.p);
+    FS_CUDA(cub::DeviceSelect::Flagged(c->tmp.p, tb2, iota, head.p, start.p, nu_d.p, nt, st));
+    c->launches += 8;
     FS_CUDA(cudaMemcpyAsync(&nu, nu_d.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     FS_CUDA(cudaStreamSynchronize(st));
   }
   *nnz_out = nu;
-  if (!colptr && !rowval && !nzval) return FSGPU_OK;
   FS_TRY(drow.ensure((size_t)nu + 1));
   FS_TRY(dcnt.ensure((size_t)n + 1));
   FS_TRY(dptr.ensure((size_t)n + 1));
   FS_CUDA(cudaMemsetAsync(dcnt.p, 0, ((size_t)n + 1) * sizeof(int64_t), st));
-  LAUNCH(c, k_csc_from_unique, nu, ku.p, nu, drow.p, dcnt.p);
+  LAUNCH(c, k_coo_segments, nu, k2.p, dV2.p, start.p, nu, nt, rbits, drow.p, dVr.p, dcnt.p);
   FS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, dcnt.p, dptr.p, n + 1, st));
   FS_TRY(c->tmp.ensure(tb));
   FS_CUDA(cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, dcnt.p, dptr.p, n + 1, st));
   c->launches += 2;
   LAUNCH(c, k_add1_i64, n + 1, dptr.p, n + 1);
+  if (!colptr && !rowval && !nzval) {
+    FS_CUDA(cudaStreamSynchronize(st));
+    c->coo_key[0] = I;
+    c->coo_key[1] = J;
+    c->coo_key[2] = V;
+    c->coo_dims[0] = m;
+    c->coo_dims[1] = n;
+    c->coo_dims[2] = nt;
+    c->coo_dims[3] = nu;
+    return FSGPU_OK;
+  }
   if (colptr) FS_TRY(download(c, colptr, dptr.p, ((size_t)n + 1) * sizeof(int64_t)));
   if (rowval) FS_TRY(download(c, rowval, drow.p, (size_t)nu * sizeof(int64_t)));
   if (nzval) FS_TRY(download(c, nzval, dVr.p, (size_t)nu * sizeof(double)));

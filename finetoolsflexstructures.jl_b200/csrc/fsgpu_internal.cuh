@@ -179,6 +179,11 @@ struct fsgpu_ctx {
   // one triangle of the result (fsgpu_fetch_matrix_uplo)
   fs::DBuf<int32_t> t_cnt, t_first, t_colptr, t_rowval;
   fs::DBuf<double> t_nzval;
+  // COO -> CSC: result of the size query, kept for the fill call (two-call convention)
+  const void* coo_key[3] = {nullptr, nullptr, nullptr};
+  int64_t coo_dims[4] = {0, 0, 0, 0};
+  fs::DBuf<int64_t> coo_row, coo_ptr;
+  fs::DBuf<double> coo_val;
   // result vector
   bool have_vector = false;
   int64_t vlen = 0;

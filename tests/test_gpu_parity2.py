@@ -542,3 +542,87 @@ def test_device_csys_kinds(fs, kind, csname):
     femm._sync_stab()
     Kg = femm.ctx.element_matrices(femm._kind(), 0, femm._params())
     assert max(relfro(Kg[e], Ko[e]) for e in range(ne)) < TOL
+
+
+# ---------------------------------------------------------------------------------------
+# COO -> CSC: duplicates are combined left to right in input order, as Julia's sparse() does -- bit for bit
+# ---------------------------------------------------------------------------------------
+def test_coo_to_csc_bitwise_against_c_port(fs, refport):
+    rng = np.random.default_rng(31)
+    m, n, nt = 5000, 3000, 400_000
+    I = rng.integers(1, m + 1, nt).astype(np.int64)
+    J = rng.integers(1, n + 1, nt).astype(np.int64)
+    # heavy duplication on a few entries (long segments) and values spanning 30 orders of magnitude: any other
+    # association of the additions changes the last bits
+    hot = rng.integers(0, nt, 60_000)
+    I[hot], J[hot] = I[hot[0]] % 7 + 1, J[hot[0]] % 5 + 1
+    V = rng.standard_normal(nt) * 10.0 ** rng.uniform(-15, 15, nt)
+    ctx = fs.Context()
+    S = ctx.coo_to_csc(I, J, V, m, n)
+    cp, rv, nz = S.colptr, S.rowval, S.nzval
+    a = [C.c_int64(nt), P(I), P(J), P(V), C.c_int64(m), C.c_int64(n), C.c_int64(m), C.c_int64(n)]
+    nnz = refport.ref_coo_to_csc(*a, None, None, None)
+    rcp, rrv, rnz = np.zeros(n + 1, np.int64), np.zeros(nnz, np.int64), np.zeros(nnz)
+    refport.ref_coo_to_csc(*a, P(rcp), P(rrv), P(rnz))
+    assert np.array_equal(cp, rcp) and np.array_equal(rv, rrv)
+    assert np.array_equal(nz, rnz), "values must be bitwise those of the sequential left-to-right sums"
+    assert np.array_equal(nz, ctx.coo_to_csc(I, J, V, m, n).nzval)  # and reproducible from run to run
+
+
+# ---------------------------------------------------------------------------------------
+# SysmatAssemblerSparseSymm (the default assembler): `S + S'` drops results that are exactly 0.0, so the stored
+# pattern depends on the VALUES.  What can be guaranteed, and is asserted here:
+#  * entries all of whose element contributions are exactly zero (membrane/bending coupling of a flat plate, the
+#    off-diagonals of a lumped mass) are dropped by the GPU path exactly as by the reference semantics;
+#  * on a mesh without exact symmetries the patterns are identical;
+#  * the two patterns can differ ONLY in entries that are sums of >= 2 non-zero element contributions cancelling by
+#    mesh symmetry -- whether such a sum is exactly 0.0 or 1e-17 of the largest entry depends on the order of the
+#    floating-point operations (in the reference: on its BLAS), never on anything structural.
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["t3", "q4"])
+def test_symm_pattern_characterised(fs, kind):
+    import scipy.sparse as sp
+
+    f = fs.femm
+    for flat in (True, False):
+        if flat:
+            xy, conn = (fx.t3block if kind == "t3" else fx.q4block)(2.0, 1.0, 7, 5)
+            xyz = fx.xyz3(xy)
+        else:
+            xyz, conn = meshes.shell_mesh(kind, n=6)
+        femm = _make_femm(fs, kind, conn)
+        geom0, dchi, u0, R0 = _fields(f, xyz)
+        f.associategeometry(femm, geom0)
+        K = f.stiffness(femm, geom0, u0, R0, dchi)  # default assembler = SparseSymm
+        normals, valid = _oracle_normals(kind, xyz, conn)
+        Dps, Dt = _iso()
+        Ko = (osh.t3ff_stiffness_elmats if kind == "t3" else osh.q4rs_stiffness_elmats)(xyz, conn, normals, valid, Dps, Dt, T_)
+        od = fx.DofField(xyz.shape[0]).numberdofs()
+        dn = od.gatherdofnums(conn)
+        n = od.nalldofs
+        cp, rv, nz = fx.assemble_matrix("symm", Ko, dn, n)
+        Kg, Kr = K.to_scipy().tocsc(), fx.csc_to_scipy(cp, rv, nz, n, n).tocsc()
+        assert relfro(Kg.toarray(), Kr.toarray()) < TOL and abs(Kg - Kg.T).max() == 0.0
+        I, J, V = fx.coo_full(Ko, dn)
+        nzc = sp.coo_matrix(((V != 0).astype(np.float64), (I - 1, J - 1)), shape=(n, n)).tocsc()  # non-zero contributions per entry
+        Pg = sp.csc_matrix((np.ones_like(Kg.data), Kg.indices, Kg.indptr), shape=(n, n))
+        Pr = sp.csc_matrix((np.ones_like(Kr.data), Kr.indices, Kr.indptr), shape=(n, n))
+        # (1) structural zeros: never stored by either
+        struct_zero = sp.coo_matrix((np.ones(len(V)), (I - 1, J - 1)), shape=(n, n)).tocsc()
+        struct_zero.data[:] = 1.0
+        only_zero = (struct_zero - (nzc > 0).astype(np.float64)).tocsc()
+        only_zero.eliminate_zeros()
+        assert Pg.multiply(only_zero).nnz == 0 and Pr.multiply(only_zero).nnz == 0
+        if flat:
+            assert only_zero.nnz > 0 and Kg.nnz < struct_zero.nnz, "the flat plate must have droppable zeros"
+        d = (Pg - Pr).tocoo()
+        sel = d.data != 0
+        if not flat:
+            assert sel.sum() == 0, "no exact symmetries: identical patterns"
+            continue
+        # (2) every difference is a cancelling multi-element sum at round-off level
+        rr, cc = d.row[sel], d.col[sel]
+        if len(rr):
+            assert np.asarray(nzc[rr, cc]).ravel().min() >= 2
+            big = max(np.abs(Kg.data).max(), np.abs(Kr.data).max())
+            assert np.abs(np.asarray((Kg + Kr)[rr, cc])).ravel().max() <= 1e-15 * big
