@@ -461,7 +461,84 @@ def extras_c3_c5(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
                            "newton_assemblies_per_s": 1e3 / tot, "elements_per_s": ne * world / (tot * 1e-3), "restoringforce_ms": ms_r,
                            "stiffness_ms": ms_s, "geostiffness_ms": ms_g, "nnz": int(bf.ctx.result_size()[2])}
     bf.ctx.close()
+
+    # ---- Q4RSComp on the C2 mesh (4-ply layup, cartesian layup csys), RED path and the order-fixed gather path ----
+    w = wl.c2_q4rs_plate(args.n)
+    t = w["thickness"]
+    mat = f.lamina_material(1500.0, 133860e6, 7706e6, 0.301, 4306e6, 4306e6, 2760e6)
+    plies = [f.Ply(f"p{k}", mat, t / 4, a) for k, a in enumerate((0.0, 90.0, 90.0, 0.0))]
+    fq = f.FEMMShellQ4RSComp(f.IntegDomain(w["conn"], f.GaussRule2x2(), t), f.CompositeLayup("Q4C", plies, np.eye(3)), device=local_rank)
+    fq.ctx.set_stream(stream.cuda_stream)
+    geom0, dchi = field(w["xyz"]), field(None, w["dofnums"], w["nfree"])
+    f.associategeometry(fq, geom0)
+    fq._startassembly(f.SysmatAssemblerFFBlock(), dchi)
+    fq._sync_stab()
+    p = fq._params()
+    ne = w["conn"].shape[0]
+    ms_qc = timed(lambda: fq.ctx.shell_op("q4rscomp_stiffness", p))
+    kms_qc = fq.ctx.last_kernel_ms
+    nnzq = fq.ctx.result_size()[2]
+    out["q4rscomp_C2mesh"] = {"workload": f"Q4RSComp 4-ply [0/90/90/0], {ne} quads per rank (the C2 mesh), GaussRule(2,2): stiffness -> CSC (FFBlock)",
+                              "elements_per_s": ne * world / (ms_qc * 1e-3), "stiffness_ms": ms_qc, "stiffness_kernel_ms": kms_qc,
+                              "roofline": roof(48.0e3, 129.0 + 8.0, nnzq, ne, ms_qc)}
+    fq.ctx.close()
+    fh = f.FEMMShellQ4RS(f.IntegDomain(w["conn"], f.GaussRule2x2(), t), f.MatDeforElastIso(w["E"], w["nu"], w["rho"]), device=local_rank)
+    fh.ctx.set_stream(stream.cuda_stream)
+    fh.ctx.set_deterministic(True)
+    f.associategeometry(fh, geom0)
+    fh._startassembly(f.SysmatAssemblerFFBlock(), dchi)
+    fh._sync_stab()
+    p = fh._params()
+    ms_det = timed(lambda: fh.ctx.shell_op("q4rs_stiffness", p))
+    out["q4rs_deterministic_C2"] = {"workload": "C2 stiffness with fsgpu_set_deterministic: element matrices -> dense buffer -> one owner per matrix block sums "
+                                                "in ascending element order (the reference loop's order), no atomics, no clearing",
+                                    "ms_per_step": ms_det, "elements_per_s": ne * world / (ms_det * 1e-3), "scatter_path": fh.ctx.scatter_path,
+                                    "bitwise_reproducible": True}
+    # ---- COO -> CSC (Julia sparse()) of the COO list the reference materialises for the first 64k C2 elements ----
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            out["coo_to_csc"] = coo_bench(w, fh, min(ne, 64000))
+        except Exception as ex_:
+            out["coo_to_csc"] = {"error": repr(ex_)}
+    fh.ctx.close()
     return out
+
+
+def coo_bench(w, femm, nsample):
+    """fsgpu_coo_to_csc (host arrays in, host arrays out: H2D + sort over the significant key bits + in-order segment
+    sums + D2H) against the C port's serial counting-sort `ref_coo_to_csc` on the same triples.  The full C2 list
+    (576 M triples, 13.8 GB) fits the device but not a bounded CPU sample; the sample is stated."""
+    from oracle import fe_external as fx
+    from oracle import shells as osh
+
+    lib = load_refport()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    conn = np.ascontiguousarray(w["conn"][:nsample])
+    n = 24
+    nt = nsample * n * n
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(w["E"], w["nu"]))
+    Dps, Dt = np.ascontiguousarray(Dps), np.ascontiguousarray(Dt)
+    pc, wt = fx.gauss_rule_2x2()
+    pc = np.ascontiguousarray(pc)
+    I, J, V = np.zeros(nt, np.int64), np.zeros(nt, np.int64), np.zeros(nt)
+    v8 = np.ascontiguousarray(np.asarray(femm._normal_valid).astype(np.uint8))
+    nF = np.asfortranarray(femm._normals)
+    nnodes, nall = w["xyz"].shape[0], w["dofnums"].size
+    lib.ref_shell_stiffness_coo(4, C.c_int64(nsample), P(conn), C.c_int64(nnodes), P(w["xyz"]), P(nF), P(v8), P(w["dofnums"]), P(Dps), P(Dt),
+                                C.c_double(w["thickness"]), C.c_double(0.1), C.c_double(1.0), 4, P(pc), P(wt), os.cpu_count() or 1, P(I), P(J), P(V))
+    cp, rv, nz = np.zeros(nall + 1, np.int64), np.zeros(nt, np.int64), np.zeros(nt)
+    t0 = time.perf_counter()
+    nnz = lib.ref_coo_to_csc(C.c_int64(nt), P(I), P(J), P(V), C.c_int64(nall), C.c_int64(nall), C.c_int64(nall), C.c_int64(nall), P(cp), P(rv), P(nz))
+    cpu_s = time.perf_counter() - t0
+    femm.ctx.coo_to_csc(I, J, V, nall, nall)  # warm-up (allocations)
+    t0 = time.perf_counter()
+    S = femm.ctx.coo_to_csc(I, J, V, nall, nall)
+    gpu_s = time.perf_counter() - t0
+    same = bool(np.array_equal(S.colptr, cp) and np.array_equal(S.rowval, rv[:nnz]) and np.array_equal(S.nzval, nz[:nnz]))
+    return {"workload": f"COO -> CSC of the {nt} triples (24 B each) the reference materialises for the first {nsample} C2 elements, {nall} x {nall}",
+            "triples": int(nt), "nnz": int(nnz), "gpu_e2e_s": gpu_s, "gpu_triples_per_s": nt / gpu_s, "cpu_serial_s": cpu_s,
+            "cpu_triples_per_s": nt / cpu_s, "speedup": cpu_s / gpu_s, "bitwise_equal_to_cpu": same,
+            "includes": "H2D of I, J, V (Int64/Int64/f64 host arrays) + conversion + D2H of colptr/rowval/nzval; CPU: serial counting sort (Julia sparse() is serial)"}
 
 
 def gathered_c2(args, rank, local_rank, world, stream, w, normals, valid):
@@ -784,6 +861,33 @@ def main():
         t = torch.tensor([float(np.sum(nz_p[c0:c1]))], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         nz_checksum_blocks = float(t.item())
+    # secondary figure: the same end-to-end call for a consumer of ONE triangle (cholesky(Symmetric(K, :L))): half the
+    # bytes cross PCIe (fsgpu_fetch_matrix_uplo); the headline e2e above is the full matrix
+    asm_l = f.SysmatAssemblerFFBlock()
+    asm_l.uplo = "L"
+
+    def e2e_step_lower():
+        g = f.NodalField.__new__(f.NodalField)
+        g.values = xyz_p
+        d = f.NodalField.__new__(f.NodalField)
+        d.values, d.dofnums, d._nfree = None, dof_p, w["nfree"]
+        femm.reset_uploads()
+        return f.stiffness(femm, asm_l, g, u0, R0, d, out=(cp_p, rv_p, nz_p))
+
+    e2e_step_lower()
+    barrier()
+    b0 = femm.ctx.d2h_bytes
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step_lower()
+    barrier()
+    tl = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    e2e_lower = {"ms_per_step": float(tl.item()) * 1e3, "value": nelem / float(tl.item()), "unit": unit,
+                 "d2h_bytes_per_step": int((femm.ctx.d2h_bytes - b0) / args.e2e_steps),
+                 "what": "lower triangle incl. diagonal (uplo = L) of the same matrix, same H2D + symbolic + numeric phases"}
+
     # free the C2 buffers before the 4M-element workload
     del K, cp_p, rv_p, nz_p, k4, k5, k6
     femm.ctx.close()
@@ -860,7 +964,7 @@ def main():
                     "host_result_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3, "includes": e2e_includes,
                     "pinned_d2h_gbs_this_box": d2h_gbs,
-                    "values_refresh_ms_same_pattern": refresh_ms},
+                    "values_refresh_ms_same_pattern": refresh_ms, "lower_triangle": e2e_lower},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "symbolic_ms": {"first": symbolic_ms, "warm": symbolic_warm_ms}, "nnz": int(nnz), "other_workloads": extras}
     sys.stdout.flush()

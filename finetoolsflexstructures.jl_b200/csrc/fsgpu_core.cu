@@ -938,6 +938,7 @@ extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int6
   DBuf<int32_t>& adjptr = c->adjptr;
   DBuf<int32_t>& adj = c->adj;
   c->tile_ok = false;
+  c->det_ready = false;
   DBuf<int64_t>&colcnt = c->scr_colcnt, &nsel = c->scr_nsel;
   FS_TRY(keys.ensure((size_t)npairs + 1));
   FS_TRY(keys2.ensure((size_t)npairs + 1));

@@ -11,6 +11,8 @@
 //        the 6x6 block K_ij over all 8*npts strain rows held in shared memory.
 //   L2 : 4 lanes per element, lane = 6x6 block (I, J).
 // All arithmetic is FP64 on the CUDA cores; the scatter uses RED.ADD.F64 into L2.
+#include <cub/cub.cuh>
+
 #include "fsgpu_internal.cuh"
 #include "fsgpu_math.cuh"
 #include "fsgpu_shell.cuh"
@@ -1930,22 +1932,149 @@ EmitRuns runs_of(fsgpu_ctx* c) {
   return EmitRuns{c->nzval.p, c->pairoff.p, c->nodeinfo.p, c->dof.p, c->colptr.p, c->nelem, c->pcols, c->nnpe, c->nodecol.p};
 }
 
+// ---- order-fixed (deterministic) assembly for every element kind: element matrices -> dense buffer, then one
+// owner per matrix block sums its contributions in ascending element order and writes the block once ------------
+// (fsgpu_set_deterministic; T3FF / T3FFComp prefer the tile kernel, which needs no intermediate buffer.)  The sums run
+// in the order of the reference's serial element loop (src/FEMMShellQ4RSModule.jl:914-945, src/FEMMCorotBeamModule.jl:
+// 993-1022): values are bitwise reproducible from run to run; no atomics, no clearing of the value array.
+__global__ void k_det_keys(const int32_t* __restrict__ conn, int nnpe, int64_t nelem, int nb, uint64_t* __restrict__ keys,
+                           int32_t* __restrict__ idx) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int nn2 = nnpe * nnpe;
+  if (k >= nelem * nn2) return;
+  const int64_t e = k / nn2;
+  const int ij = (int)(k - e * nn2), i = ij / nnpe, j = ij - i * nnpe;
+  keys[k] = ((uint64_t)conn[e * nnpe + j] << nb) | (uint64_t)conn[e * nnpe + i];  // (column node, row node)
+  idx[k] = (int32_t)k;
+}
+__global__ void k_det_heads(const uint64_t* __restrict__ keys, int64_t n, unsigned char* __restrict__ head) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+// thread = (block b, column c of the block): sums the six rows over the block's contributions, in order
+__global__ void k_det_gather(const int32_t* __restrict__ bstart, const int32_t* __restrict__ contrib, int64_t nblocks, int64_t ncontrib,
+                             const double* __restrict__ dense, const int32_t* __restrict__ conn, int nnpe, int64_t nelem,
+                             const int32_t* __restrict__ nodecol, const int32_t* __restrict__ pairoff, double* __restrict__ nz) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t b = t / 6;
+  const int c = (int)(t - b * 6);
+  if (b >= nblocks) return;
+  const int nn2 = nnpe * nnpe, n = 6 * nnpe;
+  const int k0 = bstart[b], k1 = (b + 1 < nblocks) ? bstart[b + 1] : (int)ncontrib;
+  const int q0 = contrib[k0];
+  const int e0 = q0 / nn2, i0 = (q0 - e0 * nn2) / nnpe, j0 = q0 - e0 * nn2 - i0 * nnpe;
+  const int ni = conn[(int64_t)e0 * nnpe + i0], nj = conn[(int64_t)e0 * nnpe + j0];
+  const int cb = nodecol[(int64_t)nj * 8 + c];
+  if (cb < 0) return;
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  for (int k = k0; k < k1; ++k) {
+    const int q = contrib[k];
+    const int e = q / nn2, i = (q - e * nn2) / nnpe, j = q - e * nn2 - i * nnpe;
+    const double2* src = reinterpret_cast<const double2*>(dense + (int64_t)e * n * n + (j * 6 + c) * n + i * 6);
+    const double2 v0 = src[0], v1 = src[1], v2 = src[2];
+    a[0] += v0.x;
+    a[1] += v0.y;
+    a[2] += v1.x;
+    a[3] += v1.y;
+    a[4] += v2.x;
+    a[5] += v2.y;
+  }
+  const int inf = nodecol[(int64_t)ni * 8 + 6];
+  const int oA = pairoff[((int64_t)(i0 * 2 + 0) * nelem + e0) * nnpe + j0];
+  const int oB = pairoff[((int64_t)(i0 * 2 + 1) * nelem + e0) * nnpe + j0];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int rp = EmitRuns::row_pos(inf, oA, oB, r);
+    if (rp >= 0) nz[cb + rp] = a[r];
+  }
+}
+// contribution lists per matrix block, built once per pattern (cached until the next fsgpu_symbolic)
+int det_symbolic(fsgpu_ctx* c) {
+  if (c->det_ready) return FSGPU_OK;
+  const int nn2 = c->nnpe * c->nnpe;
+  const int64_t nk = c->nelem * nn2;
+  FS_REQUIRE(nk < ((int64_t)1 << 31), FSGPU_ERR_ARG, "deterministic assembly: too many element blocks for 32-bit lists");
+  int nb = 1;
+  while (((int64_t)1 << nb) < c->nnodes) ++nb;
+  cudaStream_t st = c->stream;
+  DBuf<uint64_t> k1, k2;
+  DBuf<int32_t> i1;
+  DBuf<unsigned char> head;
+  DBuf<int32_t> nsel;
+  FS_TRY(k1.ensure((size_t)nk + 1));
+  FS_TRY(k2.ensure((size_t)nk + 1));
+  FS_TRY(i1.ensure((size_t)nk + 1));
+  FS_TRY(head.ensure((size_t)nk + 1));
+  FS_TRY(nsel.ensure(1));
+  FS_TRY(c->det_contrib.ensure((size_t)nk + 1));
+  FS_TRY(c->det_bstart.ensure((size_t)nk + 1));
+  c->det_nblocks = 0;
+  c->det_ncontrib = nk;
+  if (nk > 0) {
+    k_det_keys<<<grid_for(nk, 256), 256, 0, st>>>(c->conn.p, c->nnpe, c->nelem, nb, k1.p, i1.p);
+    size_t tb = 0, tb2 = 0;
+    // stable: within a block the contributions keep ascending (element, i, j) order
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k1.p, k2.p, i1.p, c->det_contrib.p, nk, 0, 2 * nb, st));
+    cub::CountingInputIterator<int32_t> iota(0);
+    FS_CUDA(cub::DeviceSelect::Flagged(nullptr, tb2, iota, head.p, c->det_bstart.p, nsel.p, nk, st));
+    FS_TRY(c->tmp.ensure(tb > tb2 ? tb : tb2));
+    FS_CUDA(cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k1.p, k2.p, i1.p, c->det_contrib.p, nk, 0, 2 * nb, st));
+    k_det_heads<<<grid_for(nk, 256), 256, 0, st>>>(k2.p, nk, head.p);
+    FS_CUDA(cub::DeviceSelect::Flagged(c->tmp.p, tb2, iota, head.p, c->det_bstart.p, nsel.p, nk, st));
+    c->launches += 6;
+    int32_t nbk = 0;
+    FS_CUDA(cudaMemcpyAsync(&nbk, nsel.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    FS_CUDA(cudaStreamSynchronize(st));
+    c->det_nblocks = nbk;
+  }
+  c->det_ready = true;
+  return FSGPU_OK;
+}
+int det_gather(fsgpu_ctx* c) {
+  if (c->det_nblocks > 0) {
+    k_det_gather<<<grid_for(c->det_nblocks * 6, 256), 256, 0, c->stream>>>(c->det_bstart.p, c->det_contrib.p, c->det_nblocks, c->det_ncontrib,
+                                                                           c->det_dense.p, c->conn.p, c->nnpe, c->nelem, c->nodecol.p,
+                                                                           c->pairoff.p, c->nzval.p);
+    c->launches++;
+    FS_CUDA(cudaGetLastError());
+  }
+  return FSGPU_OK;
+}
+int det_begin(fsgpu_ctx* c) {
+  FS_REQUIRE(c->target >= 0, FSGPU_ERR_STATE, "run fsgpu_symbolic before an operator (startassembly!)");
+  FS_TRY(det_symbolic(c));
+  const int n = 6 * c->nnpe;
+  FS_TRY(c->det_dense.ensure((size_t)c->nelem * n * n + 2));
+  c->have_matrix = false;
+  return FSGPU_OK;
+}
+
 int shell_stiffness(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp) {
   FS_TRY(check_ctx(c));
   ShellArgs A;
   FS_TRY(shell_args(c, p, nnpe, comp, true, A));
   const bool tile = nnpe == 3 && c->tile_ok && c->want_tile && p->transv_shear_formulation != 1;
+  const bool gather = !tile && c->want_tile && c->fast;  // order-fixed assembly through the dense element matrices
   if (tile) {
     // owner-computes: every stored entry is written exactly once, no clearing needed
     FS_REQUIRE(c->target >= 0, FSGPU_ERR_STATE, "run fsgpu_symbolic before an operator (startassembly!)");
     c->have_matrix = false;
+  } else if (gather) {
+    FS_TRY(det_begin(c));
   } else {
     FS_TRY(begin_matrix(c));
   }
-  c->last_path = tile ? 2 : (c->fast ? 1 : 0);
+  c->last_path = tile ? 2 : (gather ? 3 : (c->fast ? 1 : 0));
   FS_TRY(time_begin(c));
   if (tile) {
     FS_TRY(launch_t3_tile(c, A, comp));
+  } else if (gather) {
+    EmitDense em{c->det_dense.p, nnpe};
+    if (nnpe == 3)
+      FS_TRY(launch_t3(c, A, comp, p->transv_shear_formulation == 1, em));
+    else
+      FS_TRY(launch_q4(c, A, comp, em));
+    FS_TRY(det_gather(c));
   } else if (nnpe == 3) {
     if (c->fast)
       FS_TRY(launch_t3(c, A, comp, p->transv_shear_formulation == 1, runs_of(c)));
@@ -2017,11 +2146,19 @@ int beam_matrix(fsgpu_ctx* c, const fsgpu_beam_params* p, int op) {
   BeamArgs B;
   FS_TRY(beam_args(c, p, B));
   if (op == 3) FS_REQUIRE(c->have_velocity, FSGPU_ERR_STATE, "v1 not set (fsgpu_set_velocity)");
-  FS_TRY(begin_matrix(c));
+  const bool gather = c->want_tile && c->fast;
+  if (gather)
+    FS_TRY(det_begin(c));
+  else
+    FS_TRY(begin_matrix(c));
+  c->last_path = gather ? 3 : (c->fast ? 1 : 0);
   const int64_t n = B.nelem * 4;
   FS_TRY(time_begin(c));
   if (n > 0) {
-    if (c->fast) {
+    if (gather) {
+      k_beam_matrix<EmitDense><<<grid_for(n, 128), 128, 0, c->stream>>>(B, op, EmitDense{c->det_dense.p, 2});
+      FS_TRY(det_gather(c));
+    } else if (c->fast) {
       const size_t sm = (size_t)4 * BEAM_WARP_DBL * sizeof(double);
       const int grid = grid_for(B.nelem, 128);
 #define BEAM_GO(OPV)                                                                                                   \

@@ -169,6 +169,11 @@ struct fsgpu_ctx {
   fs::DBuf<int32_t> nel_ptr, nel; // node -> incident elements (ascending)
   fs::DBuf<int32_t> tel_ptr, tel; // tile -> elements touching its owned nodes (ascending)
   fs::DBuf<int32_t> adjoff;       // [2][nadj]: row offsets of the neighbour's runs in the node's columns
+  // order-fixed assembly (fsgpu_set_deterministic, gather path): contributions per matrix block, dense element matrices
+  bool det_ready = false;
+  int64_t det_nblocks = 0, det_ncontrib = 0;
+  fs::DBuf<int32_t> det_bstart, det_contrib;
+  fs::DBuf<double> det_dense;
   // result matrix
   bool have_matrix = false;
   int64_t rrows = 0, rcols = 0, rnnz = 0;

@@ -626,3 +626,57 @@ def test_symm_pattern_characterised(fs, kind):
             assert np.asarray(nzc[rr, cc]).ravel().min() >= 2
             big = max(np.abs(Kg.data).max(), np.abs(Kr.data).max())
             assert np.abs(np.asarray((Kg + Kr)[rr, cc])).ravel().max() <= 1e-15 * big
+
+
+# ---------------------------------------------------------------------------------------
+# fsgpu_set_deterministic for Q4RS / Q4RSComp / the beam / T3FF with AVERAGE_K (no tile kernel): the order-fixed
+# gather path -- same pattern, values within 1e-12 of the oracle, bitwise identical from run to run
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["q4", "q4comp", "t3_sheark", "beam"])
+def test_deterministic_gather_path(fs, case):
+    if os.environ.get("FSGPU_FORCE_GENERIC"):
+        pytest.skip("the gather path needs the run-structured (fast) addressing")
+    f = fs.femm
+    if case == "beam":
+        xyz, conn, u1, R1, sec = meshes.beam_lattice()
+        EB, NUB = 71240.0, 0.31
+        secs = f.FESetL2Beam(sec["A"], sec["I1"], sec["I2"], sec["I3"], sec["J"], sec["A2s"], sec["A3s"], sec["x1x2"])
+        femm = f.FEMMCorotBeam(f.IntegDomain(conn), f.MatDeforElastIso(EB, NUB, 5e-9), secs)
+        od = fx.DofField(xyz.shape[0])
+        for c in range(1, 7):
+            od.setebc([0], c)
+        od.numberdofs()
+        geom0, dchi, _, _ = _fields(f, xyz, od)
+        uf, Rf = f.NodalField(u1), f.NodalField(R1)
+        femm.ctx.set_deterministic(True)
+        ops = [(lambda a: f.stiffness(femm, a, geom0, uf, Rf, dchi), obeam.beam_stiffness_elmats(xyz, conn, u1, R1, sec, EB, NUB)),
+               (lambda a: f.geostiffness(femm, a, geom0, uf, Rf, dchi), obeam.beam_geostiffness_elmats(xyz, conn, u1, R1, sec, EB, NUB))]
+    else:
+        kind = "t3" if case.startswith("t3") else "q4"
+        comp = case.endswith("comp")
+        xyz, conn = meshes.shell_mesh(kind, n=9)
+        lay, cs = _layup()
+        od = meshes.clamp_edge_dofs(xyz)
+        femm = _make_femm(fs, kind, conn, comp, cs)
+        sheark = 1 if case == "t3_sheark" else 0
+        femm.transv_shear_formulation = sheark
+        femm.ctx.set_deterministic(True)
+        geom0, dchi, u0, R0 = _fields(f, xyz, od)
+        f.associategeometry(femm, geom0)
+        normals, valid = _oracle_normals(kind, xyz, conn, fixed=cs[:, 2] if comp else None)
+        from tests.test_gpu_parity import _oracle_K
+
+        ops = [(lambda a: f.stiffness(femm, a, geom0, u0, R0, dchi), _oracle_K(kind, comp, xyz, conn, normals, valid, cs, sheark=sheark))]
+    dn = od.gatherdofnums(conn)
+    for op, Ke in ops:
+        for asm, mk in (("ffblock", f.SysmatAssemblerFFBlock), ("sparse", f.SysmatAssemblerSparse)):
+            K1 = op(mk())
+            assert femm.ctx.scatter_path == 3, "gather path did not engage"
+            K2 = op(mk())
+            assert np.array_equal(K1.nzval, K2.nzval), "order-fixed assembly must be bitwise reproducible"
+            n = od.nfreedofs if asm == "ffblock" else od.nalldofs
+            _check_matrix(K1, fx.assemble_matrix(asm, Ke, dn, od.nalldofs, od.nfreedofs), n)
+    femm.ctx.set_deterministic(False)
+    op, Ke = ops[0]
+    op(f.SysmatAssemblerFFBlock())
+    assert femm.ctx.scatter_path == 1
