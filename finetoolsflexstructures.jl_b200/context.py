@@ -390,6 +390,36 @@ class Explicit:
         fs = None if fscale is None else f64(fscale, "C")
         check(lib.fsgpu_explicit_step(self._h, int(nsteps), ptr(fs)))
 
+    def run(self, nsteps, dt, force=None, F0=None, fscale=None, peek=None, nbtw=0):
+        """The loop of plate_expl_examples.jl:61-94 with its two closures.
+        `force(t) -> F` general (`force!(F, t)`, :86: any spatial distribution per step): the load vector is re-sent
+        every step.  The separable form F(t) = fscale(t) * F0 stays on the device: the factors of a whole stretch
+        are sampled into a table and the stretch runs without host interaction.  `peek(step, U, V, t)` (:92) is
+        called with the fetched state at step 0 and every `nbtw` steps.  Returns (U, V, A)."""
+        if force is not None:
+            self.set_load(force(0.0))
+            self.start(1.0)
+        else:
+            self.set_load(F0)
+            self.start(1.0 if fscale is None else float(fscale(0.0)))
+        if peek is not None:
+            U, V, _ = self.get_state()
+            peek(0, U, V, 0.0)
+        step = 0
+        while step < nsteps:
+            if force is not None:
+                m = 1
+                self.set_load(force((step + 1) * dt))
+                self.step(1, [1.0])
+            else:
+                m = min(nbtw - step % nbtw, nsteps - step) if nbtw > 0 else nsteps - step
+                self.step(m, None if fscale is None else [float(fscale((step + k) * dt)) for k in range(1, m + 1)])
+            step += m
+            if peek is not None and nbtw > 0 and step % nbtw == 0:
+                U, V, _ = self.get_state()
+                peek(step, U, V, step * dt)
+        return self.get_state()
+
     def step_begin(self):
         check(lib.fsgpu_explicit_step_begin(self._h))
 

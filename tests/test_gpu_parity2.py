@@ -680,3 +680,46 @@ def test_deterministic_gather_path(fs, case):
     op, Ke = ops[0]
     op(f.SysmatAssemblerFFBlock())
     assert femm.ctx.scatter_path == 1
+
+
+# ---------------------------------------------------------------------------------------
+# explicit loop with the reference's two closures: a general force!(F, t) (spatial distribution changing every step)
+# and peek(step, U, V, t) every nbtw steps (plate_expl_examples.jl:86,92)
+# ---------------------------------------------------------------------------------------
+def test_explicit_force_and_peek_closures(fs):
+    f = fs.femm
+    xy, conn = fx.t3block(1.0, 0.6, 8, 5)
+    xyz = fx.xyz3(xy)
+    xyz[:, 2] = 0.03 * np.sin(3 * xyz[:, 0])
+    od = meshes.clamp_edge_dofs(xyz, n_extra_fixed=0)
+    femm = _make_femm(fs, "t3", conn)
+    geom0, dchi, u0, R0 = _fields(f, xyz, od)
+    f.associategeometry(femm, geom0)
+    K = f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, u0, R0, dchi)
+    femm.ctx.shell_mass_diag(femm._params(), 3, nfree_only=True)
+    nf = od.nfreedofs
+    Mo = femm.ctx.fetch_vector(nf)
+    Ko = K.to_scipy().tocsr()
+    dt = 0.8 * 2 / np.sqrt(oexp.pwr_largest(Ko, Mo, 200))
+    cs = 500.0
+    rng = np.random.default_rng(9)
+    Fa, Fb = rng.standard_normal(nf), rng.standard_normal(nf)
+    force = lambda t: Fa * np.sin(4.0e4 * t) + Fb * (t * 1.0e5) ** 2  # not separable: the pattern itself moves
+    nsteps, nbtw = 60, 15
+    seen, seen_o = [], []
+    ex = fs.Explicit(femm.ctx, c_scale=cs, dt=dt)
+    U, V, A = ex.run(nsteps, dt, force=force, peek=lambda s, U, V, t: seen.append((s, t, U.copy(), V.copy())), nbtw=nbtw)
+    Uo, Vo, Ao = oexp.cd_loop(Mo, Ko, cs, np.zeros(nf), np.zeros(nf), nsteps, dt, force,
+                              peek=lambda s, U, V, t: seen_o.append((s, t, U.copy(), V.copy())) if s % nbtw == 0 else None)
+    assert relfro(U, Uo) < 1e-9 and relfro(V, Vo) < 1e-9 and relfro(A, Ao) < 1e-9
+    assert [s for s, *_ in seen] == [s for s, *_ in seen_o] == [0, 15, 30, 45, 60]
+    for (s, t, Ug, Vg), (so, to, Ur, Vr) in zip(seen[1:], seen_o[1:]):
+        assert abs(t - to) < 1e-15 and relfro(Ug, Ur) < 1e-9 and relfro(Vg, Vr) < 1e-9
+    ex.close()
+    # separable form on the device, peeked
+    ex = fs.Explicit(femm.ctx, c_scale=cs, dt=dt)
+    sc = lambda t: np.cos(3.0e4 * t)
+    U2, V2, _ = ex.run(nsteps, dt, F0=Fa, fscale=sc, peek=lambda *a: None, nbtw=7)
+    U2o, V2o, _ = oexp.cd_loop(Mo, Ko, cs, np.zeros(nf), np.zeros(nf), nsteps, dt, lambda t: Fa * sc(t))
+    assert relfro(U2, U2o) < 1e-9 and relfro(V2, V2o) < 1e-9
+    ex.close()
