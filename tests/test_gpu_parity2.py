@@ -723,3 +723,4 @@ def test_explicit_force_and_peek_closures(fs):
     U2o, V2o, _ = oexp.cd_loop(Mo, Ko, cs, np.zeros(nf), np.zeros(nf), nsteps, dt, lambda t: Fa * sc(t))
     assert relfro(U2, U2o) < 1e-9 and relfro(V2, V2o) < 1e-9
     ex.close()
+
