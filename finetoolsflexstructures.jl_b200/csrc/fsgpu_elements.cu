@@ -651,6 +651,9 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
       } else {
         kpart += node_kavg_part_h(P.hf, wb, ws, brn, set > 0);
         fold_homogeneous(P.hf, bg);
+        // sqrt(wb) = sqrt(wm) t / sqrt(12), sqrt(ws) = sqrt(wm) sqrt(stab): see the Q4 setup pass
+        // (three independent square roots: deriving qb, qs from qm as the Q4 setup pass does keeps two more doubles live
+        // through the register-bound T3 setup and measured slower, 3.36 against 3.18 ms)
         const double qm = fs_sqrt(wm), qb = fs_sqrt(wb), qs = fs_sqrt(ws);
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
@@ -800,7 +803,7 @@ __device__ __forceinline__ void q4_store_row(double* d, const double (&v)[6]) {
 // the same point by a shuffle butterfly) and stores it in the half-warp's shared tile.
 template <bool COMP>
 __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64_t e, int gp, int g4, int jn, const V3 (&X)[4],
-                                              const double4& nvown, double hq, const double* gd, double* sb_) {
+                                              const double4& nvown, double hq2, const double* gd, double* sb_) {
   const unsigned full = 0xffffffffu;
   const Q4Row row{sb_ + 208 * g4 + 6 * jn, (g4 & 1) * 24};
   double p1[5][3], p2[5][3], bs[2][3];
@@ -837,7 +840,7 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
     if (COMP) {
       Constit C;
       const double t = gd[31];
-      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t / (t * t + P.alpha * hq * hq);
+      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * hq2);
       double m, n;
       const int64_t ci = P.ncs == 1 ? 0 : (P.ncs == P.nelem ? e : e * npts + gp);
       layup_angle(g.E, P.cs + ci * 9, m, n);
@@ -857,9 +860,11 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
       }
     } else {
       const double t = P.nthick == 1 ? __ldg(P.thick) : (P.nthick == P.nelem ? __ldg(P.thick + e) : __ldg(P.thick + e * npts + gp));
-      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * hq * hq);
-      // rows are pre-scaled by sqrt(d_s): sqrt(c) * sqrt(dps) with sqrt(dps), sqrt(dts) from the host
-      const double qm = fs_sqrt(t * jw), qb = fs_sqrt((t * t * t * (1.0 / 12.0)) * jw), qs = fs_sqrt(t * stab * jw);
+      // rows are pre-scaled by sqrt(d_s): sqrt(c) * sqrt(dps) with sqrt(dps), sqrt(dts) from the host;
+      // sqrt(t jw), sqrt(t^3/12 jw) = sqrt(t jw) t / sqrt(12), sqrt(t stab jw) = sqrt(t jw) sqrt(stab) with
+      // sqrt(stab) = t / sqrt(t^2 + alpha h^2): one square root and one reciprocal square root (hq2 = h^2)
+      const double qm = fs_sqrt(t * jw), qb = qm * (t * 0.28867513459481288225), 
+                   qs = qm * (P.nstab ? fs_sqrt(__ldg(P.stabf + e)) : t * fs_rsqrt(t * t + P.alpha * hq2));
       {
         double m[3][6];
         strip_membrane(g.E, gx, gy, m);
@@ -1009,7 +1014,7 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
       const V3 d = X[a] - X[0];
       md = fmax(md, dot(d, d));
     }
-    hq = fs_sqrt(md);
+    hq = md;  // h^2: only the square enters the stabilisation factor
     if (COMP) gd = P.gdata + (size_t)__ldg(P.gof + e) * 34;
   }
   const int nbi = bi == 0 ? nn[0] : (bi == 1 ? nn[1] : (bi == 2 ? nn[2] : nn[3]));
