@@ -38,6 +38,28 @@ using namespace fsk;
 
 namespace {
 
+// RED.ADD.F64 under a predicate instead of a branch.  `if (ok) atomicAdd(p, v)` compiles to BSSY / BRA / 4 instructions of
+// 64-bit address arithmetic / REDG / BSYNC per add (a quarter of the T3 kernel's instructions); this is one IMAD.WIDE for the
+// address (base pointer + 32-bit entry index) and one predicated REDG.  The address is formed unconditionally and only used
+// when `ok`.
+__device__ __forceinline__ void red_add(double* base, int idx, double v, bool ok) {
+  double* p = base + idx;
+#ifdef FS_NO_RED
+  ok = false;
+#endif
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.global.add.f64 [%0], %1;\n\t}"
+      :
+      : "l"(p), "d"(v), "r"((int)ok)
+      : "memory");
+}
+
+__device__ __forceinline__ void red_plain(double* base, int idx, double v) {
+#ifndef FS_NO_RED
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(base + idx), "d"(v) : "memory");
+#endif
+}
+
 // ---- emitters -----------------------------------------------------------------------
 // t = e*nnpe + j (element-major, column node j), i = row node, r/c = local dof in the 6x6 block
 // Every emitter takes one finished 6x6 block (row node i, column node j of element e).  The
@@ -156,9 +178,9 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
       const int2 c1 = *reinterpret_cast<const int2*>(addr + o * 8 + 4);
       const int cb[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
       const double* sv = stage + o * kStageLd + r;
+      double* nzr = nz + rp;
 #pragma unroll
-      for (int c = 0; c < 6; ++c)
-        if (cb[c] >= 0 FS_RED_GUARD) atomicAdd(nz + cb[c] + rp, sv[c * 6]);
+      for (int c = 0; c < 6; ++c) red_add(nzr, cb[c], sv[c * 6], cb[c] >= 0);
     }
 #else
     // (build flag; measured slower: Q4 3.30 against 3.20 ms, beam 0.79 against 0.74 ms)  branch-free and unrolled:
@@ -282,33 +304,42 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   // lane = (block sub-index 0..4, row 0..5): six consecutive lanes add six consecutive rows of one column; the six
   // values of a row of a block are three 16-byte reads of the staged matrix
   __device__ __forceinline__ void q4_emit_k(const double* k0, int kel, const int* ncol, const int* pr, int lane) const {
-#ifndef FS_Q4_EMIT4  // (build flag: 4 blocks x 8 lanes per round, conflict-free reads but 48 instead of 42 RED instructions: 2.35 against 2.30 ms)
+    // Rounds of 5 blocks x 6 rows (4 x 8 with conflict-free reads measured slower: 48 instead of 42 RED instructions).
+    // The usual case -- every lane of the round has all six columns in the pattern -- is decided by one warp vote and
+    // issues its REDs without predicates (ptxas turns a predicated RED into BSSY / BRA / REDG / BSYNC); rounds that
+    // touch constrained dofs take the predicated form.
     const int sub = lane / 6, r = lane - sub * 6;
-    if (lane >= 30) return;
 #pragma unroll 1
     for (int g = 0; g < 7; ++g) {
       const int o = g * 5 + sub;
-      if (o >= 32) continue;
-#else
-    const int sub = lane >> 3, r = lane & 7;
-    if (r >= 6) return;
-#pragma unroll 1
-    for (int g = 0; g < 8; ++g) {
-      const int o = g * 4 + sub;
-#endif
-      const int h = o >> 4, bi = (o >> 2) & 3, bj = o & 3;
+      const bool in = lane < 30 && o < 32;
+      const int oo = in ? o : 0;
+      const int h = oo >> 4, bi = (oo >> 2) & 3, bj = oo & 3;
       const int rp = row_pos(ncol[(h * 4 + bi) * 8 + 6], pr[(bi * 2) * 8 + h * 4 + bj], pr[(bi * 2 + 1) * 8 + h * 4 + bj], r);
-      if (rp < 0) continue;
+      const bool act = in && rp >= 0;
       const int4 c0 = *reinterpret_cast<const int4*>(ncol + (h * 4 + bj) * 8);
       const int2 c1 = *reinterpret_cast<const int2*>(ncol + (h * 4 + bj) * 8 + 4);
+      const bool all6 = (c0.x | c0.y | c0.z | c0.w | c1.x | c1.y) >= 0;
+      const bool fast = __all_sync(0xffffffffu, !act || all6);
+      if (!act) continue;
       const double2* kv = reinterpret_cast<const double2*>(k0 + h * kel + (6 * bi + r) * kQ4KLd + 6 * bj);
       const double2 v0 = kv[0], v1 = kv[1], v2 = kv[2];
-      if (c0.x >= 0 FS_RED_GUARD) atomicAdd(nz + c0.x + rp, v0.x);
-      if (c0.y >= 0 FS_RED_GUARD) atomicAdd(nz + c0.y + rp, v0.y);
-      if (c0.z >= 0 FS_RED_GUARD) atomicAdd(nz + c0.z + rp, v1.x);
-      if (c0.w >= 0 FS_RED_GUARD) atomicAdd(nz + c0.w + rp, v1.y);
-      if (c1.x >= 0 FS_RED_GUARD) atomicAdd(nz + c1.x + rp, v2.x);
-      if (c1.y >= 0 FS_RED_GUARD) atomicAdd(nz + c1.y + rp, v2.y);
+      double* nzr = nz + rp;
+      if (fast) {
+        red_plain(nzr, c0.x, v0.x);
+        red_plain(nzr, c0.y, v0.y);
+        red_plain(nzr, c0.z, v1.x);
+        red_plain(nzr, c0.w, v1.y);
+        red_plain(nzr, c1.x, v2.x);
+        red_plain(nzr, c1.y, v2.y);
+      } else {
+        red_add(nzr, c0.x, v0.x, c0.x >= 0);
+        red_add(nzr, c0.y, v0.y, c0.y >= 0);
+        red_add(nzr, c0.z, v1.x, c0.z >= 0);
+        red_add(nzr, c0.w, v1.y, c0.w >= 0);
+        red_add(nzr, c1.x, v2.x, c1.x >= 0);
+        red_add(nzr, c1.y, v2.y, c1.y >= 0);
+      }
     }
   }
   __device__ __forceinline__ Cols cols(int nj) const {
@@ -400,12 +431,15 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
 #pragma unroll 1
     for (int g = 0; g * 5 < nlead; ++g) {
       const int k = g * 5 + sub;
-      if (lane >= 30 || k >= nlead) continue;
-      const int o = MERGE ? addr[kT3C1 + k * 4 + 3] : k + (k >= 15);  // lane that staged the block
+      const bool in = lane < 30 && k < nlead;
+      const int o = in ? (MERGE ? addr[kT3C1 + k * 4 + 3] : k + (k >= 15)) : 0;  // lane that staged the block
       const int4 c0 = *reinterpret_cast<const int4*>(addr + o * 4);
       const int4 c1 = *reinterpret_cast<const int4*>(addr + kT3C1 + o * 4);
       const int rp = row_pos(c1.z, addr[kT3P + o], addr[kT3P + 32 + o], r);
-      if (rp < 0) continue;
+      const bool act = in && rp >= 0;
+      // one vote per round: when every active lane has all six columns in the pattern the REDs carry no predicates
+      const bool fast = __all_sync(0xffffffffu, !act || (c0.x | c0.y | c0.z | c0.w | c1.x | c1.y) >= 0);
+      if (!act) continue;
       const int cb[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
       const double* sp = stage + o * kStageLd + r;
       double v[6];
@@ -419,9 +453,14 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
           for (int c = 0; c < 6; ++c) v[c] += sq[c * 6];
         }
       }
+      double* nzr = nz + rp;
+      if (fast) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c)
-        if (cb[c] >= 0 FS_RED_GUARD) atomicAdd(nz + cb[c] + rp, v[c]);
+        for (int c = 0; c < 6; ++c) red_plain(nzr, cb[c], v[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) red_add(nzr, cb[c], v[c], cb[c] >= 0);
+      }
     }
   }
   // index of (r, c) in the row-major upper triangle of a symmetric 6x6 block
@@ -450,8 +489,8 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
 #pragma unroll 1
     for (int g = 0; g * 5 < nlead; ++g) {
       const int k = g * 5 + sub;
-      if (lane >= 30 || k >= nlead) continue;
-      const int o = MERGE ? addr[kT3C1 + k * 4 + 3] : k + (k >= 15);
+      const bool in = lane < 30 && k < nlead;
+      const int o = in ? (MERGE ? addr[kT3C1 + k * 4 + 3] : k + (k >= 15)) : 0;
       const int jo = t3_lane_j(o);
       const int ln = o - jo + (jo == 2 ? 0 : jo + 1);  // lane whose own node is this block's row node
       const int4 co0 = *reinterpret_cast<const int4*>(addr + o * 4);
@@ -461,6 +500,9 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
       // direct target (row node, own node) and transposed target (own node, row node)
       const int rpd = row_pos(cl1.z, addr[kT3P + 64 + o], addr[kT3P + 96 + o], r);
       const int rpt = row_pos(co1.z, addr[kT3P + 128 + o], addr[kT3P + 160 + o], r);
+      const bool fast = __all_sync(0xffffffffu, !in || ((co0.x | co0.y | co0.z | co0.w | co1.x | co1.y | cl0.x | cl0.y | cl0.z | cl0.w |
+                                                           cl1.x | cl1.y | rpd | rpt) >= 0));
+      if (!in) continue;
       const double* so = stage + o * kStageLd;
       double vd[6], vt[6];  // S[r][c] and S[c][r]
 #pragma unroll
@@ -485,10 +527,19 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
       }
       const int cbd[6] = {co0.x, co0.y, co0.z, co0.w, co1.x, co1.y};
       const int cbt[6] = {cl0.x, cl0.y, cl0.z, cl0.w, cl1.x, cl1.y};
+      double *nzd = nz + rpd, *nzt = nz + rpt;
+      if (fast) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        if (cbd[c] >= 0 && rpd >= 0 FS_RED_GUARD) atomicAdd(nz + cbd[c] + rpd, vd[c]);
-        if (cbt[c] >= 0 && rpt >= 0 FS_RED_GUARD) atomicAdd(nz + cbt[c] + rpt, vt[c]);
+        for (int c = 0; c < 6; ++c) {
+          red_plain(nzd, cbd[c], vd[c]);
+          red_plain(nzt, cbt[c], vt[c]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          red_add(nzd, cbd[c], vd[c], cbd[c] >= 0 && rpd >= 0);
+          red_add(nzt, cbt[c], vt[c], cbt[c] >= 0 && rpt >= 0);
+        }
       }
     }
   }
