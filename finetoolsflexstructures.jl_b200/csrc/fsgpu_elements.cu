@@ -748,7 +748,8 @@ __global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, E
     for (int r = 0; r < 6; ++r)
 #pragma unroll
       for (int cc = 0; cc < 6; ++cc) acc[r][cc] = 0.0;
-    const int src = (base + jn) & 31;
+    // (the idle lanes 15 and 31 would read lane 16's / lane 0's column: a bank conflict for their whole half-warp)
+    const int src = l15 < 15 ? base + jn : lane;
 #pragma unroll
     for (int s = 0; s < NR; ++s) {
       // membrane rows of a homogeneous shell have no rotation columns in global dofs
