@@ -414,6 +414,8 @@ def extras_c3_c5(args, rank, local_rank, world, stream, hbm_peak, fp64_peak):
     geom0, dchi = field(w["xyz"]), field(None, w["dofnums"], w["nfree"])
     # associategeometry!: csys evaluated at every node of every element, accumulation, normalisation and validity
     # pass all on the device (fsgpu_associategeometry_csys)
+    f.associategeometry(femm, geom0)  # (first call: mesh upload + device allocations)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     f.associategeometry(femm, geom0)
     torch.cuda.synchronize()

@@ -1669,15 +1669,14 @@ extern "C" int fsgpu_coo_to_csc(fsgpu_ctx* c, int64_t m, int64_t n, int64_t nt, 
     if (nzval) FS_TRY(download(c, nzval, dVr.p, (size_t)nu * sizeof(double)));
     FS_CUDA(cudaStreamSynchronize(st));
     c->coo_key[0] = c->coo_key[1] = c->coo_key[2] = nullptr;
-    drow.release();
-    dptr.release();
-    dVr.release();
     return FSGPU_OK;
   }
   c->coo_key[0] = c->coo_key[1] = c->coo_key[2] = nullptr;
-  DBuf<int64_t> dI, dJ;
-  DBuf<double> dV, dV2;
-  DBuf<uint64_t> k1, k2;
+  // scratch kept in the context between calls: cudaMalloc / cudaFree of GB-sized blocks cost 0.1 - 1 s on these boxes
+  // and made the conversion time vary by 4x from call to call
+  DBuf<int64_t>&dI = c->coo_I, &dJ = c->coo_J;
+  DBuf<double>&dV = c->coo_V, &dV2 = c->coo_V2;
+  DBuf<uint64_t>&k1 = c->scr_keys, &k2 = c->scr_keys2;
   DBuf<int64_t> nu_d, dcnt;
   FS_TRY(dI.ensure((size_t)nt + 1));
   FS_TRY(dJ.ensure((size_t)nt + 1));
@@ -1697,8 +1696,8 @@ extern "C" int fsgpu_coo_to_csc(fsgpu_ctx* c, int64_t m, int64_t n, int64_t nt, 
   FS_REQUIRE(f == 0, FSGPU_ERR_DOF_RANGE, "row or column index outside the matrix");
   size_t tb = 0, tb2 = 0;
   int64_t nu = 0;
-  DBuf<unsigned char> head;
-  DBuf<int64_t> start;
+  DBuf<unsigned char>& head = c->scr_rle_flag;
+  DBuf<int64_t>& start = c->coo_start;
   FS_TRY(head.ensure((size_t)nt + 1));
   FS_TRY(start.ensure((size_t)nt + 1));
   FS_TRY(dVr.ensure((size_t)nt + 1));

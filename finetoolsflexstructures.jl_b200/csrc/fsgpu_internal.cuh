@@ -187,8 +187,8 @@ struct fsgpu_ctx {
   // COO -> CSC: result of the size query, kept for the fill call (two-call convention)
   const void* coo_key[3] = {nullptr, nullptr, nullptr};
   int64_t coo_dims[4] = {0, 0, 0, 0};
-  fs::DBuf<int64_t> coo_row, coo_ptr;
-  fs::DBuf<double> coo_val;
+  fs::DBuf<int64_t> coo_row, coo_ptr, coo_I, coo_J, coo_start;
+  fs::DBuf<double> coo_val, coo_V, coo_V2;
   // result vector
   bool have_vector = false;
   int64_t vlen = 0;
