@@ -608,6 +608,17 @@ __global__ void k_i64_to_i32_m1(const int64_t* __restrict__ in, int32_t* __restr
   if (i < n) out[i] = (int32_t)(in[i] - 1);
 }
 
+// a malformed CSR would make the step kernel read out of bounds: rowptr must start at 0 and not decrease, every
+// column index must lie in [0, n)  (0-based copies); flag[0] counts violations
+__global__ void k_csr_validate(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colval, int64_t n, int64_t nnz,
+                               int32_t* __restrict__ flag) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  bool bad = false;
+  if (i < n) bad = rowptr[i] > rowptr[i + 1] || (i == 0 && rowptr[0] != 0) || rowptr[i + 1] > nnz;
+  if (i < nnz) bad = bad || colval[i] < 0 || colval[i] >= n;
+  if (bad) atomicAdd(flag, 1);
+}
+
 }  // namespace
 
 extern "C" int fsgpu_explicit_create(fsgpu_explicit** out, fsgpu_ctx* c, int64_t n, const int64_t* rowptr,
@@ -641,6 +652,19 @@ extern "C" int fsgpu_explicit_create(fsgpu_explicit** out, fsgpu_ctx* c, int64_t
   XL(h, k_i64_to_i32_m1, nnz, w.p, h->colval.p, nnz);
   if ((rc = upload(c, h->val.p, nzval, (size_t)nnz * sizeof(double)))) return fail(rc);
   if ((rc = upload(c, h->M.p, mdiag, (size_t)n * sizeof(double)))) return fail(rc);
+  {
+    DBuf<int32_t> bad;
+    int32_t nbad = 0;
+    if ((rc = bad.ensure(1))) return fail(rc);
+    cudaMemsetAsync(bad.p, 0, sizeof(int32_t), c->stream);
+    XL(h, k_csr_validate, (n > nnz ? n : nnz), h->rowptr.p, h->colval.p, n, nnz, bad.p);
+    cudaMemcpyAsync(&nbad, bad.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    if (nbad != 0) {
+      set_error("malformed CSR: rowptr must be 1-based and non-decreasing, column indices in 1..%lld (%d violations)", (long long)n, (int)nbad);
+      return fail(FSGPU_ERR_ARG);
+    }
+  }
   cudaStreamSynchronize(c->stream);
   if ((rc = alloc_vectors(h))) return fail(rc);
   *out = h;

@@ -724,3 +724,24 @@ def test_explicit_force_and_peek_closures(fs):
     assert relfro(U2, U2o) < 1e-9 and relfro(V2, V2o) < 1e-9
     ex.close()
 
+
+
+def test_explicit_create_rejects_malformed_csr(fs):
+    """fsgpu_explicit_create validates the CSR on the device (a bad index would be an out-of-bounds read in the step kernel)."""
+    n = 50
+    rp = np.arange(1, 2 * n + 2, 2, dtype=np.int64)  # two entries per row
+    cv = np.tile(np.array([1, 2], dtype=np.int64), n)
+    nz = np.ones(2 * n)
+    M = np.ones(n)
+    ctx = fs.Context()
+    ex = fs.Explicit(ctx, K=(rp, cv, nz), mdiag=M, c_scale=0.0, dt=1e-3)  # well formed
+    ex.close()
+    bad_cv = cv.copy()
+    bad_cv[17] = n + 5
+    with pytest.raises(fs._lib.FsgpuError) as ei:
+        fs.Explicit(ctx, K=(rp, bad_cv, nz), mdiag=M, c_scale=0.0, dt=1e-3)
+    assert ei.value.code == fs._lib.ERR_ARG
+    bad_rp = rp.copy()
+    bad_rp[10] = bad_rp[12]
+    with pytest.raises(fs._lib.FsgpuError):
+        fs.Explicit(ctx, K=(bad_rp, cv, nz), mdiag=M, c_scale=0.0, dt=1e-3)
