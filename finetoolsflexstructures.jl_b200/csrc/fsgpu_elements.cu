@@ -43,20 +43,19 @@ namespace {
 // address (base pointer + 32-bit entry index) and one predicated REDG.  The address is formed unconditionally and only used
 // when `ok`.
 __device__ __forceinline__ void red_add(double* base, int idx, double v, bool ok) {
-  double* p = base + idx;
 #ifdef FS_NO_RED
   ok = false;
 #endif
   asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.global.add.f64 [%0], %1;\n\t}"
+      "{\n\t.reg .pred q;\n\t.reg .u64 a;\n\tsetp.ne.b32 q, %3, 0;\n\tmad.wide.s32 a, %1, 8, %0;\n\t@q red.global.add.f64 [a], %2;\n\t}"
       :
-      : "l"(p), "d"(v), "r"((int)ok)
+      : "l"(base), "r"(idx), "d"(v), "r"((int)ok)
       : "memory");
 }
-
+// unpredicated form: exactly one IMAD.WIDE (entry address = base pointer + 8 * index) and one REDG
 __device__ __forceinline__ void red_plain(double* base, int idx, double v) {
 #ifndef FS_NO_RED
-  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(base + idx), "d"(v) : "memory");
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %1, 8, %0;\n\tred.global.add.f64 [a], %2;\n\t}" ::"l"(base), "r"(idx), "d"(v) : "memory");
 #endif
 }
 
@@ -398,10 +397,12 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   }
   // position (relative to the column start) of dof r of a node with run masks `inf` and run offsets oA / oB
   static __device__ __forceinline__ int row_pos(int inf, int oA, int oB, int r) {
+    // branch-free: the row is in run A, in run B, or absent
     const int mA = inf & 63, mB = (inf >> 8) & 63, below = (1 << r) - 1;
-    if ((mA >> r) & 1) return oA >= 0 ? oA + __popc(mA & below) : -1;
-    if ((mB >> r) & 1) return oB >= 0 ? oB + __popc(mB & below) : -1;
-    return -1;
+    const bool inA = (mA >> r) & 1, inB = (mB >> r) & 1;
+    const int off = inA ? oA : oB, m = inA ? mA : mB;
+    const int p = off + __popc(m & below);
+    return ((inA || inB) && off >= 0) ? p : -1;
   }
   // merge groups of the warp: lanes with equal keys; the lowest lane of a group is its leader.  Writes the group
   // mask to M[0][lane] and the compact leader list to C1[k].w; returns the number of leaders.
