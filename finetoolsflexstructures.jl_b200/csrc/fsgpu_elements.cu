@@ -70,6 +70,7 @@ struct BlockRef {
 };
 struct EmitScatter {  // generic path: per-entry slot map, any dof numbering
   static constexpr bool kCoop = false;
+  static constexpr bool kDenseCoop = false;
   double* nz;
   const int32_t* slot;
   int64_t plane;  // nelem * nnpe
@@ -97,6 +98,7 @@ struct EmitScatter {  // generic path: per-entry slot map, any dof numbering
 constexpr int COOP_DBL = (2 * 32 * 8) / 2;   // T3: colb[32][8] + raw[32][8] (ints); blocks are staged over the dead strips
 struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in every column
   static constexpr bool kCoop = true;
+  static constexpr bool kDenseCoop = false;
   double* nz;
   const int32_t* pairoff;
   const int32_t* nodeinfo;
@@ -563,8 +565,28 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
 };
 struct EmitDense {
   static constexpr bool kCoop = false;
-  double* out;  // [nelem][n][n] column-major per element
+  static constexpr bool kDenseCoop = true;  // the Q4 kernel writes its staged K_e with the whole warp, coalesced
+  double* out;     // [nelem][n][n] column-major per element (fsgpu_element_matrices), or
   int nnpe;
+  int blockmajor;  // [nelem][nnpe(j)][nnpe(i)][6 c][6 r]: every 6x6 block contiguous (the order-fixed gather path reads blocks)
+  // the warp's two staged matrices (24 x 24, row stride ld, bitwise symmetric: K[a][b] is read as K[b][a] so that the
+  // fastest index runs along a staged row) -> global, 16 bytes per lane and store
+  __device__ __forceinline__ void q4_dense_from_k(const double* k0, int kel, int ld, int64_t e0, int64_t nelem, int lane) const {
+#pragma unroll 3
+    for (int j2 = lane; j2 < 2 * 288; j2 += 32) {
+      const int h = j2 >= 288, k2 = j2 - 288 * h;  // k2: index of the double2 within the element
+      if (e0 + h >= nelem) continue;
+      int src;
+      if (blockmajor) {
+        const int blk = k2 / 18, w = k2 - 18 * blk, bj = blk >> 2, bi = blk & 3, c = w / 3, r = 2 * (w - 3 * c);
+        src = (6 * bj + c) * ld + 6 * bi + r;
+      } else {
+        const int col = k2 / 12, row = 2 * (k2 - 12 * col);
+        src = col * ld + row;
+      }
+      reinterpret_cast<double2*>(out + (e0 + h) * 576)[k2] = *reinterpret_cast<const double2*>(k0 + h * kel + src);
+    }
+  }
   struct Cols {};
   struct Rows {};
   __device__ __forceinline__ Cols cols(int) const { return Cols{}; }
@@ -572,6 +594,14 @@ struct EmitDense {
   __device__ __forceinline__ void block(const BlockRef& b, const Cols&, const Rows&, const double (&a)[6][6]) const {
     const int n = 6 * nnpe;
     double* o = out + b.e * n * n;
+    if (blockmajor) {
+      double2* o2 = reinterpret_cast<double2*>(o + (b.j * nnpe + b.i) * 36);
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int r = 0; r < 6; r += 2) o2[(c * 6 + r) >> 1] = make_double2(a[r][c], a[r + 1][c]);
+      return;
+    }
 #pragma unroll
     for (int c = 0; c < 6; ++c)
 #pragma unroll
@@ -1149,6 +1179,8 @@ __global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, E
   __syncwarp();
   if constexpr (Emit::kCoop) {
     emit.q4_emit_k(wbase, Q4S_EL, ncol, pr, lane);
+  } else if constexpr (Emit::kDenseCoop) {
+    emit.q4_dense_from_k(wbase, Q4S_EL, LD, e - half, P.nelem, lane);
   } else {
     if (!active) return;
     double a[6][6];
@@ -2010,14 +2042,15 @@ __global__ void k_det_heads(const uint64_t* __restrict__ keys, int64_t n, unsign
   if (i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 // thread = (block b, column c of the block): sums the six rows over the block's contributions, in order
+template <int NNPE>
 __global__ void k_det_gather(const int32_t* __restrict__ bstart, const int32_t* __restrict__ contrib, int64_t nblocks, int64_t ncontrib,
-                             const double* __restrict__ dense, const int32_t* __restrict__ conn, int nnpe, int64_t nelem,
+                             const double* __restrict__ dense, const int32_t* __restrict__ conn, int64_t nelem,
                              const int32_t* __restrict__ nodecol, const int32_t* __restrict__ pairoff, double* __restrict__ nz) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t b = t / 6;
   const int c = (int)(t - b * 6);
   if (b >= nblocks) return;
-  const int nn2 = nnpe * nnpe, n = 6 * nnpe;
+  constexpr int nnpe = NNPE, nn2 = NNPE * NNPE, n = 6 * NNPE;  // compile-time: the index decoding is shifts / small multiplies
   const int k0 = bstart[b], k1 = (b + 1 < nblocks) ? bstart[b + 1] : (int)ncontrib;
   const int q0 = contrib[k0];
   const int e0 = q0 / nn2, i0 = (q0 - e0 * nn2) / nnpe, j0 = q0 - e0 * nn2 - i0 * nnpe;
@@ -2028,7 +2061,7 @@ __global__ void k_det_gather(const int32_t* __restrict__ bstart, const int32_t* 
   for (int k = k0; k < k1; ++k) {
     const int q = contrib[k];
     const int e = q / nn2, i = (q - e * nn2) / nnpe, j = q - e * nn2 - i * nnpe;
-    const double2* src = reinterpret_cast<const double2*>(dense + (int64_t)e * n * n + (j * 6 + c) * n + i * 6);
+    const double2* src = reinterpret_cast<const double2*>(dense + (int64_t)e * n * n + (j * nnpe + i) * 36 + c * 6);  // block-major
     const double2 v0 = src[0], v1 = src[1], v2 = src[2];
     a[0] += v0.x;
     a[1] += v0.y;
@@ -2040,6 +2073,23 @@ __global__ void k_det_gather(const int32_t* __restrict__ bstart, const int32_t* 
   const int inf = nodecol[(int64_t)ni * 8 + 6];
   const int oA = pairoff[((int64_t)(i0 * 2 + 0) * nelem + e0) * nnpe + j0];
   const int oB = pairoff[((int64_t)(i0 * 2 + 1) * nelem + e0) * nnpe + j0];
+  if ((inf & 63) == 63 && oA >= 0) {
+    // all six rows of the node in one run (no constrained dof): 48 contiguous bytes, written as 16-byte pieces
+    double* p = nz + cb + oA;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      double2* p2 = reinterpret_cast<double2*>(p);
+      p2[0] = make_double2(a[0], a[1]);
+      p2[1] = make_double2(a[2], a[3]);
+      p2[2] = make_double2(a[4], a[5]);
+    } else {
+      p[0] = a[0];
+      double2* p2 = reinterpret_cast<double2*>(p + 1);
+      p2[0] = make_double2(a[1], a[2]);
+      p2[1] = make_double2(a[3], a[4]);
+      p[5] = a[5];
+    }
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
     const int rp = EmitRuns::row_pos(inf, oA, oB, r);
@@ -2090,9 +2140,17 @@ int det_symbolic(fsgpu_ctx* c) {
 }
 int det_gather(fsgpu_ctx* c) {
   if (c->det_nblocks > 0) {
-    k_det_gather<<<grid_for(c->det_nblocks * 6, 256), 256, 0, c->stream>>>(c->det_bstart.p, c->det_contrib.p, c->det_nblocks, c->det_ncontrib,
-                                                                           c->det_dense.p, c->conn.p, c->nnpe, c->nelem, c->nodecol.p,
-                                                                           c->pairoff.p, c->nzval.p);
+#define DET_GO(NN)                                                                                                                  \
+  k_det_gather<NN><<<grid_for(c->det_nblocks * 6, 256), 256, 0, c->stream>>>(c->det_bstart.p, c->det_contrib.p, c->det_nblocks,        \
+                                                                             c->det_ncontrib, c->det_dense.p, c->conn.p, c->nelem,     \
+                                                                             c->nodecol.p, c->pairoff.p, c->nzval.p)
+    if (c->nnpe == 2)
+      DET_GO(2);
+    else if (c->nnpe == 3)
+      DET_GO(3);
+    else
+      DET_GO(4);
+#undef DET_GO
     c->launches++;
     FS_CUDA(cudaGetLastError());
   }
@@ -2127,7 +2185,7 @@ int shell_stiffness(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool co
   if (tile) {
     FS_TRY(launch_t3_tile(c, A, comp));
   } else if (gather) {
-    EmitDense em{c->det_dense.p, nnpe};
+    EmitDense em{c->det_dense.p, nnpe, 1};
     if (nnpe == 3)
       FS_TRY(launch_t3(c, A, comp, p->transv_shear_formulation == 1, em));
     else
@@ -2214,7 +2272,7 @@ int beam_matrix(fsgpu_ctx* c, const fsgpu_beam_params* p, int op) {
   FS_TRY(time_begin(c));
   if (n > 0) {
     if (gather) {
-      k_beam_matrix<EmitDense><<<grid_for(n, 128), 128, 0, c->stream>>>(B, op, EmitDense{c->det_dense.p, 2});
+      k_beam_matrix<EmitDense><<<grid_for(n, 128), 128, 0, c->stream>>>(B, op, EmitDense{c->det_dense.p, 2, 1});
       FS_TRY(det_gather(c));
     } else if (c->fast) {
       const size_t sm = (size_t)4 * BEAM_WARP_DBL * sizeof(double);
@@ -2359,7 +2417,7 @@ extern "C" int fsgpu_element_matrices(fsgpu_ctx* c, int32_t kind, int32_t op, co
   const size_t total = (size_t)c->nelem * n * n;
   FS_TRY(d.ensure(total + 1));
   FS_CUDA(cudaMemsetAsync(d.p, 0, (total + 1) * sizeof(double), c->stream));
-  EmitDense em{d.p, nnpe};
+  EmitDense em{d.p, nnpe, 0};
   if (kind == 2) {
     BeamArgs B;
     FS_TRY(beam_args(c, (const fsgpu_beam_params*)params, B));
