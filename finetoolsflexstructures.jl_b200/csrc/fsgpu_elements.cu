@@ -302,44 +302,51 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
       }
     }
   }
-  // lane = (block sub-index 0..4, row 0..5): six consecutive lanes add six consecutive rows of one column; the six
-  // values of a row of a block are three 16-byte reads of the staged matrix
+  // Emission of the warp's two staged matrices.  Lane = one ROW of K_e (row node bi = lane / 6, dof r = lane % 6; lanes
+  // 24..31 idle), fixed for the whole emission; the rounds walk (element h, column node bj) with compile-time indices.
+  // Per round a lane reads its run offset, the six column starts of node bj (one broadcast read for the warp) and the
+  // six values K[row][6 bj ..] (three 16-byte reads, conflict-free: consecutive rows are 13 sixteen-byte units apart),
+  // and adds them: the 24 lanes of a RED instruction cover four 6-row runs of ONE column.  Against the earlier
+  // 5-blocks-per-round mapping (lane = (block, row), 7 rounds) this is 8 rounds of ~30 instead of 7 of ~85 instructions.
   __device__ __forceinline__ void q4_emit_k(const double* k0, int kel, const int* ncol, const int* pr, int lane) const {
-    // Rounds of 5 blocks x 6 rows (4 x 8 with conflict-free reads measured slower: 48 instead of 42 RED instructions).
-    // The usual case -- every lane of the round has all six columns in the pattern -- is decided by one warp vote and
-    // issues its REDs without predicates (ptxas turns a predicated RED into BSSY / BRA / REDG / BSYNC); rounds that
-    // touch constrained dofs take the predicated form.
-    const int sub = lane / 6, r = lane - sub * 6;
-#pragma unroll 1
-    for (int g = 0; g < 7; ++g) {
-      const int o = g * 5 + sub;
-      const bool in = lane < 30 && o < 32;
-      const int oo = in ? o : 0;
-      const int h = oo >> 4, bi = (oo >> 2) & 3, bj = oo & 3;
-      const int rp = row_pos(ncol[(h * 4 + bi) * 8 + 6], pr[(bi * 2) * 8 + h * 4 + bj], pr[(bi * 2 + 1) * 8 + h * 4 + bj], r);
-      const bool act = in && rp >= 0;
-      const int4 c0 = *reinterpret_cast<const int4*>(ncol + (h * 4 + bj) * 8);
-      const int2 c1 = *reinterpret_cast<const int2*>(ncol + (h * 4 + bj) * 8 + 4);
-      const bool all6 = (c0.x | c0.y | c0.z | c0.w | c1.x | c1.y) >= 0;
-      const bool fast = __all_sync(0xffffffffu, !act || all6);
-      if (!act) continue;
-      const double2* kv = reinterpret_cast<const double2*>(k0 + h * kel + (6 * bi + r) * kQ4KLd + 6 * bj);
-      const double2 v0 = kv[0], v1 = kv[1], v2 = kv[2];
-      double* nzr = nz + rp;
-      if (fast) {
-        red_plain(nzr, c0.x, v0.x);
-        red_plain(nzr, c0.y, v0.y);
-        red_plain(nzr, c0.z, v1.x);
-        red_plain(nzr, c0.w, v1.y);
-        red_plain(nzr, c1.x, v2.x);
-        red_plain(nzr, c1.y, v2.y);
-      } else {
-        red_add(nzr, c0.x, v0.x, c0.x >= 0);
-        red_add(nzr, c0.y, v0.y, c0.y >= 0);
-        red_add(nzr, c0.z, v1.x, c0.z >= 0);
-        red_add(nzr, c0.w, v1.y, c0.w >= 0);
-        red_add(nzr, c1.x, v2.x, c1.x >= 0);
-        red_add(nzr, c1.y, v2.y, c1.y >= 0);
+    if (lane >= 24) return;
+    const int bi = lane / 6, r = lane - 6 * bi, below = (1 << r) - 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // this row's place in the runs of its node (element h): run A, run B, or absent
+      const int inf = ncol[(h * 4 + bi) * 8 + 6];
+      const int mA = inf & 63, mB = (inf >> 8) & 63;
+      const bool inA = (mA >> r) & 1, inB = (mB >> r) & 1;
+      const int rank = __popc((inA ? mA : mB) & below);
+      const int* po = pr + (bi * 2 + (inA ? 0 : 1)) * 8 + h * 4;  // run offsets of (row node bi, column node 0..3)
+      const int4 o4 = *reinterpret_cast<const int4*>(po);
+      const int off[4] = {o4.x, o4.y, o4.z, o4.w};
+      const double* krow = k0 + h * kel + lane * kQ4KLd;
+#pragma unroll
+      for (int bj = 0; bj < 4; ++bj) {
+        const bool act = (inA || inB) && off[bj] >= 0;
+        const int4 c0 = *reinterpret_cast<const int4*>(ncol + (h * 4 + bj) * 8);
+        const int2 c1 = *reinterpret_cast<const int2*>(ncol + (h * 4 + bj) * 8 + 4);
+        // one vote per round: no constrained column, every row present -> unpredicated REDs
+        const bool fast = __all_sync(0x00ffffffu, act && (c0.x | c0.y | c0.z | c0.w | c1.x | c1.y) >= 0);
+        const double2* kv = reinterpret_cast<const double2*>(krow + 6 * bj);
+        const double2 v0 = kv[0], v1 = kv[1], v2 = kv[2];
+        double* nzr = nz + (off[bj] + rank);
+        if (fast) {
+          red_plain(nzr, c0.x, v0.x);
+          red_plain(nzr, c0.y, v0.y);
+          red_plain(nzr, c0.z, v1.x);
+          red_plain(nzr, c0.w, v1.y);
+          red_plain(nzr, c1.x, v2.x);
+          red_plain(nzr, c1.y, v2.y);
+        } else {
+          red_add(nzr, c0.x, v0.x, act && c0.x >= 0);
+          red_add(nzr, c0.y, v0.y, act && c0.y >= 0);
+          red_add(nzr, c0.z, v1.x, act && c0.z >= 0);
+          red_add(nzr, c0.w, v1.y, act && c0.w >= 0);
+          red_add(nzr, c1.x, v2.x, act && c1.x >= 0);
+          red_add(nzr, c1.y, v2.y, act && c1.y >= 0);
+        }
       }
     }
   }
