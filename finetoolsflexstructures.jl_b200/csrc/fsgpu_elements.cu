@@ -22,10 +22,19 @@ using namespace fsm;
 using namespace fsk;
 
 #ifndef FS_T3_MINB
-#define FS_T3_MINB 3
+#define FS_T3_MINB 6
 #endif
 #ifndef FS_Q4_MINB
 #define FS_Q4_MINB 4
+#endif
+// warps per CTA (the warps of a CTA are independent: the CTA size only sets the granularity at which resident slots are
+// refilled).  T3: 2 warps x 6 CTAs per SM 2.817 ms against 2.840 (4 x 3), 2.867 (1 x 12), 3.86 (8 x 1: 186 registers);
+// Q4: 2.078 (2 x 8), 2.076 (4 x 4), 2.148 (1 x 15), 2.314 (8 x 2)
+#ifndef FS_T3_WPB
+#define FS_T3_WPB 2
+#endif
+#ifndef FS_Q4_WPB
+#define FS_Q4_WPB 4
 #endif
 
 // measurement aid (never defined in the shipped build): -DFS_NO_RED keeps all the arithmetic and addressing
@@ -622,7 +631,7 @@ struct EmitDense {
 constexpr int T3_EPW = 10;  // elements per warp (3 lanes each; lanes 30, 31 idle)
 
 template <bool COMP, bool SHEARK, class Emit>
-__global__ void __launch_bounds__(128, FS_T3_MINB) k_t3_stiffness(ShellArgs P, Emit emit) {
+__global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(ShellArgs P, Emit emit) {
   constexpr int NR = SHEARK ? 12 : 8;
   constexpr int WARP_DBL = NR * 6 * 32 + (Emit::kCoop ? COOP_DBL : 0);
   extern __shared__ double smem[];  // per warp: strips [NR*6][32], rows pre-scaled by sqrt(d_s) (+ coop scratch)
@@ -1068,7 +1077,7 @@ constexpr int Q4_WARP_DBL = 2 * Q4S_EL + 32 + 32 + 8 * 4;
 // accumulators carried; (3) accumulators -> staged K_e; (4) drilling stiffness on the staged matrix (lanes 0..3 of each
 // half-warp = the element's nodes); (5) emission from the staged matrix.
 template <bool COMP, bool CHUNKED, class Emit>
-__global__ void __launch_bounds__(128, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, Emit emit) {
+__global__ void __launch_bounds__(32 * FS_Q4_WPB, FS_Q4_MINB) k_q4_stiffness(ShellArgs P, Emit emit) {
   extern __shared__ double smem[];
   constexpr int WARP_DBL = Q4_WARP_DBL;
   constexpr int LD = EmitRuns::kQ4KLd;
@@ -1968,7 +1977,7 @@ int shell_args(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp, b
 namespace {
 template <class Emit>
 int launch_t3(fsgpu_ctx* c, const ShellArgs& A, bool comp, bool sheark, Emit em) {
-  const int wpb = 4;
+  const int wpb = FS_T3_WPB;
   const int64_t nwarps = (A.nelem + T3_EPW - 1) / T3_EPW;
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
@@ -1993,7 +2002,7 @@ int launch_t3(fsgpu_ctx* c, const ShellArgs& A, bool comp, bool sheark, Emit em)
 }
 template <class Emit>
 int launch_q4(fsgpu_ctx* c, const ShellArgs& A, bool comp, Emit em) {
-  const int wpb = 4;
+  const int wpb = FS_Q4_WPB;
   const int64_t nwarps = (A.nelem + 1) / 2;
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
