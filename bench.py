@@ -690,7 +690,7 @@ def main():
         ms = float(np.mean([x["seconds"] for x in vals])) * 1e3
         loop_s, sparse_s = float(np.mean([x["loop_s"] for x in vals])), float(np.mean([x["sparse_s"] for x in vals]))
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong",
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": unit, "cores": ncores, "kind": "port",
                                  "sample": f"first {sample} elements of the workload per step: element loop + COO append (OpenMP element-parallel, "
@@ -960,7 +960,7 @@ def main():
                "single_thread_element_loop_only_value": r1["loop_value"]}
 
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_link),
                     "host_result_bytes_per_step": int(d2h),

@@ -1284,15 +1284,18 @@ static int fetch_rows_narrow(fsgpu_ctx* c, const int32_t* rv, int64_t nnz, int64
     nz_thread = std::thread([&] {
       cudaSetDevice(c->device);
       while (rows_issued.load(std::memory_order_acquire) == 0) std::this_thread::yield();
-      const int64_t piece = (int64_t)8 << 20;  // entries (64 MB)
-      cudaEvent_t ev[2];
+      int64_t piece = (int64_t)8 << 20;  // entries (64 MB)
+      int inflight = 2;
+      if (const char* e = getenv("FSGPU_VALUE_PIECE_MB")) piece = (int64_t)(atoi(e) > 0 ? atoi(e) : 64) << 17;
+      if (const char* e = getenv("FSGPU_VALUE_INFLIGHT")) inflight = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : 2;
+      cudaEvent_t ev[8];
       for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
       int64_t k = 0;
       for (int64_t o = 0; o < nnz && nz_err == cudaSuccess; o += piece, ++k) {
-        if (k >= 2) nz_err = cudaEventSynchronize(ev[k & 1]);
+        if (k >= inflight) nz_err = cudaEventSynchronize(ev[k % inflight]);
         const int64_t m = nnz - o < piece ? nnz - o : piece;
         if (nz_err == cudaSuccess) nz_err = cudaMemcpyAsync(nzval + o, nz + o, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, c->stream2);
-        if (nz_err == cudaSuccess) nz_err = cudaEventRecord(ev[k & 1], c->stream2);
+        if (nz_err == cudaSuccess) nz_err = cudaEventRecord(ev[k % inflight], c->stream2);
       }
       if (nz_err == cudaSuccess) nz_err = cudaStreamSynchronize(c->stream2);
       for (auto& e : ev) cudaEventDestroy(e);
