@@ -92,6 +92,9 @@ struct fsgpu_ctx {
   void* ring[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t stream2 = nullptr;
+  // values into a PAGEABLE host array: pinned staging ring, moved on by host threads
+  void* vring[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t vring_ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_x = nullptr;
   // run-length form of the row indices of the current pattern (fetch of large results)
   const int32_t* rle_for = nullptr;  // device array it was built from

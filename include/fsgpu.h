@@ -222,7 +222,9 @@ int fsgpu_element_vectors(fsgpu_ctx* ctx, const fsgpu_beam_params* p, double* ou
 
 /* ---- results -------------------------------------------------------------------- */
 int fsgpu_result_size(fsgpu_ctx* ctx, int64_t* nrows, int64_t* ncols, int64_t* nnz);
-/* makematrix! equivalent; any pointer may be NULL to skip that array */
+/* makematrix! equivalent; any pointer may be NULL to skip that array.  The arrays may be pinned (fsgpu_host_alloc:
+ * direct DMA, fastest) or ordinary pageable memory (a Julia Vector): large pageable arrays are filled through the
+ * library's pinned staging rings by host threads (FSGPU_HOST_THREADS, FSGPU_VALUE_THREADS), INTEGRATION.md section 6 */
 int fsgpu_fetch_matrix(fsgpu_ctx* ctx, int64_t* colptr, int64_t* rowval, double* nzval);
 /* One triangle of a square CSC result, diagonal included: uplo = 'L' (rows >= column) or 'U' (rows <= column).
  * For consumers that read one triangle of a symmetric operator (Julia: cholesky(Symmetric(K, :L)), the

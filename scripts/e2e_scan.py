@@ -30,6 +30,7 @@ out = tuple(a for a, _t in _p)
 
 
 def step():
+    global out
     femm.reset_uploads()
     return f.stiffness(femm, f.SysmatAssemblerFFBlock(), geom0, None, None, d, out=out)
 
@@ -47,6 +48,21 @@ def timed(label, n=4):
 
 
 timed("default")
+if "pageable" in sys.argv[1:]:
+    pinned_out = out
+    out = (np.empty(nc, np.int64), np.empty(nnz, np.int64), np.empty(nnz, np.float64))
+    for a in out:
+        a[...] = 0  # touch the pages
+    timed("pageable destination (numpy arrays)")
+    t0 = time.perf_counter()
+    fsb200.context.check(fsb200.context.lib.fsgpu_fetch_matrix(femm.ctx._h, None, None, fsb200.context.ptr(out[2])))
+    print(f"  values only, pageable: {(time.perf_counter() - t0) * 1e3:.1f} ms")
+    t0 = time.perf_counter()
+    fsb200.context.check(fsb200.context.lib.fsgpu_fetch_matrix(femm.ctx._h, None, fsb200.context.ptr(out[1]), None))
+    print(f"  rows only, pageable: {(time.perf_counter() - t0) * 1e3:.1f} ms")
+    assert np.array_equal(out[1], pinned_out[1]) and np.array_equal(out[0], pinned_out[0])
+    assert np.abs(out[2] - pinned_out[2]).max() <= 1e-12 * np.abs(pinned_out[2]).max()  # RED order differs from run to run
+    sys.exit(0)
 for nth in (2, 4, 6, 8, 12, 16, 24):
     os.environ["FSGPU_HOST_THREADS"] = str(nth)
     timed(f"FSGPU_HOST_THREADS={nth}")

@@ -311,6 +311,34 @@ def test_fetch_triangle(fs, asm, narrow, monkeypatch):
 
 
 # ---------------------------------------------------------------------------------------
+# pageable destinations (a Julia `Vector`): values and colptr travel through the pinned staging ring
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("narrow", [False, True])
+def test_fetch_into_pageable_arrays_through_the_ring(fs, narrow, monkeypatch):
+    import torch
+
+    monkeypatch.setenv("FSGPU_VALUE_RING_WORDS", "4096")  # many pieces, all three staging buffers reused
+    monkeypatch.setenv("FSGPU_FETCH_NARROW_MIN", "0" if narrow else "-1")
+    f = fs.femm
+    xyz, conn = meshes.shell_mesh("q4", n=64)
+    od = meshes.clamp_edge_dofs(xyz)
+    femm = _make_femm(fs, "q4", conn)
+    geom0, dchi, u0, R0 = _fields(f, xyz, od)
+    f.associategeometry(femm, geom0)
+    f.stiffness(femm, f.SysmatAssemblerSparse(), geom0, u0, R0, dchi)
+    m, n, nnz = femm.ctx.result_size()
+    assert nnz > (1 << 20) and n > 20000
+    pinned = [torch.empty(k, dtype=dt, pin_memory=True) for k, dt in ((n + 1, torch.int64), (nnz, torch.int64), (nnz, torch.float64))]
+    Kp = femm.ctx.fetch_matrix(out=tuple(t.numpy() for t in pinned))  # pinned: direct DMA
+    Kh = femm.ctx.fetch_matrix()  # numpy arrays: pageable, the SAME device result
+    assert np.array_equal(Kh.colptr, Kp.colptr) and np.array_equal(Kh.rowval, Kp.rowval)
+    assert np.array_equal(Kh.nzval, Kp.nzval)
+    v = np.full(nnz, np.nan)
+    femm.ctx.fetch_values(v)  # values only (pattern reused)
+    assert np.array_equal(v, Kp.nzval)
+
+
+# ---------------------------------------------------------------------------------------
 # explicit loop: arbitrary load-factor table (force!(F, t) of plate_expl_examples.jl:86 sampled per step)
 # ---------------------------------------------------------------------------------------
 def test_explicit_load_factor_table(fs):
