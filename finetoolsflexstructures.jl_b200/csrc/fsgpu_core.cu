@@ -47,8 +47,40 @@ int time_end(fsgpu_ctx* c) {
   return FSGPU_OK;
 }
 
+constexpr int kVRing = 3;
+constexpr int64_t kVRingWords = (int64_t)4 << 20;  // 32 MB per staging buffer
+static bool host_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+static int value_threads() {
+  // the host copy is the slower half of this path (16 vCPUs: 4 threads 98 ms, 8 threads 73 ms for 2.6 GB)
+  int nth = (int)std::thread::hardware_concurrency() / 2;
+  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU on this host: share the cores
+    const int w = atoi(lw);
+    if (w > 1) nth /= w;
+  }
+  if (nth > 8) nth = 8;
+  if (const char* ev = getenv("FSGPU_VALUE_THREADS")) nth = atoi(ev);
+  return nth < 1 ? 1 : (nth > 32 ? 32 : nth);
+}
+static cudaError_t ensure_vring(fsgpu_ctx* c) {
+  cudaError_t err = cudaSuccess;
+  for (int k = 0; k < kVRing && err == cudaSuccess; ++k)
+    if (!c->vring[k]) {
+      err = cudaMallocHost(&c->vring[k], (size_t)kVRingWords * 8);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->vring_ev[k], cudaEventDisableTiming);
+    }
+  return err;
+}
 int upload(fsgpu_ctx* c, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return FSGPU_OK;
+  // (pageable sources: the driver's own staging costs 2.5 - 7 ms for C2's 129 MB of inputs; a pinned ring filled by host
+  // threads, as on the way back, measured 7 - 9 ms and was not kept)
   FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   return FSGPU_OK;
 }
@@ -1208,34 +1240,8 @@ __global__ void k_run_pairs(const int32_t* __restrict__ rv, const int32_t* __res
 // A DMA copy into pageable memory is staged by the driver at ~19 GB/s (C2: 134 ms for the 2.6 GB of values, and a Julia
 // `Vector` is pageable).  Here the pieces land in a pinned ring at link speed and host threads move them on with
 // non-temporal stores while the next pieces are in flight.
-constexpr int kVRing = 3;
-constexpr int64_t kVRingWords = (int64_t)4 << 20;  // 32 MB per staging buffer
-static bool host_pageable(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return true;
-  }
-  return a.type == cudaMemoryTypeUnregistered;
-}
-static int value_threads() {
-  // the host copy is the slower half of this path (16 vCPUs: 4 threads 98 ms, 8 threads 73 ms for 2.6 GB)
-  int nth = (int)std::thread::hardware_concurrency() / 2;
-  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU on this host: share the cores
-    const int w = atoi(lw);
-    if (w > 1) nth /= w;
-  }
-  if (nth > 8) nth = 8;
-  if (const char* ev = getenv("FSGPU_VALUE_THREADS")) nth = atoi(ev);
-  return nth < 1 ? 1 : (nth > 32 ? 32 : nth);
-}
 static cudaError_t words_through_ring(fsgpu_ctx* c, const void* dev, void* host, int64_t n, cudaStream_t st) {
-  cudaError_t err = cudaSuccess;
-  for (int k = 0; k < kVRing && err == cudaSuccess; ++k)
-    if (!c->vring[k]) {
-      err = cudaMallocHost(&c->vring[k], (size_t)kVRingWords * 8);
-      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->vring_ev[k], cudaEventDisableTiming);
-    }
+  cudaError_t err = ensure_vring(c);
   if (err != cudaSuccess) return err;
   const int64_t* src = static_cast<const int64_t*>(dev);
   int64_t* dst = static_cast<int64_t*>(host);

@@ -54,6 +54,11 @@ if "pageable" in sys.argv[1:]:
     for a in out:
         a[...] = 0  # touch the pages
     timed("pageable destination (numpy arrays)")
+    # pageable inputs as well: plain numpy copies of the mesh, dof numbers and (inside the FEMM) the normals
+    geom0.values = np.array(xyz_p)
+    d.dofnums = np.array(dof_p)
+    femm.integdomain.conn = np.array(conn_p)
+    timed("pageable destination and inputs")
     t0 = time.perf_counter()
     fsb200.context.check(fsb200.context.lib.fsgpu_fetch_matrix(femm.ctx._h, None, None, fsb200.context.ptr(out[2])))
     print(f"  values only, pageable: {(time.perf_counter() - t0) * 1e3:.1f} ms")
