@@ -937,24 +937,31 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
     const double jw = g.Jac * w;
     const int npts = P.rule.npts;
     if (COMP) {
+      // the factored constitutive data of this point (rotation of A, B, D, H into the element frame, 6 x 6 LDL', square
+      // roots of the pivots: ~480 FP64 instructions, the same for the four lanes of a point) comes from
+      // k_q4_laminate_prep, one thread per point
+      const double2* lp = reinterpret_cast<const double2*>(P.lam + (e * npts + gp) * 24);
+      double lv[24];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const double2 v2 = __ldg(lp + k);
+        lv[2 * k] = v2.x;
+        lv[2 * k + 1] = v2.y;
+      }
       Constit C;
-      const double t = gd[31];
-      const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * hq2);
-      double m, n;
-      const int64_t ci = P.ncs == 1 ? 0 : (P.ncs == P.nelem ? e : e * npts + gp);
-      layup_angle(g.E, P.cs + ci * 9, m, n);
-      constit_laminate(gd, gd + 9, gd + 18, gd + 27, m, n, jw, stab * jw, C);
+#pragma unroll
+      for (int i = 0, k = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) C.L6[i][j] = j < i ? lv[k++] : 0.0;
+      C.L2 = lv[23];
       double bg[8][6];
       node_strip(g.E, A, gx, gy, bs, p1, p2, bg);
       fold_constit(C, bg);
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const double d = constit_d(C, s);
-        if (d < 0.0) atomicExch(P.flag + 2, 1);
-        const double q = fs_sqrt(d);
         double v[6];
 #pragma unroll
-        for (int cc = 0; cc < 6; ++cc) v[cc] = q * bg[s][cc];
+        for (int cc = 0; cc < 6; ++cc) v[cc] = lv[15 + s] * bg[s][cc];
         q4_store_row(row(s), v);
       }
     } else {
@@ -1011,6 +1018,45 @@ __device__ __forceinline__ void q4_setup_pass(const ShellArgs& P, bool on, int64
 #pragma unroll
     for (int s = 0; s < 8; ++s) q4_store_row(row(s), z);
   }
+}
+
+// Q4RSComp: factored constitutive data per (element, integration point) -> P.lam (see ShellArgs::lam).  The layup angle
+// (src/TransformerModule.jl:92-105) needs the element triad at the point, the weights the surface Jacobian; laminate
+// thickness enters only through the stabilisation factor (src/FEMMShellQ4RSCompModule.jl:918-935).
+__global__ void k_q4_laminate_prep(ShellArgs P, double* __restrict__ lam) {
+  const int npts = P.rule.npts;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (tid >= P.nelem * npts) return;
+  const int64_t e = tid / npts;
+  const int gp = (int)(tid - e * npts);
+  V3 X[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) X[a] = ld3(P.xyz, __ldg(P.conn + e * 4 + a));
+  double md = 0.0;  // quirk: "diameter" = max distance from node 1 (src/FEMMShellQ4RSModule.jl:861-870)
+  for (int a = 1; a < 4; ++a) {
+    const V3 d = X[a] - X[0];
+    md = fmax(md, dot(d, d));
+  }
+  const Q4Geom g = q4_geometry(X, P.rule.xi[gp], P.rule.eta[gp]);
+  const double jw = g.Jac * P.rule.w[gp];
+  const double* gd = P.gdata + (size_t)__ldg(P.gof + e) * 34;
+  const double t = gd[31];
+  const double stab = P.nstab ? __ldg(P.stabf + e) : t * t * fs_rcp(t * t + P.alpha * md);
+  double m, n;
+  const int64_t ci = P.ncs == 1 ? 0 : (P.ncs == P.nelem ? e : e * npts + gp);
+  layup_angle(g.E, P.cs + ci * 9, m, n);
+  Constit C;
+  constit_laminate(gd, gd + 9, gd + 18, gd + 27, m, n, jw, stab * jw, C);
+  double* o = lam + tid * 24;
+  int k = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < i; ++j) o[k++] = C.L6[i][j];
+  for (int s = 0; s < 8; ++s) {
+    const double d = constit_d(C, s);
+    if (d < 0.0) atomicExch(P.flag + 2, 1);  // not positive definite -> FSGPU_ERR_ARG
+    o[15 + s] = fs_sqrt(d);
+  }
+  o[23] = C.L2;
 }
 
 // K_e += S' S on the FP64 tensor-core path (DMMA.8x8x4, the same peak as DFMA on B200 but one instruction per 256 FMA
@@ -1930,6 +1976,7 @@ int shell_args(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp, b
   A.conn = c->conn.p;
   A.xyz = c->xyz.p;
   A.nrm = c->nrm.p;
+  A.lam = nullptr;
   A.thick = c->thick.p;
   A.nthick = c->nthick;
   A.stabf = c->stabf.p;
@@ -2001,11 +2048,20 @@ int launch_t3(fsgpu_ctx* c, const ShellArgs& A, bool comp, bool sheark, Emit em)
   return FSGPU_OK;
 }
 template <class Emit>
-int launch_q4(fsgpu_ctx* c, const ShellArgs& A, bool comp, Emit em) {
+int launch_q4(fsgpu_ctx* c, const ShellArgs& A0, bool comp, Emit em) {
   const int wpb = FS_Q4_WPB;
-  const int64_t nwarps = (A.nelem + 1) / 2;
+  const int64_t nwarps = (A0.nelem + 1) / 2;
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
+  ShellArgs A = A0;
+  if (comp) {  // laminate constitutive data once per integration point instead of on each of its four lanes
+    const int64_t npt = A.nelem * A.rule.npts;
+    FS_TRY(c->lam_prep.ensure((size_t)npt * 24));
+    k_q4_laminate_prep<<<grid_for(npt, 128), 128, 0, c->stream>>>(A, c->lam_prep.p);
+    FS_CUDA(cudaGetLastError());
+    c->launches++;
+    A.lam = c->lam_prep.p;
+  }
   const size_t sm = (size_t)wpb * Q4_WARP_DBL * sizeof(double);
 #define Q4_GO(CO, CH)                                                                                          \
   do {                                                                                                         \

@@ -26,6 +26,9 @@ struct ShellArgs {
   int64_t ncs;
   Rule rule;
   int32_t* flag;
+  // Q4RSComp: factored laminate constitutive data per (element, integration point), [nelem][npts][24] doubles =
+  // strictly-lower L6 (15, row-major), sqrt of the 6 + 2 pivots (8), L2 (1); written by k_q4_laminate_prep
+  const double* lam;
 };
 
 __device__ __forceinline__ double4 ldg4(const double4* p) {
