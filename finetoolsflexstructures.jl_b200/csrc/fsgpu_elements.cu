@@ -639,28 +639,6 @@ struct EmitDense {
 // =====================================================================================
 constexpr int T3_EPW = 10;  // elements per warp (3 lanes each; lanes 30, 31 idle)
 
-// T3FFComp: factored laminate constitutive data per element -> P.lam ([nelem][24] doubles, see k_t3_stiffness): layup
-// angle, rotation of A, B, D, H into the element frame, 6 x 6 LDL' and the pivots' square roots once per element instead
-// of on each of its three lanes (src/FEMMShellT3FFCompModule.jl:600-627)
-__global__ void k_t3_laminate_prep(ShellArgs P, double shear_scale, double* __restrict__ lam) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= P.nelem) return;
-  const int32_t* cn = P.conn + e * 3;
-  const T3Geom g = t3_geometry(ld3(P.xyz, __ldg(cn)), ld3(P.xyz, __ldg(cn + 1)), ld3(P.xyz, __ldg(cn + 2)));
-  Constit C;
-  build_constit_t3(P, e, g.E, g.Ae, shear_scale, true, C);
-  double* o = lam + e * 24;
-  int k = 0;
-  for (int i = 0; i < 6; ++i)
-    for (int j = 0; j < i; ++j) o[k++] = C.L6[i][j];
-  o[15] = C.L2;
-  for (int s = 0; s < 8; ++s) {
-    const double d = constit_d(C, s);
-    if (d < 0.0) atomicExch(P.flag + 2, 1);  // not positive definite -> FSGPU_ERR_ARG
-    o[16 + s] = fs_sqrt(d);
-  }
-}
-
 template <bool COMP, bool SHEARK, class Emit>
 __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(ShellArgs P, Emit emit) {
   constexpr int NR = SHEARK ? 12 : 8;
@@ -683,7 +661,6 @@ __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(She
   T3Geom g;
   M3 A;
   Constit C;
-  double qlam[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // laminate: square roots of the pivots
   double wm = 0.0, wb = 0.0, ws = 0.0;  // homogeneous weights
   if (active) {
     const int32_t* cn = P.conn + e * 3;
@@ -703,23 +680,7 @@ __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(She
     validj = nv.w != 0.0;
     A = nodal_triad(g.E, v3(nv.x, nv.y, nv.z), validj);
     if constexpr (COMP) {
-      // factored laminate data of the element from k_t3_laminate_prep (the same for its three lanes): [24] = strictly
-      // lower L6 (15), L2, square roots of the pivots (8)
-      const double2* lp = reinterpret_cast<const double2*>(P.lam + e * 24);
-      double lv[24];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const double2 v2 = __ldg(lp + k);
-        lv[2 * k] = v2.x;
-        lv[2 * k + 1] = v2.y;
-      }
-#pragma unroll
-      for (int i = 0, k = 0; i < 6; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 6; ++jj) C.L6[i][jj] = jj < i ? lv[k++] : 0.0;
-      C.L2 = lv[15];
-#pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) qlam[s2] = lv[16 + s2];
+      build_constit_t3(P, e, g.E, g.Ae, SHEARK ? (1.0 / 3) : 1.0, true, C);
     } else {
       // homogeneous shell: the LDL' factors of Dps and Dt come from the host (P.hf), only the three
       // weights (membrane, bending, shear) depend on the element
@@ -786,10 +747,14 @@ __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(She
       // definite constitutive matrix (a negative pivot raises flag[2] -> FSGPU_ERR_ARG)
       double q[8];
       if constexpr (COMP) {
-        kpart += node_kavg_part_q(C, qlam, brn, set > 0);
+        kpart += node_kavg_part(C, brn, set > 0);
         fold_constit(C, bg);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) q[s] = qlam[s];
+        for (int s = 0; s < 8; ++s) {
+          const double d = constit_d(C, s);
+          if (d < 0.0) atomicExch(P.flag + 2, 1);
+          q[s] = fs_sqrt(d);
+        }
       } else {
         kpart += node_kavg_part_h(P.hf, wb, ws, brn, set > 0);
         fold_homogeneous(P.hf, bg);
@@ -2067,19 +2032,11 @@ int shell_args(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp, b
 }  // namespace fsk
 namespace {
 template <class Emit>
-int launch_t3(fsgpu_ctx* c, const ShellArgs& A0, bool comp, bool sheark, Emit em) {
+int launch_t3(fsgpu_ctx* c, const ShellArgs& A, bool comp, bool sheark, Emit em) {
   const int wpb = FS_T3_WPB;
-  const int64_t nwarps = (A0.nelem + T3_EPW - 1) / T3_EPW;
+  const int64_t nwarps = (A.nelem + T3_EPW - 1) / T3_EPW;
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
-  ShellArgs A = A0;
-  if (comp) {
-    FS_TRY(c->lam_prep.ensure((size_t)A.nelem * 24));
-    k_t3_laminate_prep<<<grid_for(A.nelem, 128), 128, 0, c->stream>>>(A, sheark ? (1.0 / 3) : 1.0, c->lam_prep.p);
-    FS_CUDA(cudaGetLastError());
-    c->launches++;
-    A.lam = c->lam_prep.p;
-  }
   const size_t sm = (size_t)wpb * ((sheark ? 12 : 8) * 6 * 32 + (Emit::kCoop ? COOP_DBL : 0)) * sizeof(double);
 #define T3_GO(CO, SK)                                                                                         \
   do {                                                                                                        \

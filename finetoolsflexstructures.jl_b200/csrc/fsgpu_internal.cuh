@@ -131,7 +131,7 @@ struct fsgpu_ctx {
   fs::DBuf<int32_t> group_of;   // [nelem] 0-based
   int64_t ncs = 0;
   fs::DBuf<double> csmat;       // [ncs][9] ROW-major
-  fs::DBuf<double> lam_prep;    // laminated shells: factored constitutive data of the current operator call (Q4RSComp [nelem][npts][24], T3FFComp [nelem][24])
+  fs::DBuf<double> lam_prep;    // Q4RSComp: [nelem][npts][24] factored constitutive data of the current operator call
   // beam
   bool have_sections = false;
   fs::DBuf<double> sec;         // [nelem][10]: A I1 I2 I3 J A2s A3s x y z

@@ -434,22 +434,6 @@ FS_HD double node_kavg_part(const Constit& C, const double (&brn)[5][2], bool sh
   double k = 0.0;
   for (int s = shear_only ? 6 : 0; s < 8; ++s) k += constit_d(C, s) * (f[s][0] * f[s][0] + f[s][1] * f[s][1]);
   return k;
-}// the same with the pivots given by their square roots q (laminate data of k_t3_laminate_prep)
-FS_HD double node_kavg_part_q(const Constit& C, const double (&q)[8], const double (&brn)[5][2], bool shear_only) {
-  double f[8][2];
-  for (int cl = 0; cl < 2; ++cl) {
-    f[0][cl] = f[1][cl] = f[2][cl] = 0.0;
-    for (int r = 0; r < 5; ++r) f[3 + r][cl] = brn[r][cl];
-    for (int s = 0; s < 6; ++s) {
-      double v = f[s][cl];
-      for (int t = s + 1; t < 6; ++t) v += C.L6[t][s] * f[t][cl];
-      f[s][cl] = v;
-    }
-    f[6][cl] += C.L2 * f[7][cl];
-  }
-  double k = 0.0;
-  for (int s = shear_only ? 6 : 0; s < 8; ++s) k += (q[s] * q[s]) * (f[s][0] * f[s][0] + f[s][1] * f[s][1]);
-  return k;
 }
 
 // ---------------------------------------------------------------------------------
