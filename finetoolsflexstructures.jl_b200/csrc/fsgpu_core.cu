@@ -299,6 +299,7 @@ extern "C" int fsgpu_set_mesh(fsgpu_ctx* c, int32_t nnpe, int64_t nelem, const i
   c->target = -1;
   c->have_matrix = c->have_vector = false;
   c->associated = false;
+  c->t3_plan_ok = false;
   c->have_sections = c->have_state = false;
   c->ngroups = 0;
   c->nthick = c->nstab = 0;
@@ -1047,6 +1048,7 @@ extern "C" int fsgpu_symbolic(fsgpu_ctx* c, int32_t target, int64_t* nrows, int6
     FS_TRY(c->nodecol.ensure((size_t)8 * nn + 8));
     LAUNCH(c, k_node_cols, nn, c->dof.p, c->nodeinfo.p, c->colptr.p, nn, ti.nc, c->nodecol.p);
     c->slot.release();
+    if (nnpe == 3) FS_TRY(fsk::t3_build_plan(c));
   } else {
     c->pairoff.release();
     FS_TRY(c->slot.ensure((size_t)36 * nnpe * nnpe * ne + 1));

@@ -117,6 +117,7 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   int64_t nc;
   int nnpe;
   const int32_t* nodecol;  // [nnodes][8]: column starts of the node's 6 dofs (-1: not a column), nodeinfo, 0
+  const unsigned* plan;  // T3: per-warp emission plan of the symbolic phase (k_t3_plan), or null
   struct Cols {
     int base[6];
   };
@@ -571,6 +572,144 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
       }
     }
   }
+  // ---- T3 emission driven by the per-warp PLAN of the symbolic phase (k_t3_plan).  The plan lists the UNIQUE matrix
+  // blocks (row node, column node) the warp's ten elements touch, each with the lanes that contribute to it, sorted by
+  // column node: a strip of five quads has 12 + 42 unique blocks instead of 30 + 60 contributions (40 % fewer REDs and L2
+  // reduction sectors), and the five blocks of a RED instruction mostly lie in the columns of one or two nodes.
+  //   Three lists: DIAGONAL blocks (contributors: D = K_e[j, j] of the lanes whose own node it is), LOWER blocks (row node >
+  //   column node) and UPPER blocks of the element edges.  A lane stages ONE edge block Y = K_e[max, min] of its edge
+  //   (own node, next node), i.e. X or X' depending on the orientation; a lower block is the sum of its contributors' Y
+  //   read by rows (16-byte reads), the upper block of the same edge the sum of the same Y read by columns.
+  //   descriptor (32 bits): [0:5) lane whose own node is the column node, [5:10) lane whose own node is the row node,
+  //   [10:12) P-plane pair of the run offsets (0: (j,j), 1: (next,j), 2: (j,next)), [12:17) lane that holds them,
+  //   [17:32) contributor lanes (5 bits each, three for a diagonal block, two for an edge block; 31 = none: the slot of
+  //   idle lane 31 is staged as zeros).  Blocks with more contributors are split over several descriptors (RED adds).
+  //   per warp: word 0 = nD | nL << 8 | nU << 16, then the descriptors of the three lists.
+  static constexpr int kT3PlanStride = 92;  // 32-bit words per warp (1 + at most 30 + 30 + 30, one pad: 16-byte multiple)
+  __device__ __forceinline__ void t3_plan_round(const int* addr, unsigned ds, bool in, int r, int4& c0, int4& c1, int& pos,
+                                                bool& act) const {
+    const int cl = (int)(ds & 31), rl = (int)((ds >> 5) & 31), ot = (int)((ds >> 10) & 3), ol = (int)((ds >> 12) & 31);
+    c0 = *reinterpret_cast<const int4*>(addr + cl * 4);
+    c1 = *reinterpret_cast<const int4*>(addr + kT3C1 + cl * 4);
+    const int inf = addr[kT3C1 + rl * 4 + 2];
+    const int mA = inf & 63, mB = (inf >> 8) & 63;
+    const bool inA = (mA >> r) & 1, inB = (mB >> r) & 1;
+    const int off = addr[kT3P + ot * 64 + (inA ? 0 : 32) + ol];
+    pos = off + __popc((inA ? mA : mB) & ((1 << r) - 1));
+    act = in && (inA || inB) && off >= 0;
+  }
+  __device__ __forceinline__ void t3_plan_red(const int4& c0, const int4& c1, bool act, int pos, const double (&v)[6]) const {
+    const bool fast = __all_sync(0xffffffffu, !act || (c0.x | c0.y | c0.z | c0.w | c1.x | c1.y) >= 0);
+    if (!act) return;
+    double* nzr = nz + pos;
+    if (fast) {
+      red_plain(nzr, c0.x, v[0]);
+      red_plain(nzr, c0.y, v[1]);
+      red_plain(nzr, c0.z, v[2]);
+      red_plain(nzr, c0.w, v[3]);
+      red_plain(nzr, c1.x, v[4]);
+      red_plain(nzr, c1.y, v[5]);
+    } else {
+      red_add(nzr, c0.x, v[0], c0.x >= 0);
+      red_add(nzr, c0.y, v[1], c0.y >= 0);
+      red_add(nzr, c0.z, v[2], c0.z >= 0);
+      red_add(nzr, c0.w, v[3], c0.w >= 0);
+      red_add(nzr, c1.x, v[4], c1.x >= 0);
+      red_add(nzr, c1.y, v[5], c1.y >= 0);
+    }
+  }
+  // sum of row r of the blocks staged by the (up to three) contributor lanes of descriptor ds
+  // (NC contributor fields are read unconditionally, an empty one as the zero block of lane 31.  Measured alternatives:
+  // a warp vote per field that skips fields no block of the round uses, 2.84 ms; the blocks of a list ordered by their
+  // number of contributors so that whole rounds skip fields, 2.83 ms -- it breaks the ordering by column node; both 2.92;
+  // against 2.71 ms for this form in the same build)
+  template <int NC>
+  static __device__ __forceinline__ void t3_plan_rows(const double* stage, unsigned ds, int r, double (&v)[6]) {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int src = (int)((ds >> (17 + 5 * k)) & 31);
+      const double2* sp = reinterpret_cast<const double2*>(stage + src * kStageLd + r * 6);
+      const double2 a0 = sp[0], a1 = sp[1], a2 = sp[2];
+      if (k == 0) {
+        v[0] = a0.x, v[1] = a0.y, v[2] = a1.x, v[3] = a1.y, v[4] = a2.x, v[5] = a2.y;
+      } else {
+        v[0] += a0.x, v[1] += a0.y, v[2] += a1.x, v[3] += a1.y, v[4] += a2.x, v[5] += a2.y;
+      }
+    }
+  }
+  // `on`: the lane holds blocks of an element (idle lanes stage zeros: lane 31 is the plan's "no contributor");
+  // `swap`: the own node is the larger one of the lane's edge (own node, next node)
+  __device__ __forceinline__ void t3_emit_plan(double* stage, const int* addr, const unsigned* pl, int lane, bool on, bool swap,
+                                               const double (&d)[21], const double (&a)[6][6]) const {
+    const int slot = lane / 6, r = lane - 6 * slot;
+    const unsigned hdr = pl[0];
+    const int nD = (int)(hdr & 255), nL = (int)((hdr >> 8) & 255), nU = (int)((hdr >> 16) & 255);
+    double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
+    // ---- diagonal blocks (idle lanes stage zeros: lane 31's slot is the plan's "no contributor")
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int q = 0; q < 6; q += 2)
+        st2[(c * 6 + q) >> 1] = on ? make_double2(d[tri(q, c)], d[tri(q + 1, c)]) : make_double2(0.0, 0.0);
+    __syncwarp();
+#pragma unroll 1
+    for (int g = 0; g * 5 < nD; ++g) {
+      const int b = g * 5 + slot;
+      const bool in = lane < 30 && b < nD;
+      const unsigned ds = pl[1 + (in ? b : 0)];
+      int4 c0, c1;
+      int pos;
+      bool act;
+      t3_plan_round(addr, ds, in, r, c0, c1, pos, act);
+      double v[6];
+      t3_plan_rows<3>(stage, ds, r, v);
+      t3_plan_red(c0, c1, act, pos, v);
+    }
+    __syncwarp();
+    // ---- edge blocks: Y = K_e[max, min] row-major (X = K_e[next, own] or its transpose)
+    // (measured: applying the orientation to the store index instead -- 36 scalar stores, no selects -- and skipping the
+    // idle lanes' stores is slower, 2.93 against 2.68 ms: more spills in the product stage)
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+      for (int c = 0; c < 6; c += 2) {
+        const double y0 = swap ? a[c][q] : a[q][c], y1 = swap ? a[c + 1][q] : a[q][c + 1];
+        st2[(q * 6 + c) >> 1] = on ? make_double2(y0, y1) : make_double2(0.0, 0.0);
+      }
+    __syncwarp();
+#pragma unroll 1
+    for (int g = 0; g * 5 < nL; ++g) {  // lower blocks: rows of the summed Y
+      const int b = g * 5 + slot;
+      const bool in = lane < 30 && b < nL;
+      const unsigned ds = pl[1 + nD + (in ? b : 0)];
+      int4 c0, c1;
+      int pos;
+      bool act;
+      t3_plan_round(addr, ds, in, r, c0, c1, pos, act);
+      double v[6];
+      t3_plan_rows<2>(stage, ds, r, v);
+      t3_plan_red(c0, c1, act, pos, v);
+    }
+#pragma unroll 1
+    for (int g = 0; g * 5 < nU; ++g) {  // upper blocks: columns of the summed Y
+      const int b = g * 5 + slot;
+      const bool in = lane < 30 && b < nU;
+      const unsigned ds = pl[1 + nD + nL + (in ? b : 0)];
+      int4 c0, c1;
+      int pos;
+      bool act;
+      t3_plan_round(addr, ds, in, r, c0, c1, pos, act);
+      double v[6];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int src = (int)((ds >> (17 + 5 * k)) & 31);
+        const double* sp = stage + src * kStageLd + r;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) v[c] = k == 0 ? sp[c * 6] : v[c] + sp[c * 6];
+      }
+      t3_plan_red(c0, c1, act, pos, v);
+    }
+  }
   __device__ __forceinline__ void block(const BlockRef&, const Cols& cb, const Rows& rw, const double (&a)[6][6]) const {
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
@@ -638,11 +777,17 @@ struct EmitDense {
 // T3FF / T3FFComp stiffness
 // =====================================================================================
 constexpr int T3_EPW = 10;  // elements per warp (3 lanes each; lanes 30, 31 idle)
+// per-warp shared memory of k_t3_stiffness: [strips | staged blocks] [addressing planes] [emission plan]
+__host__ __device__ constexpr int t3_stage_doubles(bool sheark, bool) { return (sheark ? 12 : 8) * 6 * 32; }
+__host__ __device__ constexpr int t3_warp_doubles(bool sheark, bool coop) {
+  return t3_stage_doubles(sheark, coop) + (coop ? COOP_DBL + EmitRuns::kT3PlanStride / 2 : 0);
+}
 
 template <bool COMP, bool SHEARK, class Emit>
 __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(ShellArgs P, Emit emit) {
   constexpr int NR = SHEARK ? 12 : 8;
-  constexpr int WARP_DBL = NR * 6 * 32 + (Emit::kCoop ? COOP_DBL : 0);
+  constexpr int SA = t3_stage_doubles(SHEARK, Emit::kCoop);  // strips, later the staged blocks
+  constexpr int WARP_DBL = t3_warp_doubles(SHEARK, Emit::kCoop);
   extern __shared__ double smem[];  // per warp: strips [NR*6][32], rows pre-scaled by sqrt(d_s) (+ coop scratch)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* sw = smem + (size_t)wib * WARP_DBL;
@@ -672,7 +817,13 @@ __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(She
     // addressing data: requested first (cp.async into its own shared-memory area): the element index is dead before
     // the register-heavy passes, and the loads overlap all of them (3.29 -> 3.20 ms on C4)
     const int jn0 = j == 2 ? 0 : j + 1;
-    emit.t3_async_addr(reinterpret_cast<int*>(sw + NR * 6 * 32), lane, active, j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]), e, j, jn0);
+    emit.t3_async_addr(reinterpret_cast<int*>(sw + SA), lane, active, j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]), e, j, jn0);
+    {  // this warp's emission plan: 23 chunks of 16 bytes
+      const unsigned* src = emit.plan + warp * EmitRuns::kT3PlanStride;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(sw + SA + COOP_DBL);
+      if (lane < EmitRuns::kT3PlanStride / 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + lane * 16), "l"(src + lane * 4) : "memory");
+    }
   }
   if (active) {
     g = t3_geometry(ld3(P.xyz, nn[0]), ld3(P.xyz, nn[1]), ld3(P.xyz, nn[2]));
@@ -794,7 +945,7 @@ __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(She
     // Symmetric form with in-warp merging: this lane forms D = K_e[j, j] and X = K_e[next(j), j] only.
     const int jn = j == 2 ? 0 : j + 1;
     const int nnext = jn == 0 ? nn[0] : (jn == 1 ? nn[1] : nn[2]);
-    int* addr = reinterpret_cast<int*>(sw + NR * 6 * 32);
+    int* addr = reinterpret_cast<int*>(sw + SA);
     // D is symmetric: 21 accumulators (row-major upper triangle); X is a full block.  One pass over the strain
     // rows feeds both (the own row b_j is loaded once).
     double dd[21], acc[6][6];
@@ -842,8 +993,13 @@ __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(She
 #else
     constexpr bool kMerge = false;
 #endif
+#ifdef FS_T3_OLD_EMIT  // (build flag: the emission without the plan, one block per lane and pass; 2.82 against 2.68 ms on C4)
     emit.template t3_emit_diag<kMerge>(sw, addr, lane, active, nj, dd);
     emit.template t3_emit_edge<kMerge>(sw, addr, lane, active, nj, nnext, acc);
+#else
+    (void)kMerge;
+    emit.t3_emit_plan(sw, addr, reinterpret_cast<const unsigned*>(sw + SA + COOP_DBL), lane, l15 < 15, nj > nnext, dd, acc);
+#endif
   } else {
     if (!active) return;
     typename Emit::Cols ecols = emit.cols(nj);
@@ -2037,7 +2193,7 @@ int launch_t3(fsgpu_ctx* c, const ShellArgs& A, bool comp, bool sheark, Emit em)
   const int64_t nwarps = (A.nelem + T3_EPW - 1) / T3_EPW;
   const int grid = (int)((nwarps + wpb - 1) / wpb);
   if (grid == 0) return FSGPU_OK;
-  const size_t sm = (size_t)wpb * ((sheark ? 12 : 8) * 6 * 32 + (Emit::kCoop ? COOP_DBL : 0)) * sizeof(double);
+  const size_t sm = (size_t)wpb * t3_warp_doubles(sheark, Emit::kCoop) * sizeof(double);
 #define T3_GO(CO, SK)                                                                                         \
   do {                                                                                                        \
     FS_CUDA(cudaFuncSetAttribute(k_t3_stiffness<CO, SK, Emit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
@@ -2092,6 +2248,86 @@ int launch_q4(fsgpu_ctx* c, const ShellArgs& A0, bool comp, Emit em) {
   return FSGPU_OK;
 }
 
+// ---- emission plan of the T3 fast path (EmitRuns::t3_emit_plan) ----------------------------------------------------
+// One thread per warp of ten elements.  Lane of (element el of the warp, node j): 16 (el / 5) + 3 (el % 5) + j, as in
+// k_t3_stiffness.  Three sorted lists of (key, record) pairs -- diagonal blocks keyed by the node, edge blocks keyed by
+// (column node, row node) once as the lower and once as the upper block of the edge -- are cut into descriptors of at
+// most three contributor lanes with equal keys.
+__device__ void t3_plan_insert(unsigned long long* key, unsigned* rec, int& m, unsigned long long k, unsigned r) {
+  int p = m++;
+  while (p > 0 && key[p - 1] > k) {  // insertion sort: the lists are short and nearly sorted
+    key[p] = key[p - 1];
+    rec[p] = rec[p - 1];
+    --p;
+  }
+  key[p] = k;
+  rec[p] = r;
+}
+// descriptors of one list, in key order (sorted by column node), at most maxc contributors each
+__device__ int t3_plan_emit(const unsigned long long* key, const unsigned* rec, int m, int maxc, unsigned* out) {
+  int nb = 0;
+  for (int a = 0; a < m;) {
+    int b = a;
+    while (b < m && key[b] == key[a]) ++b;
+    for (int q = a; q < b; q += maxc) {  // record: [0:17) placement fields of the descriptor, [17:22) contributor lane
+      const int n = b - q < maxc ? b - q : maxc;
+      unsigned d = rec[q] & 0x1ffffu;
+      for (int k = 0; k < 3; ++k) d |= (k < n ? (rec[q + k] >> 17) & 31u : 31u) << (17 + 5 * k);
+      out[nb++] = d;
+    }
+    a = b;
+  }
+  return nb;
+}
+__global__ void k_t3_plan(const int32_t* __restrict__ conn, int64_t nelem, int64_t nwarps, unsigned* __restrict__ plan) {
+  const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (w >= nwarps) return;
+  unsigned long long kd[30], kl[30], ku[30];
+  unsigned rd[30], rl[30], ru[30];
+  int md = 0, ml = 0, mu = 0;
+  for (int el = 0; el < T3_EPW; ++el) {
+    const int64_t e = w * T3_EPW + el;
+    if (e >= nelem) break;
+    const int l0 = 16 * (el / 5) + 3 * (el % 5);
+    int nd[3];
+    for (int j = 0; j < 3; ++j) nd[j] = conn[e * 3 + j];
+    for (int j = 0; j < 3; ++j) {
+      const int jn = j == 2 ? 0 : j + 1;
+      const unsigned L = (unsigned)(l0 + j), Ln = (unsigned)(l0 + jn);
+      const unsigned long long u = (unsigned)nd[j], un = (unsigned)nd[jn];
+      // record = column lane | row lane << 5 | P-plane pair << 10 | lane holding the offsets << 12 | contributor << 17
+      t3_plan_insert(kd, rd, md, u, L | (L << 5) | (0u << 10) | (L << 12) | (L << 17));
+      const bool up = un > u;  // the next node is the larger one: X = K_e[next, own] is the lower block
+      const unsigned long long lo = up ? u : un, hi = up ? un : u;
+      const unsigned Llo = up ? L : Ln, Lhi = up ? Ln : L;
+      t3_plan_insert(kl, rl, ml, (lo << 32) | hi, Llo | (Lhi << 5) | ((up ? 1u : 2u) << 10) | (L << 12) | (L << 17));
+      t3_plan_insert(ku, ru, mu, (hi << 32) | lo, Lhi | (Llo << 5) | ((up ? 2u : 1u) << 10) | (L << 12) | (L << 17));
+    }
+  }
+  unsigned* out = plan + w * EmitRuns::kT3PlanStride;
+  const int nD = t3_plan_emit(kd, rd, md, 3, out + 1);
+  const int nL = t3_plan_emit(kl, rl, ml, 2, out + 1 + nD);
+  const int nU = t3_plan_emit(ku, ru, mu, 2, out + 1 + nD + nL);
+  out[0] = (unsigned)nD | ((unsigned)nL << 8) | ((unsigned)nU << 16);
+  for (int k = 1 + nD + nL + nU; k < EmitRuns::kT3PlanStride; ++k) out[k] = 0;
+}
+}  // namespace
+namespace fsk {
+int t3_build_plan(fsgpu_ctx* c) {
+  if (c->nnpe != 3) return FSGPU_OK;
+  if (c->t3_plan_ok) return FSGPU_OK;  // depends on the connectivity only (reset by fsgpu_set_mesh)
+  const int64_t nwarps = (c->nelem + T3_EPW - 1) / T3_EPW;
+  if (nwarps == 0) return FSGPU_OK;
+  FS_TRY(c->t3_plan.ensure((size_t)nwarps * EmitRuns::kT3PlanStride));
+  k_t3_plan<<<grid_for(nwarps, 64), 64, 0, c->stream>>>(c->conn.p, c->nelem, nwarps, c->t3_plan.p);
+  FS_CUDA(cudaGetLastError());
+  c->launches++;
+  c->t3_plan_ok = true;
+  return FSGPU_OK;
+}
+}  // namespace fsk
+namespace {
+
 int begin_matrix(fsgpu_ctx* c) {
   FS_REQUIRE(c->target >= 0, FSGPU_ERR_STATE, "run fsgpu_symbolic before an operator (startassembly!)");
   FS_CUDA(cudaMemsetAsync(c->nzval.p, 0, ((size_t)c->pnnz + 1) * sizeof(double), c->stream));
@@ -2100,7 +2336,8 @@ int begin_matrix(fsgpu_ctx* c) {
 }
 EmitScatter scatter_of(fsgpu_ctx* c) { return EmitScatter{c->nzval.p, c->slot.p, c->nelem * c->nnpe, c->nnpe}; }
 EmitRuns runs_of(fsgpu_ctx* c) {
-  return EmitRuns{c->nzval.p, c->pairoff.p, c->nodeinfo.p, c->dof.p, c->colptr.p, c->nelem, c->pcols, c->nnpe, c->nodecol.p};
+  return EmitRuns{c->nzval.p, c->pairoff.p, c->nodeinfo.p, c->dof.p, c->colptr.p, c->nelem, c->pcols, c->nnpe, c->nodecol.p,
+                  c->nnpe == 3 ? c->t3_plan.p : nullptr};
 }
 
 // ---- order-fixed (deterministic) assembly for every element kind: element matrices -> dense buffer, then one

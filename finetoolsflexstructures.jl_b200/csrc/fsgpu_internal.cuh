@@ -154,6 +154,10 @@ struct fsgpu_ctx {
   fs::DBuf<int32_t> nodecol;  // fast path: [nnodes][8] column starts of the node's dofs (-1 none), nodeinfo, 0
   fs::DBuf<int32_t> nodeinfo; // [nnodes] bits 0-5 run-A mask, bits 8-13 run-B mask
   fs::DBuf<int32_t> pairoff;  // [nnpe(i)][2][nelem][nnpe(j)] row offset of node i's runs in node j's columns
+  // T3 fast path: per-warp emission plan (unique matrix blocks of the warp's ten elements with their contributors, sorted by
+  // column node; fsk::t3_build_plan).  Depends on the connectivity only.
+  fs::DBuf<unsigned> t3_plan;  // [nwarps][92]
+  bool t3_plan_ok = false;
   // node adjacency (kept from the symbolic phase) and the T3 tile (owner-computes) data
   fs::DBuf<int32_t> adjptr, adj;  // CSR over nodes, neighbours ascending by node id
   // scratch of the symbolic phase and of fetch_matrix, kept between calls: cudaMalloc/cudaFree of

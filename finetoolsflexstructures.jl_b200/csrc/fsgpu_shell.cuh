@@ -63,6 +63,9 @@ __device__ __forceinline__ void build_constit_t3(const ShellArgs& P, int64_t e, 
 // host: fills the kernel argument block from the context + operator parameters
 int shell_args(fsgpu_ctx* c, const fsgpu_shell_params* p, int nnpe, bool comp, bool need_normals, ShellArgs& A);
 
+// T3 fast path: per-warp emission plan (fsgpu_elements.cu), built by the symbolic phase once per mesh
+int t3_build_plan(fsgpu_ctx* c);
+
 // T3 tile (owner-computes, atomics-free) path: symbolic data and launch (fsgpu_tile.cu)
 int tile_symbolic(fsgpu_ctx* c);
 int launch_t3_tile(fsgpu_ctx* c, const ShellArgs& A, bool comp);
