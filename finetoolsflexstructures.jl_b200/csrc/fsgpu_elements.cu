@@ -818,11 +818,13 @@ __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(She
     // the register-heavy passes, and the loads overlap all of them (3.29 -> 3.20 ms on C4)
     const int jn0 = j == 2 ? 0 : j + 1;
     emit.t3_async_addr(reinterpret_cast<int*>(sw + SA), lane, active, j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]), e, j, jn0);
-    {  // this warp's emission plan: 23 chunks of 16 bytes
+    if (warp * T3_EPW < P.nelem) {  // this warp's emission plan: 23 chunks of 16 bytes
       const unsigned* src = emit.plan + warp * EmitRuns::kT3PlanStride;
       const unsigned dst = (unsigned)__cvta_generic_to_shared(sw + SA + COOP_DBL);
       if (lane < EmitRuns::kT3PlanStride / 4)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + lane * 16), "l"(src + lane * 4) : "memory");
+    } else if (lane == 0) {  // a warp of the last CTA without elements: an empty plan (there is no entry for it)
+      *reinterpret_cast<unsigned*>(sw + SA + COOP_DBL) = 0u;
     }
   }
   if (active) {
