@@ -777,6 +777,16 @@ struct EmitDense {
 // T3FF / T3FFComp stiffness
 // =====================================================================================
 constexpr int T3_EPW = 10;  // elements per warp (3 lanes each; lanes 30, 31 idle)
+// Which emission a T3 instantiation uses: the plan-driven one (EmitRuns::t3_emit_plan: 2.82 -> 2.68 ms on C4) for the
+// homogeneous shell; the laminated kernel keeps one block per lane and pass (its setup stage leaves fewer registers: with the
+// plan-driven emission it spills 432 instead of 208 bytes and C3 goes from 1.68 to 1.78 ms).  -DFS_T3_OLD_EMIT: never the plan.
+#ifdef FS_T3_OLD_EMIT
+template <bool COMP>
+constexpr bool kT3Plan = false;
+#else
+template <bool COMP>
+constexpr bool kT3Plan = !COMP;
+#endif
 // per-warp shared memory of k_t3_stiffness: [strips | staged blocks] [addressing planes] [emission plan]
 __host__ __device__ constexpr int t3_stage_doubles(bool sheark, bool) { return (sheark ? 12 : 8) * 6 * 32; }
 __host__ __device__ constexpr int t3_warp_doubles(bool sheark, bool coop) {
@@ -818,7 +828,8 @@ __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(She
     // the register-heavy passes, and the loads overlap all of them (3.29 -> 3.20 ms on C4)
     const int jn0 = j == 2 ? 0 : j + 1;
     emit.t3_async_addr(reinterpret_cast<int*>(sw + SA), lane, active, j == 0 ? nn[0] : (j == 1 ? nn[1] : nn[2]), e, j, jn0);
-    if (warp * T3_EPW < P.nelem) {  // this warp's emission plan: 23 chunks of 16 bytes
+    if constexpr (!kT3Plan<COMP>) {
+    } else if (warp * T3_EPW < P.nelem) {  // this warp's emission plan: 23 chunks of 16 bytes
       const unsigned* src = emit.plan + warp * EmitRuns::kT3PlanStride;
       const unsigned dst = (unsigned)__cvta_generic_to_shared(sw + SA + COOP_DBL);
       if (lane < EmitRuns::kT3PlanStride / 4)
@@ -995,13 +1006,12 @@ __global__ void __launch_bounds__(32 * FS_T3_WPB, FS_T3_MINB) k_t3_stiffness(She
 #else
     constexpr bool kMerge = false;
 #endif
-#ifdef FS_T3_OLD_EMIT  // (build flag: the emission without the plan, one block per lane and pass; 2.82 against 2.68 ms on C4)
-    emit.template t3_emit_diag<kMerge>(sw, addr, lane, active, nj, dd);
-    emit.template t3_emit_edge<kMerge>(sw, addr, lane, active, nj, nnext, acc);
-#else
-    (void)kMerge;
-    emit.t3_emit_plan(sw, addr, reinterpret_cast<const unsigned*>(sw + SA + COOP_DBL), lane, l15 < 15, nj > nnext, dd, acc);
-#endif
+    if constexpr (kT3Plan<COMP>) {
+      emit.t3_emit_plan(sw, addr, reinterpret_cast<const unsigned*>(sw + SA + COOP_DBL), lane, l15 < 15, nj > nnext, dd, acc);
+    } else {
+      emit.template t3_emit_diag<kMerge>(sw, addr, lane, active, nj, dd);
+      emit.template t3_emit_edge<kMerge>(sw, addr, lane, active, nj, nnext, acc);
+    }
   } else {
     if (!active) return;
     typename Emit::Cols ecols = emit.cols(nj);
