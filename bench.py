@@ -52,7 +52,11 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """rows delivered so far (GPU idle, sampler starting up) do not count"""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -73,10 +77,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.first:] or self.rows
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -778,11 +783,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler is started (and has delivered its first row) BEFORE the warm-up: nvidia-smi's start-up -- one process
+    # per rank -- otherwise competes with the launching threads for host cores inside a timed region of 16 - 100 ms;
+    # its rows cover the warm-up and the timed steps (the same load)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wait = time.perf_counter()
+    while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+        time.sleep(0.01)
+    sampler.mark()
     for _ in range(max(3, args.warmup)):
         femm.ctx.shell_op("q4rs_stiffness", params)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     l0 = femm.ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kms = []
