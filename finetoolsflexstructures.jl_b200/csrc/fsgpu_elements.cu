@@ -225,68 +225,6 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     }
 #endif
   }
-  // (build flag FS_Q4_MERGE; measured slower on C2, see the call site)  The same with IN-WARP MERGING: lanes whose blocks land on the same matrix block (`key` = row node, column node;
-  // the two quads of a warp share an edge on a block mesh: 4 of their 32 blocks coincide) are summed by the group's
-  // lowest lane out of the staging area and added once.  `on` = lane holds a block.  Uses colb[k][7] (free after the
-  // cp.async wait) for the compact list of group leaders and raw[lane][3] for the group mask.
-  __device__ __forceinline__ void coop_emit_merged(double* scratch, int* addr, int lane, bool on, unsigned long long key,
-                                                   const double (&a)[6][6]) const {
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    const unsigned full = 0xffffffffu;
-    const unsigned grp = __match_any_sync(full, on ? key : (0xffffffff00000000ull | (unsigned)lane));
-    const bool leader = on && (__ffs(grp) - 1 == lane);
-    const unsigned leaders = __ballot_sync(full, leader);
-    const int nlead = __popc(leaders);
-    double* stage = scratch;
-    int* rowp = reinterpret_cast<int*>(scratch + 32 * kStageLd);
-    int* raw = addr + 32 * 8 + lane * 4;
-    const int inf = raw[0], oA = raw[1], oB = raw[2];
-    const int mA = inf & 63, mB = (inf >> 8) & 63;
-    __syncwarp();  // every lane is done with the strips
-    raw[3] = (int)grp;
-    if (leader) addr[__popc(leaders & ((1u << lane) - 1)) * 8 + 7] = lane;
-    int ka = 0, kb = 0;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      int p = -1;
-      if ((mA >> r) & 1)
-        p = oA >= 0 ? oA + ka++ : -1;
-      else if ((mB >> r) & 1)
-        p = oB >= 0 ? oB + kb++ : -1;
-      rowp[r * 32 + lane] = p;
-    }
-    double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
-#pragma unroll
-    for (int c = 0; c < 6; ++c)
-#pragma unroll
-      for (int r = 0; r < 6; r += 2) st2[(c * 6 + r) >> 1] = make_double2(a[r][c], a[r + 1][c]);
-    __syncwarp();
-    const int sub = lane / 6, r = lane - sub * 6;
-#pragma unroll 1
-    for (int g = 0; g * 5 < nlead; ++g) {
-      const int k = g * 5 + sub;
-      if (lane >= 30 || k >= nlead) continue;
-      const int o = addr[k * 8 + 7];
-      const int rp = rowp[r * 32 + o];
-      if (rp < 0) continue;
-      const int4 c0 = *reinterpret_cast<const int4*>(addr + o * 8);
-      const int2 c1 = *reinterpret_cast<const int2*>(addr + o * 8 + 4);
-      const int cb[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
-      const double* sv = stage + o * kStageLd + r;
-      double v[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) v[c] = sv[c * 6];
-      unsigned mm = (unsigned)addr[32 * 8 + o * 4 + 3];
-      for (mm &= mm - 1; mm; mm &= mm - 1) {
-        const double* sq = stage + (__ffs(mm) - 1) * kStageLd + r;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) v[c] += sq[c * 6];
-      }
-#pragma unroll
-      for (int c = 0; c < 6; ++c)
-        if (cb[c] >= 0 FS_RED_GUARD) atomicAdd(nz + cb[c] + rp, v[c]);
-    }
-  }
   // ---- Q4 (DMMA kernel): the element matrix K_e (24 x 24, row stride kQ4KLd) is staged in shared memory by the
   // product stage; the addressing data is kept per NODE (ncol[8][8]: the nodecol rows of the warp's 2 x 4 nodes) and per
   // block (pr[32][2]: run offsets oA, oB of block (bi, bj)), fetched with cp.async while the setup / product stages run
@@ -368,25 +306,6 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
         }
       }
     }
-  }
-  __device__ __forceinline__ Cols cols(int nj) const {
-    Cols c;
-    const int32_t* dj = dof + (int64_t)nj * 6;
-    int cd[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cd[k] = __ldg(dj + k);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) c.base[k] = cd[k] < nc ? __ldg(colptr + cd[k]) : -1;
-    return c;
-  }
-  __device__ __forceinline__ Rows rows(int64_t e, int i, int j, int ni) const {
-    Rows r;
-    const int inf = __ldg(nodeinfo + ni);
-    r.mA = inf & 63;
-    r.mB = (inf >> 8) & 63;
-    r.oA = __ldg(pairoff + ((int64_t)(i * 2 + 0) * nelem + e) * nnpe + j);
-    r.oB = __ldg(pairoff + ((int64_t)(i * 2 + 1) * nelem + e) * nnpe + j);
-    return r;
   }
   // ---- T3 path: cooperative emission (optionally with IN-WARP MERGING, build flag FS_T3_MERGE).  A lane (element,
   // own node j) forms only two products: D = K_e[j, j] and X = K_e[next(j), j]; K_e[j, next(j)] = X' by symmetry.
@@ -708,22 +627,6 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
         for (int c = 0; c < 6; ++c) v[c] = k == 0 ? sp[c * 6] : v[c] + sp[c * 6];
       }
       t3_plan_red(c0, c1, act, pos, v);
-    }
-  }
-  __device__ __forceinline__ void block(const BlockRef&, const Cols& cb, const Rows& rw, const double (&a)[6][6]) const {
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      if (cb.base[c] < 0) continue;
-      double* pa = nz + cb.base[c] + rw.oA;
-      double* pb = nz + cb.base[c] + rw.oB;
-      int ka = 0, kb = 0;
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        if ((rw.mA >> r) & 1)
-          atomicAdd(pa + ka++, a[r][c]);
-        else if ((rw.mB >> r) & 1)
-          atomicAdd(pb + kb++, a[r][c]);
-      }
     }
   }
 };
