@@ -16,7 +16,7 @@ from oracle import fe_external as fx
 from oracle import layup as oly
 from oracle import shells as osh
 from tests import meshes
-from tests.test_gpu_parity import E_, NU_, RHO_, T_, TOL, _check_matrix, _fs_layup, _iso, _layup, _make_femm, _oracle_normals, relfro
+from tests.test_gpu_parity import E_, NU_, RHO_, T_, TOL, _check_matrix, _fs_layup, _iso, _layup, _make_femm, _oracle_K, _oracle_normals, relfro
 
 pytestmark = pytest.mark.gpu
 
@@ -308,6 +308,37 @@ def test_fetch_triangle(fs, asm, narrow, monkeypatch):
     T = f.stiffness(femm, a, geom0, u0, R0, dchi)
     ref = sp.tril(Kc, format="csc")
     assert abs(T.to_scipy() - ref).max() < 1e-12 * abs(ref).max()
+
+
+# ---------------------------------------------------------------------------------------
+# T3 emission plan on meshes that are not manifold strips: a fan of 14 triangles around one node (the ten elements of
+# the first warp all contribute to one diagonal block: four descriptors of <= 3 contributors), an edge shared by four
+# triangles (more than two contributors per edge block), rotated connectivities, a partly filled second warp
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sheark", [0, 1])
+def test_t3_plan_fans_and_nonmanifold_edges(fs, sheark):
+    f = fs.femm
+    nf = 14
+    ang = np.linspace(0.0, 2 * np.pi, nf, endpoint=False)
+    ring = np.column_stack([np.cos(ang), np.sin(ang), 0.25 * np.cos(3 * ang)])
+    xyz = np.vstack([[0.0, 0.0, 0.4], ring, [[2.0, 0.1, 0.9], [2.0, 0.2, -0.8], [1.9, 1.0, 0.1], [2.1, -1.0, 0.0]]])
+    fan = [[1, 2 + k, 2 + (k + 1) % nf] if k % 3 else [2 + (k + 1) % nf, 1, 2 + k] for k in range(nf)]  # rotated connectivities
+    a, b = 2, nf + 2  # ring node 1 and the first extra node: an edge with four triangles on it
+    tj = [[a, b, nf + 3], [b, a, nf + 4], [a, b, nf + 5], [b, a, 3]]
+    conn = np.array(fan[:10] + tj[:2] + fan[10:] + tj[2:], dtype=np.int64)
+    assert conn.shape[0] == 18 and conn.max() == xyz.shape[0] and conn.min() == 1
+    od = meshes.clamp_edge_dofs(xyz, n_extra_fixed=4)
+    femm = _make_femm(fs, "t3", conn)
+    femm.transv_shear_formulation = sheark
+    geom0, dchi, u0, R0 = _fields(f, xyz, od)
+    f.associategeometry(femm, geom0)
+    normals, valid = _oracle_normals("t3", xyz, conn)
+    Ko = _oracle_K("t3", False, xyz, conn, normals, valid, sheark=sheark)
+    for asm, a_ in (("ffblock", f.SysmatAssemblerFFBlock()), ("sparse", f.SysmatAssemblerSparse())):
+        K = f.stiffness(femm, a_, geom0, u0, R0, dchi)
+        assert femm.ctx.scatter_path == 1  # the run-structured path with the plan-driven emission
+        n = od.nfreedofs if asm == "ffblock" else od.nalldofs
+        _check_matrix(K, fx.assemble_matrix(asm, Ko, od.gatherdofnums(conn), od.nalldofs, od.nfreedofs), n)
 
 
 # ---------------------------------------------------------------------------------------
