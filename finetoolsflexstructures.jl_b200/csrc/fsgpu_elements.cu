@@ -36,6 +36,9 @@ using namespace fsk;
 #ifndef FS_Q4_WPB
 #define FS_Q4_WPB 4
 #endif
+#ifndef FS_T3_PLAN_LD
+#define FS_T3_PLAN_LD 38
+#endif
 
 // measurement aid (never defined in the shipped build): -DFS_NO_RED keeps all the arithmetic and addressing
 // but issues no RED, which gives the compute-side time of the scatter kernels
@@ -504,6 +507,8 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
   //   [17:32) contributor lanes (5 bits each, three for a diagonal block, two for an edge block; 31 = none: the slot of
   //   idle lane 31 is staged as zeros).  Blocks with more contributors are split over several descriptors (RED adds).
   //   per warp: word 0 = nD | nL << 8 | nU << 16, then the descriptors of the three lists.
+  // doubles per staged block of the plan-driven emission (measured: 38 2.69 ms, 40 3.08, 42 2.68, 44 2.73, 46 2.70)
+  static constexpr int kT3PlanLd = FS_T3_PLAN_LD;
   static constexpr int kT3PlanStride = 92;  // 32-bit words per warp (1 + at most 30 + 30 + 30, one pad: 16-byte multiple)
   __device__ __forceinline__ void t3_plan_round(const int* addr, unsigned ds, bool in, int r, int4& c0, int4& c1, int& pos,
                                                 bool& act) const {
@@ -547,7 +552,7 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const int src = (int)((ds >> (17 + 5 * k)) & 31);
-      const double2* sp = reinterpret_cast<const double2*>(stage + src * kStageLd + r * 6);
+      const double2* sp = reinterpret_cast<const double2*>(stage + src * kT3PlanLd + r * 6);
       const double2 a0 = sp[0], a1 = sp[1], a2 = sp[2];
       if (k == 0) {
         v[0] = a0.x, v[1] = a0.y, v[2] = a1.x, v[3] = a1.y, v[4] = a2.x, v[5] = a2.y;
@@ -563,7 +568,7 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
     const int slot = lane / 6, r = lane - 6 * slot;
     const unsigned hdr = pl[0];
     const int nD = (int)(hdr & 255), nL = (int)((hdr >> 8) & 255), nU = (int)((hdr >> 16) & 255);
-    double2* st2 = reinterpret_cast<double2*>(stage + lane * kStageLd);
+    double2* st2 = reinterpret_cast<double2*>(stage + lane * kT3PlanLd);
     // ---- diagonal blocks (idle lanes stage zeros: lane 31's slot is the plan's "no contributor")
 #pragma unroll
     for (int c = 0; c < 6; ++c)
@@ -622,7 +627,7 @@ struct EmitRuns {  // fast path: rows of a node form <= 2 consecutive runs in ev
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int src = (int)((ds >> (17 + 5 * k)) & 31);
-        const double* sp = stage + src * kStageLd + r;
+        const double* sp = stage + src * kT3PlanLd + r;
 #pragma unroll
         for (int c = 0; c < 6; ++c) v[c] = k == 0 ? sp[c * 6] : v[c] + sp[c * 6];
       }
