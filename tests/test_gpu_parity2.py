@@ -342,6 +342,26 @@ def test_t3_plan_fans_and_nonmanifold_edges(fs, sheark):
 
 
 # ---------------------------------------------------------------------------------------
+# the reference's own NAFEMS LE5 test (Z-section with creases: invalid nodal normals at half of the nodes), end to end:
+# GPU-assembled stiffness, host solve, the reference's golden numbers (test/test_shell_statics.jl:530-531)
+# ---------------------------------------------------------------------------------------
+def test_le5_z_section_golden_through_the_gpu(fs):
+    from tests.test_oracle_goldens import LE5_GOLDEN, le5_problem
+
+    f = fs.femm
+    xyz, conn, E, nu, th, d, F = le5_problem()
+    femm = f.FEMMShellT3FF(f.IntegDomain(conn, None, th), f.MatDeforElastIso(E, nu, 1.0), stab_alpha=0.2)
+    geom0, dchi, u0, R0 = _fields(f, xyz, d)
+    f.associategeometry(femm, geom0)
+    assert (~np.asarray(femm._normal_valid, dtype=bool)).sum() == 18
+    K = f.stiffness(femm, geom0, u0, R0, dchi)  # default assembler: SysmatAssemblerSparseSymm
+    fx.solve_blocked(K.to_scipy().tocsc(), F, d)
+    uz = d.values[:, 2]
+    assert abs(uz.min() - LE5_GOLDEN[0]) < 1e-9 * abs(LE5_GOLDEN[0])
+    assert abs(uz.max() - LE5_GOLDEN[1]) < 1e-9 * abs(LE5_GOLDEN[1])
+
+
+# ---------------------------------------------------------------------------------------
 # pageable destinations (a Julia `Vector`): values and colptr travel through the pinned staging ring
 # ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("narrow", [False, True])

@@ -54,6 +54,100 @@ def test_q4rs_scordelis_lo(n, ref):
     assert abs(_scordelis(n, True) - ref) / ref < 1e-9
 
 
+def _twisted_beam(n, quad, t, force, direction, uex):
+    """Twisted cantilever (MacNeal-Harder), test/test_shell_statics.jl:276-352 (T3FF, default stabilisation) and
+    test/test_q4rs_shell_statics.jl:292-348 (Q4RS, stab_fun t^2 / (t^2 + 0.05 h^2)): tip deflection under a unit tip force."""
+    E, nu, W, L = 0.29e8, 0.22, 1.1, 12.0
+    nL, nW = 2 * n, n
+    tol = W / nW / 100
+    xy, conn = (fx.q4block if quad else fx.t3block)(L, W, nL, nW)
+    a, y = xy[:, 0] / L * (np.pi / 2), xy[:, 1] - W / 2
+    xyz = np.column_stack([xy[:, 0], y * np.cos(a), y * np.sin(a)])
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(E, nu))
+    d = fx.DofField(xyz.shape[0])
+    l1 = fx.selectnode_box(xyz, [0, 0, -INF, INF, -INF, INF], tol)
+    for c in range(1, 7):
+        d.setebc(l1, c)
+    d.numberdofs()
+    if quad:
+        nrm, val = osh.q4rs_associategeometry(xyz, conn)
+        Ke = osh.q4rs_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, t, stab_fun=osh.stab_lyly(0.05))
+    else:
+        nrm, val = osh.t3ff_associategeometry(xyz, conn)
+        Ke = osh.t3ff_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, t)
+    na = d.nalldofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, d.gatherdofnums(conn), na), na, na)
+    nl = fx.selectnode_box(xyz, [L, L, 0, 0, 0, 0], tol)
+    assert len(nl) == 1
+    F = np.zeros((xyz.shape[0], 6))
+    F[nl[0], direction - 1] = force  # FESetP1 + PointRule: the force itself
+    fx.solve_blocked(K, F, d)
+    return d.values[nl, direction - 1][0] / uex * 100
+
+
+_TWISTED_CASES = [(0.32, 1.0, 2, 0.001753248285256), (0.32, 1.0, 3, 0.005424534868469),
+                  (0.0032, 1.0e-6, 2, 0.001294), (0.0032, 1.0e-6, 3, 0.005256)]
+# test/test_shell_statics.jl:355-372
+_TWISTED_T3 = [39.709921740907355, 68.87306876326497, 86.01944734315117, 95.04101960524827,
+               53.10262177376127, 83.8593790803426, 94.91359387874728, 98.21549248655576,
+               48.16757753755567, 79.43420077873479, 92.54464819755955, 96.85008269135751,
+               50.577029703967334, 80.34160167730624, 92.48675665271801, 96.7096641005938]
+# test/test_q4rs_shell_statics.jl:352-368
+_TWISTED_Q4 = [57.52004303100694, 82.57318302555431, 94.20131995162048, 98.37454367262973,
+               76.28227868667001, 93.90901921611645, 98.28145099724978, 99.43562910255783,
+               68.51008267652144, 90.66189189880987, 97.4223162100464, 99.27913153086936,
+               76.09971224380796, 93.00031411228612, 97.58071557550575, 99.2319932521005]
+
+
+@pytest.mark.parametrize("quad", [False, True])
+@pytest.mark.parametrize("case", range(4))
+@pytest.mark.parametrize("k", range(3))  # n = 2, 4, 8 (the reference also runs n = 16)
+def test_twisted_beam(quad, case, k):
+    t, force, direction, uex = _TWISTED_CASES[case]
+    ref = (_TWISTED_Q4 if quad else _TWISTED_T3)[4 * case + k]
+    v = _twisted_beam(2 ** (k + 1), quad, t, force, direction, uex)
+    # the reference tests use rtol 1e-3; the thin beam (t / L = 2.7e-4) is ill-conditioned: the solver's round-off shows at 1e-7
+    assert abs(v - ref) / ref < (1e-8 if t > 0.01 else 2e-5)
+
+
+def le5_problem():
+    """NAFEMS LE5 Z-section cantilever under torsion, test/test_shell_statics.jl:440-535: mesh of the reference's Abaqus deck
+    (tests/golden/le5_mesh.npz, made by tests/golden/make_le5_fixture.py), translations fixed at x = 0, two tip forces of
+    0.6 MN, stab_fun t^2 / (t^2 + 0.2 h^2).  Half of its nodes lie on the creases of the section: invalid nodal normals."""
+    import os
+
+    m = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "le5_mesh.npz"))
+    xyz, conn = m["xyz"], m["conn"]
+    E, nu, th = 210e9, 0.3, 0.1
+    tol = th / 1000
+    d = fx.DofField(xyz.shape[0])
+    l1 = fx.selectnode_box(xyz, [0, 0, -INF, INF, -INF, INF], tol)
+    for c in (1, 2, 3):
+        d.setebc(l1, c)
+    d.numberdofs()
+    F = np.zeros((xyz.shape[0], 6))
+    F[fx.selectnode_box(xyz, [10, 10, 1, 1, 0, 0], tol)[0], 2] = 0.6e6
+    F[fx.selectnode_box(xyz, [10, 10, -1, -1, 0, 0], tol)[0], 2] = -0.6e6
+    return xyz, conn, E, nu, th, d, F
+
+
+LE5_GOLDEN = (-0.01568028415401719, 0.015401663810490641)  # test/test_shell_statics.jl:530-531 (min, max of u_z)
+
+
+def test_t3ff_le5_z_section():
+    xyz, conn, E, nu, th, d, F = le5_problem()
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(E, nu))
+    nrm, val = osh.t3ff_associategeometry(xyz, conn)
+    assert (~val.astype(bool)).sum() == 18  # the crease nodes: element normals, no drilling stiffness there
+    Ke = osh.t3ff_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, th, stab_fun=osh.stab_lyly(0.2))
+    na = d.nalldofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, d.gatherdofnums(conn), na), na, na)
+    fx.solve_blocked(K, F, d)
+    uz = d.values[:, 2]
+    assert abs(uz.min() - LE5_GOLDEN[0]) < 1e-10 * abs(LE5_GOLDEN[0])  # the reference test uses isapprox (1.5e-8)
+    assert abs(uz.max() - LE5_GOLDEN[1]) < 1e-10 * abs(LE5_GOLDEN[1])
+
+
 def test_t3ff_fv12_frequencies():
     """test/test_shell_dynamics.jl:26-133: K + lumped M, 8 non-rigid frequencies (:119-127)."""
     E, nu, rho, th, L, n = 200e3 * 1e6, 0.3, 8000.0, 0.05, 10.0, 8
