@@ -1,12 +1,15 @@
-"""Extracts the mesh of the reference's NAFEMS LE5 test (Z-section cantilever, test/test_shell_statics.jl:440-535) from its
-Abaqus input deck into a small fixture, tests/golden/le5_mesh.npz, as the reference's `import_ABAQUS` + `compactnodes`
-deliver it: node coordinates in file order with the unconnected nodes removed, S3R connectivities renumbered (1-based).
+"""Extracts the meshes of two of the reference's tests from their Abaqus input decks into small fixtures, as the reference's
+`import_ABAQUS` + `compactnodes` deliver them (node coordinates in file order with the unconnected nodes removed, triangle
+connectivities renumbered, 1-based):
+  tests/golden/le5_mesh.npz          NAFEMS LE5 Z-section cantilever, test/test_shell_statics.jl:440-535 (nle5xf3c.inp)
+  tests/golden/barrelvault_mesh.npz  irregular barrel vault of the resultants test, test/test_shell_statics.jl:577-764
+                                     (barrelvault_stri3_irreg.inp; two coincident node pairs are left for `mergenodes`)
 Run in the build container (the reference tree is not available on the GPU box):  python tests/golden/make_le5_fixture.py"""
 import os
 
 import numpy as np
 
-SRC = "/root/reference/test/nle5xf3c.inp"
+DECKS = {"le5_mesh.npz": "/root/reference/test/nle5xf3c.inp", "barrelvault_mesh.npz": "/root/reference/test/barrelvault_stri3_irreg.inp"}
 
 
 def parse(path):
@@ -30,12 +33,13 @@ def parse(path):
 
 
 if __name__ == "__main__":
-    ids, xyz, conn = parse(SRC)
-    order = np.argsort(ids, kind="stable")  # import_ABAQUS stores node k at row k (ids are ascending in the deck)
-    ids, xyz = ids[order], xyz[order]
-    used = np.isin(ids, conn)  # findunconnnodes / compactnodes: connected nodes keep their relative order
-    new = np.zeros(ids.max() + 1, dtype=np.int64)
-    new[ids[used]] = np.arange(1, used.sum() + 1)
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "le5_mesh.npz")
-    np.savez_compressed(out, xyz=xyz[used], conn=new[conn])
-    print("wrote", out, xyz[used].shape, conn.shape)
+    for name, src in DECKS.items():
+        ids, xyz, conn = parse(src)
+        order = np.argsort(ids, kind="stable")  # import_ABAQUS stores node k at row k (ids are ascending in the deck)
+        ids, xyz = ids[order], xyz[order]
+        used = np.isin(ids, conn)  # findunconnnodes / compactnodes: connected nodes keep their relative order
+        new = np.zeros(ids.max() + 1, dtype=np.int64)
+        new[ids[used]] = np.arange(1, used.sum() + 1)
+        out = os.path.join(os.path.dirname(os.path.abspath(__file__)), name)
+        np.savez_compressed(out, xyz=xyz[used], conn=new[conn])
+        print("wrote", out, xyz[used].shape, conn.shape)

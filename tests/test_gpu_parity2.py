@@ -362,6 +362,29 @@ def test_le5_z_section_golden_through_the_gpu(fs):
 
 
 # ---------------------------------------------------------------------------------------
+# the reference's resultants test (irregular barrel vault, cylindrical output csys, nodal fields by FinEtools'
+# inverse-distance rule; test/test_shell_statics.jl:577-728) through the GPU path: stiffness, host solve, batched
+# inspectintegpoints, the reference's 16 (min, max) numbers with the reference's tolerance
+# ---------------------------------------------------------------------------------------
+def test_barrelvault_resultant_fields_through_the_gpu(fs):
+    from tests.test_oracle_goldens import barrelvault_resultants_problem, check_barrelvault_fields
+
+    f = fs.femm
+    P = barrelvault_resultants_problem()
+    xyz, conn, d = P["xyz"], P["conn"], P["dof"]
+    femm = f.FEMMShellT3FF(f.IntegDomain(conn, None, P["th"]), f.MatDeforElastIso(P["E"], P["nu"], 1.0), stab_alpha=0.2)
+    femm.drilling_stiffness_scale = 0.1
+    geom0, dchi, u0, R0 = _fields(f, xyz, d)
+    f.associategeometry(femm, geom0)
+    K = f.stiffness(femm, geom0, u0, R0, dchi)
+    fx.solve_blocked(K.to_scipy().tocsc(), fx.distribloads_t3(xyz, conn, [-0.625, 0, 0, 0, 0, 0]), d)
+    assert np.abs(d.values - P["u"]).max() < 1e-9 * np.abs(P["u"]).max()  # the oracle's solution of the same problem
+    names = {osh.BENDING_MOMENT: "moment", osh.MEMBRANE_FORCE: "membrane", osh.TRANSVERSE_SHEAR: "shear"}
+    u = f.NodalField(d.values.copy())
+    check_barrelvault_fields(P, lambda q: f.inspectintegpoints(femm, geom0, u, None, names[q], outputcsys=P["ocs"])[:, 0, :])
+
+
+# ---------------------------------------------------------------------------------------
 # pageable destinations (a Julia `Vector`): values and colptr travel through the pinned staging ring
 # ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("narrow", [False, True])

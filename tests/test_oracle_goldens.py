@@ -148,6 +148,65 @@ def test_t3ff_le5_z_section():
     assert abs(uz.max() - LE5_GOLDEN[1]) < 1e-10 * abs(LE5_GOLDEN[1])
 
 
+def barrelvault_resultants_problem():
+    """Irregular barrel vault of the reference's resultants test, test/test_shell_statics.jl:577-690 (mesh of its Abaqus deck,
+    tests/golden/barrelvault_mesh.npz; mergenodes, diaphragm + two symmetry planes, self-weight along -x, stab_fun with 0.2,
+    drilling_stiffness_scale 0.1), solved with the oracle.  Returns what the resultant / nodal-field checks need."""
+    import os
+
+    m = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "barrelvault_mesh.npz"))
+    E, nu, th = 3.0e6, 0.0, 3.0
+    tol, R, L = th / 20, 25.0 * 12, 50.0 * 12
+    xyz, conn = fx.mergenodes(m["xyz"], m["conn"], th / 10)
+    assert xyz.shape[0] == 43
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(E, nu))
+    d = fx.DofField(xyz.shape[0])
+    for box, comps in (([-INF, INF, -INF, INF, 0, 0], (1, 2)), ([-INF, INF, -INF, INF, L / 2, L / 2], (3, 4, 5)), ([-INF, INF, 0, 0, -INF, INF], (2, 4, 6))):
+        l1 = fx.selectnode_box(xyz, box, tol)
+        for c in comps:
+            d.setebc(l1, c)
+    d.numberdofs()
+    nrm, val = osh.t3ff_associategeometry(xyz, conn)
+    stab = osh.stab_lyly(0.2)
+    Ke = osh.t3ff_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, th, stab_fun=stab, drilling_stiffness_scale=0.1)
+    na = d.nalldofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, d.gatherdofnums(conn), na), na, na)
+    fx.solve_blocked(K, fx.distribloads_t3(xyz, conn, [-0.625, 0, 0, 0, 0, 0]), d)
+    # output csys `cylindrical!` of the test (:660-673), evaluated at the integration point (the centroid)
+    cen = xyz[conn - 1].mean(axis=1)
+    r = -cen.copy()
+    r[:, 2] = 0.0
+    e3 = r / np.linalg.norm(r, axis=1)[:, None]
+    e2 = np.tile([0.0, 0.0, 1.0], (len(cen), 1))
+    ocs = np.stack([np.cross(e2, e3), e2, e3], axis=2)
+    return dict(xyz=xyz, conn=conn, nrm=nrm, val=val, Dps=Dps, Dt=Dt, th=th, stab=stab, dof=d, u=d.values.copy(), cen=cen, ocs=ocs,
+                E=E, nu=nu)
+
+
+# test/test_shell_statics.jl:675-728: (min, max) of the nodal fields of the three moments, membrane forces, two shear forces
+BARRELVAULT_FIELDS = {
+    osh.BENDING_MOMENT: [(-1520.6449167366522, 14.067403309095397), (-73.8262145426215, 425.93651541819503), (-0.005341121492547284, 953.0929383629322)],
+    osh.MEMBRANE_FORCE: [(-306.83173146926623, 309.5860993742647), (-1011.4832977998705, 2167.0403478574167), (-687.3500043290137, 69.38703021678862)],
+    osh.TRANSVERSE_SHEAR: [(-13.784764125688811, 21.165312065421237), (-7.4216963152916255, 25.679801383392967)],
+}
+
+
+def check_barrelvault_fields(P, resultants_of):
+    """`resultants_of(quantity) -> (ne, 3)` in the output csys; the nodal fields by FinEtools' inverse-distance rule against
+    the reference's numbers with the reference's own tolerance (rtol 0.01: its numbers predate the current revision)."""
+    for quant, gold in BARRELVAULT_FIELDS.items():
+        fld = fx.field_from_integpoints_invdist(P["xyz"], P["conn"], P["cen"][:, None, :], resultants_of(quant)[:, None, :])
+        for k, (lo, hi) in enumerate(gold):
+            assert abs(fld[:, k].min() - lo) <= 0.01 * abs(lo), (quant, k, fld[:, k].min(), lo)
+            assert abs(fld[:, k].max() - hi) <= 0.01 * abs(hi), (quant, k, fld[:, k].max(), hi)
+
+
+def test_t3ff_resultant_fields_barrelvault():
+    P = barrelvault_resultants_problem()
+    check_barrelvault_fields(P, lambda q: osh.t3ff_resultants(P["xyz"], P["conn"], P["nrm"], P["val"], P["Dps"], P["Dt"], P["th"], P["u"], q,
+                                                              ocs=P["ocs"], stab_fun=P["stab"]))
+
+
 def test_t3ff_fv12_frequencies():
     """test/test_shell_dynamics.jl:26-133: K + lumped M, 8 non-rigid frequencies (:119-127)."""
     E, nu, rho, th, L, n = 200e3 * 1e6, 0.3, 8000.0, 0.05, 10.0, 8
