@@ -382,6 +382,15 @@ def test_barrelvault_resultant_fields_through_the_gpu(fs):
     names = {osh.BENDING_MOMENT: "moment", osh.MEMBRANE_FORCE: "membrane", osh.TRANSVERSE_SHEAR: "shear"}
     u = f.NodalField(d.values.copy())
     check_barrelvault_fields(P, lambda q: f.inspectintegpoints(femm, geom0, u, None, names[q], outputcsys=P["ocs"])[:, 0, :])
+    # the mirror of FinEtools' fieldfromintegpoints / elemfieldfromintegpoints on top of the batched resultants
+    from tests.test_oracle_goldens import BARRELVAULT_FIELDS
+
+    for q, gold in BARRELVAULT_FIELDS.items():
+        fld = f.fieldfromintegpoints(femm, geom0, u, names[q], list(range(1, len(gold) + 1)), outputcsys=P["ocs"]).values
+        for k, (lo, hi) in enumerate(gold):
+            assert abs(fld[:, k].min() - lo) <= 0.01 * abs(lo) and abs(fld[:, k].max() - hi) <= 0.01 * abs(hi)
+        ef = f.elemfieldfromintegpoints(femm, geom0, u, names[q], 1, outputcsys=P["ocs"])
+        assert ef.shape == (conn.shape[0], 1)
 
 
 # ---------------------------------------------------------------------------------------
