@@ -348,6 +348,71 @@ def test_beam_buckling_factors():
     assert np.linalg.norm(np.array([48.5475, 124.1839]) - fs[1:3]) / np.linalg.norm([48.5475, 124.1839]) < 1e-5
 
 
+def _rect_section(b, h, x1x2, n):
+    """CrossSectionRectangle(s -> b, s -> h, s -> x1x2) (src/CrossSectionModule.jl:127-180): Bernoulli (A2s = A3s = Inf),
+    torsion constant from the Dierckx spline of the aspect-ratio table."""
+    from scipy.interpolate import UnivariateSpline
+
+    xs = [1, 1.5, 2.0, 2.5, 3.0, 4.0, 5.0, 6.0, 10, 20, 40, 80, 200, 2000]
+    ys = [0.141, 0.196, 0.229, 0.249, 0.263, 0.281, 0.291, 0.299, 0.312, 0.317, 0.325, 0.33, 1 / 3, 1 / 3]
+    c = float(UnivariateSpline(xs, ys, k=3, s=0)(max(b, h) / min(b, h)))
+    one = np.ones(n)
+    return dict(A=b * h * one, I1=(b * h**3 / 12 + b**3 * h / 12) * one, I2=b * h**3 / 12 * one, I3=b**3 * h / 12 * one,
+                J=c * max(b, h) * min(b, h) ** 3 * one, A2s=INF * one, A3s=INF * one, x1x2=np.tile(np.asarray(x1x2, dtype=float), (n, 1)))
+
+
+def test_beam_l_frame_frequencies():
+    """test/test_beam_modal.jl:19-74: L-shaped frame of two legs (4 elements each), clamped at one end; consistent mass
+    with rotation inertia (the default of `mass`); the two lowest frequencies [11.2732, 30.5269] Hz to 3e-5."""
+    E, nu, rho, b, h, L, n = 71240.0, 0.31, 5e-9, 3.0, 30.0, 240.0, 4
+    s = np.linspace(0.0, 1.0, n + 1)[:, None]
+    leg1 = np.array([[0.0, 0, L]]) + s * np.array([[L, 0, 0.0]])  # frame_member([0 0 L; L 0 L], n, cs)
+    leg2 = np.array([[L, 0.0, L]]) + s[1:] * np.array([[0.0, 0, -L]])  # second leg, its first node merged with the corner
+    xyz = np.vstack([leg1, leg2])
+    conn = np.column_stack([np.arange(1, 2 * n + 1), np.arange(2, 2 * n + 2)])
+    sec = _rect_section(b, h, [0.0, 1.0, 0.0], 2 * n)
+    d = fx.DofField(xyz.shape[0])
+    for i in range(1, 7):
+        d.setebc(fx.selectnode_box(xyz, [0, 0, 0, 0, L, L], L / 10000), i)
+    d.numberdofs()
+    nn = xyz.shape[0]
+    u0, R0 = np.zeros((nn, 3)), obeam.initial_Rfield(nn)
+    dn, na, nf = d.gatherdofnums(conn), d.nalldofs, d.nfreedofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", obeam.beam_stiffness_elmats(xyz, conn, u0, R0, sec, E, nu), dn, na), na, na).toarray()[:nf, :nf]
+    M = fx.csc_to_scipy(*fx.assemble_matrix("symm", obeam.beam_mass_elmats(xyz, conn, u0, R0, sec, rho, 1), dn, na), na, na).toarray()[:nf, :nf]
+    fs = np.sqrt(sla.eigh(K, M, eigvals_only=True)[:2]) / (2 * np.pi)
+    ref = np.array([11.2732, 30.5269])
+    assert np.linalg.norm(ref - fs) / np.linalg.norm(ref) <= 3.0e-5  # the reference's own tolerance (its numbers have 6 digits)
+
+
+@pytest.mark.parametrize("direction", [1, 3])
+def test_beam_simply_supported_uniform_load(direction):
+    """test/test_beam_linear_statics.jl:19-80 (load along x, bending about the weak axis) and :100-167 (load along z, strong
+    axis): beam on two cylindrical joints under `distribloads_global`; midspan deflection 5 q L^4 / (384 E I) to 1e-5."""
+    E, nu, b, h, L, q, n = 30002 * 1000.0, 0.0, 2.0, 18.0, 240.0, 1.0, 4
+    I = b**3 * h / 12 if direction == 1 else b * h**3 / 12
+    xyz = np.zeros((n + 1, 3))
+    xyz[:, 1] = np.linspace(-L / 2, L / 2, n + 1)  # frame_member([0 -L/2 0; 0 L/2 0], n, cs)
+    conn = np.column_stack([np.arange(1, n + 1), np.arange(2, n + 2)])
+    sec = _rect_section(b, h, [-1.0, 0.0, 0.0], n)
+    d = fx.DofField(n + 1)
+    fixed = (1, 2, 3, 4, 5) if direction == 1 else (1, 2, 3, 5, 6)  # cylindrical joints
+    for node in (0, n):
+        for i in fixed:
+            d.setebc([node], i)
+    d.numberdofs()
+    u0, R0 = np.zeros((n + 1, 3)), obeam.initial_Rfield(n + 1)
+    dn, na = d.gatherdofnums(conn), d.nalldofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", obeam.beam_stiffness_elmats(xyz, conn, u0, R0, sec, E, nu), dn, na), na, na)
+    force = [q, 0, 0] if direction == 1 else [0, 0, q]
+    Fv = fx.assemble_vector(obeam.beam_distribloads_elvecs(xyz, conn, u0, R0, sec, force), dn, na)
+    F = np.zeros((n + 1, 6))
+    F.ravel()[:] = Fv[d.dofnums.ravel() - 1]
+    fx.solve_blocked(K, F, d)
+    deflex = 5 * q * L**4 / (384 * E * I)
+    assert abs(d.values[n // 2, direction - 1] - deflex) / deflex < 1.0e-5
+
+
 def test_assembler_equivalence():
     """test/test_utilities.jl:12-47: SysmatAssemblerSparseCSRSymm == SysmatAssemblerSparseSymm."""
     m1 = np.array([[0.24406, 0.599773, 0.833404, 0.0420141], [0.786024, 0.00206713, 0.995379, 0.780298], [0.845816, 0.198459, 0.355149, 0.224996]])
