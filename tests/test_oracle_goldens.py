@@ -315,6 +315,51 @@ def test_layup_barbero_5_7():
     assert np.abs(p.Dts - np.diag([G12, 2760.0])).max() < 1e-12 * E1
 
 
+def _layup(plies):
+    return oly.CompositeLayup("sample", plies)
+
+
+def test_layup_matrices_of_the_reference_suite():
+    """Laminate matrices the reference's own suite holds as numbers (test/test_composite_layup.jl; phun("MPa") = 1e6 and
+    phun("m") = 1 there: the numbers below are per MPa and per metre of thickness)."""
+    E1, E2, G12, nu12 = 67192.0, 12139.0, 7638.0, 0.365  # Barbero Ex. 5.7 lamina (:465-470)
+    mod = oly.lamina_moduli(E1, E2, nu12, G12, G12, G12)
+    dps = np.array([[68849.10243290635, 4540.006665496835, 0.0], [4540.006665496834, 12438.374426018723, 0.0], [0.0, 0.0, 7637.999999999999]])
+    assert np.linalg.norm(oly.Ply("p", mod, 1.0, 45.0).Dps - dps) < 1e-15 * E2 * 1e3  # :476-482 (1e-15 E2 in Pa)
+    # one ply at 45 degrees, thickness 1: A (:484-492 / :444-450)
+    A, B, D = _layup([oly.Ply("p", mod, 1.0, 45.0)]).laminate_stiffnesses()
+    a45 = np.array([[30229.872547479692, 14953.872547479687, 14102.68200172191], [14953.872547479687, 30229.872547479685, 14102.682001721907],
+                    [14102.682001721909, 14102.682001721909, 18051.865881982852]])
+    assert np.linalg.norm(A - a45) < 1e-9 * E2
+    # balanced +45 / -45 fabric, two plies of 0.5: the shear coupling cancels (:520-553)
+    A, B, D = _layup([oly.Ply("p1", mod, 0.5, 45.0), oly.Ply("p2", mod, 0.5, -45.0)]).laminate_stiffnesses()
+    abal = a45.copy()
+    abal[0, 2] = abal[1, 2] = abal[2, 0] = abal[2, 1] = 0.0
+    assert np.linalg.norm(A - abal) < 1e-9 * E2
+    # symmetric cross-ply [0/90/0/90/0]: no extension-bending coupling (:560-594)
+    A, B, D = _layup([oly.Ply(f"p{k}", mod, 0.001, a) for k, a in enumerate((0, 90, 0, 90, 0))]).laminate_stiffnesses()
+    assert np.linalg.norm(B) < 1e-15 * E2
+    # an isotropic ply at any angle: A = E / (1 - nu^2) [1 nu 0; nu 1 0; 0 0 (1 - nu) / 2] t (:306-330)
+    E, nu, t = 200e3, 0.3, 0.005
+    iso = oly.lamina_moduli(E, E, nu, E / 2 / (1 + nu), E / 2 / (1 + nu), E / 2 / (1 + nu))
+    atrue = E / (1 - nu**2) * np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]]) * t
+    for ang in (0.0, 47.0, 90.0, 129.0, 180.0):
+        A, B, D = _layup([oly.Ply("p", iso, t, ang)]).laminate_stiffnesses()
+        assert np.linalg.norm(A - atrue) < 1e-12 * np.linalg.norm(atrue)
+
+
+@pytest.mark.parametrize("npairs,v,tol", [(1, 1585193.0, 1e-6), (5, 317039.0, 2e-6), (20, 79260.0, 5e-6)])
+def test_layup_barbero_3_1_coupling(npairs, v, tol):
+    """test/test_composite_layup.jl:720-762 (Barbero Ex. 3.1, [0/90]_n of 10 mm): B = [-v 0 0; 0 v 0; 0 0 0] N.  The reference
+    runs npairs = 1 (to 1e-6); its table also holds the integer-rounded values for 5 and 20 pairs."""
+    mod = oly.lamina_moduli(133860.0, 7706.0, 0.301, 4306.0, 4306.0, 2760.0)
+    plies = []
+    for _ in range(npairs):
+        plies += [oly.Ply("p", mod, 10.0 / npairs / 2, 0.0), oly.Ply("p", mod, 10.0 / npairs / 2, 90.0)]
+    A, B, D = _layup(plies).laminate_stiffnesses()
+    assert np.linalg.norm(B - np.array([[-v, 0, 0], [0, v, 0], [0, 0, 0]])) < tol * v
+
+
 def test_beam_buckling_factors():
     """test/test_beam_buckling.jl:19-85: stiffness + geostiffness + update_rotation_field!,
     buckling factors [48.5475, 124.1839] (:30, tolerance 1e-3)."""
