@@ -348,7 +348,7 @@ def test_layup_matrices_of_the_reference_suite():
         assert np.linalg.norm(A - atrue) < 1e-12 * np.linalg.norm(atrue)
 
 
-@pytest.mark.parametrize("npairs,v,tol", [(1, 1585193.0, 1e-6), (5, 317039.0, 2e-6), (20, 79260.0, 5e-6)])
+@pytest.mark.parametrize("npairs,v,tol", [(1, 1585193.0, 1e-6), (5, 317039.0, 2e-6), (20, 79260.0, 1e-5)])
 def test_layup_barbero_3_1_coupling(npairs, v, tol):
     """test/test_composite_layup.jl:720-762 (Barbero Ex. 3.1, [0/90]_n of 10 mm): B = [-v 0 0; 0 v 0; 0 0 0] N.  The reference
     runs npairs = 1 (to 1e-6); its table also holds the integer-rounded values for 5 and 20 pairs."""
