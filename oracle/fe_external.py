@@ -473,3 +473,24 @@ def field_from_integpoints_invdist(xyz, conn, loc, values):
     nz = den > 0
     out[nz] = num[nz] / den[nz, None]
     return out
+
+
+def q4_to_t3(conn4):
+    """FinEtools `Q4toT3(fens, fes)` (MeshModificationModule, un-vendored FinEtools 8.2.5), default orientation: quad
+    (1, 2, 3, 4) -> triangles (1, 2, 3) and (1, 3, 4), two per quad in quad order.  Pinned by the Raasch hook goldens of
+    test/test_shell_statics.jl:226-231 (the alternate diagonal misses them by 3e-6 .. 1e-5, this one matches to 1e-10)."""
+    c = np.asarray(conn4, dtype=np.int64)
+    out = np.empty((2 * c.shape[0], 3), dtype=np.int64)
+    out[0::2] = c[:, [0, 1, 2]]
+    out[1::2] = c[:, [0, 2, 3]]
+    return out
+
+
+def boundary_edges(conn):
+    """FinEtools `meshboundary` of a surface mesh: the element edges that belong to exactly one element, as node pairs."""
+    c = np.asarray(conn, dtype=np.int64)
+    n = c.shape[1]
+    e = np.concatenate([np.stack([c[:, i], c[:, (i + 1) % n]], axis=1) for i in range(n)])
+    key = np.sort(e, axis=1)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    return e[cnt[inv.ravel()] == 1]

@@ -112,7 +112,7 @@ def test_twisted_beam(quad, case, k):
 
 def le5_problem():
     """NAFEMS LE5 Z-section cantilever under torsion, test/test_shell_statics.jl:440-535: mesh of the reference's Abaqus deck
-    (tests/golden/le5_mesh.npz, made by tests/golden/make_le5_fixture.py), translations fixed at x = 0, two tip forces of
+    (tests/golden/le5_mesh.npz, made by tests/golden/make_mesh_fixtures.py), translations fixed at x = 0, two tip forces of
     0.6 MN, stab_fun t^2 / (t^2 + 0.2 h^2).  Half of its nodes lie on the creases of the section: invalid nodal normals."""
     import os
 
@@ -205,6 +205,40 @@ def test_t3ff_resultant_fields_barrelvault():
     P = barrelvault_resultants_problem()
     check_barrelvault_fields(P, lambda q: osh.t3ff_resultants(P["xyz"], P["conn"], P["nrm"], P["val"], P["Dps"], P["Dt"], P["th"], P["u"], q,
                                                               ocs=P["ocs"], stab_fun=P["stab"]))
+
+
+# test/test_shell_statics.jl:226-231
+@pytest.mark.parametrize("mesh,ref", [("1x9", 91.7059961843231), ("3x18", 95.9355786538892), ("5x36", 97.19276899988246), ("10x72", 98.38896641657374)])
+def test_t3ff_raasch_hook(mesh, ref):
+    """Raasch hook (strongly curved strip, in-plane shear at the free end), test/test_shell_statics.jl:140-236: the S4 meshes
+    of the reference's Abaqus decks (tests/golden/raasch_meshes.npz) split by `Q4toT3`, clamped at x = 0, a line load of 0.05
+    on the boundary edges of the free end (`meshboundary` + `selectelem` box + GaussRule(1, 2)), tip deflection in percent."""
+    import os
+
+    m = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "raasch_meshes.npz"))
+    xyz, conn = m[f"xyz_{mesh}"], fx.q4_to_t3(m[f"conn_{mesh}"])
+    E, nu, th = 3300.0, 0.35, 2.0
+    tol = th / 2
+    Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(E, nu))
+    d = fx.DofField(xyz.shape[0])
+    l1 = fx.selectnode_box(xyz, [0, 0, -INF, INF, -INF, INF], tol)
+    for c in range(1, 7):
+        d.setebc(l1, c)
+    d.numberdofs()
+    nrm, val = osh.t3ff_associategeometry(xyz, conn)
+    Ke = osh.t3ff_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, th, stab_fun=osh.stab_lyly(0.2))
+    na = d.nalldofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, d.gatherdofnums(conn), na), na, na)
+    lo = np.array([97.9615, -16.0, 0.0]) - tol
+    hi = np.array([97.9615, -16.0, 20.0]) + tol
+    F = np.zeros((xyz.shape[0], 6))
+    for i, j in fx.boundary_edges(conn) - 1:
+        if np.all((xyz[[i, j]] >= lo) & (xyz[[i, j]] <= hi)):  # selectelem: all nodes of the edge in the inflated box
+            F[[i, j], 2] += 0.05 * np.linalg.norm(xyz[i] - xyz[j]) / 2
+    fx.solve_blocked(K, F, d)
+    nl = fx.selectnode_box(xyz, [97.9615, 97.9615, -16, -16, 0, 0], tol)
+    v = d.values[nl, 2][0] / 5.02 * 100
+    assert abs(v - ref) / ref < 1e-8  # the reference test uses rtol 1e-4
 
 
 def test_t3ff_fv12_frequencies():
