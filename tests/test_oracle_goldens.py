@@ -266,6 +266,71 @@ def _boundary_nodes(xyz, ax, ay, tol):
     return np.nonzero((np.abs(xyz[:, 0]) < tol) | (np.abs(xyz[:, 0] - ax) < tol) | (np.abs(xyz[:, 1]) < tol) | (np.abs(xyz[:, 1] - ay) < tol))[0]
 
 
+@pytest.mark.parametrize("composite", [False, True])
+def test_simply_supported_plate_frequencies(composite):
+    """test/test_composite_shell_dynamics.jl:17-110 (T3FF) and :113-204 (T3FFComp, the same isotropic plate as four plies at
+    +-45 degrees): square plate, translations fixed on the boundary, 8 lowest frequencies; both against the same numbers."""
+    ax, n, E, nu, rho = 1.0, 8, 1000.0e6, 0.396, 2.0
+    th, tol = ax / 1000, ax / n / 100
+    xy, conn = fx.t3block(ax, ax, n, n)
+    xyz = fx.xyz3(xy)
+    d = fx.DofField(xyz.shape[0])
+    for c in (1, 2, 3):
+        d.setebc(_boundary_nodes(xyz, ax, ax, tol), c)  # connectednodes(meshboundary(fes))
+    d.numberdofs()
+    if composite:
+        D6 = fx.moduli_iso(E, nu)
+        lay = oly.CompositeLayup("petyt_9.2", [oly.Ply(f"ply_{k}", D6, th / 4, a, rho) for k, a in enumerate((45, -45, 45, -45))])
+        cs = oly.cartesian_csys((1, 2, 3))
+        nrm, val = osh.t3ff_associategeometry(xyz, conn, normal_dir=cs[:, 2])
+        A, B, D = lay.laminate_stiffnesses()
+        Ke = osh.t3ffcomp_stiffness_elmats(xyz, conn, nrm, val, A, B, D, lay.laminate_transverse_stiffness(), lay.thickness, cs)
+        Me = osh.t3ffcomp_mass_elmats(xyz, conn, *lay.laminate_inertia())
+    else:
+        Dps, Dt = osh.shell_material_stiffness(fx.moduli_iso(E, nu))
+        nrm, val = osh.t3ff_associategeometry(xyz, conn)
+        Ke = osh.t3ff_stiffness_elmats(xyz, conn, nrm, val, Dps, Dt, th)
+        Me = osh.t3ff_mass_elmats(xyz, conn, rho, th)
+    dn, na, nf = d.gatherdofnums(conn), d.nalldofs, d.nfreedofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, dn, na), na, na).toarray()[:nf, :nf]
+    M = fx.csc_to_scipy(*fx.assemble_matrix("symm", Me, dn, na), na, na).toarray()[:nf, :nf]
+    fs = np.sqrt(sla.eigh(K, M, eigvals_only=True)[:8]) / (2 * np.pi)
+    ref = np.array([21.822774909379287, 54.52203720717488, 54.60475772077202, 86.5480437899711, 108.65349048567792, 108.78050954575491,
+                    138.29506871044424, 140.89370172063866])
+    assert np.linalg.norm(fs - ref) < 1e-7 * np.linalg.norm(ref), np.linalg.norm(fs - ref) / np.linalg.norm(ref)  # reference: 1e-3
+
+
+@pytest.mark.parametrize("angles,axes,ref,tol", [((0, 90), (1, 2, 3), 42.62, 1e-2), ((-45, 45), (1, 2, 3), 47.86476186783638, 1e-6),
+                                                   ((-45, 45), (-2, 1, 3), 47.86476186783638, 1e-6)])
+def test_unsymmetric_laminate_fundamental_frequency(angles, axes, ref, tol):
+    """test/test_composite_shell_dynamics.jl:736-933: simply supported square plate of an UNSYMMETRIC two-ply laminate
+    (extension-bending coupling B != 0), 50 x 50 cells; fundamental frequency 42.62 Hz for [0/90] (4 digits, reference
+    tolerance 1e-2) and 47.86476186783638 Hz for [-45/45], also with the layup csys rotated by 90 degrees."""
+    import scipy.sparse.linalg as spla
+
+    ax, n, rho, th = 1.0, 50, 1500.0, 0.010
+    D6 = oly.lamina_moduli(133860.0e6, 7706.0e6, 0.301, 4306.0e6, 4306.0e6, 2760.0e6)
+    lay = oly.CompositeLayup("example_3.1", [oly.Ply(f"p{k}", D6, th / 2, a, rho) for k, a in enumerate(angles)])
+    cs = oly.cartesian_csys(axes)
+    xy, conn = fx.t3block(ax, ax, n, n)
+    xyz = fx.xyz3(xy)
+    d = fx.DofField(xyz.shape[0])
+    for c in (1, 2, 3):
+        d.setebc(_boundary_nodes(xyz, ax, ax, ax / n / 100), c)
+    d.numberdofs()
+    nrm, val = osh.t3ff_associategeometry(xyz, conn, normal_dir=cs[:, 2])
+    A, B, D = lay.laminate_stiffnesses()
+    assert np.abs(B).max() > 1e-3 * np.abs(A).max() * th  # the coupling this case is about
+    Ke = osh.t3ffcomp_stiffness_elmats(xyz, conn, nrm, val, A, B, D, lay.laminate_transverse_stiffness(), lay.thickness, cs)
+    Me = osh.t3ffcomp_mass_elmats(xyz, conn, *lay.laminate_inertia())
+    dn, na, nf = d.gatherdofnums(conn), d.nalldofs, d.nfreedofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, dn, na), na, na)[:nf, :nf].tocsc()
+    M = fx.csc_to_scipy(*fx.assemble_matrix("symm", Me, dn, na), na, na)[:nf, :nf].tocsc()
+    ev = spla.eigsh(K, k=3, M=M, sigma=0.0, which="LM", return_eigenvectors=False)
+    f1 = np.sqrt(ev.min()) / (2 * np.pi)
+    assert abs(f1 - ref) / ref < tol, f1
+
+
 @pytest.mark.parametrize("nplies,axes", [(10, (1, 2, 3)), (3, (2, -1, 3)), (5, (-1, -2, 3)), (4, (-2, 1, 3))])
 def test_t3ffcomp_nayak_frequencies(nplies, axes):
     """test/test_composite_shell_dynamics.jl:354-460: 9 nondimensional frequencies, norm < 1e-13."""
