@@ -331,6 +331,40 @@ def test_unsymmetric_laminate_fundamental_frequency(angles, axes, ref, tol):
     assert abs(f1 - ref) / ref < tol, f1
 
 
+@pytest.mark.parametrize("tl,axes", [(1 / 5, (1, 2, 3)), (1 / 10, (1, 2, 3)), (1 / 100, (1, 2, 3)), (1 / 100, (2, -1, 3)), (1 / 100, (-2, 1, 3))])
+def test_nayak_4_4_thickness_ratios(tl, axes):
+    """test/test_composite_shell_dynamics.jl:462-596: [0/90/90/0] simply supported plate at three thickness ratios (thick
+    plates: the laminate's transverse shear stiffness matters); nondimensional fundamental frequency against Nayak's table
+    (10.989, 15.270, 18.755) within the reference's 3 %."""
+    import scipy.sparse.linalg as spla
+
+    ax, n, rho = 0.1, 32, 1500.0
+    E1 = 143.52e9
+    E2 = E1 / 40
+    th = ax * tl
+    D6 = oly.lamina_moduli(E1, E2, 0.25, E2 * 0.6, E2 * 0.6, E2 * 0.5)
+    lay = oly.CompositeLayup("Nayak 4.4", [oly.Ply(f"p{k}", D6, th / 4, a, rho) for k, a in enumerate((0, 90, 90, 0))])
+    cs = oly.cartesian_csys(axes)
+    xy, conn = fx.t3block(ax, ax, n, n)
+    xyz = fx.xyz3(xy)
+    tol = ax / n / 100
+    d = fx.DofField(xyz.shape[0])
+    d.setebc(fx.selectnode_box(xyz, [0, 0, 0, 0, -INF, INF], tol), 2)
+    for c in (1, 2, 3):
+        d.setebc(_boundary_nodes(xyz, ax, ax, tol), c)
+    d.numberdofs()
+    nrm, val = osh.t3ff_associategeometry(xyz, conn, normal_dir=cs[:, 2])
+    A, B, D = lay.laminate_stiffnesses()
+    Ke = osh.t3ffcomp_stiffness_elmats(xyz, conn, nrm, val, A, B, D, lay.laminate_transverse_stiffness(), lay.thickness, cs)
+    Me = osh.t3ffcomp_mass_elmats(xyz, conn, *lay.laminate_inertia())
+    dn, na, nf = d.gatherdofnums(conn), d.nalldofs, d.nfreedofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", Ke, dn, na), na, na)[:nf, :nf].tocsc()
+    M = fx.csc_to_scipy(*fx.assemble_matrix("symm", Me, dn, na), na, na)[:nf, :nf].tocsc()
+    f1 = np.sqrt(spla.eigsh(K, k=3, M=M, sigma=0.0, which="LM", return_eigenvectors=False).min()) / (2 * np.pi)
+    ref = {1 / 5: 10.989, 1 / 10: 15.270, 1 / 100: 18.755}[tl]
+    assert abs(ref - 2 * np.pi * f1 * ax**2 / th * np.sqrt(rho / E2)) / ref < 3.0e-2
+
+
 @pytest.mark.parametrize("nplies,axes", [(10, (1, 2, 3)), (3, (2, -1, 3)), (5, (-1, -2, 3)), (4, (-2, 1, 3))])
 def test_t3ffcomp_nayak_frequencies(nplies, axes):
     """test/test_composite_shell_dynamics.jl:354-460: 9 nondimensional frequencies, norm < 1e-13."""
