@@ -107,6 +107,7 @@ _SIGNATURES = {
     "fsgpu_corotbeam_distribloads": [_vp, _P(BeamParams), _vp, _i64, _i32],
     "fsgpu_shell_mass_diag": [_vp, _P(ShellParams), _i32, _i32],
     "fsgpu_shell_resultants": [_vp, _P(ShellParams), _i32, _i32, _vp, _vp, _i64, _vp],
+    "fsgpu_shell_nodal_field": [_vp, _P(ShellParams), _i32, _i32, _vp, _vp, _i64, _vp],
     "fsgpu_update_rotation_field": [_vp, _vp, _vp],
     "fsgpu_element_matrices": [_vp, _i32, _i32, _vp, _vp],
     "fsgpu_element_vectors": [_vp, _P(BeamParams), _vp],

@@ -291,6 +291,19 @@ class Context:
         check(lib.fsgpu_shell_resultants(self._h, C.byref(params), kind, quantity, ptr(uu), ptr(cs), ncs, ptr(out)))
         return out
 
+    def shell_nodal_field(self, params, kind, quantity, u, outputcsys=None):
+        """fieldfromintegpoints on the device: (nnodes, 3) nodal means of the resultants (inverse squared distance)."""
+        uu = f64(u, "F")
+        out = np.zeros((self.nnodes, 3), order="F")
+        if outputcsys is None:
+            cs, ncs = None, 0
+        else:
+            cs = np.asarray(outputcsys, dtype=np.float64).reshape(-1, 3, 3)
+            ncs = cs.shape[0]
+            cs = np.ascontiguousarray(np.transpose(cs, (0, 2, 1)))
+        check(lib.fsgpu_shell_nodal_field(self._h, C.byref(params), kind, quantity, ptr(uu), ptr(cs), ncs, ptr(out)))
+        return out
+
     def update_rotation_field(self, dchi_values):
         d = f64(dchi_values, "F")
         out = np.zeros((self.nnodes, 9), order="F")

@@ -2704,12 +2704,13 @@ extern "C" int fsgpu_element_matrices(fsgpu_ctx* c, int32_t kind, int32_t op, co
   return FSGPU_OK;
 }
 
-extern "C" int fsgpu_shell_resultants(fsgpu_ctx* c, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
-                                      const double* outputcsys, int64_t ncs, double* out) {
+// resultants of every integration point on the device: dout [nelem][npts][3]
+static int resultants_device(fsgpu_ctx* c, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
+                             const double* outputcsys, int64_t ncs, DBuf<double>& dout, int* npts_out) {
   FS_TRY(check_ctx(c));
   FS_REQUIRE(kind == 3 || kind == 4 || kind == 13 || kind == 14, FSGPU_ERR_ARG,
              "kind must be 3 (T3FF), 4 (Q4RS), 13 (T3FFComp) or 14 (Q4RSComp)");
-  FS_REQUIRE(quantity >= 1 && quantity <= 3 && u && out, FSGPU_ERR_ARG, "quantity must be 1 (bending), 2 (shear) or 3 (membrane)");
+  FS_REQUIRE(quantity >= 1 && quantity <= 3 && u, FSGPU_ERR_ARG, "quantity must be 1 (bending), 2 (shear) or 3 (membrane)");
   const bool comp = kind > 10;
   kind = comp ? kind - 10 : kind;
   ShellArgs A;
@@ -2717,7 +2718,7 @@ extern "C" int fsgpu_shell_resultants(fsgpu_ctx* c, const fsgpu_shell_params* p,
   const int npts = kind == 3 ? 1 : c->rule.npts;
   FS_REQUIRE(ncs == 0 || ncs == 1 || ncs == c->nelem || ncs == c->nelem * npts, FSGPU_ERR_ARG, "bad output csys count");
   const int64_t n = c->nnodes, nout = c->nelem * npts * 3;
-  DBuf<double> du, dcs, dout, tmpc;
+  DBuf<double> du, dcs, tmpc;
   FS_TRY(du.ensure((size_t)n * 6 + 1));
   FS_TRY(c->tmp.ensure((size_t)n * 6 * sizeof(double)));
   FS_TRY(upload(c, c->tmp.p, u, (size_t)n * 6 * sizeof(double)));
@@ -2745,7 +2746,87 @@ extern "C" int fsgpu_shell_resultants(fsgpu_ctx* c, const fsgpu_shell_params* p,
     c->launches++;
   }
   FS_CUDA(cudaGetLastError());
-  FS_TRY(download(c, out, dout.p, (size_t)nout * sizeof(double)));
+  *npts_out = npts;
+  return FSGPU_OK;
+}
+extern "C" int fsgpu_shell_resultants(fsgpu_ctx* c, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
+                                      const double* outputcsys, int64_t ncs, double* out) {
+  DBuf<double> dout;
+  int npts = 0;
+  FS_TRY(resultants_device(c, p, kind, quantity, u, outputcsys, ncs, dout, &npts));
+  FS_TRY(download(c, out, dout.p, (size_t)c->nelem * npts * 3 * sizeof(double)));
+  FS_CUDA(cudaStreamSynchronize(c->stream));
+  return FSGPU_OK;
+}
+
+// FinEtools' fieldfromintegpoints with nodevalmethod = :invdistance (FEMMBaseModule, FinEtools 8.2.5; called on the shells by
+// test/test_shell_resultants.jl:123): every integration point adds value / (d + dmin / 1e9) to the nodes of its element, d the
+// SQUARED distance node - point (the centroid for the T3 shells, the integration point for the Q4 shells: the `loc` of the
+// reference's inspectintegpoints), dmin the smallest positive d of the element; the nodal value is the weighted mean.
+__global__ void k_nodal_invdist(const int32_t* __restrict__ conn, const double4* __restrict__ xyz, int nnpe, int npts, Rule rule,
+                                int64_t nelem, const double* __restrict__ val, double* __restrict__ num, double* __restrict__ den) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (tid >= nelem * npts) return;
+  const int64_t e = tid / npts;
+  const int q = (int)(tid - e * npts);
+  int nd[4];
+  V3 X[4];
+  for (int a = 0; a < nnpe; ++a) {
+    nd[a] = conn[e * nnpe + a];
+    X[a] = ld3(xyz, nd[a]);
+  }
+  V3 loc = v3(0, 0, 0);
+  if (nnpe == 3) {
+    loc = (1.0 / 3.0) * (X[0] + X[1] + X[2]);
+  } else {
+    const double xi = rule.xi[q], eta = rule.eta[q];
+    const double N[4] = {0.25 * (1 - xi) * (1 - eta), 0.25 * (1 + xi) * (1 - eta), 0.25 * (1 + xi) * (1 + eta), 0.25 * (1 - xi) * (1 + eta)};
+    for (int a = 0; a < 4; ++a) loc = loc + N[a] * X[a];
+  }
+  double d[4], dmin = 1.0e300;
+  for (int a = 0; a < nnpe; ++a) {
+    const V3 r = X[a] - loc;
+    d[a] = dot(r, r);
+    if (d[a] > 0.0 && d[a] < dmin) dmin = d[a];
+  }
+  dmin *= 1.0e-9;
+  for (int a = 0; a < nnpe; ++a) {
+    const double w = 1.0 / (d[a] + dmin);
+    for (int k = 0; k < 3; ++k) atomicAdd(num + (int64_t)nd[a] * 3 + k, w * val[tid * 3 + k]);
+    atomicAdd(den + nd[a], w);
+  }
+}
+// nodal means, written column-major (nnodes x 3) as a NodalField's values
+__global__ void k_nodal_mean(const double* __restrict__ num, const double* __restrict__ den, int64_t nnodes, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nnodes * 3) return;
+  const int64_t node = i / 3;
+  const int k = (int)(i - node * 3);
+  out[k * nnodes + node] = den[node] > 0.0 ? num[i] / den[node] : 0.0;
+}
+extern "C" int fsgpu_shell_nodal_field(fsgpu_ctx* c, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
+                                       const double* outputcsys, int64_t ncs, double* out) {
+  FS_REQUIRE(out != nullptr, FSGPU_ERR_ARG, "null output");
+  DBuf<double> dout, num, den, res;
+  int npts = 0;
+  FS_TRY(resultants_device(c, p, kind, quantity, u, outputcsys, ncs, dout, &npts));
+  const int64_t n = c->nnodes;
+  FS_TRY(num.ensure((size_t)n * 3 + 1));
+  FS_TRY(den.ensure((size_t)n + 1));
+  FS_TRY(res.ensure((size_t)n * 3 + 1));
+  FS_CUDA(cudaMemsetAsync(num.p, 0, (size_t)n * 3 * sizeof(double), c->stream));
+  FS_CUDA(cudaMemsetAsync(den.p, 0, (size_t)n * sizeof(double), c->stream));
+  if (c->nelem > 0) {
+    k_nodal_invdist<<<grid_for(c->nelem * npts, 128), 128, 0, c->stream>>>(c->conn.p, c->xyz.p, c->nnpe, npts, c->rule, c->nelem, dout.p,
+                                                                          num.p, den.p);
+    c->launches++;
+  }
+  if (n > 0) {
+    k_nodal_mean<<<grid_for(n * 3, 256), 256, 0, c->stream>>>(num.p, den.p, n, res.p);
+    c->launches++;
+  }
+  FS_CUDA(cudaGetLastError());
+  FS_TRY(download(c, out, res.p, (size_t)n * 3 * sizeof(double)));
   FS_CUDA(cudaStreamSynchronize(c->stream));
   return FSGPU_OK;
 }

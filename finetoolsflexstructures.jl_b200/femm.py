@@ -680,12 +680,15 @@ def _nodal_field_invdist(xyz, conn, loc, values):
 def fieldfromintegpoints(femm, geom0, u, quantity, component, outputcsys=None):
     """FinEtools `fieldfromintegpoints(femm, geom, u, quantity, component; outputcsys)` with its default
     `nodevalmethod = :invdistance` (as called by test/test_shell_resultants.jl:123 and the shell examples): the batched
-    resultants of the device (`inspectintegpoints`) averaged to the nodes on the host.  `component`: 1-based index or
-    indices; returns a NodalField with one column per component."""
-    res = inspectintegpoints(femm, geom0, u, None, quantity, outputcsys)
+    resultants averaged to the nodes on the device (`fsgpu_shell_nodal_field`; `_nodal_field_invdist` is the same rule in
+    NumPy, kept as the tests' mirror).  `component`: 1-based index or indices; returns a NodalField with one column per
+    component."""
+    _require_associated(femm)
+    femm._sync_mesh(geom0)
+    femm._sync_stab()
     comp = np.atleast_1d(np.asarray(component, dtype=np.int64)) - 1
-    xyz = np.asarray(geom0.values, dtype=np.float64)
-    return NodalField(_nodal_field_invdist(xyz, femm.integdomain.conn, _integration_point_locations(femm, geom0), res[:, :, comp]))
+    fld = femm.ctx.shell_nodal_field(femm._params(), femm._kind(), _QUANTITY[quantity], u.values, outputcsys)
+    return NodalField(fld[:, comp])
 
 
 def elemfieldfromintegpoints(femm, geom0, u, quantity, component, outputcsys=None):

@@ -211,6 +211,11 @@ int fsgpu_shell_mass_diag(fsgpu_ctx* ctx, const fsgpu_shell_params* p, int32_t k
  * u: nnodes x 6 column-major (the displacement/rotation field); out: 3 x npts x nelem. */
 int fsgpu_shell_resultants(fsgpu_ctx* ctx, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
                            const double* outputcsys, int64_t ncs, double* out);
+/* fieldfromintegpoints (FinEtools FEMMBaseModule, nodevalmethod = :invdistance; test/test_shell_resultants.jl:123-126): the
+ * same resultants averaged to the nodes on the device, weights 1 / (squared distance node - integration point); same
+ * arguments as fsgpu_shell_resultants; out: nnodes x 3 column-major (the three components of the quantity as nodal fields) */
+int fsgpu_shell_nodal_field(fsgpu_ctx* ctx, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
+                            const double* outputcsys, int64_t ncs, double* out);
 /* R <- exp(dtheta) R per node (src/RotUtilModule.jl:29-42); dchi_values nnodes x 6 column-major */
 int fsgpu_update_rotation_field(fsgpu_ctx* ctx, const double* dchi_values, double* Rfield_out);
 
