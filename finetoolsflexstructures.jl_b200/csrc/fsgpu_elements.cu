@@ -2751,6 +2751,7 @@ static int resultants_device(fsgpu_ctx* c, const fsgpu_shell_params* p, int32_t 
 }
 extern "C" int fsgpu_shell_resultants(fsgpu_ctx* c, const fsgpu_shell_params* p, int32_t kind, int32_t quantity, const double* u,
                                       const double* outputcsys, int64_t ncs, double* out) {
+  FS_REQUIRE(out != nullptr, FSGPU_ERR_ARG, "null output");
   DBuf<double> dout;
   int npts = 0;
   FS_TRY(resultants_device(c, p, kind, quantity, u, outputcsys, ncs, dout, &npts));
