@@ -591,6 +591,31 @@ def test_beam_simply_supported_uniform_load(direction):
     assert abs(d.values[n // 2, direction - 1] - deflex) / deflex < 1.0e-5
 
 
+@pytest.mark.parametrize("force,deflex", [([-1e-5, 0, 0], [-1.91840e-06, 0.0, -7.18697e-07]), ([0, 1e-5, 0], [0.0, 4.78846e-03, 0.0])])
+def test_beam_l_frame_tip_deflection(force, deflex):
+    """test/test_beam_linear_statics.jl:349-437 (in-plane tip force) and :445-533 (out-of-plane: bending + torsion of the
+    thin 0.6 x 30 section): L-frame of two legs with 8 elements each, clamped at one end, tip force 1e-5; tip deflection
+    against the reference's 6-digit numbers to 1e-5."""
+    E, nu, b, h, L, n = 71240.0, 0.31, 0.6, 30.0, 240.0, 8
+    s = np.linspace(0.0, 1.0, n + 1)[:, None]
+    xyz = np.vstack([np.array([[0.0, 0, L]]) + s * np.array([[L, 0, 0.0]]), np.array([[L, 0.0, L]]) + s[1:] * np.array([[0.0, 0, -L]])])
+    conn = np.column_stack([np.arange(1, 2 * n + 1), np.arange(2, 2 * n + 2)])
+    sec = _rect_section(b, h, [0.0, 1.0, 0.0], 2 * n)
+    d = fx.DofField(xyz.shape[0])
+    for i in range(1, 7):
+        d.setebc(fx.selectnode_box(xyz, [0, 0, 0, 0, L, L], L / 10000), i)
+    d.numberdofs()
+    nn = xyz.shape[0]
+    u0, R0 = np.zeros((nn, 3)), obeam.initial_Rfield(nn)
+    dn, na = d.gatherdofnums(conn), d.nalldofs
+    K = fx.csc_to_scipy(*fx.assemble_matrix("symm", obeam.beam_stiffness_elmats(xyz, conn, u0, R0, sec, E, nu), dn, na), na, na)
+    tip = fx.selectnode_box(xyz, [L, L, 0, 0, 0, 0], L / 10000)
+    F = np.zeros((nn, 6))
+    F[tip[0], :3] = force
+    fx.solve_blocked(K, F, d)
+    assert np.linalg.norm(d.values[tip[0], :3] - np.array(deflex)) / np.linalg.norm(deflex) < 1.0e-5
+
+
 def test_assembler_equivalence():
     """test/test_utilities.jl:12-47: SysmatAssemblerSparseCSRSymm == SysmatAssemblerSparseSymm."""
     m1 = np.array([[0.24406, 0.599773, 0.833404, 0.0420141], [0.786024, 0.00206713, 0.995379, 0.780298], [0.845816, 0.198459, 0.355149, 0.224996]])
