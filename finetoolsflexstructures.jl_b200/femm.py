@@ -645,44 +645,12 @@ def inspectintegpoints(femm, geom0, u, felist=None, quantity="moment", outputcsy
     return out if felist is None else out[np.asarray(felist) - 1]
 
 
-def _integration_point_locations(femm, geom0):
-    """(nelem, npts, 3): the `loc` the reference's inspectintegpoints hands to its inspector -- the centroid for the T3
-    shells (src/FEMMShellT3FFModule.jl:888), the integration point for the Q4 shells (src/FEMMShellQ4RSModule.jl:1103)."""
-    conn = np.asarray(femm.integdomain.conn)
-    X = np.asarray(geom0.values, dtype=np.float64)[conn - 1]
-    if femm._nnpe == 3:
-        return X.mean(axis=1)[:, None, :]
-    pc, _ = femm.integdomain.rule if femm.integdomain.rule is not None else GaussRule2x2()
-    return np.stack([np.einsum("a,eai->ei", _q4_shape(xi, eta)[0], X) for xi, eta in pc], axis=1)
-
-
-def _nodal_field_invdist(xyz, conn, loc, values):
-    """FinEtools' inverse-distance rule of `fieldfromintegpoints` (FEMMBaseModule, FinEtools 8.2.5): every integration point
-    adds value / (d + dmin / 1e9) to the nodes of its element, d the SQUARED distance node - point, dmin the smallest
-    positive one of the element; a node's value is the weighted mean.  conn (ne, nn) 1-based, loc (ne, npts, 3),
-    values (ne, npts, ncomp) -> (nnodes, ncomp).  (Pinned by the goldens of test/test_shell_statics.jl:690-728.)"""
-    c = np.asarray(conn) - 1
-    num = np.zeros((xyz.shape[0], values.shape[2]))
-    den = np.zeros(xyz.shape[0])
-    for q in range(loc.shape[1]):
-        d = ((xyz[c] - loc[:, q, None, :]) ** 2).sum(axis=2)
-        dmin = np.where(d > 0, d, np.inf).min(axis=1) / 1.0e9
-        w = 1.0 / (d + dmin[:, None])
-        for a in range(c.shape[1]):
-            np.add.at(num, c[:, a], w[:, a, None] * values[:, q, :])
-            np.add.at(den, c[:, a], w[:, a])
-    out = np.zeros_like(num)
-    nz = den > 0
-    out[nz] = num[nz] / den[nz, None]
-    return out
-
-
 def fieldfromintegpoints(femm, geom0, u, quantity, component, outputcsys=None):
     """FinEtools `fieldfromintegpoints(femm, geom, u, quantity, component; outputcsys)` with its default
     `nodevalmethod = :invdistance` (as called by test/test_shell_resultants.jl:123 and the shell examples): the batched
-    resultants averaged to the nodes on the device (`fsgpu_shell_nodal_field`; `_nodal_field_invdist` is the same rule in
-    NumPy, kept as the tests' mirror).  `component`: 1-based index or indices; returns a NodalField with one column per
-    component."""
+    resultants averaged to the nodes on the device (`fsgpu_shell_nodal_field`: weights 1 / squared distance between the
+    node and the integration point -- the centroid for the T3 shells).  `component`: 1-based index or indices; returns a
+    NodalField with one column per component."""
     _require_associated(femm)
     femm._sync_mesh(geom0)
     femm._sync_stab()

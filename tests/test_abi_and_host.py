@@ -237,18 +237,3 @@ def test_workload_generators_match_finetools_block_meshes():
         X, Ct = wl.t3block(3.0, 2.0, nL, nW)
         assert np.array_equal(c, Ct)
 
-
-def test_nodal_field_invdist_matches_the_oracle_restatement():
-    """Host-side mirror of FinEtools' inverse-distance `fieldfromintegpoints` (femm._nodal_field_invdist) against the
-    oracle's restatement, which the reference's resultants goldens pin (tests/test_oracle_goldens.py)."""
-    import fsb200
-    from oracle import fe_external as fx
-
-    rng = np.random.default_rng(5)
-    xyz = rng.standard_normal((40, 3))
-    conn = rng.integers(1, 41, size=(70, 4))
-    loc = xyz[conn - 1].mean(axis=1)[:, None, :] + 0.1 * rng.standard_normal((70, 4, 3))
-    vals = rng.standard_normal((70, 4, 2))
-    a = fsb200.femm._nodal_field_invdist(xyz, conn, loc, vals)
-    b = fx.field_from_integpoints_invdist(xyz, conn, loc, vals)
-    assert np.array_equal(a, b)
