@@ -570,6 +570,23 @@ function shell_resultants(c::Context, params::ShellParams, kind::Integer, quanti
         c.h, Ref(params), kind, _QUANTITY[quantity], pointer(uv), cs, ncs, pointer(out)))
     return out
 end
+"""
+    shell_nodal_field(c, params, kind, quantity, u, nnodes; outputcsys) -> Matrix{Float64}(nnodes, 3)
+
+`fieldfromintegpoints` with the default `nodevalmethod = :invdistance`, evaluated on the device (`fsgpu_shell_nodal_field`):
+the three components of `quantity` as nodal fields.  FinEtools' own `fieldfromintegpoints` also works unchanged on top of
+the `inspectintegpoints` methods below; this call avoids the per-point inspector callback.
+"""
+function shell_nodal_field(c::Context, params::ShellParams, kind::Integer, quantity::Symbol, u::NodalField{Float64}, nnodes::Integer;
+        outputcsys::Union{Nothing,Array{Float64,3}} = nothing)
+    out = Matrix{Float64}(undef, nnodes, 3)
+    cs, ncs = outputcsys === nothing ? (C_NULL, 0) : (pointer(outputcsys), size(outputcsys, 3))
+    uv = u.values
+    GC.@preserve uv outputcsys out _check(ccall((:fsgpu_shell_nodal_field, libfsgpu), Cint,
+        (Ptr{Cvoid}, Ref{ShellParams}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+        c.h, Ref(params), kind, _QUANTITY[quantity], pointer(uv), cs, ncs, pointer(out)))
+    return out
+end
 function _inspect(c::Context, self, kind::Integer, comp::Bool, geom0, u, felist, inspector, idat, quantity; context...)
     fes = self.integdomain.fes
     nnpe = nodesperelem(fes)
@@ -817,7 +834,7 @@ end
 
 export SysmatAssemblerGPU, SysvecAssemblerGPU, Context, default_context, invalidate!, ExplicitGPU, sparse_gpu
 export set_load!, set_timestep!, start!, step!, state, run!, omega_max_sq, kinetic_energy, set_deterministic!
-export shell_resultants, result_block!, result_block_size, update_rotation_field_gpu!, CSysKind, register_csys_kind!
+export shell_resultants, shell_nodal_field, result_block!, result_block_size, update_rotation_field_gpu!, CSysKind, register_csys_kind!
 export pinned_vector, refresh_values!
 export SPARSE, SPARSE_SYMM, SPARSE_DIAG, FFBLOCK, FFBLOCK_DIAG, CSR_SYMM, CSYS_CYLINDRICAL, CSYS_SPHERICAL, CSYS_NORMAL_AXIS
 
